@@ -1,0 +1,1628 @@
+// Host side of libparrot_b200.so: configuration, parameter inventory, workspace
+// carving, TMA tensor maps, GEMM job tables, and the forward / backward /
+// sampling / optimizer orchestration behind the C ABI of include/parrot_b200.h.
+//
+// Reference call sites replaced (all in /root/reference/model.py unless noted):
+//   Parrot.compute_cost 552-824, step 651-724, sample_model_fun 827-1059,
+//   initial_states 529-549, Encoder.apply 233-247; train.py:100-108 (optimizer).
+#include "../../include/parrot_b200.h"
+#include "kernels.cuh"
+
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+using namespace pb;
+
+// ------------------------------------------------------------------ utilities
+static thread_local std::string g_err;
+static std::atomic<long long> g_launches{0};
+
+#define CK(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess) {                                                                  \
+      char buf_[512];                                                                         \
+      snprintf(buf_, sizeof buf_, "%s:%d CUDA error %s: %s", __FILE__, __LINE__, #call,      \
+               cudaGetErrorString(e_));                                                       \
+      throw std::runtime_error(buf_);                                                         \
+    }                                                                                         \
+  } while (0)
+#define REQUIRE(cond, msg)                                                     \
+  do {                                                                         \
+    if (!(cond)) throw std::runtime_error(std::string("parrot_b200: ") + msg); \
+  } while (0)
+#define LAUNCH(kern, grid, block, smem, st, ...)        \
+  do {                                                  \
+    kern<<<grid, block, smem, st>>>(__VA_ARGS__);       \
+    g_launches.fetch_add(1, std::memory_order_relaxed); \
+    CK(cudaGetLastError());                             \
+  } while (0)
+
+template <typename F>
+static int guard(F&& f) {
+  try {
+    f();
+    return 0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return 1;
+  }
+}
+
+static inline int rup(int x, int m) { return (x + m - 1) / m * m; }
+static inline long long rupl(long long x, long long m) { return (x + m - 1) / m * m; }
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+static inline int gs_blocks(long long n, int block = 256) {
+  long long b = (n + block - 1) / block;
+  if (b > 148 * 16) b = 148 * 16;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+    REQUIRE(p && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available");
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// ------------------------------------------------------------------ dimensions
+struct Dims {
+  int H, R, D, A, C, U, B, T, E, S, K, Dtot, IN, NC;
+  int Np, Hp, Cp, Rp, Dp, Dtp, Ap;
+  bool enc, spk, weak, full, gmm, sampling;
+};
+static Dims make_dims(const parrot_config& c) {
+  Dims d;
+  d.H = c.rnn_h_dim; d.R = c.readouts_dim; d.D = c.output_dim; d.A = c.attention_size;
+  d.enc = c.encoder_type == 1;
+  d.E = c.encoder_dim; d.IN = c.input_dim; d.NC = c.num_characters;
+  d.C = d.enc ? 2 * c.encoder_dim : c.input_dim;
+  d.U = c.text_len; d.B = c.batch_size; d.T = c.seq_len; d.S = c.speaker_dim; d.K = c.k_gmm;
+  d.gmm = c.which_cost == 1;
+  d.Dtot = d.gmm ? 2 * d.D * d.K + d.K : d.D;
+  d.spk = c.use_speaker != 0;
+  d.full = c.full_feedback != 0;
+  d.weak = c.weak_feedback != 0 || d.full;
+  d.sampling = c.sampling != 0;
+  d.Np = rup(d.B, 16); d.Hp = rup(d.H, 64); d.Cp = rup(d.C, 64); d.Rp = rup(d.R, 64);
+  d.Dp = rup(d.D, 64); d.Dtp = rup(d.Dtot, 64); d.Ap = 64;
+  return d;
+}
+static void check_cfg(const parrot_config& c) {
+  REQUIRE(c.layer_norm == 0, "layer_norm=True is not implemented on the device path yet");
+  REQUIRE(c.batch_size >= 1 && c.batch_size <= 256, "batch_size per device must be in [1, 256]");
+  REQUIRE(c.seq_len >= 1 && c.text_len >= 1, "seq_len / text_len must be positive");
+  REQUIRE(3 * c.attention_size <= 64 && c.attention_size <= 32, "attention_size must be <= 21");
+  REQUIRE(c.which_cost == 0 || c.k_gmm <= 32, "k_gmm must be <= 32");
+  REQUIRE(c.encoder_type == 0 || c.encoder_type == 1, "encoder_type must be 0 (None) or 1 (bidirectional)");
+  REQUIRE(c.encoder_type == 1 || c.num_characters == c.input_dim, "model.py:224 num_characters == input_dim");
+  REQUIRE(c.rnn_h_dim >= 64 && c.rnn_h_dim % 64 == 0, "rnn_h_dim must be a multiple of 64");
+  REQUIRE(c.readouts_dim >= 16, "readouts_dim too small");
+}
+
+// ------------------------------------------------------------------ parameters
+struct PInfo {
+  std::string name;
+  long long off;
+  int rows, cols;  // cols == 0: vector of `rows`
+  long long numel() const { return cols ? (long long)rows * cols : rows; }
+};
+struct PReg {
+  std::vector<PInfo> v;
+  std::map<std::string, int> idx;
+  long long total = 0;
+  void add(const std::string& n, int r, int c) {
+    PInfo p{n, total, r, c};
+    idx[n] = (int)v.size();
+    v.push_back(p);
+    total += rupl(p.numel(), 64);
+  }
+  void lin(const std::string& n, int i, int o) { add(n + ".W", i, o); add(n + ".b", o, 0); }
+  void fork(const std::string& n, int i, const std::vector<std::string>& outs, const std::vector<int>& dims) {
+    for (size_t k = 0; k < outs.size(); ++k) lin(n + "/fork_" + outs[k], i, dims[k]);
+  }
+  void gru(const std::string& n, int d) {
+    add(n + ".state_to_state", d, d);
+    add(n + ".state_to_gates", d, 2 * d);
+    add(n + ".initial_state", d, 0);
+  }
+  // Linear bricks may be named without the ".W" suffix
+  const PInfo& get(const std::string& n) const {
+    auto it = idx.find(n);
+    if (it == idx.end()) it = idx.find(n + ".W");
+    if (it == idx.end()) throw std::runtime_error("parrot_b200: unknown parameter " + n);
+    return v[it->second];
+  }
+  bool has(const std::string& n) const { return idx.count(n) != 0; }
+};
+// Same inventory and order as oracle.param_shapes (model.py:251-506); tests compare the two.
+static PReg make_params(const parrot_config& c) {
+  const Dims d = make_dims(c);
+  PReg P;
+  const std::string root = "/parrot";
+  auto ln = [](int i) { return std::to_string(i); };
+  if (d.enc) {
+    P.add(root + "/encoder/embed_label.W", d.NC, d.IN);
+    for (const char* dir : {"forward", "backward"}) {
+      const std::string base = root + "/encoder/encoder/" + dir;
+      P.gru(base + "/gatedrecurrent", d.E);
+      P.fork(base + "/fork", d.IN, {"inputs", "gate_inputs"}, {d.E, 2 * d.E});
+    }
+  }
+  for (int i = 1; i <= 3; ++i) P.gru(root + "/rnn" + ln(i), d.H);
+  for (int i = 1; i <= 3; ++i) P.lin(root + "/h" + ln(i) + "_to_readout", d.H, d.R);
+  P.fork(root + "/h1_to_h2", d.H, {"rnn2_inputs", "rnn2_gates"}, {d.H, 2 * d.H});
+  P.fork(root + "/h1_to_h3", d.H, {"rnn3_inputs", "rnn3_gates"}, {d.H, 2 * d.H});
+  P.fork(root + "/h2_to_h3", d.H, {"rnn3_inputs", "rnn3_gates"}, {d.H, 2 * d.H});
+  if (!d.gmm) P.lin(root + "/readout_to_output", d.R, d.D);
+  else P.fork(root + "/readout_to_output", d.R, {"gmm_mu", "gmm_sigma", "gmm_coeff"}, {d.D * d.K, d.D * d.K, d.K});
+  for (int i = 1; i <= 3; ++i)
+    P.fork(root + "/inp_to_h" + ln(i), d.C, {"rnn" + ln(i) + "_inputs", "rnn" + ln(i) + "_gates"}, {d.H, 2 * d.H});
+  P.fork(root + "/h1_to_att", d.H, {"alpha", "beta", "kappa"}, {d.A, d.A, d.A});
+  P.lin(root + "/att_to_readout", d.C, d.R);
+  if (d.spk) {
+    P.add(root + "/lookuptable.W", c.num_speakers, d.S);
+    for (int i = 1; i <= 3; ++i)
+      P.fork(root + "/speaker_to_h" + ln(i), d.S, {"rnn" + ln(i) + "_inputs", "rnn" + ln(i) + "_gates"},
+             {d.H, 2 * d.H});
+    P.lin(root + "/speaker_to_readout", d.S, d.R);
+    if (!d.gmm) P.lin(root + "/speaker_to_output", d.S, d.D);
+    else P.fork(root + "/speaker_to_output", d.S, {"gmm_mu", "gmm_sigma", "gmm_coeff"}, {d.D * d.K, d.D * d.K, d.K});
+  }
+  if (d.full) {
+    P.fork(root + "/out_to_h2", d.D, {"rnn2_inputs", "rnn2_gates"}, {d.H, 2 * d.H});
+    P.fork(root + "/out_to_h3", d.D, {"rnn3_inputs", "rnn3_gates"}, {d.H, 2 * d.H});
+  }
+  if (d.weak) P.fork(root + "/out_to_h1", d.D, {"rnn1_inputs", "rnn1_gates"}, {d.H, 2 * d.H});
+  P.add(root + ".initial_w", d.C, 0);
+  return P;
+}
+
+// ------------------------------------------------------------------ model
+struct Plane {
+  bf16* hi = nullptr;
+  bf16* lo = nullptr;
+  int rows = 0;       // rows per slot
+  int pitch = 0;      // elements per row (multiple of 64)
+  int slots = 1;
+  long long rows_alloc = 0;  // total rows allocated (slots*rows rounded up to 128)
+};
+struct WPack {
+  std::string name;
+  int in = 0, out = 0;
+  Plane fwd, bwd;     // fwd: [out_p128][in_p64] (W^T), bwd: [in_p128][out_p64] (W)
+  int fwd_map = -1, bwd_map = -1;
+  bool need_bwd = true;
+};
+struct Table {
+  int off = 0, count = 0, n_cols = 0;
+};
+struct Buf {
+  size_t off;
+  size_t bytes;
+};
+struct WGrad {
+  int xt_map, a_k, dyt_map, b_row, in, out;
+  long long goff;
+};
+
+struct parrot_model {
+  parrot_config cfg;
+  Dims d;
+  PReg P;
+  float* params = nullptr;
+  float* grads = nullptr;
+  uint8_t* ws = nullptr;
+  size_t ws_bytes = 0, ws_used = 0;
+  bool dry = true;
+  std::map<std::string, Buf> bufs;
+  std::vector<CUtensorMap> maps;
+  std::vector<MapRaw> raws;
+  CUtensorMap* d_maps = nullptr;
+  MapRaw* d_raws = nullptr;
+  std::vector<Job> jobs;
+  Job* d_jobs = nullptr;
+  ScanCtx ctx;
+  ScanCtx* d_ctx = nullptr;
+  std::map<std::string, WPack> packs;
+  std::map<std::string, Plane> planes;
+  std::map<std::string, int> map_scan, map_plain, map_tA, map_tB;  // plane name -> hi map index
+  std::map<std::string, Table> tables;
+  std::vector<WGrad> wgrads;
+  bool dirty = true;
+  float last_start_flag = 1.0f;
+  bool have_fwd = false;
+
+  // ---- workspace ----
+  void* alloc(const std::string& name, size_t bytes) {
+    ws_used = (ws_used + 1023) & ~size_t(1023);
+    const size_t off = ws_used;
+    ws_used += bytes;
+    if (!name.empty()) bufs[name] = Buf{off, bytes};
+    if (dry) return nullptr;
+    REQUIRE(ws_used <= ws_bytes, "workspace too small");
+    return ws + off;
+  }
+  float* falloc(const std::string& name, long long n) { return (float*)alloc(name, (size_t)n * 4); }
+  float* fbuf(const std::string& name) const {
+    auto it = bufs.find(name);
+    if (it == bufs.end()) throw std::runtime_error("parrot_b200: unknown buffer " + name);
+    return (float*)(ws + it->second.off);
+  }
+  float* pp(const std::string& n) const { return params + P.get("/parrot" + n).off; }
+  float* gp(const std::string& n) const { return grads + P.get("/parrot" + n).off; }
+
+  Plane make_plane(const std::string& name, int rows, int cols, int slots) {
+    Plane p;
+    p.rows = rows;
+    p.pitch = rup(cols, 64);
+    p.slots = slots;
+    p.rows_alloc = rupl((long long)rows * slots, 128);
+    const size_t bytes = (size_t)p.rows_alloc * p.pitch * 2;
+    p.hi = (bf16*)alloc(name + ".hi", bytes);
+    p.lo = (bf16*)alloc(name + ".lo", bytes);
+    planes[name] = p;
+    return p;
+  }
+  // returns the index of the hi map; lo map follows
+  int make_map(const Plane& p, int rank, int box_rows) {
+    const int idx = (int)maps.size();
+    for (int w = 0; w < 2; ++w) {
+      CUtensorMap m;
+      memset(&m, 0, sizeof m);
+      MapRaw r;
+      r.base = w ? p.lo : p.hi;
+      r.row_pitch = p.pitch;
+      r.box_rows = box_rows;
+      r.cols = p.pitch;
+      if (rank == 2) {
+        r.slot_pitch = 0; r.rows = (int)p.rows_alloc; r.slots = 1;
+      } else {
+        r.slot_pitch = (long long)p.rows * p.pitch; r.rows = p.rows; r.slots = p.slots;
+      }
+      if (!dry) {
+        cuuint64_t dims[3] = {(cuuint64_t)p.pitch, (cuuint64_t)(rank == 2 ? p.rows_alloc : p.rows),
+                              (cuuint64_t)p.slots};
+        cuuint64_t strides[2] = {(cuuint64_t)p.pitch * 2, (cuuint64_t)p.rows * p.pitch * 2};
+        cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
+        cuuint32_t es[3] = {1, 1, 1};
+        CUresult res = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, (void*)r.base, dims,
+                                    strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (res != CUDA_SUCCESS) {
+          char b[256];
+          snprintf(b, sizeof b, "cuTensorMapEncodeTiled failed (%d) rank %d rows %d pitch %d box %d", (int)res,
+                   rank, p.rows, p.pitch, box_rows);
+          throw std::runtime_error(b);
+        }
+      }
+      maps.push_back(m);
+      raws.push_back(r);
+    }
+    return idx;
+  }
+  WPack& add_pack(const std::string& pname, bool need_bwd) {
+    const PInfo& pi = P.get("/parrot" + pname);
+    WPack w;
+    w.name = pname; w.in = pi.rows; w.out = pi.cols; w.need_bwd = need_bwd;
+    w.fwd = make_plane("pack.f" + pname, rup(w.out, 128), w.in, 1);
+    w.fwd_map = make_map(w.fwd, 2, 128);
+    if (need_bwd) {
+      w.bwd = make_plane("pack.b" + pname, rup(w.in, 128), w.out, 1);
+      w.bwd_map = make_map(w.bwd, 2, 128);
+    }
+    packs[pname] = w;
+    return packs[pname];
+  }
+};
+
+static const int NT = 128;  // sample tile of the batched (outside-the-scan) products
+
+// ------------------------------------------------------------------ job builders
+static Seg mkseg(int a_map, int a_row, int a_k, int b_map, int b_row, int b_k, int b_slot, int nkb) {
+  Seg s;
+  s.a_map = a_map; s.a_row = a_row; s.a_k = a_k; s.b_map = b_map; s.b_row = b_row; s.b_k = b_k;
+  s.b_slot = b_slot; s.nkb = nkb;
+  return s;
+}
+static Job blank_job() {
+  Job j;
+  memset(&j, 0, sizeof j);
+  j.pa.scale = 1.0f;
+  return j;
+}
+
+static std::string LN(int l) { return std::to_string(l + 1); }
+
+// forward scan jobs of one layer (gates or candidate): model.py:655-662, 692-722
+static void build_fwd_layer_jobs(parrot_model& M, std::vector<Job>& out, int layer, bool gates, int lag) {
+  const Dims& d = M.d;
+  const int rows = gates ? 2 * d.H : d.H;
+  const std::string l = LN(layer);
+  const std::string fk = gates ? "_gates" : "_inputs";
+  for (int mt = 0; mt < cdiv(rows, 128); ++mt) {
+    Job j = blank_job();
+    j.epi = gates ? EPI_GATES : EPI_CAND;
+    j.lag = lag; j.layer = layer; j.row0 = mt * 128;
+    j.m_valid = std::min(128, rows - mt * 128);
+    int ns = 0;
+    const int hmap = M.map_scan["h" + l];
+    if (gates)
+      j.seg[ns++] = mkseg(M.packs["/rnn" + l + ".state_to_gates"].fwd_map, mt * 128, 0, hmap, 0, 0, 0, d.Hp / 64);
+    else
+      j.seg[ns++] = mkseg(M.packs["/rnn" + l + ".state_to_state"].fwd_map, mt * 128, 0, M.map_scan["rh" + l], 0, 0,
+                          0, d.Hp / 64);
+    // attention context: layer 1 consumes w_{t-1} (slot t), layers 2,3 consume w_t (slot t+1)
+    j.seg[ns++] = mkseg(M.packs["/inp_to_h" + l + "/fork_rnn" + l + fk].fwd_map, mt * 128, 0, M.map_scan["w"], 0, 0,
+                        layer == 0 ? 0 : 1, d.Cp / 64);
+    if (layer >= 1)
+      j.seg[ns++] = mkseg(M.packs["/h1_to_h" + l + "/fork_rnn" + l + fk].fwd_map, mt * 128, 0, M.map_scan["h1"], 0, 0,
+                          1, d.Hp / 64);
+    if (layer == 2)
+      j.seg[ns++] = mkseg(M.packs["/h2_to_h3/fork_rnn3" + fk].fwd_map, mt * 128, 0, M.map_scan["h2"], 0, 0, 1,
+                          d.Hp / 64);
+    if ((layer == 0 && d.weak) || (layer > 0 && d.full))
+      j.seg[ns++] = mkseg(M.packs["/out_to_h" + l + "/fork_rnn" + l + fk].fwd_map, mt * 128, 0, M.map_scan["xin"], 0,
+                          0, 0, d.Dp / 64);
+    j.nseg = ns;
+    out.push_back(j);
+  }
+}
+
+// batched product over all frames: out[sample][f0 + row] = sum_seg ...
+struct PlainSeg {
+  int a_map, a_k, b_map, b_row0, b_k, nkb;
+};
+static void build_plain_jobs(std::vector<Job>& out, int Mrows, int f0, long long n_samples,
+                             const std::vector<PlainSeg>& segs, const PlainArgs& pa) {
+  for (int mt = 0; mt < cdiv(Mrows, 128); ++mt)
+    for (int nt = 0; nt < cdiv(n_samples, NT); ++nt) {
+      Job j = blank_job();
+      j.epi = EPI_PLAIN;
+      j.row0 = f0 + mt * 128;
+      j.m_valid = std::min(128, Mrows - mt * 128);
+      j.n0 = nt * NT;
+      j.nseg = (int)segs.size();
+      for (size_t s = 0; s < segs.size(); ++s)
+        j.seg[s] = mkseg(segs[s].a_map, mt * 128, segs[s].a_k, segs[s].b_map, segs[s].b_row0 + nt * NT, segs[s].b_k,
+                         NO_SLOT, segs[s].nkb);
+      j.pa = pa;
+      out.push_back(j);
+    }
+}
+
+static void push_table(parrot_model& M, const std::string& name, const std::vector<Job>& js, int n_cols) {
+  Table t;
+  t.off = (int)M.jobs.size();
+  t.count = (int)js.size();
+  t.n_cols = n_cols;
+  M.jobs.insert(M.jobs.end(), js.begin(), js.end());
+  M.tables[name] = t;
+}
+
+static void run_table(parrot_model& M, const std::string& name, int tick, int T, int reverse, cudaStream_t st) {
+  const Table& t = M.tables.at(name);
+  if (t.count == 0) return;
+  EngineParams P;
+  P.jobs = M.d_jobs + t.off; P.njobs = t.count; P.maps = M.d_maps; P.raws = M.d_raws; P.ctx = M.d_ctx;
+  P.tick = tick; P.T = T; P.n_cols = t.n_cols; P.reverse = reverse;
+  if (M.cfg.gemm_impl == 1) {
+    const int grid = std::min(t.count, 148 * 8);
+    LAUNCH(job_kernel_simt, grid, 128, 0, st, P);
+  } else {
+    const int grid = std::min(t.count, 148);
+    LAUNCH(job_kernel_tc, grid, ENGINE_THREADS, SMEM_BYTES + 1024, st, P);
+  }
+}
+
+// ------------------------------------------------------------------ build
+static void build(parrot_model& M) {
+  const Dims& d = M.d;
+  M.ws_used = 0;
+  M.bufs.clear(); M.maps.clear(); M.raws.clear(); M.jobs.clear(); M.packs.clear(); M.planes.clear();
+  M.tables.clear(); M.wgrads.clear();
+  const int T = d.T, B = d.B, H = d.H, Np = d.Np;
+  const bool train = !d.sampling;
+
+  // ---- weight packs
+  for (int l = 0; l < 3; ++l) {
+    const std::string s = LN(l);
+    M.add_pack("/rnn" + s + ".state_to_gates", train);
+    M.add_pack("/rnn" + s + ".state_to_state", train);
+    M.add_pack("/inp_to_h" + s + "/fork_rnn" + s + "_inputs", train);
+    M.add_pack("/inp_to_h" + s + "/fork_rnn" + s + "_gates", train);
+    M.add_pack("/h" + s + "_to_readout", train);
+    if ((l == 0 && d.weak) || (l > 0 && d.full)) {
+      M.add_pack("/out_to_h" + s + "/fork_rnn" + s + "_inputs", false);
+      M.add_pack("/out_to_h" + s + "/fork_rnn" + s + "_gates", false);
+    }
+  }
+  for (const char* nm : {"/h1_to_h2/fork_rnn2", "/h1_to_h3/fork_rnn3", "/h2_to_h3/fork_rnn3"}) {
+    M.add_pack(std::string(nm) + "_inputs", train);
+    M.add_pack(std::string(nm) + "_gates", train);
+  }
+  M.add_pack("/att_to_readout", train);
+  std::vector<std::string> out_forks;
+  std::vector<int> out_off, out_dim;
+  if (!d.gmm) {
+    out_forks = {"/readout_to_output"}; out_off = {0}; out_dim = {d.D};
+  } else {
+    out_forks = {"/readout_to_output/fork_gmm_mu", "/readout_to_output/fork_gmm_sigma",
+                 "/readout_to_output/fork_gmm_coeff"};
+    out_off = {0, d.D * d.K, 2 * d.D * d.K};
+    out_dim = {d.D * d.K, d.D * d.K, d.K};
+  }
+  for (auto& f : out_forks) M.add_pack(f, train);
+
+  // ---- fp32 staging of small derived quantities
+  M.falloc("att_wT", (long long)3 * d.A * H);
+  M.falloc("att_b", 3 * d.A);
+  for (int l = 0; l < 3; ++l) M.falloc("bias_l" + LN(l), 3 * H);
+  M.falloc("bias_ro", d.R);
+  M.falloc("bias_out", d.Dtot);
+  for (int l = 0; l < 3; ++l) M.falloc("base" + LN(l), (long long)B * 3 * H);
+  if (d.spk) {
+    M.falloc("spk_emb", (long long)B * d.S);
+    M.falloc("spk_ro", (long long)B * d.R);
+    M.falloc("spk_out", (long long)B * d.Dtot);
+    M.falloc("spk_dproj", (long long)B * 3 * H);
+    M.falloc("spk_demb", (long long)B * d.S);
+    M.falloc("spk_dro", (long long)B * d.R);
+    M.falloc("spk_dout", (long long)B * d.Dtot);
+  }
+  // ---- carried state (model.py:534-546)
+  for (int l = 0; l < 3; ++l) M.falloc("last_h" + LN(l), (long long)B * H);
+  M.falloc("last_k", (long long)B * d.A);
+  M.falloc("last_w", (long long)B * d.C);
+  M.falloc("cost", 4);
+  M.falloc("opt_stats", 4);
+
+  // ---- encoder
+  M.falloc("ctx", (long long)B * d.U * d.C);
+  if (d.enc) {
+    const int E = d.E;
+    const long long LNn = (long long)B * d.U;
+    M.falloc("enc_proj", (long long)d.NC * 2 * 3 * E);  // per character: [dir][xi(E) | xg(2E)]
+    M.falloc("enc_dproj", (long long)d.NC * 2 * 3 * E);
+    M.alloc("enc_lab", (size_t)LNn * 4);
+    for (int dir = 0; dir < 2; ++dir) {
+      const std::string s = std::to_string(dir);
+      M.falloc("enc_xi" + s, LNn * E); M.falloc("enc_xg" + s, LNn * 2 * E);
+      M.falloc("enc_z" + s, LNn * E); M.falloc("enc_r" + s, LNn * E); M.falloc("enc_c" + s, LNn * E);
+      M.falloc("enc_sp" + s, LNn * E);
+      if (train) {
+        M.falloc("enc_dxi" + s, LNn * E); M.falloc("enc_dxg" + s, LNn * 2 * E);
+        M.falloc("enc_ds0" + s, (long long)std::max(B, d.U) * E);
+        M.falloc("enc_rs" + s, LNn * E);
+      }
+    }
+    M.falloc("enc_out", LNn * 2 * E);
+    if (train) M.falloc("enc_dout", LNn * 2 * E);
+    M.falloc("enc_xcat", LNn * 3 * E);
+  }
+
+  // ---- scan state / stashes
+  ScanCtx& X = M.ctx;
+  memset(&X, 0, sizeof X);
+  X.T = T; X.B = B; X.Np = Np; X.H = H; X.Hp = d.Hp; X.C = d.C; X.Cp = d.Cp; X.A = d.A; X.U = d.U;
+  for (int l = 0; l < 3; ++l) {
+    const std::string s = LN(l);
+    LayerBuf& L = X.L[l];
+    L.h = M.falloc("h" + s, (long long)(T + 1) * B * H);
+    Plane ph = M.make_plane("h" + s, Np, H, T + 1);
+    L.h_hi = ph.hi; L.h_lo = ph.lo;
+    Plane pr = M.make_plane("rh" + s, Np, H, T);
+    L.rh_hi = pr.hi; L.rh_lo = pr.lo;
+    L.z = M.falloc("z" + s, (long long)T * B * H);
+    L.r = M.falloc("r" + s, (long long)T * B * H);
+    L.c = M.falloc("c" + s, (long long)T * B * H);
+    L.base = M.dry ? nullptr : M.fbuf("base" + s);
+    L.fb = nullptr;
+    M.map_scan["h" + s] = M.make_map(ph, 3, Np);
+    M.map_scan["rh" + s] = M.make_map(pr, 3, Np);
+    M.map_plain["h" + s] = M.make_map(ph, 2, NT);
+    if (train) {
+      L.dh = M.falloc("dh" + s, (long long)(T + 1) * B * H);
+      L.da = M.falloc("da" + s, (long long)T * B * 3 * H);
+      Plane pd = M.make_plane("da" + s, Np, 3 * d.Hp, T);
+      L.da_hi = pd.hi; L.da_lo = pd.lo;
+      M.map_scan["da" + s] = M.make_map(pd, 3, Np);
+    }
+  }
+  M.falloc("w", (long long)(T + 1) * B * d.C);
+  Plane pw = M.make_plane("w", Np, d.C, T + 1);
+  M.map_scan["w"] = M.make_map(pw, 3, Np);
+  M.map_plain["w"] = M.make_map(pw, 2, NT);
+  M.falloc("kappa", (long long)(T + 1) * B * d.A);
+  M.falloc("phi", (long long)T * B * d.U);
+  M.falloc("ab", (long long)T * B * 2 * d.A);
+  M.falloc("att_e", (long long)T * B * 3 * d.A);
+  if (d.weak) {
+    Plane px = M.make_plane("xin", Np, d.D, d.sampling ? T + 1 : T);
+    M.map_scan["xin"] = M.make_map(px, 3, Np);
+  }
+  if (train) {
+    X.dw = M.falloc("dw", (long long)(T + 1) * B * d.C);
+    M.falloc("dk_carry", (long long)B * d.A);
+    M.falloc("datt", (long long)T * B * 3 * d.A);
+    M.make_plane("datt", Np, d.Ap, T);
+    M.falloc("dctx", (long long)B * d.U * d.C);
+  }
+  // ---- readout / emitter
+  const int TR = d.sampling ? 1 : T;  // the sampler keeps one step of readouts
+  M.falloc("ro", (long long)TR * B * d.R);
+  Plane pro = M.make_plane("ro", Np, d.R, TR);
+  M.map_plain["ro"] = M.make_map(pro, 2, d.sampling ? Np : NT);
+  M.falloc("pred", (long long)TR * B * d.Dtot);
+  M.falloc("cost_tb", (long long)TR * B);
+  if (d.sampling) {
+    M.falloc("samp_x", (long long)T * B * d.D);
+    M.falloc("samp_pi", (long long)T * B * (d.gmm ? d.K : d.D));
+  }
+  if (train) {
+    M.falloc("next_x", (long long)T * B * d.D);
+    M.falloc("dpred", (long long)T * B * d.Dtot);
+    Plane pdp = M.make_plane("dpred", Np, d.Dtot, T);
+    M.map_plain["dpred"] = M.make_map(pdp, 2, NT);
+    M.falloc("dread", (long long)T * B * d.R);
+    Plane pdr = M.make_plane("dread", Np, d.R, T);
+    M.map_plain["dread"] = M.make_map(pdr, 2, NT);
+    // transposed operand planes for the weight gradients: [features][samples]
+    auto tplane = [&](const std::string& nm, int feat_pitch, long long samples, bool as_a) {
+      Plane p = M.make_plane("T." + nm, rup(feat_pitch, 128), (int)samples, 1);
+      if (as_a) M.map_tA[nm] = M.make_map(p, 2, 128);
+      else M.map_tB[nm] = M.make_map(p, 2, NT);
+    };
+    for (int l = 0; l < 3; ++l) {
+      tplane("h" + LN(l), d.Hp, (long long)(T + 1) * Np, true);
+      tplane("rh" + LN(l), d.Hp, (long long)T * Np, true);
+      tplane("da" + LN(l), 3 * d.Hp, (long long)T * Np, false);
+    }
+    tplane("w", d.Cp, (long long)(T + 1) * Np, true);
+    if (d.weak) tplane("xin", d.Dp, (long long)T * Np, true);
+    tplane("ro", d.Rp, (long long)T * Np, true);
+    tplane("dread", d.Rp, (long long)T * Np, false);
+    tplane("dpred", d.Dtp, (long long)T * Np, false);
+    tplane("datt", d.Ap, (long long)T * Np, false);
+    M.alloc("opt_scratch", 1024 * 8);
+    M.falloc("bias_scratch", (long long)std::max(3 * H, d.R) + d.Dtot + 128);
+  }
+  M.alloc("gemm_scratch", 1024 * 8);
+
+  // ============================ job tables ============================
+  if (train) {
+    std::vector<Job> A, Bj;
+    for (int l = 0; l < 3; ++l) build_fwd_layer_jobs(M, A, l, true, l);
+    for (int l = 0; l < 3; ++l) build_fwd_layer_jobs(M, Bj, l, false, l);
+    push_table(M, "fwdA", A, Np);
+    push_table(M, "fwdB", Bj, Np);
+  } else {
+    for (int l = 0; l < 3; ++l) {
+      std::vector<Job> A, Bj;
+      build_fwd_layer_jobs(M, A, l, true, 0);
+      build_fwd_layer_jobs(M, Bj, l, false, 0);
+      push_table(M, "sampA" + LN(l), A, Np);
+      push_table(M, "sampB" + LN(l), Bj, Np);
+    }
+  }
+  auto planes_of = [&](const std::string& nm) -> Plane& { return M.planes.at(nm); };
+  // readouts (model.py:739-753): [h1,h2,h3,w] . [W1;W2;W3;Wa]
+  {
+    std::vector<Job> js;
+    PlainArgs pa;
+    memset(&pa, 0, sizeof pa);
+    pa.scale = 1.0f;
+    pa.out = M.dry ? nullptr : M.fbuf("ro");
+    pa.bias = M.dry ? nullptr : M.fbuf("bias_ro");
+    pa.hi = planes_of("ro").hi; pa.lo = planes_of("ro").lo;
+    pa.ldo = d.R; pa.ldp = planes_of("ro").pitch;
+    pa.n_pad = Np; pa.n_valid = B;
+    pa.flags = PF_PLANE_PADDED | (d.spk ? PF_ACC : 0);
+    if (train) {
+      pa.n_total = T * Np;
+      std::vector<PlainSeg> segs;
+      for (int l = 0; l < 3; ++l)
+        segs.push_back({M.packs["/h" + LN(l) + "_to_readout"].fwd_map, 0, M.map_plain["h" + LN(l)], Np, 0, d.Hp / 64});
+      segs.push_back({M.packs["/att_to_readout"].fwd_map, 0, M.map_plain["w"], Np, 0, d.Cp / 64});
+      build_plain_jobs(js, d.R, 0, (long long)T * Np, segs, pa);
+      push_table(M, "readout", js, NT);
+    } else {
+      // sampler: one step, operands taken from the scan maps at slot t+1
+      pa.n_total = Np;
+      for (int mt = 0; mt < cdiv(d.R, 128); ++mt) {
+        Job j = blank_job();
+        j.epi = EPI_PLAIN; j.row0 = mt * 128; j.m_valid = std::min(128, d.R - mt * 128);
+        int ns = 0;
+        for (int l = 0; l < 3; ++l)
+          j.seg[ns++] = mkseg(M.packs["/h" + LN(l) + "_to_readout"].fwd_map, mt * 128, 0, M.map_scan["h" + LN(l)], 0,
+                              0, 1, d.Hp / 64);
+        j.seg[ns++] = mkseg(M.packs["/att_to_readout"].fwd_map, mt * 128, 0, M.map_scan["w"], 0, 0, 1, d.Cp / 64);
+        j.nseg = ns;
+        j.pa = pa;
+        js.push_back(j);
+      }
+      push_table(M, "readout", js, Np);
+    }
+  }
+  // output layer (model.py:755, 766)
+  {
+    std::vector<Job> js;
+    for (size_t f = 0; f < out_forks.size(); ++f) {
+      PlainArgs pa;
+      memset(&pa, 0, sizeof pa);
+      pa.scale = 1.0f;
+      pa.out = M.dry ? nullptr : M.fbuf("pred");
+      pa.bias = M.dry ? nullptr : M.fbuf("bias_out");
+      pa.ldo = d.Dtot; pa.n_pad = Np; pa.n_valid = B;
+      pa.n_total = train ? T * Np : Np;
+      pa.flags = d.spk ? PF_ACC : 0;
+      std::vector<PlainSeg> segs = {{M.packs[out_forks[f]].fwd_map, 0, M.map_plain["ro"], 0, 0, d.Rp / 64}};
+      if (train) build_plain_jobs(js, out_dim[f], out_off[f], (long long)T * Np, segs, pa);
+      else {
+        for (int mt = 0; mt < cdiv(out_dim[f], 128); ++mt) {
+          Job j = blank_job();
+          j.epi = EPI_PLAIN; j.row0 = out_off[f] + mt * 128; j.m_valid = std::min(128, out_dim[f] - mt * 128);
+          j.nseg = 1;
+          j.seg[0] = mkseg(M.packs[out_forks[f]].fwd_map, mt * 128, 0, M.map_plain["ro"], 0, 0, NO_SLOT, d.Rp / 64);
+          j.pa = pa;
+          js.push_back(j);
+        }
+      }
+    }
+    push_table(M, "output", js, train ? NT : Np);
+  }
+  if (train) {
+    // dread = dpred . Wout^T
+    {
+      std::vector<Job> js;
+      PlainArgs pa;
+      memset(&pa, 0, sizeof pa);
+      pa.scale = 1.0f;
+      pa.out = M.dry ? nullptr : M.fbuf("dread");
+      pa.hi = planes_of("dread").hi; pa.lo = planes_of("dread").lo;
+      pa.ldo = d.R; pa.ldp = planes_of("dread").pitch;
+      pa.n_pad = Np; pa.n_valid = B; pa.n_total = T * Np; pa.flags = PF_PLANE_PADDED;
+      std::vector<PlainSeg> segs;
+      for (size_t f = 0; f < out_forks.size(); ++f)
+        segs.push_back({M.packs[out_forks[f]].bwd_map, 0, M.map_plain["dpred"], 0, out_off[f], cdiv(out_dim[f], 64)});
+      build_plain_jobs(js, d.R, 0, (long long)T * Np, segs, pa);
+      push_table(M, "dread", js, NT);
+    }
+    // dh_l[slot t+1] = dread . W_l^T ; dw[slot t+1] = dread . Wa^T   (fresh stores)
+    {
+      std::vector<Job> js;
+      for (int l = 0; l < 4; ++l) {
+        PlainArgs pa;
+        memset(&pa, 0, sizeof pa);
+        pa.scale = 1.0f;
+        const int F = l < 3 ? H : d.C;
+        pa.out = M.dry ? nullptr : (l < 3 ? M.ctx.L[l].dh + (long long)B * H : M.ctx.dw + (long long)B * d.C);
+        pa.ldo = F; pa.n_pad = Np; pa.n_valid = B; pa.n_total = T * Np;
+        const std::string pk = l < 3 ? "/h" + LN(l) + "_to_readout" : "/att_to_readout";
+        std::vector<PlainSeg> segs = {{M.packs[pk].bwd_map, 0, M.map_plain["dread"], 0, 0, d.Rp / 64}};
+        build_plain_jobs(js, F, 0, (long long)T * Np, segs, pa);
+      }
+      push_table(M, "dh_readout", js, NT);
+    }
+    // backward scan, product 1: d(r*h) = da_c . Ws^T
+    {
+      std::vector<Job> js;
+      for (int l = 0; l < 3; ++l)
+        for (int mt = 0; mt < cdiv(H, 128); ++mt) {
+          Job j = blank_job();
+          j.epi = EPI_BWD_RH; j.layer = l; j.lag = 2 - l; j.row0 = mt * 128; j.m_valid = std::min(128, H - mt * 128);
+          j.nseg = 1;
+          j.seg[0] = mkseg(M.packs["/rnn" + LN(l) + ".state_to_state"].bwd_map, mt * 128, 0, M.map_scan["da" + LN(l)],
+                           0, 0, 0, d.Hp / 64);
+          js.push_back(j);
+        }
+      push_table(M, "bwd1", js, Np);
+    }
+    // backward scan, product 2: dgrads into the carried state gradients.  Job time = step s of layer 3;
+    // segments of layer 2 / layer 1 refer to steps s+1 / s+2 (reverse wavefront).
+    {
+      std::vector<Job> js;
+      const int gk = d.Hp;  // column offset of the gate block inside the da planes
+      auto seg_c = [&](const std::string& pk, int mt, int layer, int slot) {
+        return mkseg(M.packs[pk].bwd_map, mt * 128, 0, M.map_scan["da" + LN(layer)], 0, 0, slot, d.Hp / 64);
+      };
+      auto seg_g = [&](const std::string& pk, int mt, int layer, int slot) {
+        return mkseg(M.packs[pk].bwd_map, mt * 128, 0, M.map_scan["da" + LN(layer)], 0, gk, slot, 2 * d.Hp / 64);
+      };
+      auto add = [&](int rows, int aux, int slot_off, const std::vector<std::pair<std::string, std::pair<int, int>>>& src) {
+        // src: (pack name, (layer, slot)) ; "_inputs" packs pair with the cell block, "_gates"/state_to_gates with gates
+        for (int mt = 0; mt < cdiv(rows, 128); ++mt) {
+          Job j = blank_job();
+          j.epi = EPI_BWD_STATE; j.aux = aux; j.lag = 0; j.row0 = mt * 128; j.m_valid = std::min(128, rows - mt * 128);
+          j.pa.n_pad = slot_off;
+          int ns = 0;
+          for (auto& s : src) {
+            const bool is_gate = s.first.find("_gates") != std::string::npos;
+            j.seg[ns++] = is_gate ? seg_g(s.first, mt, s.second.first, s.second.second)
+                                  : seg_c(s.first, mt, s.second.first, s.second.second);
+          }
+          j.nseg = ns;
+          js.push_back(j);
+        }
+      };
+      typedef std::pair<std::string, std::pair<int, int>> S;
+      add(H, 2, 0, {S("/rnn3.state_to_gates", {2, 0})});
+      add(H, 1, 1, {S("/h2_to_h3/fork_rnn3_inputs", {2, 0}), S("/h2_to_h3/fork_rnn3_gates", {2, 0}),
+                    S("/rnn2.state_to_gates", {1, 1})});
+      add(H, 0, 1, {S("/h1_to_h3/fork_rnn3_inputs", {2, 0}), S("/h1_to_h3/fork_rnn3_gates", {2, 0})});
+      add(H, 0, 2, {S("/h1_to_h2/fork_rnn2_inputs", {1, 1}), S("/h1_to_h2/fork_rnn2_gates", {1, 1}),
+                    S("/rnn1.state_to_gates", {0, 2})});
+      add(d.C, 3, 1, {S("/inp_to_h3/fork_rnn3_inputs", {2, 0}), S("/inp_to_h3/fork_rnn3_gates", {2, 0})});
+      add(d.C, 3, 2, {S("/inp_to_h2/fork_rnn2_inputs", {1, 1}), S("/inp_to_h2/fork_rnn2_gates", {1, 1}),
+                      S("/inp_to_h1/fork_rnn1_inputs", {0, 2}), S("/inp_to_h1/fork_rnn1_gates", {0, 2})});
+      push_table(M, "bwd2", js, Np);
+    }
+    // weight gradients: dW[in][out] = sum_samples X[s][in] * dY[s][out]
+    {
+      auto wg = [&](const std::string& xt, int a_k, const std::string& dyt, int b_row, const std::string& pname) {
+        const PInfo& pi = M.P.get("/parrot" + pname);
+        M.wgrads.push_back(WGrad{M.map_tA[xt], a_k, M.map_tB[dyt], b_row, pi.rows, pi.cols, pi.off});
+      };
+      for (int l = 0; l < 3; ++l) {
+        const std::string s = LN(l);
+        wg("rh" + s, 0, "da" + s, 0, "/rnn" + s + ".state_to_state");
+        wg("h" + s, 0, "da" + s, d.Hp, "/rnn" + s + ".state_to_gates");
+        const int wshift = l == 0 ? 0 : Np;
+        wg("w", wshift, "da" + s, 0, "/inp_to_h" + s + "/fork_rnn" + s + "_inputs");
+        wg("w", wshift, "da" + s, d.Hp, "/inp_to_h" + s + "/fork_rnn" + s + "_gates");
+        wg("h" + s, Np, "dread", 0, "/h" + s + "_to_readout.W");
+        if ((l == 0 && d.weak) || (l > 0 && d.full)) {
+          wg("xin", 0, "da" + s, 0, "/out_to_h" + s + "/fork_rnn" + s + "_inputs");
+          wg("xin", 0, "da" + s, d.Hp, "/out_to_h" + s + "/fork_rnn" + s + "_gates");
+        }
+      }
+      wg("h1", Np, "da2", 0, "/h1_to_h2/fork_rnn2_inputs"); wg("h1", Np, "da2", d.Hp, "/h1_to_h2/fork_rnn2_gates");
+      wg("h1", Np, "da3", 0, "/h1_to_h3/fork_rnn3_inputs"); wg("h1", Np, "da3", d.Hp, "/h1_to_h3/fork_rnn3_gates");
+      wg("h2", Np, "da3", 0, "/h2_to_h3/fork_rnn3_inputs"); wg("h2", Np, "da3", d.Hp, "/h2_to_h3/fork_rnn3_gates");
+      wg("w", Np, "dread", 0, "/att_to_readout.W");
+      for (size_t f = 0; f < out_forks.size(); ++f) wg("ro", 0, "dpred", out_off[f], out_forks[f] + ".W");
+      wg("h1", Np, "datt", 0, "/h1_to_att/fork_alpha.W");
+      wg("h1", Np, "datt", d.A, "/h1_to_att/fork_beta.W");
+      wg("h1", Np, "datt", 2 * d.A, "/h1_to_att/fork_kappa.W");
+      std::vector<Job> js;
+      const int nkb = cdiv((long long)T * Np, 64);
+      for (auto& g : M.wgrads)
+        for (int mt = 0; mt < cdiv(g.in, 128); ++mt)
+          for (int nt = 0; nt < cdiv(g.out, NT); ++nt) {
+            Job j = blank_job();
+            j.epi = EPI_PLAIN; j.row0 = mt * 128; j.m_valid = std::min(128, g.in - mt * 128); j.n0 = nt * NT;
+            j.nseg = 1;
+            j.seg[0] = mkseg(g.xt_map, mt * 128, g.a_k, g.dyt_map, g.b_row + nt * NT, 0, NO_SLOT, nkb);
+            j.pa.out = M.grads ? M.grads + g.goff : nullptr;
+            j.pa.ldo = g.out; j.pa.n_total = g.out; j.pa.flags = PF_TRANS; j.pa.scale = 1.0f;
+            js.push_back(j);
+          }
+      push_table(M, "wgrad", js, NT);
+    }
+  }
+}
+
+// allocations that hold the device copies of the host-built tables (must be last in build order)
+static void build_device_tables(parrot_model& M) {
+  M.d_maps = (CUtensorMap*)M.alloc("dev_maps", M.maps.size() * sizeof(CUtensorMap));
+  M.d_raws = (MapRaw*)M.alloc("dev_raws", M.raws.size() * sizeof(MapRaw));
+  M.d_jobs = (Job*)M.alloc("dev_jobs", M.jobs.size() * sizeof(Job));
+  M.d_ctx = (ScanCtx*)M.alloc("dev_ctx", sizeof(ScanCtx));
+}
+
+static void upload_tables(parrot_model& M, cudaStream_t st) {
+  CK(cudaMemcpyAsync(M.d_maps, M.maps.data(), M.maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(M.d_raws, M.raws.data(), M.raws.size() * sizeof(MapRaw), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(M.d_jobs, M.jobs.data(), M.jobs.size() * sizeof(Job), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(M.d_ctx, &M.ctx, sizeof(ScanCtx), cudaMemcpyHostToDevice, st));
+}
+
+static void ensure_kernel_attrs() {
+  static bool done = false;
+  if (done) return;
+  CK(cudaFuncSetAttribute(job_kernel_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES + 1024));
+  done = true;
+}
+
+// ------------------------------------------------------------------ small helpers
+static void sgemm(cudaStream_t st, const float* A, long long sam, long long sak, const float* B, long long sbk,
+                  long long sbn, float* C, long long ldc, int Mr, int N, int K, const float* bias, float beta,
+                  const int* gather = nullptr) {
+  SGemm g;
+  g.A = A; g.sam = sam; g.sak = sak; g.B = B; g.sbk = sbk; g.sbn = sbn; g.C = C; g.ldc = ldc;
+  g.bias = bias; g.a_gather = gather; g.M = Mr; g.N = N; g.K = K; g.alpha = 1.0f; g.beta = beta;
+  dim3 grid(cdiv(N, 32), cdiv(Mr, 32));
+  LAUNCH(sgemm_kernel, grid, 256, 0, st, g);
+}
+static void colsum(cudaStream_t st, const float* src, long long ld, long long rows, int cols, float* out, int acc) {
+  LAUNCH(colsum_kernel, cdiv(cols, 32), 256, 0, st, src, ld, rows, cols, out, acc);
+}
+static void pack_plane(cudaStream_t st, const float* src, long long src_ld, int rows, int cols, const Plane& dst,
+                       int transpose) {
+  dim3 grid(cdiv(cols, 32), cdiv(rows, 32));
+  dim3 block(32, 8);
+  LAUNCH(pack_planes_kernel, grid, block, 0, st, src, src_ld, rows, cols, dst.hi, dst.lo, (long long)dst.pitch,
+         transpose);
+}
+static void transpose_planes(cudaStream_t st, const Plane& src, int feat_cols, const Plane& dst) {
+  const long long rows = (long long)src.rows * src.slots;
+  dim3 grid(cdiv(feat_cols, 32), cdiv(rows, 32));
+  dim3 block(32, 8);
+  LAUNCH(transpose_plane_kernel, grid, block, 0, st, src.hi, (long long)src.pitch, rows, feat_cols, dst.hi,
+         (long long)dst.pitch);
+  LAUNCH(transpose_plane_kernel, grid, block, 0, st, src.lo, (long long)src.pitch, rows, feat_cols, dst.lo,
+         (long long)dst.pitch);
+}
+
+// ------------------------------------------------------------------ weights -> operand planes
+static void pack_weights(parrot_model& M, cudaStream_t st) {
+  const Dims& d = M.d;
+  for (auto& kv : M.packs) {
+    WPack& w = kv.second;
+    const float* src = M.params + M.P.get("/parrot" + w.name).off;
+    pack_plane(st, src, w.out, w.in, w.out, w.fwd, 1);
+    if (w.need_bwd) pack_plane(st, src, w.out, w.in, w.out, w.bwd, 0);
+  }
+  // attention projection, transposed fp32 [3A][H]
+  const char* an[3] = {"alpha", "beta", "kappa"};
+  for (int i = 0; i < 3; ++i) {
+    const std::string n = std::string("/h1_to_att/fork_") + an[i];
+    LAUNCH(transpose_f32_kernel, gs_blocks((long long)d.H * d.A), 256, 0, st, M.pp(n + ".W"), d.H, d.A,
+           M.fbuf("att_wT") + (long long)i * d.A * d.H);
+    CK(cudaMemcpyAsync(M.fbuf("att_b") + i * d.A, M.pp(n + ".b"), d.A * 4, cudaMemcpyDeviceToDevice, st));
+  }
+  // summed Fork biases per layer: [cell | gates]
+  for (int l = 0; l < 3; ++l) {
+    const std::string s = LN(l);
+    for (int part = 0; part < 2; ++part) {
+      const std::string fk = part == 0 ? "_inputs.b" : "_gates.b";
+      const float* src[4] = {nullptr, nullptr, nullptr, nullptr};
+      int ns = 0;
+      src[ns++] = M.pp("/inp_to_h" + s + "/fork_rnn" + s + fk);
+      if (l >= 1) src[ns++] = M.pp("/h1_to_h" + s + "/fork_rnn" + s + fk);
+      if (l == 2) src[ns++] = M.pp("/h2_to_h3/fork_rnn3" + fk);
+      if ((l == 0 && d.weak) || (l > 0 && d.full)) src[ns++] = M.pp("/out_to_h" + s + "/fork_rnn" + s + fk);
+      const int n = part == 0 ? d.H : 2 * d.H;
+      LAUNCH(vec_sum_kernel, gs_blocks(n), 256, 0, st, M.fbuf("bias_l" + s) + (part == 0 ? 0 : d.H), n, src[0], src[1],
+             src[2], src[3]);
+    }
+  }
+  LAUNCH(vec_sum_kernel, gs_blocks(d.R), 256, 0, st, M.fbuf("bias_ro"), d.R, M.pp("/h1_to_readout.b"),
+         M.pp("/h2_to_readout.b"), M.pp("/h3_to_readout.b"), M.pp("/att_to_readout.b"));
+  if (!d.gmm) {
+    CK(cudaMemcpyAsync(M.fbuf("bias_out"), M.pp("/readout_to_output.b"), d.D * 4, cudaMemcpyDeviceToDevice, st));
+  } else {
+    const int DK = d.D * d.K;
+    CK(cudaMemcpyAsync(M.fbuf("bias_out"), M.pp("/readout_to_output/fork_gmm_mu.b"), DK * 4, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(M.fbuf("bias_out") + DK, M.pp("/readout_to_output/fork_gmm_sigma.b"), DK * 4, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(M.fbuf("bias_out") + 2 * DK, M.pp("/readout_to_output/fork_gmm_coeff.b"), d.K * 4, cudaMemcpyDeviceToDevice, st));
+  }
+  // encoder: per-character Fork projections  proj[ch][dir][xi | xg]
+  if (d.enc) {
+    const int E = d.E;
+    const char* dn[2] = {"forward", "backward"};
+    for (int dir = 0; dir < 2; ++dir) {
+      const std::string base = std::string("/encoder/encoder/") + dn[dir] + "/fork/fork_";
+      float* dst = M.fbuf("enc_proj") + dir * 3 * E;
+      sgemm(st, M.pp("/encoder/embed_label.W"), d.IN, 1, M.pp(base + "inputs.W"), E, 1, dst, 6 * E, d.NC, E, d.IN,
+            M.pp(base + "inputs.b"), 0.0f);
+      sgemm(st, M.pp("/encoder/embed_label.W"), d.IN, 1, M.pp(base + "gate_inputs.W"), 2 * E, 1, dst + E, 6 * E, d.NC,
+            2 * E, d.IN, M.pp(base + "gate_inputs.b"), 0.0f);
+    }
+  }
+  M.dirty = false;
+}
+
+// per-call time-constant inputs of the recurrent layers and of the readout (speaker conditioning)
+static void prep_base(parrot_model& M, const int32_t* d_speaker, cudaStream_t st) {
+  const Dims& d = M.d;
+  for (int l = 0; l < 3; ++l)
+    LAUNCH(base_rows_kernel, gs_blocks((long long)d.B * 3 * d.H), 256, 0, st, M.fbuf("bias_l" + LN(l)),
+           (const float*)nullptr, d.B, 3 * d.H, M.fbuf("base" + LN(l)));
+  if (!d.spk) return;
+  REQUIRE(d_speaker != nullptr, "use_speaker=True needs speaker indices (model.py:556-557)");
+  float* emb = M.fbuf("spk_emb");
+  LAUNCH(gather_rows_kernel, gs_blocks((long long)d.B * d.S), 256, 0, st, M.pp("/lookuptable.W"), d_speaker,
+         (long long)d.B, d.S, emb);
+  for (int l = 0; l < 3; ++l) {
+    const std::string s = LN(l), pre = "/speaker_to_h" + s + "/fork_rnn" + s;
+    sgemm(st, emb, d.S, 1, M.pp(pre + "_inputs.W"), d.H, 1, M.fbuf("base" + s), 3 * d.H, d.B, d.H, d.S,
+          M.pp(pre + "_inputs.b"), 1.0f);
+    sgemm(st, emb, d.S, 1, M.pp(pre + "_gates.W"), 2 * d.H, 1, M.fbuf("base" + s) + d.H, 3 * d.H, d.B, 2 * d.H, d.S,
+          M.pp(pre + "_gates.b"), 1.0f);
+  }
+  sgemm(st, emb, d.S, 1, M.pp("/speaker_to_readout.W"), d.R, 1, M.fbuf("spk_ro"), d.R, d.B, d.R, d.S,
+        M.pp("/speaker_to_readout.b"), 0.0f);
+  if (!d.gmm) {
+    sgemm(st, emb, d.S, 1, M.pp("/speaker_to_output.W"), d.D, 1, M.fbuf("spk_out"), d.Dtot, d.B, d.D, d.S,
+          M.pp("/speaker_to_output.b"), 0.0f);
+  } else {
+    const int DK = d.D * d.K;
+    const char* fk[3] = {"gmm_mu", "gmm_sigma", "gmm_coeff"};
+    const int off[3] = {0, DK, 2 * DK}, dim[3] = {DK, DK, d.K};
+    for (int f = 0; f < 3; ++f) {
+      const std::string n = std::string("/speaker_to_output/fork_") + fk[f];
+      sgemm(st, emb, d.S, 1, M.pp(n + ".W"), dim[f], 1, M.fbuf("spk_out") + off[f], d.Dtot, d.B, dim[f], d.S,
+            M.pp(n + ".b"), 0.0f);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ encoder
+static void enc_args(parrot_model& M, EncArgs& a) {
+  const Dims& d = M.d;
+  memset(&a, 0, sizeof a);
+  const bool ax0 = M.cfg.encoder_time_axis == 0;
+  a.L = ax0 ? d.B : d.U;
+  a.N = ax0 ? d.U : d.B;
+  a.E = d.E;
+  const char* dn[2] = {"forward", "backward"};
+  for (int dir = 0; dir < 2; ++dir) {
+    const std::string s = std::to_string(dir);
+    const std::string g = std::string("/encoder/encoder/") + dn[dir] + "/gatedrecurrent";
+    a.xi[dir] = M.fbuf("enc_xi" + s); a.xg[dir] = M.fbuf("enc_xg" + s);
+    a.Wg[dir] = M.pp(g + ".state_to_gates"); a.Ws[dir] = M.pp(g + ".state_to_state");
+    a.s0[dir] = M.pp(g + ".initial_state");
+    a.z[dir] = M.fbuf("enc_z" + s); a.r[dir] = M.fbuf("enc_r" + s); a.c[dir] = M.fbuf("enc_c" + s);
+    a.sprev[dir] = M.fbuf("enc_sp" + s);
+    if (!d.sampling) {
+      a.dxi[dir] = M.fbuf("enc_dxi" + s); a.dxg[dir] = M.fbuf("enc_dxg" + s); a.ds0[dir] = M.fbuf("enc_ds0" + s);
+    }
+  }
+  a.out = M.fbuf("enc_out");
+  if (!d.sampling) a.dout = M.fbuf("enc_dout");
+}
+
+static void encoder_fwd(parrot_model& M, const int32_t* d_labels, const float* d_lmask, cudaStream_t st) {
+  const Dims& d = M.d;
+  const long long n = (long long)d.B * d.U * d.C;
+  if (!d.enc) {
+    // encoder_type None: "labels" already are the (B, U, input_dim) context features (model.py:235-236)
+    LAUNCH(context_mask_kernel, gs_blocks(n), 256, 0, st, (const float*)d_labels, d_lmask, d.B, d.U, d.C, 0,
+           M.fbuf("ctx"), 0);
+    return;
+  }
+  EncArgs a;
+  enc_args(M, a);
+  LAUNCH(enc_gather_kernel, gs_blocks((long long)a.L * a.N * 6 * d.E), 256, 0, st, M.fbuf("enc_proj"), d_labels, a.L,
+         a.N, d.U, M.cfg.encoder_time_axis, d.E, (float*)a.xi[0], (float*)a.xg[0], (float*)a.xi[1], (float*)a.xg[1],
+         (int*)M.fbuf("enc_lab"));
+  dim3 grid(cdiv(a.N, ENC_ROWS), 2);
+  const size_t smem = (size_t)ENC_ROWS * d.E * 4 * 4;
+  LAUNCH(encoder_fwd_kernel, grid, 256, smem, st, a);
+  LAUNCH(context_mask_kernel, gs_blocks(n), 256, 0, st, M.fbuf("enc_out"), d_lmask, d.B, d.U, d.C,
+         M.cfg.encoder_time_axis, M.fbuf("ctx"), 0);
+}
+
+static void encoder_bwd(parrot_model& M, const float* d_lmask, cudaStream_t st) {
+  const Dims& d = M.d;
+  if (!d.enc) return;
+  const int E = d.E;
+  EncArgs a;
+  enc_args(M, a);
+  const long long n = (long long)d.B * d.U * d.C;
+  // enc_dout <- dctx * mask (in the encoder's own layout)
+  LAUNCH(context_mask_kernel, gs_blocks(n), 256, 0, st, M.fbuf("enc_dout"), d_lmask, d.B, d.U, d.C,
+         M.cfg.encoder_time_axis, M.fbuf("dctx"), 1);
+  dim3 grid(cdiv(a.N, ENC_ROWS), 2);
+  const size_t smem = (size_t)ENC_ROWS * E * 5 * 4;
+  LAUNCH(encoder_bwd_kernel, grid, 256, smem, st, a);
+  const long long LNn = (long long)a.L * a.N;
+  const char* dn[2] = {"forward", "backward"};
+  CK(cudaMemsetAsync(M.fbuf("enc_dproj"), 0, (size_t)d.NC * 6 * E * 4, st));
+  for (int dir = 0; dir < 2; ++dir) {
+    const std::string s = std::to_string(dir);
+    const std::string g = std::string("/encoder/encoder/") + dn[dir] + "/gatedrecurrent";
+    colsum(st, a.ds0[dir], E, a.N, E, M.gp(g + ".initial_state"), 0);
+    float* rs = M.fbuf("enc_rs" + s);
+    LAUNCH(mul_kernel, gs_blocks(LNn * E), 256, 0, st, rs, a.sprev[dir], a.r[dir], LNn * E);
+    sgemm(st, rs, 1, E, a.dxi[dir], E, 1, M.gp(g + ".state_to_state"), E, E, E, (int)LNn, nullptr, 0.0f);
+    sgemm(st, a.sprev[dir], 1, E, a.dxg[dir], 2 * E, 1, M.gp(g + ".state_to_gates"), 2 * E, E, 2 * E, (int)LNn,
+          nullptr, 0.0f);
+    float* dp = M.fbuf("enc_dproj") + dir * 3 * E;
+    LAUNCH(scatter_rows_kernel, gs_blocks((long long)d.NC * E), 256, 0, st, a.dxi[dir], (long long)E,
+           (const int*)M.fbuf("enc_lab"), (int)LNn, E, d.NC, dp, (long long)6 * E);
+    LAUNCH(scatter_rows_kernel, gs_blocks((long long)d.NC * 2 * E), 256, 0, st, a.dxg[dir], (long long)2 * E,
+           (const int*)M.fbuf("enc_lab"), (int)LNn, 2 * E, d.NC, dp + E, (long long)6 * E);
+  }
+  const float* Wemb = M.pp("/encoder/embed_label.W");
+  float* dWemb = M.gp("/encoder/embed_label.W");
+  for (int dir = 0; dir < 2; ++dir) {
+    const std::string base = std::string("/encoder/encoder/") + dn[dir] + "/fork/fork_";
+    const float* dp = M.fbuf("enc_dproj") + dir * 3 * E;
+    const char* fk[2] = {"inputs", "gate_inputs"};
+    const int off[2] = {0, E}, dim[2] = {E, 2 * E};
+    for (int f = 0; f < 2; ++f) {
+      // dW_f (IN x dim) = Wemb^T (IN x NC) . dproj (NC x dim)
+      sgemm(st, Wemb, 1, d.IN, dp + off[f], 6 * E, 1, M.gp(base + fk[f] + ".W"), dim[f], d.IN, dim[f], d.NC, nullptr,
+            0.0f);
+      colsum(st, dp + off[f], 6 * E, d.NC, dim[f], M.gp(base + fk[f] + ".b"), 0);
+      // dWemb (NC x IN) += dproj (NC x dim) . W_f^T (dim x IN)
+      sgemm(st, dp + off[f], 6 * E, 1, M.pp(base + fk[f] + ".W"), 1, dim[f], dWemb, d.IN, d.NC, d.IN, dim[f], nullptr,
+            1.0f);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ decoder scan
+static void init_slots(parrot_model& M, bool use_initial, cudaStream_t st) {
+  const Dims& d = M.d;
+  for (int l = 0; l < 3; ++l) {
+    const std::string s = LN(l);
+    const float* src = use_initial ? M.pp("/rnn" + s + ".initial_state") : M.fbuf("last_h" + s);
+    const Plane& p = M.planes.at("h" + s);
+    LAUNCH(state_to_slot_kernel, gs_blocks((long long)d.B * d.H), 256, 0, st, src, (long long)(use_initial ? 0 : d.H),
+           d.B, d.H, d.Np, p.pitch, M.ctx.L[l].h, p.hi, p.lo);
+  }
+  const Plane& pw = M.planes.at("w");
+  LAUNCH(state_to_slot_kernel, gs_blocks((long long)d.B * d.C), 256, 0, st,
+         use_initial ? M.pp(".initial_w") : M.fbuf("last_w"), (long long)(use_initial ? 0 : d.C), d.B, d.C, d.Np,
+         pw.pitch, M.fbuf("w"), pw.hi, pw.lo);
+  if (use_initial) CK(cudaMemsetAsync(M.fbuf("kappa"), 0, (size_t)d.B * d.A * 4, st));
+  else CK(cudaMemcpyAsync(M.fbuf("kappa"), M.fbuf("last_k"), (size_t)d.B * d.A * 4, cudaMemcpyDeviceToDevice, st));
+}
+
+static void attention_step(parrot_model& M, int t, bool sampling, cudaStream_t st) {
+  const Dims& d = M.d;
+  AttnFwdArgs a;
+  a.B = d.B; a.U = d.U; a.C = d.C; a.A = d.A; a.H = d.H; a.Np = d.Np;
+  const Plane& pw = M.planes.at("w");
+  a.Cp = pw.pitch;
+  a.type = M.cfg.attention_type;
+  a.eps = M.cfg.epsilon; a.align = M.cfg.attention_alignment;
+  a.sharp = sampling ? M.cfg.sharpening_coeff : 1.0f;
+  a.timing = sampling ? M.cfg.timing_coeff : 1.0f;
+  a.h1 = M.ctx.L[0].h + (long long)(t + 1) * d.B * d.H;
+  a.wT = M.fbuf("att_wT"); a.batt = M.fbuf("att_b"); a.ctx = M.fbuf("ctx");
+  a.k_prev = M.fbuf("kappa") + (long long)t * d.B * d.A;
+  a.k_out = M.fbuf("kappa") + (long long)(t + 1) * d.B * d.A;
+  a.w_out = M.fbuf("w") + (long long)(t + 1) * d.B * d.C;
+  a.w_hi = pw.hi + (long long)(t + 1) * d.Np * pw.pitch;
+  a.w_lo = pw.lo + (long long)(t + 1) * d.Np * pw.pitch;
+  a.phi_out = M.fbuf("phi") + (long long)t * d.B * d.U;
+  a.ab_out = M.fbuf("ab") + (long long)t * d.B * 2 * d.A;
+  a.e_out = M.fbuf("att_e") + (long long)t * d.B * 3 * d.A;
+  const size_t smem = (size_t)(d.H + 6 * d.A + d.U) * 4;
+  LAUNCH(attention_fwd_kernel, d.B, 256, smem, st, a);
+}
+
+static void scan_fwd(parrot_model& M, const float* d_features, const float* d_noise, float level, float start_flag,
+                     cudaStream_t st) {
+  const Dims& d = M.d;
+  if (d.weak) {
+    const Plane& px = M.planes.at("xin");
+    const bool noisy = d_noise != nullptr && level != 0.0f;
+    LAUNCH(frames_to_planes_kernel, gs_blocks((long long)d.T * d.B * d.D), 256, 0, st, d_features,
+           noisy ? d_noise : (const float*)nullptr, level, d.T, d.B, d.D, d.Np, px.pitch, px.hi, px.lo,
+           (float*)nullptr);
+  }
+  init_slots(M, start_flag != 0.0f, st);
+  M.last_start_flag = start_flag;
+  // layer wavefront: tick tau runs layer 1 at step tau, layer 2 at tau-1, layer 3 at tau-2
+  for (int tick = 0; tick < d.T + 2; ++tick) {
+    run_table(M, "fwdA", tick, d.T, 0, st);
+    run_table(M, "fwdB", tick, d.T, 0, st);
+    if (tick < d.T) attention_step(M, tick, false, st);
+  }
+}
+
+// ------------------------------------------------------------------ readout / emitter
+static EmitArgs emit_args(parrot_model& M, const float* d_features, const float* d_fmask, int unnormalised) {
+  const Dims& d = M.d;
+  EmitArgs e;
+  memset(&e, 0, sizeof e);
+  e.N = d.T * d.B; e.D = d.D; e.k = d.K; e.which = d.gmm ? 1 : 0; e.Dtot = d.Dtot; e.eps = M.cfg.epsilon;
+  e.pred = M.fbuf("pred");
+  e.target = d_features + (long long)d.B * d.D;   // features[1:]  (model.py:559)
+  e.mask = d_fmask + d.B;                         // features_mask[1:] (model.py:560)
+  e.cost_tb = M.fbuf("cost_tb");
+  if (!d.sampling) {
+    e.dpred = M.fbuf("dpred");
+    const Plane& p = M.planes.at("dpred");
+    e.dpred_hi = p.hi; e.dpred_lo = p.lo; e.B = d.B; e.Np = d.Np; e.Dp = p.pitch;
+    e.scale = M.fbuf("cost") + (unnormalised ? 4 : 3);
+  }
+  return e;
+}
+
+static void readout_emit_fwd(parrot_model& M, const float* d_features, const float* d_fmask, float* d_cost,
+                             cudaStream_t st) {
+  const Dims& d = M.d;
+  if (d.spk) {
+    LAUNCH(bcast_rows_kernel, gs_blocks((long long)d.T * d.B * d.R), 256, 0, st, M.fbuf("ro"), M.fbuf("spk_ro"), d.T,
+           (long long)d.B * d.R);
+    LAUNCH(bcast_rows_kernel, gs_blocks((long long)d.T * d.B * d.Dtot), 256, 0, st, M.fbuf("pred"), M.fbuf("spk_out"),
+           d.T, (long long)d.B * d.Dtot);
+  }
+  run_table(M, "readout", 0, 1, 0, st);
+  run_table(M, "output", 0, 1, 0, st);
+  EmitArgs e = emit_args(M, d_features, d_fmask, 0);
+  LAUNCH(emit_cost_kernel, cdiv((long long)e.N * 32, 256), 256, 0, st, e);
+  LAUNCH(masked_mean_kernel, 1, 1024, 0, st, M.fbuf("cost_tb"), e.mask, (long long)e.N, M.fbuf("cost"));
+  if (d_cost) CK(cudaMemcpyAsync(d_cost, M.fbuf("cost"), 16, cudaMemcpyDeviceToDevice, st));
+}
+
+static void apply_updates(parrot_model& M, cudaStream_t st) {
+  const Dims& d = M.d;
+  for (int l = 0; l < 3; ++l)
+    CK(cudaMemcpyAsync(M.fbuf("last_h" + LN(l)), M.ctx.L[l].h + (long long)d.T * d.B * d.H, (size_t)d.B * d.H * 4,
+                       cudaMemcpyDeviceToDevice, st));
+  CK(cudaMemcpyAsync(M.fbuf("last_k"), M.fbuf("kappa") + (long long)d.T * d.B * d.A, (size_t)d.B * d.A * 4,
+                     cudaMemcpyDeviceToDevice, st));
+  CK(cudaMemcpyAsync(M.fbuf("last_w"), M.fbuf("w") + (long long)d.T * d.B * d.C, (size_t)d.B * d.C * 4,
+                     cudaMemcpyDeviceToDevice, st));
+}
+
+// ------------------------------------------------------------------ backward
+struct FwdInputs {
+  const float* features = nullptr;
+  const float* fmask = nullptr;
+  const int32_t* labels = nullptr;
+  const float* lmask = nullptr;
+  const int32_t* speaker = nullptr;
+};
+static std::map<parrot_model*, FwdInputs> g_inputs;
+
+static void readout_emit_bwd(parrot_model& M, int unnormalised, cudaStream_t st) {
+  const Dims& d = M.d;
+  const FwdInputs& in = g_inputs[&M];
+  EmitArgs e = emit_args(M, in.features, in.fmask, unnormalised);
+  LAUNCH(emit_grad_kernel, cdiv((long long)e.N * 32, 256), 256, 0, st, e);
+  run_table(M, "dread", 0, 1, 0, st);
+  for (int l = 0; l < 3; ++l) CK(cudaMemsetAsync(M.ctx.L[l].dh, 0, (size_t)d.B * d.H * 4, st));
+  CK(cudaMemsetAsync(M.ctx.dw, 0, (size_t)d.B * d.C * 4, st));
+  run_table(M, "dh_readout", 0, 1, 0, st);
+}
+
+static void attention_bwd_step(parrot_model& M, int t, cudaStream_t st) {
+  const Dims& d = M.d;
+  AttnBwdArgs a;
+  a.B = d.B; a.U = d.U; a.C = d.C; a.A = d.A; a.H = d.H; a.Np = d.Np; a.Ap = d.Ap;
+  a.type = M.cfg.attention_type; a.eps = M.cfg.epsilon; a.align = M.cfg.attention_alignment;
+  a.dw = M.ctx.dw + (long long)(t + 1) * d.B * d.C;
+  a.ctx = M.fbuf("ctx");
+  a.ab = M.fbuf("ab") + (long long)t * d.B * 2 * d.A;
+  a.e = M.fbuf("att_e") + (long long)t * d.B * 3 * d.A;
+  a.kappa = M.fbuf("kappa") + (long long)(t + 1) * d.B * d.A;
+  a.dk_carry = M.fbuf("dk_carry");
+  a.watt = M.fbuf("att_wT");
+  a.dh1 = M.ctx.L[0].dh + (long long)(t + 1) * d.B * d.H;
+  a.datt = M.fbuf("datt") + (long long)t * d.B * 3 * d.A;
+  const Plane& p = M.planes.at("datt");
+  a.datt_hi = p.hi + (long long)t * d.Np * p.pitch;
+  a.datt_lo = p.lo + (long long)t * d.Np * p.pitch;
+  const size_t smem = (size_t)(d.C + d.U + 3 * d.A * 8 + 3 * d.A) * 4;
+  LAUNCH(attention_bwd_kernel, d.B, 256, smem, st, a);
+}
+
+static void scan_bwd(parrot_model& M, cudaStream_t st) {
+  const Dims& d = M.d;
+  CK(cudaMemsetAsync(M.fbuf("dk_carry"), 0, (size_t)d.B * d.A * 4, st));
+  const int blocks = gs_blocks((long long)d.B * d.H);
+  // reverse layer wavefront: tick tau -> layer 3 at s = T-1-tau, layer 2 at s+1, attention + layer 1 at s+2
+  for (int tick = 0; tick < d.T + 2; ++tick) {
+    const int s = d.T - 1 - tick;
+    if (s + 2 >= 0 && s + 2 < d.T) attention_bwd_step(M, s + 2, st);
+    for (int l = 2; l >= 0; --l) {
+      const int t = s + (2 - l);
+      if (t >= 0 && t < d.T) LAUNCH(gru_bwd_pre_kernel, blocks, 256, 0, st, M.d_ctx, l, t);
+    }
+    run_table(M, "bwd1", tick, d.T, 1, st);
+    run_table(M, "bwd2", tick, d.T, 1, st);
+  }
+}
+
+static void add_to(parrot_model& M, cudaStream_t st, const std::string& pname, const float* src, int n) {
+  LAUNCH(add_vec_kernel, gs_blocks(n), 256, 0, st, M.gp(pname), src, (long long)n);
+}
+
+static void weight_grads(parrot_model& M, cudaStream_t st) {
+  const Dims& d = M.d;
+  const int T = d.T, B = d.B, H = d.H;
+  // operand transposes [samples][features] -> [features][samples]
+  auto tp = [&](const std::string& nm, int feat) { transpose_planes(st, M.planes.at(nm), feat, M.planes.at("T." + nm)); };
+  for (int l = 0; l < 3; ++l) {
+    tp("h" + LN(l), d.H); tp("rh" + LN(l), d.H); tp("da" + LN(l), 3 * d.Hp);
+  }
+  tp("w", d.C);
+  if (d.weak) tp("xin", d.D);
+  tp("ro", d.R); tp("dread", d.R); tp("dpred", d.Dtot); tp("datt", 3 * d.A);
+  run_table(M, "wgrad", 0, 1, 0, st);
+  // bias gradients: column sums of the pre-activation gradients
+  float* scratch = M.fbuf("bias_scratch");
+  for (int l = 0; l < 3; ++l) {
+    const std::string s = LN(l);
+    colsum(st, M.ctx.L[l].da, 3 * H, (long long)T * B, 3 * H, scratch, 0);
+    for (int part = 0; part < 2; ++part) {
+      const std::string fk = part == 0 ? "_inputs.b" : "_gates.b";
+      const float* src = scratch + (part == 0 ? 0 : H);
+      const int n = part == 0 ? H : 2 * H;
+      add_to(M, st, "/inp_to_h" + s + "/fork_rnn" + s + fk, src, n);
+      if (l >= 1) add_to(M, st, "/h1_to_h" + s + "/fork_rnn" + s + fk, src, n);
+      if (l == 2) add_to(M, st, "/h2_to_h3/fork_rnn3" + fk, src, n);
+      if ((l == 0 && d.weak) || (l > 0 && d.full)) add_to(M, st, "/out_to_h" + s + "/fork_rnn" + s + fk, src, n);
+      if (d.spk) add_to(M, st, "/speaker_to_h" + s + "/fork_rnn" + s + fk, src, n);
+    }
+  }
+  colsum(st, M.fbuf("dread"), d.R, (long long)T * B, d.R, scratch, 0);
+  for (int l = 0; l < 3; ++l) add_to(M, st, "/h" + LN(l) + "_to_readout.b", scratch, d.R);
+  add_to(M, st, "/att_to_readout.b", scratch, d.R);
+  if (d.spk) add_to(M, st, "/speaker_to_readout.b", scratch, d.R);
+  float* sc2 = scratch + std::max(3 * H, d.R);  // dpred sums
+  colsum(st, M.fbuf("dpred"), d.Dtot, (long long)T * B, d.Dtot, sc2, 0);
+  if (!d.gmm) {
+    add_to(M, st, "/readout_to_output.b", sc2, d.D);
+    if (d.spk) add_to(M, st, "/speaker_to_output.b", sc2, d.D);
+  } else {
+    const int DK = d.D * d.K;
+    const char* fk[3] = {"gmm_mu", "gmm_sigma", "gmm_coeff"};
+    const int off[3] = {0, DK, 2 * DK}, dim[3] = {DK, DK, d.K};
+    for (int f = 0; f < 3; ++f) {
+      add_to(M, st, std::string("/readout_to_output/fork_") + fk[f] + ".b", sc2 + off[f], dim[f]);
+      if (d.spk) add_to(M, st, std::string("/speaker_to_output/fork_") + fk[f] + ".b", sc2 + off[f], dim[f]);
+    }
+  }
+  colsum(st, M.fbuf("datt"), 3 * d.A, (long long)T * B, 3 * d.A, scratch, 0);
+  add_to(M, st, "/h1_to_att/fork_alpha.b", scratch, d.A);
+  add_to(M, st, "/h1_to_att/fork_beta.b", scratch + d.A, d.A);
+  add_to(M, st, "/h1_to_att/fork_kappa.b", scratch + 2 * d.A, d.A);
+}
+
+static void speaker_grads(parrot_model& M, cudaStream_t st) {
+  const Dims& d = M.d;
+  if (!d.spk) return;
+  const FwdInputs& in = g_inputs[&M];
+  const int T = d.T, B = d.B, H = d.H, S = d.S;
+  const float* emb = M.fbuf("spk_emb");
+  float* demb = M.fbuf("spk_demb");
+  CK(cudaMemsetAsync(demb, 0, (size_t)B * S * 4, st));
+  auto through = [&](const float* dproj, long long ld, int N, const std::string& wname) {
+    // dW (S x N) = emb^T . dproj ; demb += dproj . W^T
+    sgemm(st, emb, 1, S, dproj, ld, 1, M.gp(wname + ".W"), N, S, N, B, nullptr, 0.0f);
+    sgemm(st, dproj, ld, 1, M.pp(wname + ".W"), 1, N, demb, S, B, S, N, nullptr, 1.0f);
+  };
+  float* dp = M.fbuf("spk_dproj");
+  for (int l = 0; l < 3; ++l) {
+    const std::string s = LN(l), pre = "/speaker_to_h" + s + "/fork_rnn" + s;
+    LAUNCH(timesum_kernel, gs_blocks((long long)B * 3 * H), 256, 0, st, M.ctx.L[l].da, T, (long long)B * 3 * H, dp);
+    through(dp, 3 * H, H, pre + "_inputs");
+    through(dp + H, 3 * H, 2 * H, pre + "_gates");
+  }
+  float* dro = M.fbuf("spk_dro");
+  LAUNCH(timesum_kernel, gs_blocks((long long)B * d.R), 256, 0, st, M.fbuf("dread"), T, (long long)B * d.R, dro);
+  through(dro, d.R, d.R, "/speaker_to_readout");
+  float* dout = M.fbuf("spk_dout");
+  LAUNCH(timesum_kernel, gs_blocks((long long)B * d.Dtot), 256, 0, st, M.fbuf("dpred"), T, (long long)B * d.Dtot, dout);
+  if (!d.gmm) through(dout, d.Dtot, d.D, "/speaker_to_output");
+  else {
+    const int DK = d.D * d.K;
+    through(dout, d.Dtot, DK, "/speaker_to_output/fork_gmm_mu");
+    through(dout + DK, d.Dtot, DK, "/speaker_to_output/fork_gmm_sigma");
+    through(dout + 2 * DK, d.Dtot, d.K, "/speaker_to_output/fork_gmm_coeff");
+  }
+  LAUNCH(scatter_rows_kernel, gs_blocks((long long)M.cfg.num_speakers * S), 256, 0, st, demb, (long long)S, in.speaker,
+         B, S, M.cfg.num_speakers, M.gp("/lookuptable.W"), (long long)S);
+}
+
+static void backward(parrot_model& M, int unnormalised, cudaStream_t st) {
+  const Dims& d = M.d;
+  REQUIRE(M.have_fwd, "parrot_backward called before parrot_compute_cost");
+  REQUIRE(!d.sampling, "sampling handles have no backward");
+  const FwdInputs& in = g_inputs[&M];
+  CK(cudaMemsetAsync(M.grads, 0, (size_t)(M.P.total + 1) * 4, st));
+  CK(cudaMemcpyAsync(M.grads + M.P.total, M.fbuf("cost") + 2, 4, cudaMemcpyDeviceToDevice, st));
+  readout_emit_bwd(M, unnormalised, st);
+  scan_bwd(M, st);
+  if (M.last_start_flag != 0.0f) {
+    for (int l = 0; l < 3; ++l) colsum(st, M.ctx.L[l].dh, d.H, d.B, d.H, M.gp("/rnn" + LN(l) + ".initial_state"), 0);
+    colsum(st, M.ctx.dw, d.C, d.B, d.C, M.gp(".initial_w"), 0);
+  }
+  // dctx = sum_t phi_t (x) dw_t
+  {
+    dim3 grid(cdiv(d.C, 32), cdiv(d.U, 32), d.B);
+    LAUNCH(dctx_kernel, grid, 256, 0, st, M.fbuf("phi"), M.ctx.dw + (long long)d.B * d.C, d.T, d.B, d.U, d.C,
+           M.fbuf("dctx"));
+  }
+  encoder_bwd(M, in.lmask, st);
+  weight_grads(M, st);
+  speaker_grads(M, st);
+}
+
+// ------------------------------------------------------------------ sampling
+static void sample_scan(parrot_model& M, const int32_t* d_labels, const float* d_lmask, const int32_t* d_speaker,
+                        const float* d_unis, const float* d_normals, uint64_t seed, cudaStream_t st) {
+  const Dims& d = M.d;
+  REQUIRE(d.sampling, "parrot_sample_scan needs a handle created with cfg.sampling = 1");
+  if (M.dirty) pack_weights(M, st);
+  prep_base(M, d_speaker, st);
+  encoder_fwd(M, d_labels, d_lmask, st);
+  init_slots(M, true, st);   // model.py:830-832: always the initial states
+  const Plane* px = d.weak ? &M.planes.at("xin") : nullptr;
+  if (px) {
+    CK(cudaMemsetAsync(px->hi, 0, (size_t)d.Np * px->pitch * 2, st));  // x_0 = 0 (model.py:834-835)
+    CK(cudaMemsetAsync(px->lo, 0, (size_t)d.Np * px->pitch * 2, st));
+  }
+  for (int t = 0; t < d.T; ++t) {
+    run_table(M, "sampA1", t, d.T, 0, st);
+    run_table(M, "sampB1", t, d.T, 0, st);
+    attention_step(M, t, true, st);
+    run_table(M, "sampA2", t, d.T, 0, st);
+    run_table(M, "sampB2", t, d.T, 0, st);
+    run_table(M, "sampA3", t, d.T, 0, st);
+    run_table(M, "sampB3", t, d.T, 0, st);
+    if (d.spk) {
+      CK(cudaMemcpyAsync(M.fbuf("ro"), M.fbuf("spk_ro"), (size_t)d.B * d.R * 4, cudaMemcpyDeviceToDevice, st));
+      CK(cudaMemcpyAsync(M.fbuf("pred"), M.fbuf("spk_out"), (size_t)d.B * d.Dtot * 4, cudaMemcpyDeviceToDevice, st));
+    }
+    run_table(M, "readout", t, d.T, 0, st);
+    run_table(M, "output", t, d.T, 0, st);
+    SampleArgs a;
+    memset(&a, 0, sizeof a);
+    a.B = d.B; a.D = d.D; a.k = d.K; a.Dtot = d.Dtot; a.which = d.gmm ? 1 : 0;
+    a.eps = M.cfg.epsilon; a.bias = M.cfg.sampling_bias;
+    a.pred = M.fbuf("pred");
+    a.unis = d_unis ? d_unis + (long long)t * d.B : nullptr;
+    a.normals = d_normals ? d_normals + (long long)t * d.B * d.D : nullptr;
+    a.seed = seed; a.step = t;
+    a.x_out = M.fbuf("samp_x") + (long long)t * d.B * d.D;
+    a.pi_out = M.fbuf("samp_pi") + (long long)t * d.B * (d.gmm ? d.K : d.D);
+    if (px) {
+      a.x_hi = px->hi + (long long)(t + 1) * d.Np * px->pitch;
+      a.x_lo = px->lo + (long long)(t + 1) * d.Np * px->pitch;
+      a.Np = d.Np; a.Dp = px->pitch;
+    }
+    LAUNCH(sample_emit_kernel, cdiv((long long)d.B * 32, 128), 128, 0, st, a);
+  }
+}
+
+// =========================================================================== C ABI
+extern "C" {
+
+const char* parrot_last_error(void) { return g_err.c_str(); }
+int parrot_abi_version(void) { return 1; }
+int64_t parrot_launch_count(void) { return g_launches.load(); }
+
+int parrot_param_count(const parrot_config* cfg, int32_t* count, int64_t* total_floats) {
+  return guard([&] {
+    PReg P = make_params(*cfg);
+    *count = (int32_t)P.v.size();
+    *total_floats = P.total;
+  });
+}
+int parrot_param_info(const parrot_config* cfg, int32_t i, char* name, int32_t name_cap, int64_t* offset,
+                      int32_t* rows, int32_t* cols) {
+  return guard([&] {
+    PReg P = make_params(*cfg);
+    REQUIRE(i >= 0 && i < (int)P.v.size(), "parameter index out of range");
+    snprintf(name, name_cap, "%s", P.v[i].name.c_str());
+    *offset = P.v[i].off; *rows = P.v[i].rows; *cols = P.v[i].cols;
+  });
+}
+
+int parrot_workspace_bytes(const parrot_config* cfg, size_t* bytes) {
+  return guard([&] {
+    check_cfg(*cfg);
+    parrot_model M;
+    M.cfg = *cfg; M.d = make_dims(*cfg); M.P = make_params(*cfg); M.dry = true;
+    build(M);
+    build_device_tables(M);
+    *bytes = M.ws_used + 4096;
+  });
+}
+
+int parrot_create(const parrot_config* cfg, float* d_params, float* d_grads, void* d_workspace,
+                  size_t workspace_bytes, void* stream, parrot_model** out) {
+  return guard([&] {
+    check_cfg(*cfg);
+    cudaStream_t st = (cudaStream_t)stream;
+    parrot_model* M = new parrot_model;
+    try {
+      M->cfg = *cfg; M->d = make_dims(*cfg); M->P = make_params(*cfg);
+      M->params = d_params; M->grads = d_grads;
+      M->ws = (uint8_t*)d_workspace; M->ws_bytes = workspace_bytes; M->dry = false;
+      REQUIRE(((uintptr_t)d_workspace & 1023) == 0, "workspace must be 1024-byte aligned");
+      CK(cudaMemsetAsync(d_workspace, 0, workspace_bytes, st));
+      build(*M);
+      build_device_tables(*M);
+      upload_tables(*M, st);
+      // constant 1.0 for unnormalised backward: cost[4]
+      const float one = 1.0f;
+      CK(cudaMemcpyAsync(M->fbuf("cost") + 4, &one, 4, cudaMemcpyHostToDevice, st));
+      ensure_kernel_attrs();
+      CK(cudaStreamSynchronize(st));  // host-side tables are read by the copies above
+      M->dirty = true;
+    } catch (...) {
+      delete M;
+      throw;
+    }
+    *out = M;
+  });
+}
+int parrot_destroy(parrot_model* m) {
+  return guard([&] {
+    g_inputs.erase(m);
+    delete m;
+  });
+}
+int parrot_buffer_info(parrot_model* m, const char* name, int64_t* byte_offset, int64_t* numel) {
+  return guard([&] {
+    auto it = m->bufs.find(name);
+    REQUIRE(it != m->bufs.end(), std::string("unknown buffer ") + name);
+    *byte_offset = (int64_t)it->second.off;
+    *numel = (int64_t)(it->second.bytes / 4);
+  });
+}
+int parrot_pack_weights(parrot_model* m, void* stream) {
+  return guard([&] { pack_weights(*m, (cudaStream_t)stream); });
+}
+int parrot_mark_params_dirty(parrot_model* m) {
+  m->dirty = true;
+  return 0;
+}
+
+int parrot_encoder_fwd(parrot_model* m, const int32_t* d_labels, const float* d_labels_mask, void* stream) {
+  return guard([&] {
+    if (m->dirty) pack_weights(*m, (cudaStream_t)stream);
+    g_inputs[m].labels = d_labels; g_inputs[m].lmask = d_labels_mask;
+    encoder_fwd(*m, d_labels, d_labels_mask, (cudaStream_t)stream);
+  });
+}
+int parrot_encoder_bwd(parrot_model* m, void* stream) {
+  return guard([&] { encoder_bwd(*m, g_inputs[m].lmask, (cudaStream_t)stream); });
+}
+int parrot_decoder_scan_fwd(parrot_model* m, const float* d_features, const float* d_feedback_noise,
+                            float noise_level, float start_flag, void* stream) {
+  return guard([&] {
+    if (m->dirty) pack_weights(*m, (cudaStream_t)stream);
+    g_inputs[m].features = d_features;
+    scan_fwd(*m, d_features, d_feedback_noise, noise_level, start_flag, (cudaStream_t)stream);
+  });
+}
+int parrot_decoder_scan_bwd(parrot_model* m, void* stream) {
+  return guard([&] { scan_bwd(*m, (cudaStream_t)stream); });
+}
+int parrot_readout_emit_fwd(parrot_model* m, const float* d_features, const float* d_features_mask, float* d_cost,
+                            void* stream) {
+  return guard([&] {
+    g_inputs[m].features = d_features; g_inputs[m].fmask = d_features_mask;
+    readout_emit_fwd(*m, d_features, d_features_mask, d_cost, (cudaStream_t)stream);
+  });
+}
+int parrot_readout_emit_bwd(parrot_model* m, int unnormalised, void* stream) {
+  return guard([&] { readout_emit_bwd(*m, unnormalised, (cudaStream_t)stream); });
+}
+
+int parrot_attention_step(const parrot_config* cfg, const float* d_h1, const float* d_wT, const float* d_batt,
+                          const float* d_ctx, const float* d_k_prev, float* d_k_out, float* d_w_out,
+                          float* d_phi_out, float* d_ab_out, float* d_e_out, int training, void* stream) {
+  return guard([&] {
+    const Dims d = make_dims(*cfg);
+    AttnFwdArgs a;
+    memset(&a, 0, sizeof a);
+    a.B = d.B; a.U = d.U; a.C = d.C; a.A = d.A; a.H = d.H; a.Np = d.Np; a.Cp = d.Cp;
+    a.type = cfg->attention_type; a.eps = cfg->epsilon; a.align = cfg->attention_alignment;
+    a.sharp = training ? 1.0f : cfg->sharpening_coeff;
+    a.timing = training ? 1.0f : cfg->timing_coeff;
+    a.h1 = d_h1; a.wT = d_wT; a.batt = d_batt; a.ctx = d_ctx; a.k_prev = d_k_prev; a.k_out = d_k_out;
+    a.w_out = d_w_out; a.phi_out = d_phi_out; a.ab_out = d_ab_out; a.e_out = d_e_out;
+    const size_t smem = (size_t)(d.H + 6 * d.A + d.U) * 4;
+    LAUNCH(attention_fwd_kernel, d.B, 256, smem, (cudaStream_t)stream, a);
+  });
+}
+
+int parrot_compute_cost(parrot_model* m, const float* d_features, const float* d_features_mask,
+                        const int32_t* d_labels, const float* d_labels_mask, const int32_t* d_speaker,
+                        float start_flag, const float* d_feedback_noise, float noise_level,
+                        const float* d_gmm_unis, const float* d_gmm_normals, float* d_cost, void* stream) {
+  return guard([&] {
+    cudaStream_t st = (cudaStream_t)stream;
+    parrot_model& M = *m;
+    REQUIRE(!M.d.sampling, "parrot_compute_cost needs a training handle (cfg.sampling = 0)");
+    FwdInputs& in = g_inputs[m];
+    in.features = d_features; in.fmask = d_features_mask; in.labels = d_labels; in.lmask = d_labels_mask;
+    in.speaker = d_speaker;
+    if (M.dirty) pack_weights(M, st);
+    prep_base(M, d_speaker, st);
+    encoder_fwd(M, d_labels, d_labels_mask, st);
+    scan_fwd(M, d_features, d_feedback_noise, noise_level, start_flag, st);
+    readout_emit_fwd(M, d_features, d_features_mask, d_cost, st);
+    if (M.d.gmm && d_gmm_unis && d_gmm_normals) {
+      // next_x = sample_gmm(mu, sigma, coeff) (model.py:782), all frames at once, no sampling bias
+      SampleArgs a;
+      memset(&a, 0, sizeof a);
+      a.B = M.d.T * M.d.B; a.D = M.d.D; a.k = M.d.K; a.Dtot = M.d.Dtot; a.which = 1;
+      a.eps = M.cfg.epsilon; a.bias = 0.0f;
+      a.pred = M.fbuf("pred"); a.unis = d_gmm_unis; a.normals = d_gmm_normals;
+      a.x_out = M.fbuf("next_x"); a.pi_out = M.fbuf("dpred");  // coeff parked in dpred until backward
+      LAUNCH(sample_emit_kernel, cdiv((long long)a.B * 32, 128), 128, 0, st, a);
+    }
+    apply_updates(M, st);
+    M.have_fwd = true;
+  });
+}
+int parrot_backward(parrot_model* m, int unnormalised, void* stream) {
+  return guard([&] { backward(*m, unnormalised, (cudaStream_t)stream); });
+}
+int parrot_sample_scan(parrot_model* m, const int32_t* d_labels, const float* d_labels_mask,
+                       const int32_t* d_speaker, const float* d_unis, const float* d_normals, uint64_t seed,
+                       void* stream) {
+  return guard([&] { sample_scan(*m, d_labels, d_labels_mask, d_speaker, d_unis, d_normals, seed, (cudaStream_t)stream); });
+}
+
+int parrot_adam_clip_step(float* d_params, const float* d_grads, float* d_m, float* d_v, int64_t n,
+                          float grad_scale, float threshold, float learning_rate, float beta1, float beta2,
+                          float epsilon, int64_t time_step, float* d_stats, double* d_scratch, void* stream) {
+  return guard([&] {
+    cudaStream_t st = (cudaStream_t)stream;
+    const int parts = 592;
+    LAUNCH(sumsq_partial_kernel, parts, 1024, 0, st, d_grads, (long long)n, d_scratch);
+    LAUNCH(clip_finalize_kernel, 1, 32, 0, st, d_scratch, parts, grad_scale, threshold, d_stats);
+    // blocks Adam: lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t)
+    const double t1 = (double)time_step;
+    const float lr_t = (float)(learning_rate * std::sqrt(1.0 - std::pow((double)beta2, t1)) /
+                               (1.0 - std::pow((double)beta1, t1)));
+    LAUNCH(adam_kernel, 148 * 8, 256, 0, st, d_params, d_grads, d_m, d_v, (long long)n, d_stats, grad_scale, lr_t,
+           beta1, beta2, epsilon);
+  });
+}
+
+size_t parrot_gemm_nt_workspace_bytes(int32_t Mr, int32_t N, int32_t K) {
+  const size_t kp = (size_t)rup(K, 64);
+  size_t b = 0;
+  b += 2 * ((size_t)rup(Mr, 128) * kp * 2 + 1024);
+  b += 2 * ((size_t)rup(N, 128) * kp * 2 + 1024);
+  b += (size_t)cdiv(Mr, 128) * cdiv(N, NT) * sizeof(Job) + 16 * sizeof(CUtensorMap) + 16 * sizeof(MapRaw) +
+       sizeof(ScanCtx) + 16 * 1024;
+  return b;
+}
+
+int parrot_gemm_nt(const float* d_A, const float* d_B, float* d_C, int32_t Mr, int32_t N, int32_t K, int32_t impl,
+                   void* d_workspace, size_t workspace_bytes, void* stream) {
+  return guard([&] {
+    cudaStream_t st = (cudaStream_t)stream;
+    parrot_model M;
+    memset(&M.cfg, 0, sizeof M.cfg);
+    M.cfg.gemm_impl = impl;
+    M.ws = (uint8_t*)d_workspace; M.ws_bytes = workspace_bytes; M.dry = false;
+    REQUIRE(((uintptr_t)d_workspace & 1023) == 0, "workspace must be 1024-byte aligned");
+    CK(cudaMemsetAsync(d_workspace, 0, workspace_bytes, st));
+    Plane pa = M.make_plane("A", rup(Mr, 128), K, 1);
+    Plane pb = M.make_plane("B", rup(N, 128), K, 1);
+    const int ma = M.make_map(pa, 2, 128);
+    const int mb = M.make_map(pb, 2, NT);
+    pack_plane(st, d_A, K, Mr, K, pa, 0);
+    pack_plane(st, d_B, K, N, K, pb, 0);
+    std::vector<Job> js;
+    PlainArgs pargs;
+    memset(&pargs, 0, sizeof pargs);
+    pargs.out = d_C; pargs.ldo = N; pargs.n_total = N; pargs.flags = PF_TRANS; pargs.scale = 1.0f;
+    std::vector<PlainSeg> segs = {{ma, 0, mb, 0, 0, cdiv(K, 64)}};
+    build_plain_jobs(js, Mr, 0, N, segs, pargs);
+    push_table(M, "g", js, NT);
+    build_device_tables(M);
+    memset(&M.ctx, 0, sizeof M.ctx);
+    upload_tables(M, st);
+    ensure_kernel_attrs();
+    run_table(M, "g", 0, 1, 0, st);
+    CK(cudaStreamSynchronize(st));
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,511 @@
+// GEMM job engine for the Parrot decoder hot path.
+//
+// Every dense contraction on the path -- the per-step GRU gate / candidate
+// products inside the scan, their reverse-time dgrads, and the batched
+// readout / feedback / weight-gradient products outside it -- is expressed as a
+// *job*: one 128-row output tile  D[128 x N] = sum_seg A_seg[128 x K_seg] * B_seg[N x K_seg]^T
+// followed by a fused epilogue.  Operands are bf16 hi/lo planes (x = hi + lo to
+// ~2^-17), both K-major; the tile is computed as hi*hi + lo*hi + hi*lo with
+// fp32 accumulation in TMEM ("bf16x3", see DESIGN.md: single-pass bf16/tf32 fail
+// the reference-parity gate through an 800-step recurrence).
+//
+// Weights are the M-side (A) operand so that the 128-lane TMEM datapath is full
+// at batch 64 (SURVEY hard part 2); the batch / frame axis is the N side.
+//
+// kernel roles (192 threads, 1 CTA / SM):
+//   warp 0      TMA producer: cp.async.bulk.tensor -> 128B-swizzled smem ring
+//   warp 1      tcgen05.mma issuer (one elected lane), owns the TMEM allocation
+//   warps 2..5  epilogue: tcgen05.ld 32 lanes x 32 columns -> fused epilogue -> global
+//
+// A SIMT twin (job_kernel_simt) executes the same job table with plain loads and
+// fp32 FMAs through the same epilogues.  It exists for verification only: the
+// tests compare it with the tensor-core path at BASELINE sizes where the CPU
+// oracle is too slow.
+#pragma once
+#include <cuda.h>
+#include "ptx.cuh"
+
+namespace pb {
+
+typedef __nv_bfloat16 bf16;
+
+constexpr int TILE_M = 128;
+constexpr int KB = 64;  // k elements per pipeline block (one 128-byte swizzle span)
+constexpr int MAX_SEG = 6;
+constexpr int NO_SLOT = -(1 << 30);
+constexpr int ENGINE_THREADS = 192;
+constexpr int SMEM_BYTES = 200 * 1024;
+
+enum Epi : int {
+  EPI_PLAIN = 0,      // out = acc*scale (+bias) (+= out), optional hi/lo planes
+  EPI_GATES = 1,      // forward scan: sigmoid -> z / r, r*h_prev planes
+  EPI_CAND = 2,       // forward scan: tanh -> c, h_t, planes
+  EPI_BWD_RH = 3,     // backward scan: d(r*h) -> gate pre-activation grads
+  EPI_BWD_STATE = 4,  // backward scan: accumulate into a carried-state gradient
+};
+
+struct Seg {
+  int a_map;   // tensor-map index of the A hi plane (lo plane = a_map + 1)
+  int a_row;   // first row of the tile in A
+  int a_k;     // first k column in A
+  int b_map;   // tensor-map index of the B hi plane (lo = b_map + 1)
+  int b_row;   // first row (sample) in B
+  int b_k;     // first k column in B
+  int b_slot;  // NO_SLOT: B map is 2-D; else 3-D and the slot coordinate is t + b_slot
+  int nkb;     // number of 64-wide k blocks
+};
+
+struct PlainArgs {
+  float* out;
+  const float* bias;   // indexed by output row (feature); may be null
+  bf16* hi;            // optional bf16 planes of the result, [sample][feature]
+  bf16* lo;
+  long long ldo;       // leading dimension of out (floats)
+  long long ldp;       // leading dimension of the planes (elements)
+  long long out_tstride;  // added per scan step t (scan-resident plain jobs)
+  int n_pad;           // >0: sample n = q*n_pad + r, stored at row q*n_valid + r when r < n_valid
+  int n_valid;
+  int n_total;         // samples >= n_total are not stored
+  int flags;           // 1 accumulate, 2 store transposed (out[row*ldo + n]), 4 planes indexed by padded n
+  float scale;
+  int pad_;
+};
+enum { PF_ACC = 1, PF_TRANS = 2, PF_PLANE_PADDED = 4 };
+
+struct Job {
+  int nseg, epi, lag, layer;
+  int row0;     // first output row (feature) of the tile
+  int m_valid;  // rows of the tile that exist
+  int n0;       // first sample column
+  int aux;      // epilogue specific
+  Seg seg[MAX_SEG];
+  PlainArgs pa;
+};
+
+// raw addresses behind each tensor map (SIMT twin + debugging)
+struct MapRaw {
+  const bf16* base;
+  long long row_pitch;   // elements
+  long long slot_pitch;  // elements (0 for 2-D)
+  int rows, cols;        // extents per slot
+  int slots;
+  int box_rows;
+};
+
+// ---- scan context (device resident; see scan.cu for the phase structure) ----
+struct LayerBuf {
+  float* h;            // [T+1][B][H]   state sequence, slot 0 = state entering the segment
+  bf16 *h_hi, *h_lo;   // [T+1][Np][Hp]
+  bf16 *rh_hi, *rh_lo; // [T][Np][Hp]   (reset * previous state), B operand of the candidate product
+  float *z, *r, *c;    // [T][B][H]
+  const float* base;   // [B][3H]  time-constant input: summed Fork biases (+ speaker), [cell | gates]
+  const float* fb;     // [T][B][3H] teacher-forcing feedback term or null
+  // backward
+  float* dh;           // [T+1][B][H]  gradient wrt h slot s (accumulated)
+  float* drh;          // [B][H] scratch: d(r*h) of the current step
+  float* da;           // [T][B][3H]   pre-activation grads [cell | gates] (fp32, for bias / feedback grads)
+  bf16 *da_hi, *da_lo; // [T][Np][3Hp] (cell at 0, gates at Hp)
+};
+struct ScanCtx {
+  int T, B, Np, H, Hp, C, Cp, A, U;
+  LayerBuf L[3];
+  float* dw;           // [T+1][B][C] gradient wrt w slot s
+};
+
+struct EngineParams {
+  const Job* jobs;
+  int njobs;
+  const CUtensorMap* maps;
+  const MapRaw* raws;
+  const ScanCtx* ctx;
+  int tick;       // scan tick; t = tick - job.lag (forward) or as given by dir
+  int T;          // jobs whose t falls outside [0, T) are skipped
+  int n_cols;     // UMMA N of every job in this launch (box rows of every B map used)
+  int reverse;    // 0: t = tick - lag ; 1: t = (T - 1) - (tick - lag)
+};
+
+__device__ __forceinline__ int job_time(const EngineParams& P, const Job& jb) {
+  int t = P.tick - jb.lag;
+  if (P.reverse) t = (P.T - 1) - t;
+  return t;
+}
+
+// A segment whose B operand is slot-indexed is skipped when its slot falls outside the plane
+// (merged backward jobs straddle three pipeline stages; at the ends of the sweep some are absent).
+__device__ __forceinline__ bool seg_valid(const EngineParams& P, const Seg& sg, int t) {
+  if (sg.b_slot == NO_SLOT) return true;
+  const int s = t + sg.b_slot;
+  return s >= 0 && s < P.raws[sg.b_map].slots;
+}
+// total number of k blocks of the job at time t; 0 means "skip this job"
+__device__ __forceinline__ int job_total_kb(const EngineParams& P, const Job& jb, int t) {
+  if (jb.epi != EPI_BWD_STATE && (t < 0 || t >= P.T)) return 0;
+  int n = 0;
+  for (int s = 0; s < jb.nseg; ++s)
+    if (seg_valid(P, jb.seg[s], t)) n += jb.seg[s].nkb;
+  return n;
+}
+
+// ------------------------------------------------------------------ epilogues
+// Thread <-> output row (feature).  v[j] is the accumulator for sample n_base + j.
+__device__ __forceinline__ void epi_plain(const Job& jb, int t, int row, int n_base, int ncols,
+                                          const float* v) {
+  const PlainArgs& a = jb.pa;
+  if (row >= jb.m_valid) return;
+  const int f = jb.row0 + row;
+  const float bias = a.bias ? a.bias[f] : 0.0f;
+  float* out = a.out ? a.out + (long long)t * a.out_tstride : nullptr;
+#pragma unroll 4
+  for (int j = 0; j < ncols; ++j) {
+    const int n = jb.n0 + n_base + j;
+    if (n >= a.n_total) break;
+    long long srow = n;
+    if (a.n_pad > 0) {
+      const int q = n / a.n_pad, r = n - q * a.n_pad;
+      if (r >= a.n_valid) continue;
+      srow = (long long)q * a.n_valid + r;
+    }
+    float y = v[j] * a.scale + bias;
+    if (out) {
+      float* p = (a.flags & PF_TRANS) ? out + (long long)f * a.ldo + srow : out + srow * a.ldo + f;
+      if (a.flags & PF_ACC) y += *p;
+      *p = y;
+    }
+    if (a.hi) {
+      const long long prow = (a.flags & PF_PLANE_PADDED) ? (long long)n : srow;
+      bf16 h, l;
+      split_bf16(y, h, l);
+      a.hi[prow * a.ldp + f] = h;
+      a.lo[prow * a.ldp + f] = l;
+    }
+  }
+}
+
+// forward scan, gates tile: rows [0, 2H) of [update | reset]   (model.py:659-662)
+__device__ __forceinline__ void epi_gates(const Job& jb, const ScanCtx& c, int t, int row, int n_base,
+                                          int ncols, const float* v) {
+  if (row >= jb.m_valid) return;
+  const LayerBuf& L = c.L[jb.layer];
+  const int H = c.H, f = jb.row0 + row;
+  const bool is_z = f < H;
+  const int fr = is_z ? f : f - H;
+#pragma unroll 4
+  for (int j = 0; j < ncols; ++j) {
+    const int b = n_base + j;
+    if (b >= c.B) break;
+    float pre = L.base[(long long)b * 3 * H + H + f];
+    if (L.fb) pre += L.fb[((long long)t * c.B + b) * 3 * H + H + f];
+    const float g = sigmoidf_exact(v[j] + pre);
+    const long long o = ((long long)t * c.B + b) * H + fr;
+    if (is_z) {
+      L.z[o] = g;
+    } else {
+      L.r[o] = g;
+      const float hp = L.h[o];  // slot t == state before this step
+      bf16 hh, ll;
+      split_bf16(g * hp, hh, ll);
+      const long long po = ((long long)t * c.Np + b) * c.Hp + fr;
+      L.rh_hi[po] = hh;
+      L.rh_lo[po] = ll;
+    }
+  }
+}
+
+// forward scan, candidate tile: rows [0, H)
+__device__ __forceinline__ void epi_cand(const Job& jb, const ScanCtx& c, int t, int row, int n_base,
+                                         int ncols, const float* v) {
+  if (row >= jb.m_valid) return;
+  const LayerBuf& L = c.L[jb.layer];
+  const int H = c.H, f = jb.row0 + row;
+#pragma unroll 4
+  for (int j = 0; j < ncols; ++j) {
+    const int b = n_base + j;
+    if (b >= c.B) break;
+    float pre = L.base[(long long)b * 3 * H + f];
+    if (L.fb) pre += L.fb[((long long)t * c.B + b) * 3 * H + f];
+    const float cc = tanhf(v[j] + pre);
+    const long long o = ((long long)t * c.B + b) * H + f;
+    const float zz = L.z[o];
+    const float hp = L.h[o];
+    const float hn = cc * zz + hp * (1.0f - zz);
+    L.c[o] = cc;
+    L.h[o + (long long)c.B * H] = hn;  // slot t + 1
+    bf16 hh, ll;
+    split_bf16(hn, hh, ll);
+    const long long po = ((long long)(t + 1) * c.Np + b) * c.Hp + f;
+    L.h_hi[po] = hh;
+    L.h_lo[po] = ll;
+  }
+}
+
+// backward scan: tile of d(r*h) = da_c * Ws^T, rows = state features [0, H).
+// Finishes the GRU step backward for those features:
+//   dr = drh * h_prev ; dh_prev += drh * r ; da_g = [dz z(1-z) | dr r(1-r)] -> planes + fp32
+// (dz part and da_c were produced by the elementwise pre-pass, scan_bwd.cu)
+__device__ __forceinline__ void epi_bwd_rh(const Job& jb, const ScanCtx& c, int t, int row, int n_base,
+                                           int ncols, const float* v) {
+  if (row >= jb.m_valid) return;
+  const LayerBuf& L = c.L[jb.layer];
+  const int H = c.H, f = jb.row0 + row;
+#pragma unroll 4
+  for (int j = 0; j < ncols; ++j) {
+    const int b = n_base + j;
+    if (b >= c.B) break;
+    const long long o = ((long long)t * c.B + b) * H + f;
+    const float drh = v[j];
+    const float r = L.r[o];
+    const float hp = L.h[o];
+    const float dr = drh * hp;
+    L.dh[o] += drh * r;  // slot t (state before the step)
+    const float dag = dr * r * (1.0f - r);
+    L.da[((long long)t * c.B + b) * 3 * H + 2 * H + f] = dag;
+    bf16 hh, ll;
+    split_bf16(dag, hh, ll);
+    const long long po = ((long long)t * c.Np + b) * (3 * c.Hp) + c.Hp + H + f;
+    L.da_hi[po] = hh;
+    L.da_lo[po] = ll;
+  }
+}
+
+// backward scan: accumulate a dgrad tile into a carried gradient buffer.
+//   aux = 0..2 : dh of layer aux, slot = t + jb.pa.n_pad(slot offset) ; aux = 3 : dw
+__device__ __forceinline__ void epi_bwd_state(const Job& jb, const ScanCtx& c, int t, int row, int n_base,
+                                              int ncols, const float* v) {
+  if (row >= jb.m_valid) return;
+  const int f = jb.row0 + row;
+  const int slot = t + jb.pa.n_pad;
+  float* dst;
+  int F;
+  if (jb.aux == 3) {
+    dst = c.dw; F = c.C;
+  } else {
+    dst = c.L[jb.aux].dh; F = c.H;
+  }
+#pragma unroll 4
+  for (int j = 0; j < ncols; ++j) {
+    const int b = n_base + j;
+    if (b >= c.B) break;
+    dst[((long long)slot * c.B + b) * F + f] += v[j];
+  }
+}
+
+__device__ __forceinline__ void run_epilogue(const Job& jb, const ScanCtx* ctx, int t, int row, int n_base,
+                                             int ncols, const float* v) {
+  switch (jb.epi) {
+    case EPI_PLAIN: epi_plain(jb, t, row, n_base, ncols, v); break;
+    case EPI_GATES: epi_gates(jb, *ctx, t, row, n_base, ncols, v); break;
+    case EPI_CAND: epi_cand(jb, *ctx, t, row, n_base, ncols, v); break;
+    case EPI_BWD_RH: epi_bwd_rh(jb, *ctx, t, row, n_base, ncols, v); break;
+    case EPI_BWD_STATE: epi_bwd_state(jb, *ctx, t, row, n_base, ncols, v); break;
+  }
+}
+
+// ---------------------------------------------------------- tensor-core kernel
+__global__ void __launch_bounds__(ENGINE_THREADS, 1) job_kernel_tc(const EngineParams P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // 1024-byte alignment is required by the 128B swizzle atoms
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_cols = P.n_cols;
+  const uint32_t a_bytes = TILE_M * KB * 2;          // 16 KB
+  const uint32_t b_bytes = (uint32_t)n_cols * KB * 2;
+  const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
+  int nstages = (SMEM_BYTES - 2048) / (int)stage_bytes;
+  if (nstages > 8) nstages = 8;
+
+  uint8_t* tiles = smem;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)nstages * stage_bytes);
+  uint64_t* empty_bar = full_bar + 8;
+  uint64_t* tfull_bar = empty_bar + 8;   // [2] accumulator ready
+  uint64_t* tempty_bar = tfull_bar + 2;  // [2] accumulator drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < nstages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+    fence_proxy_async_smem();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int j = blockIdx.x; j < P.njobs; j += gridDim.x) {
+        const Job& jb = P.jobs[j];
+        const int t = job_time(P, jb);
+        if (job_total_kb(P, jb, t) == 0) continue;
+        for (int s = 0; s < jb.nseg; ++s) {
+          const Seg sg = jb.seg[s];
+          if (!seg_valid(P, sg, t)) continue;
+          const CUtensorMap* ma = P.maps + sg.a_map;
+          const CUtensorMap* mb = P.maps + sg.b_map;
+          for (int kb = 0; kb < sg.nkb; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* st = tiles + (size_t)stage * stage_bytes;
+            mbar_expect_tx(&full_bar[stage], stage_bytes);
+            tma_load_2d(st, ma, &full_bar[stage], sg.a_k + kb * KB, sg.a_row);
+            tma_load_2d(st + a_bytes, ma + 1, &full_bar[stage], sg.a_k + kb * KB, sg.a_row);
+            if (sg.b_slot == NO_SLOT) {
+              tma_load_2d(st + 2 * a_bytes, mb, &full_bar[stage], sg.b_k + kb * KB, sg.b_row);
+              tma_load_2d(st + 2 * a_bytes + b_bytes, mb + 1, &full_bar[stage], sg.b_k + kb * KB, sg.b_row);
+            } else {
+              tma_load_3d(st + 2 * a_bytes, mb, &full_bar[stage], sg.b_k + kb * KB, sg.b_row, t + sg.b_slot);
+              tma_load_3d(st + 2 * a_bytes + b_bytes, mb + 1, &full_bar[stage], sg.b_k + kb * KB, sg.b_row,
+                          t + sg.b_slot);
+            }
+            if (++stage == nstages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------ MMA issuer
+    const uint32_t idesc = umma_idesc_bf16(TILE_M, n_cols);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int j = blockIdx.x; j < P.njobs; j += gridDim.x) {
+      const Job& jb = P.jobs[j];
+      const int t = job_time(P, jb);
+      const int total_kb = job_total_kb(P, jb, t);
+      if (total_kb == 0) continue;
+      const int buf = it & 1;
+      const uint32_t use = (uint32_t)(it >> 1);
+      mbar_wait(&tempty_bar[buf], (use & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)buf * 256u;
+      for (int kbi = 0; kbi < total_kb; ++kbi) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint8_t* st = tiles + (size_t)stage * stage_bytes;
+          const uint64_t da_hi = umma_desc_sw128(st);
+          const uint64_t da_lo = umma_desc_sw128(st + a_bytes);
+          const uint64_t db_hi = umma_desc_sw128(st + 2 * a_bytes);
+          const uint64_t db_lo = umma_desc_sw128(st + 2 * a_bytes + b_bytes);
+#pragma unroll
+          for (int k = 0; k < KB / 16; ++k) {
+            const uint64_t adv = (uint64_t)((k * 16 * 2) >> 4);  // 32 bytes per k16 step
+            umma_bf16(tmem_d, da_hi + adv, db_hi + adv, idesc, (kbi | k) != 0);
+            umma_bf16(tmem_d, da_lo + adv, db_hi + adv, idesc, 1);
+            umma_bf16(tmem_d, da_hi + adv, db_lo + adv, idesc, 1);
+          }
+          umma_commit(&empty_bar[stage]);                       // frees the smem slot
+          if (kbi == total_kb - 1) umma_commit(&tfull_bar[buf]);  // accumulator complete
+        }
+        __syncwarp();
+        if (++stage == nstages) { stage = 0; phase ^= 1; }
+      }
+      ++it;
+    }
+  } else {
+    // ------------------------------------------------ epilogue warps 2..5
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    int it = 0;
+    for (int j = blockIdx.x; j < P.njobs; j += gridDim.x) {
+      const Job& jb = P.jobs[j];
+      const int t = job_time(P, jb);
+      if (job_total_kb(P, jb, t) == 0) continue;
+      const int buf = it & 1;
+      const uint32_t use = (uint32_t)(it >> 1);
+      mbar_wait(&tfull_bar[buf], use & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t)buf * 256u + ((uint32_t)(q * 32) << 16);
+      for (int n0 = 0; n0 < n_cols; n0 += 32) {
+        float v[32];
+        const int nc = (n_cols - n0 >= 32) ? 32 : 16;
+        if (nc == 32) tmem_ld_32x32(taddr + n0, v);
+        else tmem_ld_32x16(taddr + n0, v);
+        tmem_ld_wait();
+        run_epilogue(jb, P.ctx, t, row, n0, nc, v);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+      ++it;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------ SIMT twin
+// 128 threads, thread <-> output row.  Operands are rebuilt as hi + lo in fp32,
+// so the only difference from the tensor-core path is the dropped lo*lo term
+// (~2^-34 relative) and the summation order.
+__global__ void __launch_bounds__(128) job_kernel_simt(const EngineParams P) {
+  __shared__ float As[TILE_M][KB + 1];
+  __shared__ float Bs[32][KB + 1];
+  const int tid = threadIdx.x;
+  for (int j = blockIdx.x; j < P.njobs; j += gridDim.x) {
+    const Job& jb = P.jobs[j];
+    const int t = job_time(P, jb);
+    if (job_total_kb(P, jb, t) == 0) continue;
+    for (int n0 = 0; n0 < P.n_cols; n0 += 32) {
+      const int nc = (P.n_cols - n0 >= 32) ? 32 : (P.n_cols - n0);
+      float acc[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) acc[i] = 0.0f;
+      for (int s = 0; s < jb.nseg; ++s) {
+        const Seg sg = jb.seg[s];
+        if (!seg_valid(P, sg, t)) continue;
+        const MapRaw ra = P.raws[sg.a_map], ral = P.raws[sg.a_map + 1];
+        const MapRaw rb = P.raws[sg.b_map], rbl = P.raws[sg.b_map + 1];
+        const long long bslot = (sg.b_slot == NO_SLOT) ? 0 : (long long)(t + sg.b_slot) * rb.slot_pitch;
+        for (int kb = 0; kb < sg.nkb; ++kb) {
+          __syncthreads();
+          for (int e = tid; e < TILE_M * KB; e += 128) {
+            const int r = e / KB, k = e % KB;
+            const int gr = sg.a_row + r, gk = sg.a_k + kb * KB + k;
+            float x = 0.0f;
+            if (gr < ra.rows && gk < ra.cols) {
+              const long long o = (long long)gr * ra.row_pitch + gk;
+              x = __bfloat162float(ra.base[o]) + __bfloat162float(ral.base[o]);
+            }
+            As[r][k] = x;
+          }
+          for (int e = tid; e < 32 * KB; e += 128) {
+            const int r = e / KB, k = e % KB;
+            const int gr = sg.b_row + n0 + r, gk = sg.b_k + kb * KB + k;
+            float x = 0.0f;
+            if (r < nc && gr < rb.rows && gk < rb.cols) {
+              const long long o = bslot + (long long)gr * rb.row_pitch + gk;
+              x = __bfloat162float(rb.base[o]) + __bfloat162float(rbl.base[o]);
+            }
+            Bs[r][k] = x;
+          }
+          __syncthreads();
+          for (int k = 0; k < KB; ++k) {
+            const float a = As[tid][k];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) acc[i] = fmaf(a, Bs[i][k], acc[i]);
+          }
+        }
+      }
+      run_epilogue(jb, P.ctx, t, tid, n0, nc, acc);
+    }
+  }
+}
+
+}  // namespace pb

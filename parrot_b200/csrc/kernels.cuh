@@ -1,0 +1,1080 @@
+// Non-GEMM kernels of the Parrot hot path (sm_100a): attention window (K7),
+// GRU backward pre-pass, operand packing, emitter costs (K10/K11), GMM sampling
+// (K12), optimizer (K14), encoder recurrence (K2), and a strided SIMT GEMM for
+// the handful of tiny products that are not worth a tensor-core launch.
+#pragma once
+#include "engine.cuh"
+
+namespace pb {
+
+#define SQRT_1_2PI_F 0.3989422917366028f
+
+// =========================================================================
+// Attention window forward, one decoder step (model.py:664-690 / 931-958).
+// One CTA per batch row.  phi is summed over the A mixture components serially
+// in component order and w over text positions serially in position order, with
+// contraction disabled, so that results track the reference's elementwise
+// multiply + axis-sum to the last ulp of expf (bit-exact argmax requirement).
+// =========================================================================
+struct AttnFwdArgs {
+  int B, U, C, A, H, Np, Cp;
+  int type;  // 0 graves, 1 softmax
+  float eps, align, sharp, timing;
+  const float* h1;      // [B][H]
+  const float* wT;      // [3A][H]  h1_to_att weights transposed: alpha | beta | kappa
+  const float* batt;    // [3A]
+  const float* ctx;     // [B][U][C]
+  const float* k_prev;  // [B][A]
+  float* k_out;         // [B][A]
+  float* w_out;         // [B][C]
+  bf16* w_hi;           // [Np][Cp] or null
+  bf16* w_lo;
+  float* phi_out;       // [B][U]
+  float* ab_out;        // [B][2A]  alpha | beta
+  float* e_out;         // [B][3A]  exp(a_hat) (softmax: probabilities) | exp(b_hat) | exp(k_hat)
+};
+
+__global__ void __launch_bounds__(256) attention_fwd_kernel(const AttnFwdArgs a) {
+  extern __shared__ float sh[];
+  float* sh_h = sh;                 // H
+  float* sh_hat = sh_h + a.H;       // 3A
+  float* sh_abk = sh_hat + 3 * a.A; // 3A : alpha, beta, kappa
+  float* sh_phi = sh_abk + 3 * a.A; // U
+  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int A = a.A;
+  for (int i = tid; i < a.H; i += blockDim.x) sh_h[i] = a.h1[(long long)b * a.H + i];
+  __syncthreads();
+  for (int j = warp; j < 3 * A; j += (blockDim.x >> 5)) {
+    const float* wr = a.wT + (long long)j * a.H;
+    float s = 0.0f;
+    for (int k = lane; k < a.H; k += 32) s = fmaf(sh_h[k], wr[k], s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) sh_hat[j] = s + a.batt[j];
+  }
+  __syncthreads();
+  if (tid < A) {
+    float ea;
+    if (a.type == 1) {
+      float m = sh_hat[0];
+      for (int i = 1; i < A; ++i) m = fmaxf(m, sh_hat[i]);
+      float sum = 0.0f;
+      for (int i = 0; i < A; ++i) sum += expf(sh_hat[i] - m);
+      ea = expf(sh_hat[tid] - m) / sum;
+    } else {
+      ea = expf(sh_hat[tid]);
+    }
+    const float eb = expf(sh_hat[A + tid]);
+    const float ek = expf(sh_hat[2 * A + tid]);
+    const float alpha = ea + a.eps;
+    const float beta = (a.sharp == 1.0f ? eb : eb * a.sharp) + a.eps;
+    const float step = (a.timing == 1.0f) ? a.align * ek : (a.align * ek) / a.timing;
+    const float kappa = a.k_prev[(long long)b * A + tid] + step;
+    sh_abk[tid] = alpha;
+    sh_abk[A + tid] = beta;
+    sh_abk[2 * A + tid] = kappa;
+    a.k_out[(long long)b * A + tid] = kappa;
+    a.ab_out[(long long)b * 2 * A + tid] = alpha;
+    a.ab_out[(long long)b * 2 * A + A + tid] = beta;
+    a.e_out[(long long)b * 3 * A + tid] = ea;
+    a.e_out[(long long)b * 3 * A + A + tid] = eb;
+    a.e_out[(long long)b * 3 * A + 2 * A + tid] = ek;
+  }
+  __syncthreads();
+  for (int u = tid; u < a.U; u += blockDim.x) {
+    const float uf = (float)u;
+    float phi = 0.0f;
+    for (int i = 0; i < A; ++i) {
+      const float d = __fsub_rn(sh_abk[2 * A + i], uf);
+      const float d2 = __fmul_rn(d, d);
+      float term;
+      if (a.type == 1) {
+        const float t1 = __fmul_rn(sh_abk[i], sqrtf(sh_abk[A + i]));
+        term = __fmul_rn(t1, expf(__fmul_rn(__fmul_rn(-0.5f, sh_abk[A + i]), d2)));
+      } else {
+        term = __fmul_rn(sh_abk[i], expf(__fmul_rn(-sh_abk[A + i], d2)));
+      }
+      phi = __fadd_rn(phi, term);
+    }
+    if (a.type == 1) phi = __fmul_rn(SQRT_1_2PI_F, phi);
+    sh_phi[u] = phi;
+    a.phi_out[(long long)b * a.U + u] = phi;
+  }
+  __syncthreads();
+  const float* cb = a.ctx + (long long)b * a.U * a.C;
+  for (int c = tid; c < a.C; c += blockDim.x) {
+    float w = 0.0f;
+#pragma unroll 8
+    for (int u = 0; u < a.U; ++u) w = __fadd_rn(w, __fmul_rn(sh_phi[u], cb[(long long)u * a.C + c]));
+    a.w_out[(long long)b * a.C + c] = w;
+    if (a.w_hi) {
+      bf16 hh, ll;
+      split_bf16(w, hh, ll);
+      a.w_hi[(long long)b * a.Cp + c] = hh;
+      a.w_lo[(long long)b * a.Cp + c] = ll;
+    }
+  }
+}
+
+// =========================================================================
+// Attention window backward, one decoder step (training form: sharp = timing = 1).
+// Consumes dw (total gradient wrt w_t), the carried d(kappa), writes the gradient
+// wrt the three attention pre-activations (fp32 + planes for the weight grads),
+// adds datt * Watt^T into dh1, and updates the carried d(kappa).
+// =========================================================================
+struct AttnBwdArgs {
+  int B, U, C, A, H, Np, Ap;   // Ap = padded 3A (plane width)
+  int type;
+  float eps, align;
+  const float* dw;      // [B][C]
+  const float* ctx;     // [B][U][C]
+  const float* ab;      // [B][2A]
+  const float* e;       // [B][3A]
+  const float* kappa;   // [B][A] kappa_t
+  float* dk_carry;      // [B][A] in: d/d kappa_t from step t+1 ; out: d/d kappa_{t-1}
+  const float* watt;    // [3A][H] transposed h1_to_att weights
+  float* dh1;           // [B][H] accumulated
+  float* datt;          // [B][3A] fp32
+  bf16* datt_hi;        // [Np][Ap]
+  bf16* datt_lo;
+};
+
+__global__ void __launch_bounds__(256) attention_bwd_kernel(const AttnBwdArgs a) {
+  extern __shared__ float sh[];
+  float* sh_dw = sh;                    // C
+  float* sh_dphi = sh_dw + a.C;         // U
+  float* sh_red = sh_dphi + a.U;        // 3A * 8 warps
+  float* sh_datt = sh_red + 3 * a.A * 8;// 3A
+  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int A = a.A, nwarp = blockDim.x >> 5;
+  for (int i = tid; i < a.C; i += blockDim.x) sh_dw[i] = a.dw[(long long)b * a.C + i];
+  __syncthreads();
+  const float* cb = a.ctx + (long long)b * a.U * a.C;
+  for (int u = warp; u < a.U; u += nwarp) {
+    const float* row = cb + (long long)u * a.C;
+    float s = 0.0f;
+    for (int c = lane; c < a.C; c += 32) s = fmaf(sh_dw[c], row[c], s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) sh_dphi[u] = s;
+  }
+  __syncthreads();
+  // per-component reductions over u
+  for (int i = 0; i < A; ++i) {
+    const float al = a.ab[(long long)b * 2 * A + i];
+    const float be = a.ab[(long long)b * 2 * A + A + i];
+    const float ka = a.kappa[(long long)b * A + i];
+    float da = 0.0f, db = 0.0f, dk = 0.0f;
+    for (int u = tid; u < a.U; u += blockDim.x) {
+      const float d = ka - (float)u;
+      const float d2 = d * d;
+      float g = sh_dphi[u];
+      if (a.type == 1) {
+        g *= SQRT_1_2PI_F;
+        const float sb = sqrtf(be);
+        const float ee = expf(-0.5f * be * d2);
+        da += g * sb * ee;
+        db += g * al * ee * (0.5f / sb - sb * 0.5f * d2);
+        dk += g * al * sb * ee * (-be * d);
+      } else {
+        const float ee = expf(-be * d2);
+        da += g * ee;
+        db += g * al * ee * (-d2);
+        dk += g * al * ee * (-2.0f * be * d);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      da += __shfl_xor_sync(0xffffffffu, da, o);
+      db += __shfl_xor_sync(0xffffffffu, db, o);
+      dk += __shfl_xor_sync(0xffffffffu, dk, o);
+    }
+    if (lane == 0) {
+      sh_red[(0 * A + i) * 8 + warp] = da;
+      sh_red[(1 * A + i) * 8 + warp] = db;
+      sh_red[(2 * A + i) * 8 + warp] = dk;
+    }
+  }
+  __syncthreads();
+  if (tid < 3 * A) {
+    float s = 0.0f;
+    for (int w = 0; w < nwarp; ++w) s += sh_red[tid * 8 + w];
+    sh_red[tid * 8] = s;
+  }
+  __syncthreads();
+  if (tid < A) {
+    const float da = sh_red[(0 * A + tid) * 8];
+    const float db = sh_red[(1 * A + tid) * 8];
+    const float dk = sh_red[(2 * A + tid) * 8] + a.dk_carry[(long long)b * A + tid];
+    const float ea = a.e[(long long)b * 3 * A + tid];
+    const float eb = a.e[(long long)b * 3 * A + A + tid];
+    const float ek = a.e[(long long)b * 3 * A + 2 * A + tid];
+    float da_hat;
+    if (a.type == 1) {
+      float dot = 0.0f;
+      for (int i = 0; i < A; ++i) dot += sh_red[(0 * A + i) * 8] * a.e[(long long)b * 3 * A + i];
+      da_hat = ea * (da - dot);
+    } else {
+      da_hat = da * ea;
+    }
+    sh_datt[tid] = da_hat;
+    sh_datt[A + tid] = db * eb;
+    sh_datt[2 * A + tid] = dk * a.align * ek;
+    a.dk_carry[(long long)b * A + tid] = dk;
+  }
+  __syncthreads();
+  if (tid < 3 * A) {
+    const float v = sh_datt[tid];
+    a.datt[(long long)b * 3 * A + tid] = v;
+    bf16 hh, ll;
+    split_bf16(v, hh, ll);
+    a.datt_hi[(long long)b * a.Ap + tid] = hh;
+    a.datt_lo[(long long)b * a.Ap + tid] = ll;
+  }
+  for (int f = tid; f < a.H; f += blockDim.x) {
+    float s = 0.0f;
+    for (int j = 0; j < 3 * A; ++j) s = fmaf(sh_datt[j], a.watt[(long long)j * a.H + f], s);
+    a.dh1[(long long)b * a.H + f] += s;
+  }
+}
+
+// =========================================================================
+// GRU backward pre-pass for one layer / step: everything that is elementwise in
+// dh_t (see oracle _gru_bwd).  Produces da_c and the update half of da_g.
+// =========================================================================
+__global__ void gru_bwd_pre_kernel(const ScanCtx* cp, int layer, int t) {
+  const ScanCtx& c = *cp;
+  const LayerBuf& L = c.L[layer];
+  const int H = c.H;
+  const long long n = (long long)c.B * H;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / H), f = (int)(i % H);
+    const long long o = ((long long)t * c.B + b) * H + f;
+    const float dh = L.dh[o + n];  // slot t + 1
+    const float z = L.z[o], cc = L.c[o], hp = L.h[o];
+    const float dc = dh * z;
+    const float dz = dh * (cc - hp);
+    L.dh[o] += dh * (1.0f - z);
+    const float dac = dc * (1.0f - cc * cc);
+    const float dagz = dz * z * (1.0f - z);
+    const long long ao = ((long long)t * c.B + b) * 3 * H;
+    L.da[ao + f] = dac;
+    L.da[ao + H + f] = dagz;
+    const long long po = ((long long)t * c.Np + b) * (3 * c.Hp);
+    bf16 hh, ll;
+    split_bf16(dac, hh, ll);
+    L.da_hi[po + f] = hh;
+    L.da_lo[po + f] = ll;
+    split_bf16(dagz, hh, ll);
+    L.da_hi[po + c.Hp + f] = hh;
+    L.da_lo[po + c.Hp + f] = ll;
+  }
+}
+
+// =========================================================================
+// Operand packing: fp32 -> bf16 hi/lo planes, optionally transposed.
+// =========================================================================
+// dst planes [R_out][ld] ; src fp32 [rows][cols] row-major.
+// transpose=1: dst[c][r] = src[r][c] (dst rows = src cols)
+__global__ void pack_planes_kernel(const float* __restrict__ src, long long src_ld, int rows, int cols,
+                                   bf16* __restrict__ hi, bf16* __restrict__ lo, long long dst_ld,
+                                   int transpose) {
+  __shared__ float tile[32][33];
+  const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  if (!transpose) {
+    for (int j = ty; j < 32; j += 8) {
+      const int r = by + j, c = bx + tx;
+      if (r < rows && c < cols) {
+        bf16 hh, ll;
+        split_bf16(src[(long long)r * src_ld + c], hh, ll);
+        hi[(long long)r * dst_ld + c] = hh;
+        lo[(long long)r * dst_ld + c] = ll;
+      }
+    }
+  } else {
+    for (int j = ty; j < 32; j += 8) {
+      const int r = by + j, c = bx + tx;
+      tile[j][tx] = (r < rows && c < cols) ? src[(long long)r * src_ld + c] : 0.0f;
+    }
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {
+      const int c = bx + j, r = by + tx;  // dst row = c, dst col = r
+      if (r < rows && c < cols) {
+        bf16 hh, ll;
+        split_bf16(tile[tx][j], hh, ll);
+        hi[(long long)c * dst_ld + r] = hh;
+        lo[(long long)c * dst_ld + r] = ll;
+      }
+    }
+  }
+}
+
+// bf16 plane transpose: dst[c][r] = src[r][c]   (for the weight-gradient operands)
+__global__ void transpose_plane_kernel(const bf16* __restrict__ src, long long src_ld, long long rows, int cols,
+                                       bf16* __restrict__ dst, long long dst_ld) {
+  __shared__ bf16 tile[32][34];
+  const long long by = (long long)blockIdx.y * 32;
+  const int bx = blockIdx.x * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  for (int j = ty; j < 32; j += 8) {
+    const long long r = by + j;
+    const int c = bx + tx;
+    tile[j][tx] = (r < rows && c < cols) ? src[r * src_ld + c] : __float2bfloat16(0.0f);
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const int c = bx + j;
+    const long long r = by + tx;
+    if (r < rows && c < cols) dst[(long long)c * dst_ld + r] = tile[tx][j];
+  }
+}
+
+// fp32 [T][B][F] (optionally + level * noise) -> planes [T][Np][Fp]
+__global__ void frames_to_planes_kernel(const float* __restrict__ src, const float* __restrict__ noise,
+                                        float level, int T, int B, int F, int Np, int Fp,
+                                        bf16* __restrict__ hi, bf16* __restrict__ lo, float* __restrict__ copy) {
+  const long long n = (long long)T * B * F;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int f = (int)(i % F);
+    const long long tb = i / F;
+    const int b = (int)(tb % B);
+    const long long t = tb / B;
+    float x = src[i];
+    if (noise) x += level * noise[i];
+    if (copy) copy[i] = x;
+    bf16 hh, ll;
+    split_bf16(x, hh, ll);
+    const long long o = (t * Np + b) * Fp + f;
+    hi[o] = hh;
+    lo[o] = ll;
+  }
+}
+
+// state rows [B][F] fp32 -> fp32 slot + planes slot
+__global__ void state_to_slot_kernel(const float* __restrict__ src, long long src_bstride, int B, int F, int Np,
+                                     int Fp, float* __restrict__ dst, bf16* __restrict__ hi,
+                                     bf16* __restrict__ lo) {
+  const long long n = (long long)B * F;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / F), f = (int)(i % F);
+    const float x = src[(long long)b * src_bstride + f];
+    if (dst) dst[i] = x;
+    if (hi) {
+      bf16 hh, ll;
+      split_bf16(x, hh, ll);
+      hi[(long long)b * Fp + f] = hh;
+      lo[(long long)b * Fp + f] = ll;
+    }
+  }
+}
+
+// =========================================================================
+// Strided SIMT GEMM for the tiny / odd products:
+//   C[m][n] = alpha * sum_k A(m,k) * B(k,n) + beta * C[m][n] (+ bias[n])
+// A(m,k) = A[m*sam + k*sak], B(k,n) = B[k*sbk + n*sbn], C row-major ldc.
+// Optional row gather on A: m -> a_rows[m].
+// =========================================================================
+struct SGemm {
+  const float* A; long long sam, sak;
+  const float* B; long long sbk, sbn;
+  float* C; long long ldc;
+  const float* bias;
+  const int* a_gather;
+  int M, N, K;
+  float alpha, beta;
+};
+__global__ void __launch_bounds__(256) sgemm_kernel(const SGemm g) {
+  __shared__ float As[32][33], Bs[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const int m0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int k0 = 0; k0 < g.K; k0 += 32) {
+    for (int j = ty; j < 32; j += 8) {
+      const int m = m0 + j, k = k0 + tx;
+      float x = 0.0f;
+      if (m < g.M && k < g.K) {
+        const long long mr = g.a_gather ? g.a_gather[m] : m;
+        x = g.A[mr * g.sam + (long long)k * g.sak];
+      }
+      As[j][tx] = x;
+      const int kk = k0 + j, n = n0 + tx;
+      Bs[j][tx] = (kk < g.K && n < g.N) ? g.B[(long long)kk * g.sbk + (long long)n * g.sbn] : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int k = 0; k < 32; ++k) {
+      const float bv = Bs[k][tx];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[i] = fmaf(As[ty + 8 * i][k], bv, acc[i]);
+    }
+    __syncthreads();
+  }
+  const int n = n0 + tx;
+  if (n < g.N) {
+    for (int i = 0; i < 4; ++i) {
+      const int m = m0 + ty + 8 * i;
+      if (m < g.M) {
+        float y = g.alpha * acc[i];
+        if (g.bias) y += g.bias[n];
+        float* p = g.C + (long long)m * g.ldc + n;
+        if (g.beta != 0.0f) y += g.beta * *p;
+        *p = y;
+      }
+    }
+  }
+}
+
+// column sums: out[f] (+)= sum_rows src[r][f]      (bias gradients)
+__global__ void colsum_kernel(const float* __restrict__ src, long long ld, long long rows, int cols,
+                              float* __restrict__ out, int accumulate) {
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  float s = 0.0f;
+  if (c < cols)
+    for (long long r = ty; r < rows; r += 8) s += src[r * ld + c];
+  red[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && c < cols) {
+    float t = 0.0f;
+    for (int j = 0; j < 8; ++j) t += red[j][tx];
+    out[c] = accumulate ? out[c] + t : t;
+  }
+}
+
+__global__ void add_vec_kernel(float* __restrict__ dst, const float* __restrict__ src, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    dst[i] += src[i];
+}
+
+// dst[t][b][f] = sum over t of src  -> [b][f]   (speaker-path gradients)
+__global__ void timesum_kernel(const float* __restrict__ src, int T, long long bf, float* __restrict__ dst) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < bf;
+       i += (long long)gridDim.x * blockDim.x) {
+    float s = 0.0f;
+    for (int t = 0; t < T; ++t) s += src[(long long)t * bf + i];
+    dst[i] = s;
+  }
+}
+
+// scatter-add rows: dst[idx[m]][:] += src[m][:]   (lookup-table gradients; deterministic: one thread per
+// (table row, column) walks all m)
+__global__ void scatter_rows_kernel(const float* __restrict__ src, long long src_ld, const int* __restrict__ idx,
+                                    int M, int F, int rows, float* __restrict__ dst, long long dst_ld) {
+  const long long n = (long long)rows * F;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / F), f = (int)(i % F);
+    float s = 0.0f;
+    for (int m = 0; m < M; ++m)
+      if (idx[m] == r) s += src[(long long)m * src_ld + f];
+    dst[(long long)r * dst_ld + f] += s;
+  }
+}
+
+// dst[c][r] = src[r][c]  (fp32)
+__global__ void transpose_f32_kernel(const float* __restrict__ src, int rows, int cols, float* __restrict__ dst) {
+  const long long n = (long long)rows * cols;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / cols), c = (int)(i % cols);
+    dst[(long long)c * rows + r] = src[i];
+  }
+}
+
+// dst[i] = sum_j src_j[i]  (null sources ignored)
+__global__ void vec_sum_kernel(float* __restrict__ dst, int n, const float* s0, const float* s1, const float* s2,
+                               const float* s3) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float v = 0.0f;
+    if (s0) v += s0[i];
+    if (s1) v += s1[i];
+    if (s2) v += s2[i];
+    if (s3) v += s3[i];
+    dst[i] = v;
+  }
+}
+
+// dst[t][b][f] = src[b][f] for all t
+__global__ void bcast_rows_kernel(float* __restrict__ dst, const float* __restrict__ src, int T, long long bf) {
+  const long long n = (long long)T * bf;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    dst[i] = src[i % bf];
+}
+
+__global__ void mul_kernel(float* __restrict__ dst, const float* __restrict__ a, const float* __restrict__ b,
+                           long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    dst[i] = a[i] * b[i];
+}
+
+// gather the per-character encoder projections: proj [NC][2][3E] -> xi[dir] [L][N][E], xg[dir] [L][N][2E]
+// label of (l, n): time_axis 0 -> labels[l*U + n] (L=B, N=U) ; 1 -> labels[n*U + l] (L=U, N=B)
+__global__ void enc_gather_kernel(const float* __restrict__ proj, const int* __restrict__ labels, int L, int N,
+                                  int U, int time_axis, int E, float* xi0, float* xg0, float* xi1, float* xg1,
+                                  int* __restrict__ lab_out) {
+  const long long n = (long long)L * N * 6 * E;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(i % (6 * E));
+    const long long ln = i / (6 * E);
+    const int l = (int)(ln / N), nn = (int)(ln % N);
+    const int ch = time_axis == 0 ? labels[(long long)l * U + nn] : labels[(long long)nn * U + l];
+    if (j == 0) lab_out[ln] = ch;
+    const float v = proj[(long long)ch * 6 * E + j];
+    const int dir = j / (3 * E), jj = j % (3 * E);
+    float* xi = dir ? xi1 : xi0;
+    float* xg = dir ? xg1 : xg0;
+    if (jj < E) xi[ln * E + jj] = v;
+    else xg[ln * 2 * E + (jj - E)] = v;
+  }
+}
+
+// =========================================================================
+// Emitter: MSE (model.py:757-764) and diagonal-GMM NLL (model.py:65-91, 774-781)
+// =========================================================================
+// One warp per frame.  pred layout for GMM: [mu (D*k) | sigma_hat (D*k) | coeff_hat (k)], index d*k + j.
+struct EmitArgs {
+  int N;          // frames = T*B
+  int D, k, which;  // which: 0 MSE, 1 GMM
+  int Dtot;       // row pitch of pred
+  float eps;
+  const float* pred;
+  const float* target;  // [N][D]
+  const float* mask;    // [N]
+  float* cost_tb;       // [N]
+  // backward
+  float* dpred;         // [N][Dtot] fp32
+  bf16* dpred_hi;       // planes [q*Np + r][Dp]
+  bf16* dpred_lo;
+  int B, Np, Dp;
+  const float* scale;   // device scalar: 1/(sum mask + 1e-5) or 1 (unnormalised)
+};
+
+__global__ void __launch_bounds__(256) emit_cost_kernel(const EmitArgs a) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= a.N) return;
+  const float* p = a.pred + (long long)warp * a.Dtot;
+  const float* y = a.target + (long long)warp * a.D;
+  if (a.which == 0) {
+    float s = 0.0f;
+    for (int d = lane; d < a.D; d += 32) {
+      const float e = p[d] - y[d];
+      s += e * e;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) a.cost_tb[warp] = s;
+    return;
+  }
+  const int k = a.k, D = a.D;
+  // lane j < k owns component j
+  float inner = 0.0f, lw = -INFINITY;
+  if (lane < k) {
+    for (int d = 0; d < D; ++d) {
+      const float mu = p[d * k + lane];
+      const float sg = expf(p[D * k + d * k + lane]) + a.eps;
+      const float df = y[d] - mu;
+      inner += (df * df) / (sg * sg) + 2.0f * logf(sg) + 1.8378770664093453f;
+    }
+    inner *= -0.5f;
+  }
+  // softmax over coeff_hat
+  float ch = (lane < k) ? p[2 * D * k + lane] : -INFINITY;
+  float m = ch;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  float ex = (lane < k) ? expf(ch - m) : 0.0f;
+  float sum = ex;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float pi = ex / sum + a.eps;
+  if (lane < k) lw = logf(pi) + inner;
+  float mx = lw;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float se = (lane < k) ? expf(lw - mx) : 0.0f;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
+  if (lane == 0) a.cost_tb[warp] = -(logf(se) + mx);
+}
+
+// gradient of sum_n cost_tb[n] * mask[n] * scale wrt pred
+__global__ void __launch_bounds__(256) emit_grad_kernel(const EmitArgs a) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= a.N) return;
+  const float* p = a.pred + (long long)warp * a.Dtot;
+  const float* y = a.target + (long long)warp * a.D;
+  float* g = a.dpred + (long long)warp * a.Dtot;
+  const int q = warp / a.B, r = warp % a.B;
+  bf16* ghi = a.dpred_hi + ((long long)q * a.Np + r) * a.Dp;
+  bf16* glo = a.dpred_lo + ((long long)q * a.Np + r) * a.Dp;
+  const float sc = a.mask[warp] * a.scale[0];
+  auto put = [&](int idx, float v) {
+    g[idx] = v;
+    bf16 hh, ll;
+    split_bf16(v, hh, ll);
+    ghi[idx] = hh;
+    glo[idx] = ll;
+  };
+  if (a.which == 0) {
+    for (int d = lane; d < a.D; d += 32) put(d, 2.0f * (p[d] - y[d]) * sc);
+    return;
+  }
+  const int k = a.k, D = a.D;
+  float inner = 0.0f, lw = -INFINITY;
+  if (lane < k) {
+    for (int d = 0; d < D; ++d) {
+      const float mu = p[d * k + lane];
+      const float sg = expf(p[D * k + d * k + lane]) + a.eps;
+      const float df = y[d] - mu;
+      inner += (df * df) / (sg * sg) + 2.0f * logf(sg) + 1.8378770664093453f;
+    }
+    inner *= -0.5f;
+  }
+  float ch = (lane < k) ? p[2 * D * k + lane] : -INFINITY;
+  float m = ch;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  float ex = (lane < k) ? expf(ch - m) : 0.0f;
+  float sum = ex;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float sm = ex / sum;
+  const float pi = sm + a.eps;
+  if (lane < k) lw = logf(pi) + inner;
+  float mx = lw;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float se = (lane < k) ? expf(lw - mx) : 0.0f;
+  float sse = se;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sse += __shfl_xor_sync(0xffffffffu, sse, o);
+  const float rho = se / sse;                      // responsibility of component `lane`
+  const float dpi = (lane < k) ? -(rho / pi) * sc : 0.0f;
+  float dot = dpi * sm;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+  if (lane < k) {
+    put(2 * D * k + lane, sm * (dpi - dot));
+    for (int d = 0; d < D; ++d) {
+      const float mu = p[d * k + lane];
+      const float esg = expf(p[D * k + d * k + lane]);
+      const float sg = esg + a.eps;
+      const float df = y[d] - mu;
+      const float dmu = -(rho * df / (sg * sg)) * sc;
+      const float dsg = -(rho * ((df * df) / (sg * sg * sg) - 1.0f / sg)) * sc;
+      put(d * k + lane, dmu);
+      put(D * k + d * k + lane, dsg * esg);
+    }
+  }
+}
+
+// masked mean: out[0] = sum(cost*mask)/(sum(mask)+1e-5) ; out[1] = sum(cost*mask); out[2] = sum(mask);
+// out[3] = 1/(sum(mask)+1e-5).  Single block, fixed order => deterministic.
+__global__ void __launch_bounds__(1024) masked_mean_kernel(const float* __restrict__ cost,
+                                                            const float* __restrict__ mask, long long n,
+                                                            float* __restrict__ out) {
+  __shared__ float s1[32], s2[32];
+  float a = 0.0f, b = 0.0f;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    a += cost[i] * mask[i];
+    b += mask[i];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+  if ((threadIdx.x & 31) == 0) { s1[threadIdx.x >> 5] = a; s2[threadIdx.x >> 5] = b; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float x = 0.0f, y = 0.0f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { x += s1[i]; y += s2[i]; }
+    out[0] = x / (y + 1e-5f);
+    out[1] = x;
+    out[2] = y;
+    out[3] = 1.0f / (y + 1e-5f);
+  }
+}
+
+// =========================================================================
+// GMM sampling, one step (model.py:94-118, 1024-1033).  One warp per row.
+// pred: [B][Dtot] = [mu | sigma_hat | coeff_hat];  x = mu_j + sigma_j * normal.
+// Noise is either injected (unis/normals non-null: parity tests) or drawn from a
+// counter-based Philox-4x32-10 stream keyed by (seed, step, row).
+// =========================================================================
+__device__ __forceinline__ void philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                           uint32_t k1, uint32_t* out) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+__device__ __forceinline__ float u01(uint32_t x) { return ((x >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+
+struct SampleArgs {
+  int B, D, k, Dtot, which;
+  float eps, bias;           // sampling_bias
+  const float* pred;         // [B][Dtot]
+  const float* unis;         // [B] or null
+  const float* normals;      // [B][D] or null
+  unsigned long long seed; int step;
+  float* x_out;              // [B][D]
+  float* pi_out;             // [B][k] (GMM) / [B][D] (MSE: copy of x)
+  bf16* x_hi; bf16* x_lo; int Np, Dp;   // planes of x for the feedback product (nullable)
+};
+__global__ void __launch_bounds__(128) sample_emit_kernel(const SampleArgs a) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= a.B) return;
+  const float* p = a.pred + (long long)row * a.Dtot;
+  auto putx = [&](int d, float v) {
+    a.x_out[(long long)row * a.D + d] = v;
+    if (a.x_hi) {
+      bf16 hh, ll;
+      split_bf16(v, hh, ll);
+      a.x_hi[(long long)row * a.Dp + d] = hh;
+      a.x_lo[(long long)row * a.Dp + d] = ll;
+    }
+  };
+  if (a.which == 0) {
+    for (int d = lane; d < a.D; d += 32) {
+      putx(d, p[d]);
+      a.pi_out[(long long)row * a.D + d] = p[d];
+    }
+    return;
+  }
+  const int k = a.k, D = a.D;
+  float ch = (lane < k) ? p[2 * D * k + lane] * (1.0f + a.bias) : -INFINITY;
+  float m = ch;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  float ex = (lane < k) ? expf(ch - m) : 0.0f;
+  float sum = ex;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float pi = ex / sum + a.eps;
+  if (lane < k) a.pi_out[(long long)row * k + lane] = pi;
+  uint32_t rnd[4];
+  float u;
+  if (a.unis) u = a.unis[row];
+  else {
+    philox4x32((uint32_t)row, (uint32_t)a.step, 0u, 0u, (uint32_t)a.seed, (uint32_t)(a.seed >> 32), rnd);
+    u = u01(rnd[0]);
+  }
+  // first component whose running sum exceeds u (theano MultinomialFromUniform)
+  int idx = 0;
+  {
+    float cum = 0.0f;
+    bool done = false;
+    for (int j = 0; j < k; ++j) {
+      const float pj = __shfl_sync(0xffffffffu, pi, j);
+      cum = __fadd_rn(cum, pj);
+      if (!done && u < cum) { idx = j; done = true; }
+    }
+  }
+  for (int d = lane; d < D; d += 32) {
+    const float mu = p[d * k + idx];
+    const float sg = expf(p[D * k + d * k + idx] - a.bias) + a.eps;
+    float z;
+    if (a.normals) z = a.normals[(long long)row * D + d];
+    else {
+      philox4x32((uint32_t)row, (uint32_t)a.step, (uint32_t)(d + 1), 1u, (uint32_t)a.seed,
+                 (uint32_t)(a.seed >> 32), rnd);
+      z = sqrtf(-2.0f * logf(u01(rnd[0]))) * cospif(2.0f * u01(rnd[1]));
+    }
+    putx(d, mu + sg * z);
+  }
+}
+
+// =========================================================================
+// Optimizer: StepClipping(threshold) + Adam (train.py:100-108), flat buffers.
+// =========================================================================
+__global__ void __launch_bounds__(1024) sumsq_partial_kernel(const float* __restrict__ g, long long n,
+                                                              double* __restrict__ partial) {
+  __shared__ double sh[32];
+  double s = 0.0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const double v = (double)g[i];
+    s += v * v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += sh[i];
+    partial[blockIdx.x] = t;
+  }
+}
+// stats[0] = grad norm (after scaling by gscale), stats[1] = clip multiplier
+__global__ void clip_finalize_kernel(const double* __restrict__ partial, int nparts, float gscale,
+                                     float threshold, float* __restrict__ stats) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < nparts; ++i) t += partial[i];
+    const float norm = (float)sqrt(t) * fabsf(gscale);
+    stats[0] = norm;
+    stats[1] = (norm < threshold) ? 1.0f : threshold / norm;
+  }
+}
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, long long n, const float* __restrict__ stats, float gscale,
+                            float lr_t, float b1, float b2, float eps) {
+  const float mult = stats[1] * gscale;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float gi = g[i] * mult;
+    const float mi = b1 * m[i] + (1.0f - b1) * gi;
+    const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] = p[i] - lr_t * mi / (sqrtf(vi) + eps);
+  }
+}
+
+// =========================================================================
+// Encoder GRU recurrence (model.py:233-247 through blocks Bidirectional /
+// GatedRecurrent).  xi/xg are the gathered Fork projections [L][N][E] / [L][N][2E].
+// One CTA per (direction, chunk of ENC_ROWS rows); fp32 SIMT, weights from L2.
+// Stashes z, r, c and the state sequence for the backward pass.
+// =========================================================================
+constexpr int ENC_ROWS = 8;
+struct EncArgs {
+  int L, N, E;
+  const float* xi[2];     // [L][N][E]
+  const float* xg[2];     // [L][N][2E]
+  const float* Wg[2];     // [E][2E] state_to_gates
+  const float* Ws[2];     // [E][E]  state_to_state
+  const float* s0[2];     // [E] initial_state
+  float* out;             // [L][N][2E]  forward | backward halves
+  float* z[2]; float* r[2]; float* c[2];   // [L][N][E]
+  float* sprev[2];        // [L][N][E] state entering step i
+  // backward
+  const float* dout;      // [L][N][2E]
+  float* dxi[2]; float* dxg[2];
+  float* ds0[2];          // [N][E] gradient wrt the initial state rows (summed later)
+};
+
+__global__ void __launch_bounds__(256) encoder_fwd_kernel(const EncArgs a) {
+  extern __shared__ float sh[];
+  const int E = a.E, dir = blockIdx.y;
+  const int n0 = blockIdx.x * ENC_ROWS;
+  const int rows = min(ENC_ROWS, a.N - n0);
+  float* s = sh;                    // [ENC_ROWS][E]
+  float* rs = s + ENC_ROWS * E;     // [ENC_ROWS][E]
+  float* g = rs + ENC_ROWS * E;     // [ENC_ROWS][2E]
+  const int tid = threadIdx.x;
+  for (int i = tid; i < ENC_ROWS * E; i += blockDim.x) s[i] = a.s0[dir][i % E];
+  __syncthreads();
+  for (int step = 0; step < a.L; ++step) {
+    const int i = dir == 0 ? step : a.L - 1 - step;
+    // gates
+    for (int j = tid; j < 2 * E; j += blockDim.x) {
+      float acc[ENC_ROWS];
+#pragma unroll
+      for (int n = 0; n < ENC_ROWS; ++n) acc[n] = 0.0f;
+      for (int k = 0; k < E; ++k) {
+        const float w = a.Wg[dir][(long long)k * 2 * E + j];
+#pragma unroll
+        for (int n = 0; n < ENC_ROWS; ++n) acc[n] = fmaf(s[n * E + k], w, acc[n]);
+      }
+      for (int n = 0; n < rows; ++n) {
+        const long long o = ((long long)i * a.N + n0 + n);
+        g[n * 2 * E + j] = sigmoidf_exact(acc[n] + a.xg[dir][o * 2 * E + j]);
+      }
+    }
+    __syncthreads();
+    for (int e = tid; e < rows * E; e += blockDim.x) {
+      const int n = e / E, f = e % E;
+      const long long o = ((long long)i * a.N + n0 + n) * E + f;
+      const float z = g[n * 2 * E + f], r = g[n * 2 * E + E + f];
+      a.z[dir][o] = z;
+      a.r[dir][o] = r;
+      a.sprev[dir][o] = s[n * E + f];
+      rs[n * E + f] = s[n * E + f] * r;
+    }
+    __syncthreads();
+    for (int j = tid; j < E; j += blockDim.x) {
+      float acc[ENC_ROWS];
+#pragma unroll
+      for (int n = 0; n < ENC_ROWS; ++n) acc[n] = 0.0f;
+      for (int k = 0; k < E; ++k) {
+        const float w = a.Ws[dir][(long long)k * E + j];
+#pragma unroll
+        for (int n = 0; n < ENC_ROWS; ++n) acc[n] = fmaf(rs[n * E + k], w, acc[n]);
+      }
+      for (int n = 0; n < rows; ++n) {
+        const long long o = ((long long)i * a.N + n0 + n);
+        const float cc = tanhf(acc[n] + a.xi[dir][o * E + j]);
+        const float z = g[n * 2 * E + j];
+        const float sn = cc * z + s[n * E + j] * (1.0f - z);
+        a.c[dir][o * E + j] = cc;
+        a.out[o * 2 * E + dir * E + j] = sn;
+        g[n * 2 * E + E + j] = sn;  // park the new state in the (now dead) reset half
+      }
+    }
+    __syncthreads();
+    for (int e = tid; e < rows * E; e += blockDim.x) {
+      const int n = e / E, f = e % E;
+      s[n * E + f] = g[n * 2 * E + E + f];
+    }
+    __syncthreads();
+  }
+}
+
+// reverse-time encoder recurrence: consumes dout, writes dxi / dxg and ds0.
+// Needs W^T products: d(rs) = da_c * Ws^T, ds += da_g * Wg^T  (uncoalesced reads of W rows are fine here:
+// 2 x 196 KB of weights stay in L1/L2).
+__global__ void __launch_bounds__(256) encoder_bwd_kernel(const EncArgs a) {
+  extern __shared__ float sh[];
+  const int E = a.E, dir = blockIdx.y;
+  const int n0 = blockIdx.x * ENC_ROWS;
+  const int rows = min(ENC_ROWS, a.N - n0);
+  float* ds = sh;                      // [ENC_ROWS][E]
+  float* dac = ds + ENC_ROWS * E;      // [ENC_ROWS][E]
+  float* dag = dac + ENC_ROWS * E;     // [ENC_ROWS][2E]
+  float* dsn = dag + ENC_ROWS * 2 * E; // [ENC_ROWS][E] next ds
+  const int tid = threadIdx.x;
+  for (int i = tid; i < ENC_ROWS * E; i += blockDim.x) ds[i] = 0.0f;
+  __syncthreads();
+  for (int step = a.L - 1; step >= 0; --step) {
+    const int i = dir == 0 ? step : a.L - 1 - step;
+    for (int e = tid; e < ENC_ROWS * E; e += blockDim.x) {
+      const int n = e / E, f = e % E;
+      float v_dac = 0.0f, v_dz = 0.0f, v_keep = 0.0f;
+      if (n < rows) {
+        const long long o = ((long long)i * a.N + n0 + n) * E + f;
+        const float d = ds[e] + a.dout[((long long)i * a.N + n0 + n) * 2 * E + dir * E + f];
+        const float z = a.z[dir][o], cc = a.c[dir][o], sp = a.sprev[dir][o];
+        v_dac = d * z * (1.0f - cc * cc);
+        v_dz = d * (cc - sp) * z * (1.0f - z);
+        v_keep = d * (1.0f - z);
+        a.dxi[dir][o] = v_dac;
+        a.dxg[dir][((long long)i * a.N + n0 + n) * 2 * E + f] = v_dz;
+      }
+      dac[e] = v_dac;
+      dag[n * 2 * E + f] = v_dz;
+      dsn[e] = v_keep;
+    }
+    __syncthreads();
+    // d(rs)[n][k] = sum_j dac[n][j] * Ws[k][j]
+    for (int e = tid; e < rows * E; e += blockDim.x) {
+      const int n = e / E, k = e % E;
+      const float* wr = a.Ws[dir] + (long long)k * E;
+      float acc = 0.0f;
+      for (int j = 0; j < E; ++j) acc = fmaf(dac[n * E + j], wr[j], acc);
+      const long long o = ((long long)i * a.N + n0 + n) * E + k;
+      const float r = a.r[dir][o], sp = a.sprev[dir][o];
+      const float dr = acc * sp;
+      dsn[e] += acc * r;
+      const float v = dr * r * (1.0f - r);
+      dag[n * 2 * E + E + k] = v;
+      a.dxg[dir][((long long)i * a.N + n0 + n) * 2 * E + E + k] = v;
+    }
+    __syncthreads();
+    // ds[n][k] += sum_j dag[n][j] * Wg[k][j]
+    for (int e = tid; e < rows * E; e += blockDim.x) {
+      const int n = e / E, k = e % E;
+      const float* wr = a.Wg[dir] + (long long)k * 2 * E;
+      float acc = 0.0f;
+      for (int j = 0; j < 2 * E; ++j) acc = fmaf(dag[n * 2 * E + j], wr[j], acc);
+      ds[e] = dsn[e] + acc;
+    }
+    __syncthreads();
+  }
+  for (int e = tid; e < rows * E; e += blockDim.x) {
+    const int n = e / E, f = e % E;
+    a.ds0[dir][(long long)(n0 + n) * E + f] = ds[e];
+  }
+}
+
+// ctx[b][u][:] = enc[...] * labels_mask[b][u]   (model.py:645-646); handles the time-axis layout.
+// enc is [L][N][C2]; axis0 literal: (L,N) = (B,U) ; axis1: (L,N) = (U,B).
+__global__ void context_mask_kernel(const float* __restrict__ enc, const float* __restrict__ lmask, int B,
+                                    int U, int C, int time_axis, float* __restrict__ ctx, int backward) {
+  const long long n = (long long)B * U * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const long long bu = i / C;
+    const int u = (int)(bu % U), b = (int)(bu / U);
+    const long long eo = (time_axis == 0) ? i : (((long long)u * B + b) * C + c);
+    if (!backward) ctx[i] = enc[eo] * lmask[bu];
+    else const_cast<float*>(enc)[eo] = ctx[i] * lmask[bu];  // denc <- dctx * mask
+  }
+}
+
+// gather rows of a table: dst[m][:] = table[idx[m]][:]
+__global__ void gather_rows_kernel(const float* __restrict__ table, const int* __restrict__ idx, long long M,
+                                   int F, float* __restrict__ dst) {
+  const long long n = M * F;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long m = i / F;
+    const int f = (int)(i % F);
+    dst[i] = table[(long long)idx[m] * F + f];
+  }
+}
+
+// dctx[b][u][c] = sum_t phi[t][b][u] * dw[t][b][c]      (one CTA per (b, 32-u tile, 32-c tile))
+__global__ void __launch_bounds__(256) dctx_kernel(const float* __restrict__ phi, const float* __restrict__ dw,
+                                                   int T, int B, int U, int C, float* __restrict__ dctx) {
+  __shared__ float Ps[32][33], Ds[32][33];
+  const int b = blockIdx.z, u0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int t0 = 0; t0 < T; t0 += 32) {
+    for (int j = ty; j < 32; j += 8) {
+      const int t = t0 + j;
+      Ps[j][tx] = (t < T && u0 + tx < U) ? phi[((long long)t * B + b) * U + u0 + tx] : 0.0f;
+      Ds[j][tx] = (t < T && c0 + tx < C) ? dw[((long long)t * B + b) * C + c0 + tx] : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int k = 0; k < 32; ++k) {
+      const float d = Ds[k][tx];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[i] = fmaf(Ps[k][ty + 8 * i], d, acc[i]);
+    }
+    __syncthreads();
+  }
+  for (int i = 0; i < 4; ++i) {
+    const int u = u0 + ty + 8 * i, c = c0 + tx;
+    if (u < U && c < C) dctx[((long long)b * U + u) * C + c] = acc[i];
+  }
+}
+
+__global__ void fill_kernel(float* __restrict__ p, long long n, float v) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    p[i] = v;
+}
+
+// base[b][:] = bias_sum[:] (+ spk[b][:])
+__global__ void base_rows_kernel(const float* __restrict__ bias, const float* __restrict__ spk, int B, int F,
+                                 float* __restrict__ base) {
+  const long long n = (long long)B * F;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    float v = bias[i % F];
+    if (spk) v += spk[i];
+    base[i] = v;
+  }
+}
+
+}  // namespace pb

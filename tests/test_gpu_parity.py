@@ -1,0 +1,131 @@
+"""GPU parity tests: parrot_b200.Parrot (CUDA, through the C ABI) vs the numpy oracle on seeded inputs.
+
+Gates (BASELINE.json north_star): emitted frames within 1e-3 relative of the oracle, argmax of the
+alignment phi bit-exact wherever the oracle's own argmax is unambiguous (tests/util.stable_argmax_mask).
+Gradients are held to 2e-3 of each tensor's max-abs (bf16x3 operands, different summation order).
+"""
+import numpy as np
+import pytest
+import torch
+
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+FWD_TOL = 1e-3
+GRAD_TOL = 2e-3
+
+CASES = {
+    'mse_weak': dict(weak_feedback=True),
+    'gmm_full_spk': dict(which_cost='GMM', full_feedback=True, use_speaker=True),
+    'softmax_att_noise': dict(attention_type='softmax', weak_feedback=True, feedback_noise_level=0.3),
+    'no_feedback': dict(),
+}
+
+
+def _run_pair(cfg, B, T, U, gain, impl, start_flags=(1.0,), axis=0, align=None, check_grads=True):
+    cfg = dict(cfg)
+    if align is not None:
+        cfg['attention_alignment'] = align
+    orc = util.make_oracle(cfg, gain=gain, encoder_time_axis=axis)
+    o64 = util.make_oracle(cfg, gain=gain, dtype=np.float64, encoder_time_axis=axis)
+    dev = util.make_device_model(cfg, orc, gemm_impl=impl, encoder_time_axis=axis)
+    out = []
+    for si, sf in enumerate(start_flags):
+        bt = util.make_batch(cfg, B, T, U, seed=10 + si)
+        spk = bt['speaker'] if cfg.get('use_speaker') else None
+        kw = dict(feedback_noise=bt['feedback_noise'], noise_level=cfg.get('feedback_noise_level'))
+        c_o, up_o, av_o, _ = orc.compute_cost(bt['features'], bt['features_mask'], bt['labels'], bt['labels_mask'],
+                                               spk, sf, B, gmm_unis=bt['gmm_unis'], gmm_normals=bt['gmm_normals'], **kw)
+        c64, _, av64, _ = o64.compute_cost(bt['features'], bt['features_mask'], bt['labels'], bt['labels_mask'],
+                                           spk, sf, B, gmm_unis=bt['gmm_unis'], gmm_normals=bt['gmm_normals'], **kw)
+        c_d, up_d, av_d, _ = dev.compute_cost(bt['features'], bt['features_mask'], bt['labels'], bt['labels_mask'],
+                                               spk, sf, B, feedback_noise=bt['feedback_noise'],
+                                               noise_level=cfg.get('feedback_noise_level'),
+                                               gmm_noise=(bt['gmm_unis'], bt['gmm_normals']))
+        torch.cuda.synchronize()
+        assert abs(c_d.item() - c_o) / abs(c_o) < FWD_TOL, (c_d.item(), c_o)
+        names = ['next_x', 'k', 'w', 'coeff', 'phi', 'pi_att']
+        for nm, a, b in zip(names, av_d, av_o):
+            if b is None:
+                continue
+            err = util.rel_err(a.cpu().numpy(), b)
+            assert err < FWD_TOL, (nm, err)
+        ok = util.stable_argmax_mask(av_o[4], av64[4])
+        am_d = av_d[4].cpu().numpy().argmax(-1)
+        assert ok.mean() > 0.5
+        assert (am_d[ok] == av_o[4].argmax(-1)[ok]).all()
+        for (n1, v1), (n2, v2) in zip(up_d, up_o):
+            assert n1 == n2 and util.rel_err(v1.cpu().numpy(), v2) < FWD_TOL, n1
+        if check_grads:
+            g_o = orc.backward()
+            g_d = dev.backward()
+            torch.cuda.synchronize()
+            worst = ('', 0.0)
+            for n in g_o:
+                e = util.rel_err(g_d[n].cpu().numpy(), g_o[n])
+                if np.abs(g_o[n]).max() < 1e-12:
+                    e = float(np.abs(g_d[n].cpu().numpy()).max())
+                if e > worst[1]:
+                    worst = (n, e)
+            assert worst[1] < GRAD_TOL, worst
+            assert abs(dev.flat_grads[-1].item() - bt['features_mask'][1:].sum()) < 1e-3
+        out.append((c_d.item(), c_o))
+    return out
+
+
+@pytest.mark.parametrize('impl', ['simt', 'tcgen05'])
+@pytest.mark.parametrize('case', sorted(CASES))
+def test_compute_cost_and_grads_tiny(case, impl):
+    """Config 1 scale (H=64): every option, forward + backward, against the oracle."""
+    cfg = dict(util.TINY, **CASES[case])
+    _run_pair(cfg, B=8, T=12, U=16, gain=0.5, impl=impl, align=0.4)
+
+
+@pytest.mark.parametrize('impl', ['simt', 'tcgen05'])
+def test_state_carry_two_segments(impl):
+    """TBPTT: start_flag=1 then start_flag=0 must carry last_h*, last_k, last_w (model.py:633-643, 786-791)."""
+    cfg = dict(util.TINY, weak_feedback=True)
+    _run_pair(cfg, B=8, T=10, U=16, gain=0.5, impl=impl, start_flags=(1.0, 0.0), align=0.4)
+
+
+def test_init_scale_and_intended_encoder_axis():
+    """Reference init (N(0, 0.01)) and encoder_time_axis=1."""
+    cfg = dict(util.TINY, weak_feedback=True, which_cost='GMM')
+    orc_cfg = dict(cfg)
+    _run_pair(orc_cfg, B=5, T=9, U=11, gain=None, impl='tcgen05', axis=1)
+
+
+def test_medium_hidden_odd_batch():
+    """H=256, B=20 (padded to 32 rows), ragged masks, C != H."""
+    cfg = dict(util.TINY, rnn_h_dim=256, readouts_dim=192, encoder_dim=32, weak_feedback=True)
+    _run_pair(cfg, B=20, T=16, U=24, gain=0.5, impl='tcgen05', align=0.5)
+
+
+@pytest.mark.parametrize('case', ['mse_weak', 'gmm_full_spk'])
+def test_sample_model_matches_oracle(case):
+    """Free-running generation (model.py:827-1059) with injected GMM noise."""
+    cfg = dict(util.TINY, **CASES[case])
+    cfg.update(sampling_bias=0.5, sharpening_coeff=1.3, timing_coeff=1.2, attention_alignment=0.5)
+    B, T, U = 6, 20, 16
+    orc = util.make_oracle(cfg, gain=0.5)
+    dev = util.make_device_model(cfg, orc)
+    bt = util.make_batch(cfg, B, T, U, seed=5)
+    spk = bt['speaker'] if cfg.get('use_speaker') else None
+    ref = orc.sample_model(bt['labels'], bt['labels_mask'], None, spk, B, T,
+                           gmm_unis=bt['gmm_unis'], gmm_normals=bt['gmm_normals'])
+    out = dev.sample_model(bt['labels'], bt['labels_mask'], None, spk, B, T,
+                           gmm_noise=(bt['gmm_unis'], bt['gmm_normals']))
+    for nm, a, b in zip(['x', 'k', 'w', 'pi', 'phi', 'pi_att'], out, ref):
+        assert util.rel_err(a, b) < FWD_TOL, nm
+
+
+def test_sample_model_philox_runs():
+    cfg = dict(util.TINY, which_cost='GMM', weak_feedback=True)
+    orc = util.make_oracle(cfg, gain=0.5)
+    dev = util.make_device_model(cfg, orc)
+    bt = util.make_batch(cfg, 4, 8, 12, seed=5)
+    a = dev.sample_model(bt['labels'], bt['labels_mask'], None, None, 4, 8, seed=1)
+    b = dev.sample_model(bt['labels'], bt['labels_mask'], None, None, 4, 8, seed=1)
+    c = dev.sample_model(bt['labels'], bt['labels_mask'], None, None, 4, 8, seed=2)
+    assert np.isfinite(a[0]).all() and (a[0] == b[0]).all() and not (a[0] == c[0]).all()

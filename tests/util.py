@@ -1,0 +1,67 @@
+"""Shared helpers of the parity tests: matching oracle / device models and seeded synthetic batches
+(SURVEY.md 8d 'Synthetic inputs')."""
+import numpy as np
+
+from oracle.parrot_oracle import OracleParrot
+
+TINY = dict(input_dim=24, output_dim=63, rnn_h_dim=64, readouts_dim=64, num_characters=43,
+            attention_size=10, encoder_dim=64, k_gmm=20, num_speakers=5, speaker_dim=16,
+            encoder_type='bidirectional')
+
+
+def make_batch(cfg, B, T, U, seed=0, ragged=True, dtype=np.float32):
+    """features (T+1,B,D) ~ N(0,1); masks with lengths ~ U{0.6..1}; labels ~ U{0..num_characters}."""
+    rng = np.random.default_rng(seed)
+    D = cfg.get('output_dim', 63)
+    feats = rng.standard_normal((T + 1, B, D)).astype(dtype)
+    fm = np.ones((T + 1, B), dtype)
+    lm = np.ones((B, U), dtype)
+    if ragged:
+        for b in range(B):
+            fl = int(rng.integers(int(0.6 * (T + 1)), T + 2))
+            fm[fl:, b] = 0
+            ul = int(rng.integers(max(2, int(0.6 * U)), U + 1))
+            lm[b, ul:] = 0
+    labels = rng.integers(0, cfg.get('num_characters', 43), (B, U)).astype(np.int32)
+    spk = rng.integers(0, cfg.get('num_speakers', 21), (B, 1)).astype(np.int32)
+    return dict(features=feats, features_mask=fm, labels=labels, labels_mask=lm, speaker=spk,
+                feedback_noise=rng.standard_normal((T, B, D)).astype(dtype),
+                gmm_unis=rng.random((T, B)).astype(dtype),
+                gmm_normals=rng.standard_normal((T, B, D)).astype(dtype))
+
+
+def make_oracle(cfg, seed=0, gain=None, dtype=np.float32, encoder_time_axis=0, bias_std=0.1):
+    m = OracleParrot(dtype=dtype, encoder_time_axis=encoder_time_axis, **cfg)
+    m.initialize(np.random.default_rng(seed), gain=gain)
+    if bias_std:
+        rng = np.random.default_rng(seed + 1000)
+        for n in m.params:
+            if n.endswith('.b') or n.endswith('initial_state') or n.endswith('initial_w'):
+                m.params[n] = (rng.standard_normal(m.params[n].shape) * bias_std).astype(dtype)
+    return m
+
+
+def make_device_model(cfg, oracle, gemm_impl='tcgen05', encoder_time_axis=0):
+    from parrot_b200.model import Parrot
+    m = Parrot(gemm_impl=gemm_impl, encoder_time_axis=encoder_time_axis, **cfg)
+    m.initialize()
+    m.set_parameter_values({n: np.asarray(v, np.float32) for n, v in oracle.params.items()})
+    return m
+
+
+def rel_err(a, b):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    den = np.abs(b).max()
+    return float(np.abs(a - b).max() / (den if den > 0 else 1.0))
+
+
+def stable_argmax_mask(phi32, phi64, margin=1e-4):
+    """Frames where the oracle's own argmax is unambiguous: the top-2 gap of phi (float64) exceeds
+    ``margin`` relative, and phi is not underflowed to ~0.  Bit-exact argmax is demanded there."""
+    p = np.asarray(phi64, np.float64)
+    srt = np.sort(p, axis=-1)
+    top, second = srt[..., -1], srt[..., -2]
+    ok = (top > 1e-30) & ((top - second) > margin * top)
+    ok &= (np.asarray(phi32).argmax(-1) == p.argmax(-1))
+    return ok
