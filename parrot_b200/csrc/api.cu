@@ -11,6 +11,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <map>
@@ -38,11 +39,29 @@ static std::atomic<long long> g_launches{0};
   do {                                                                         \
     if (!(cond)) throw std::runtime_error(std::string("parrot_b200: ") + msg); \
   } while (0)
-#define LAUNCH(kern, grid, block, smem, st, ...)        \
-  do {                                                  \
-    kern<<<grid, block, smem, st>>>(__VA_ARGS__);       \
-    g_launches.fetch_add(1, std::memory_order_relaxed); \
-    CK(cudaGetLastError());                             \
+static bool debug_sync() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PARROT_DEBUG_SYNC");
+    v = (e && e[0] && e[0] != '0') ? 1 : 0;
+  }
+  return v == 1;
+}
+static thread_local const char* g_ctx = "";   // what the host was launching (debug messages)
+#define LAUNCH(kern, grid, block, smem, st, ...)                                                     \
+  do {                                                                                               \
+    kern<<<grid, block, smem, st>>>(__VA_ARGS__);                                                    \
+    g_launches.fetch_add(1, std::memory_order_relaxed);                                              \
+    CK(cudaGetLastError());                                                                          \
+    if (debug_sync()) {                                                                              \
+      cudaError_t e2_ = cudaStreamSynchronize(st);                                                   \
+      if (e2_ != cudaSuccess) {                                                                      \
+        char b2_[512];                                                                               \
+        snprintf(b2_, sizeof b2_, "kernel %s failed (%s) while running [%s]", #kern,                 \
+                 cudaGetErrorString(e2_), g_ctx);                                                    \
+        throw std::runtime_error(b2_);                                                               \
+      }                                                                                              \
+    }                                                                                                \
   } while (0)
 
 template <typename F>
@@ -102,7 +121,10 @@ static Dims make_dims(const parrot_config& c) {
   d.weak = c.weak_feedback != 0 || d.full;
   d.sampling = c.sampling != 0;
   d.Np = rup(d.B, 16); d.Hp = rup(d.H, 64); d.Cp = rup(d.C, 64); d.Rp = rup(d.R, 64);
-  d.Dp = rup(d.D, 64); d.Dtp = rup(d.Dtot, 64); d.Ap = 64;
+  d.Dp = rup(d.D, 64); d.Ap = 64;
+  // planes of d(pred): the GMM blocks [mu | sigma | coeff] start at 64-aligned columns (TMA inner
+  // coordinates must stay 16-byte aligned)
+  d.Dtp = d.gmm ? 2 * rup(d.D * d.K, 64) + rup(d.K, 64) : rup(d.D, 64);
   return d;
 }
 static void check_cfg(const parrot_config& c) {
@@ -420,6 +442,9 @@ static void push_table(parrot_model& M, const std::string& name, const std::vect
 static void run_table(parrot_model& M, const std::string& name, int tick, int T, int reverse, cudaStream_t st) {
   const Table& t = M.tables.at(name);
   if (t.count == 0) return;
+  static thread_local char ctxbuf[128];
+  snprintf(ctxbuf, sizeof ctxbuf, "table %s tick %d njobs %d n_cols %d", name.c_str(), tick, t.count, t.n_cols);
+  g_ctx = ctxbuf;
   EngineParams P;
   P.jobs = M.d_jobs + t.off; P.njobs = t.count; P.maps = M.d_maps; P.raws = M.d_raws; P.ctx = M.d_ctx;
   P.tick = tick; P.T = T; P.n_cols = t.n_cols; P.reverse = reverse;
@@ -460,10 +485,11 @@ static void build(parrot_model& M) {
   }
   M.add_pack("/att_to_readout", train);
   std::vector<std::string> out_forks;
-  std::vector<int> out_off, out_dim;
+  std::vector<int> out_off, out_dim, out_poff;
   if (!d.gmm) {
-    out_forks = {"/readout_to_output"}; out_off = {0}; out_dim = {d.D};
+    out_forks = {"/readout_to_output"}; out_off = {0}; out_dim = {d.D}; out_poff = {0};
   } else {
+    out_poff = {0, rup(d.D * d.K, 64), 2 * rup(d.D * d.K, 64)};
     out_forks = {"/readout_to_output/fork_gmm_mu", "/readout_to_output/fork_gmm_sigma",
                  "/readout_to_output/fork_gmm_coeff"};
     out_off = {0, d.D * d.K, 2 * d.D * d.K};
@@ -579,7 +605,7 @@ static void build(parrot_model& M) {
   if (train) {
     M.falloc("next_x", (long long)T * B * d.D);
     M.falloc("dpred", (long long)T * B * d.Dtot);
-    Plane pdp = M.make_plane("dpred", Np, d.Dtot, T);
+    Plane pdp = M.make_plane("dpred", Np, d.Dtp, T);
     M.map_plain["dpred"] = M.make_map(pdp, 2, NT);
     M.falloc("dread", (long long)T * B * d.R);
     Plane pdr = M.make_plane("dread", Np, d.R, T);
@@ -701,7 +727,7 @@ static void build(parrot_model& M) {
       pa.n_pad = Np; pa.n_valid = B; pa.n_total = T * Np; pa.flags = PF_PLANE_PADDED;
       std::vector<PlainSeg> segs;
       for (size_t f = 0; f < out_forks.size(); ++f)
-        segs.push_back({M.packs[out_forks[f]].bwd_map, 0, M.map_plain["dpred"], 0, out_off[f], cdiv(out_dim[f], 64)});
+        segs.push_back({M.packs[out_forks[f]].bwd_map, 0, M.map_plain["dpred"], 0, out_poff[f], cdiv(out_dim[f], 64)});
       build_plain_jobs(js, d.R, 0, (long long)T * Np, segs, pa);
       push_table(M, "dread", js, NT);
     }
@@ -797,7 +823,7 @@ static void build(parrot_model& M) {
       wg("h1", Np, "da3", 0, "/h1_to_h3/fork_rnn3_inputs"); wg("h1", Np, "da3", d.Hp, "/h1_to_h3/fork_rnn3_gates");
       wg("h2", Np, "da3", 0, "/h2_to_h3/fork_rnn3_inputs"); wg("h2", Np, "da3", d.Hp, "/h2_to_h3/fork_rnn3_gates");
       wg("w", Np, "dread", 0, "/att_to_readout.W");
-      for (size_t f = 0; f < out_forks.size(); ++f) wg("ro", 0, "dpred", out_off[f], out_forks[f] + ".W");
+      for (size_t f = 0; f < out_forks.size(); ++f) wg("ro", 0, "dpred", out_poff[f], out_forks[f] + ".W");
       wg("h1", Np, "datt", 0, "/h1_to_att/fork_alpha.W");
       wg("h1", Np, "datt", d.A, "/h1_to_att/fork_beta.W");
       wg("h1", Np, "datt", 2 * d.A, "/h1_to_att/fork_kappa.W");
@@ -1137,6 +1163,7 @@ static EmitArgs emit_args(parrot_model& M, const float* d_features, const float*
     e.dpred = M.fbuf("dpred");
     const Plane& p = M.planes.at("dpred");
     e.dpred_hi = p.hi; e.dpred_lo = p.lo; e.B = d.B; e.Np = d.Np; e.Dp = p.pitch;
+    e.DK = d.D * d.K; e.poff1 = rup(d.D * d.K, 64); e.poff2 = 2 * rup(d.D * d.K, 64);
     e.scale = M.fbuf("cost") + (unnormalised ? 4 : 3);
   }
   return e;
@@ -1243,7 +1270,7 @@ static void weight_grads(parrot_model& M, cudaStream_t st) {
   }
   tp("w", d.C);
   if (d.weak) tp("xin", d.D);
-  tp("ro", d.R); tp("dread", d.R); tp("dpred", d.Dtot); tp("datt", 3 * d.A);
+  tp("ro", d.R); tp("dread", d.R); tp("dpred", d.Dtp); tp("datt", 3 * d.A);
   run_table(M, "wgrad", 0, 1, 0, st);
   // bias gradients: column sums of the pre-activation gradients
   float* scratch = M.fbuf("bias_scratch");
@@ -1587,16 +1614,23 @@ size_t parrot_gemm_nt_workspace_bytes(int32_t Mr, int32_t N, int32_t K) {
   const size_t kp = (size_t)rup(K, 64);
   size_t b = 0;
   b += 2 * ((size_t)rup(Mr, 128) * kp * 2 + 1024);
-  b += 2 * ((size_t)rup(N, 128) * kp * 2 + 1024);
+  b += 2 * ((size_t)3 * rup(N, 256) * kp * 2 + 1024);
   b += (size_t)cdiv(Mr, 128) * cdiv(N, NT) * sizeof(Job) + 16 * sizeof(CUtensorMap) + 16 * sizeof(MapRaw) +
        sizeof(ScanCtx) + 16 * 1024;
   return b;
 }
 
-int parrot_gemm_nt(const float* d_A, const float* d_B, float* d_C, int32_t Mr, int32_t N, int32_t K, int32_t impl,
+int parrot_gemm_nt(const float* d_A, const float* d_B, float* d_C, int32_t Mr, int32_t N, int32_t K, int32_t impl_flags,
                    void* d_workspace, size_t workspace_bytes, void* stream) {
   return guard([&] {
     cudaStream_t st = (cudaStream_t)stream;
+    // impl_flags: bit 0 = SIMT twin; bits 8..15 = sample tile (0 -> 128); bit 16 = 3-D (slot-indexed) B map;
+    // bit 17 = split K into two segments
+    const int impl = impl_flags & 1;
+    int ntile = (impl_flags >> 8) & 0xff;
+    if (ntile == 0) ntile = NT;
+    if (ntile == 255) ntile = 256;
+    const bool use3d = (impl_flags >> 16) & 1, twoseg = (impl_flags >> 17) & 1;
     parrot_model M;
     memset(&M.cfg, 0, sizeof M.cfg);
     M.cfg.gemm_impl = impl;
@@ -1604,18 +1638,39 @@ int parrot_gemm_nt(const float* d_A, const float* d_B, float* d_C, int32_t Mr, i
     REQUIRE(((uintptr_t)d_workspace & 1023) == 0, "workspace must be 1024-byte aligned");
     CK(cudaMemsetAsync(d_workspace, 0, workspace_bytes, st));
     Plane pa = M.make_plane("A", rup(Mr, 128), K, 1);
-    Plane pb = M.make_plane("B", rup(N, 128), K, 1);
+    // 3-D variant: B is one slot of rup(N, ntile) rows inside a 3-slot plane, addressed as slot 1 (t=0, b_slot=1)
+    const int brows = use3d ? rup(N, ntile) : rup(N, 128);
+    Plane pb = M.make_plane("B", brows, K, use3d ? 3 : 1);
+    REQUIRE(!use3d || N <= ntile, "3-D test needs N <= tile");
     const int ma = M.make_map(pa, 2, 128);
-    const int mb = M.make_map(pb, 2, NT);
+    const int mb = M.make_map(pb, use3d ? 3 : 2, ntile);
     pack_plane(st, d_A, K, Mr, K, pa, 0);
-    pack_plane(st, d_B, K, N, K, pb, 0);
+    Plane pb1 = pb;
+    if (use3d) { pb1.hi += (long long)brows * pb.pitch; pb1.lo += (long long)brows * pb.pitch; }
+    pack_plane(st, d_B, K, N, K, pb1, 0);
     std::vector<Job> js;
     PlainArgs pargs;
     memset(&pargs, 0, sizeof pargs);
     pargs.out = d_C; pargs.ldo = N; pargs.n_total = N; pargs.flags = PF_TRANS; pargs.scale = 1.0f;
-    std::vector<PlainSeg> segs = {{ma, 0, mb, 0, 0, cdiv(K, 64)}};
-    build_plain_jobs(js, Mr, 0, N, segs, pargs);
-    push_table(M, "g", js, NT);
+    const int nkb = cdiv(K, 64);
+    for (int mt = 0; mt < cdiv(Mr, 128); ++mt)
+      for (int nt = 0; nt < cdiv(N, ntile); ++nt) {
+        Job j = blank_job();
+        j.epi = EPI_PLAIN; j.row0 = mt * 128; j.m_valid = std::min(128, Mr - mt * 128); j.n0 = nt * ntile;
+        const int slot = use3d ? 1 : NO_SLOT;
+        if (twoseg && nkb >= 2) {
+          const int k1 = nkb / 2;
+          j.nseg = 2;
+          j.seg[0] = mkseg(ma, mt * 128, 0, mb, nt * ntile, 0, slot, k1);
+          j.seg[1] = mkseg(ma, mt * 128, k1 * 64, mb, nt * ntile, k1 * 64, slot, nkb - k1);
+        } else {
+          j.nseg = 1;
+          j.seg[0] = mkseg(ma, mt * 128, 0, mb, nt * ntile, 0, slot, nkb);
+        }
+        j.pa = pargs;
+        js.push_back(j);
+      }
+    push_table(M, "g", js, ntile);
     build_device_tables(M);
     memset(&M.ctx, 0, sizeof M.ctx);
     upload_tables(M, st);

@@ -555,6 +555,7 @@ struct EmitArgs {
   bf16* dpred_hi;       // planes [q*Np + r][Dp]
   bf16* dpred_lo;
   int B, Np, Dp;
+  int DK, poff1, poff2;   // GMM: plane column of block f is poff_f + (idx - f*DK)
   const float* scale;   // device scalar: 1/(sum mask + 1e-5) or 1 (unnormalised)
 };
 
@@ -621,8 +622,10 @@ __global__ void __launch_bounds__(256) emit_grad_kernel(const EmitArgs a) {
     g[idx] = v;
     bf16 hh, ll;
     split_bf16(v, hh, ll);
-    ghi[idx] = hh;
-    glo[idx] = ll;
+    int pc = idx;
+    if (a.which == 1) pc = idx < a.DK ? idx : (idx < 2 * a.DK ? a.poff1 + (idx - a.DK) : a.poff2 + (idx - 2 * a.DK));
+    ghi[pc] = hh;
+    glo[pc] = ll;
   };
   if (a.which == 0) {
     for (int d = lane; d < a.D; d += 32) put(d, 2.0f * (p[d] - y[d]) * sc);

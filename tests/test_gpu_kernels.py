@@ -51,7 +51,29 @@ def test_gemm_tc_matches_simt_large():
     A = rng.standard_normal((512, 2304)).astype(np.float32)
     B = rng.standard_normal((300, 2304)).astype(np.float32)
     a = _gemm(A, B, 0); b = _gemm(A, B, 1)
-    assert np.abs(a - b).max() / np.abs(b).max() < 1e-5
+    assert np.abs(a - b).max() / np.abs(b).max() < 5e-5
+
+
+@pytest.mark.parametrize('impl', [1, 0], ids=['simt', 'tcgen05'])
+@pytest.mark.parametrize('variant', ['tile16', 'tile64', 'tile256', 'slots3d_16', 'slots3d_64', 'twoseg',
+                                     'slots3d_16_twoseg'])
+def test_gemm_engine_variants(impl, variant):
+    """The scan uses sample tiles of the padded batch (16..256 columns), slot-indexed 3-D TMA maps and
+    multi-segment jobs; exercise each against float64."""
+    flags = impl
+    M, N, K = 256, 200, 320
+    if variant.startswith('tile'):
+        t = int(variant[4:]); flags |= (255 if t == 256 else t) << 8
+    if 'slots3d' in variant:
+        t = int(variant.split('_')[1]); flags |= (t << 8) | (1 << 16); N = t - 3
+    if 'twoseg' in variant:
+        flags |= 1 << 17
+    rng = np.random.default_rng(2)
+    A = rng.standard_normal((M, K)).astype(np.float32)
+    B = rng.standard_normal((N, K)).astype(np.float32)
+    ref = A.astype(np.float64) @ B.astype(np.float64).T
+    out = _gemm(A, B, flags)
+    assert np.abs(out - ref).max() / np.abs(ref).max() < 5e-5
 
 
 @pytest.mark.parametrize('att', ['graves', 'softmax'])
