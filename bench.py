@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""Benchmark of the Parrot attention-RNN hot path (BASELINE.json metric:
+"vocoder acoustic frames/sec (fwd+bwd)"), one JSON line on stdout.
+
+    python bench.py                                   # N=1, configs[1] "Parrot base" on cuda:0
+    python bench.py --gpus 1 --steps 5 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 \
+        --master-port 29511 bench.py --gpus 8 --steps 5 --warmup 3        # weak scaling, 64 rows / GPU
+    python bench.py --impl reference --steps 2 --warmup 1   # CPU arm: numpy restatement of the Theano path
+
+A "step" is one full training step over one synthetic batch: compute_cost (encoder, T decoder
+steps, readout, emitter, cost) + backward (BPTT, weight gradients) + gradient allreduce (N>1) +
+StepClipping/Adam.  frames/s = B_global * T / step time.
+
+  value        inputs already resident in HBM when the timed region starts
+  e2e          same metric through the public API with HOST (pinned) inputs: the host->device copies
+               of the batch and a device->host read of the cost are inside the timed region
+  roofline     the dominant kernel (job_kernel_tc, the tcgen05 gate-GEMM engine) over the forward
+               scan: algorithmic FLOPs per launch / average launch duration (CUDA events, separate
+               profiled steps after the timed region) against the measured bf16 peak
+  cpu_baseline the numpy oracle (a port of the reference's Theano CPU path) timed on the host cores
+               on a bounded sample of the same workload
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = 'vocoder acoustic frames/sec (fwd+bwd)'
+UNIT = 'frames/s'
+
+# BASELINE.json configs[1] "Parrot base" as mapped by SURVEY.md 8d (config 2)
+BASE = dict(input_dim=420, output_dim=63, rnn_h_dim=1024, readouts_dim=1024, weak_feedback=True,
+            which_cost='MSE', num_characters=43, attention_type='graves', attention_size=10,
+            attention_alignment=0.15, encoder_type='bidirectional', encoder_dim=128)
+B_PER_GPU, T_FRAMES, U_TEXT = 64, 800, 128
+
+
+def workload_config(args, world):
+    cfg = dict(BASE)
+    if args.which_cost:
+        cfg['which_cost'] = args.which_cost
+    B, T, U = args.batch or B_PER_GPU, args.frames or T_FRAMES, args.text or U_TEXT
+    if args.hidden:
+        cfg['rnn_h_dim'] = cfg['readouts_dim'] = args.hidden
+    return cfg, B, T, U
+
+
+def make_batch(cfg, B, T, U, seed):
+    from tests import util
+    bt = util.make_batch(cfg, B, T, U, seed=seed)
+    return bt
+
+
+def algorithmic_flops(cfg, B, T):
+    """gate-GEMM FLOPs per decoder step, forward: 2*B*(18 H^2 + 9 C H) (+ feedback D->3H)."""
+    H = cfg['rnn_h_dim']
+    C = 2 * cfg['encoder_dim']
+    per_step = 2.0 * B * (18 * H * H + 9 * C * H)
+    return per_step, per_step * T
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d['hbm_gbs'], tf_burst=d['bf16_tflops'], tf_sustained=d['bf16_tflops_sustained'],
+                    source='measured')
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source='fallback')
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.stop_flag = False
+
+    def run(self):
+        q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,' \
+            'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,' \
+            'clocks_event_reasons.sw_power_cap'
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q,
+                                      '--format=csv,noheader,nounits'], capture_output=True, text=True,
+                                     timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(',')])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        sm = sorted(float(s[0]) for s in self.samples)
+        reasons = []
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for i, n in enumerate(names):
+            if any(s[3 + i].lower().startswith('active') for s in self.samples):
+                reasons.append(n)
+        return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': float(self.samples[0][1]), 'reasons': reasons,
+                'samples': len(sm), 'power_w_max': max(float(s[2]) for s in self.samples)}
+
+
+# --------------------------------------------------------------------------- CPU arms
+def oracle_step_time(cfg, B, T, U, steps, warmup, with_adam=True):
+    """Oracle (numpy, BLAS-threaded) fwd + bwd (+ Adam) on a (B, T) sample; returns seconds per step."""
+    from oracle.parrot_oracle import OracleAdamClip
+    from tests import util
+    orc = util.make_oracle(cfg, gain=None, bias_std=0)
+    opt = OracleAdamClip(orc.shapes, learning_rate=1e-4, threshold=9.0)
+    bt = util.make_batch(cfg, B, T, U, seed=0)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        orc.compute_cost(bt['features'], bt['features_mask'], bt['labels'], bt['labels_mask'], None, 1.0, B)
+        g = orc.backward()
+        if with_adam:
+            opt.step(orc.params, g)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return float(np.median(times))
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path.  Theano/Blocks (Python 2) cannot
+    run in this image, so this is the oracle port (numpy float32, BLAS threads = host cores)."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    cfg, B, T, U = workload_config(args, 1)
+    Ts = min(T, args.ref_frames)
+    sec = oracle_step_time(cfg, B, Ts, U, max(1, args.steps), max(0, min(args.warmup, 1)))
+    fps = B * Ts / sec
+    cores = os.cpu_count()
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': fps, 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'Parrot base (BASELINE configs[1]): B=%d H=%d E=%d U=%d, bounded sample T=%d of %d '
+                               'frames (per-step cost is T-independent)' % (B, cfg['rnn_h_dim'], cfg['encoder_dim'], U, Ts, T),
+                   'which_cost': cfg['which_cost']},
+        'cpu_baseline': {'value': fps, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                         'sample': 'numpy restatement of the Theano CPU path, fwd+bwd+Adam, B=%d T=%d' % (B, Ts)},
+        'e2e': {'value': fps, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------- GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', type=str, default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--which_cost', type=str, default=None)
+    ap.add_argument('--batch', type=int, default=None, help='rows per GPU (default 64)')
+    ap.add_argument('--frames', type=int, default=None, help='T (default 800)')
+    ap.add_argument('--text', type=int, default=None, help='U (default 128)')
+    ap.add_argument('--hidden', type=int, default=None)
+    ap.add_argument('--ref_frames', type=int, default=40, help='bounded T of the CPU arms')
+    ap.add_argument('--profile_steps', type=int, default=1)
+    ap.add_argument('--no_cpu_baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from parrot_b200 import Parrot, _lib, parallel
+    from parrot_b200.algorithms import Adam, CompositeRule, GradientDescent, StepClipping
+    import ctypes as C
+
+    rank, world, local = parallel.init_from_env()
+    assert world == args.gpus or world == 1 and args.gpus == 1, 'launch with torchrun for --gpus > 1'
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    cfg, B, T, U = workload_config(args, world)
+    W = max(3, args.warmup)
+    K = max(1, args.steps)
+
+    model = Parrot(device=dev, **cfg)
+    model.initialize(seed=0)                       # identical replicas (train.py:30-31 init)
+    algo = GradientDescent(model=model, parameters=None,
+                           step_rule=CompositeRule([StepClipping(9.0), Adam(1e-4)]))
+    bt = make_batch(cfg, B, T, U, seed=100 + rank)
+    host = {k: torch.from_numpy(np.ascontiguousarray(bt[k])).pin_memory()
+            for k in ('features', 'features_mask', 'labels', 'labels_mask')}
+    devb = {k: v.to(dev) for k, v in host.items()}
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    lib = _lib.load()
+
+    def step(src):
+        cost, _, _, _ = model.compute_cost(src['features'], src['features_mask'], src['labels'],
+                                           src['labels_mask'], None, 1.0, B)
+        algo.step()
+        return cost
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(src, n, read_cost):
+        barrier()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        l0 = lib.parrot_launch_count()
+        e0.record()
+        for _ in range(n):
+            c = step(src)
+            if read_cost:
+                c.item()                            # device -> host read of the step's result
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        t = torch.tensor([ms], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), lib.parrot_launch_count() - l0
+
+    for _ in range(W):
+        step(devb)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_dev, launches = timed(devb, K, False)
+    ms_e2e, _ = timed(host, K, True)
+    if rank == 0:
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
+    frames_global = B * world * T
+    value = frames_global * K / (ms_dev * 1e-3)
+    e2e = frames_global * K / (ms_e2e * 1e-3)
+
+    # ---- profiled steps: per-launch durations of the dominant kernels (rank 0)
+    roof = None
+    extra = {}
+    if rank == 0:
+        h = model._last
+        lib.parrot_set_profiling(h.ptr, 1)
+        for _ in range(max(1, args.profile_steps)):
+            step(devb)
+        torch.cuda.synchronize()
+
+        def prof(key):
+            tot = C.c_double(); n = C.c_int64()
+            _lib.check(lib.parrot_get_profile(h.ptr, key.encode(), C.byref(tot), C.byref(n)))
+            return tot.value, n.value
+        pk = peaks()
+        per_step_flops, _ = algorithmic_flops(cfg, B, T)
+        msA, nA = prof('fwdA'); msB, nB = prof('fwdB')
+        P = max(1, args.profile_steps)
+        # every fwdA/fwdB launch pair of a tick covers one decoder step's worth of gate FLOPs (T+2 ticks for T steps)
+        scan_ms = (msA + msB) / P
+        achieved_tf = per_step_flops * T / (scan_ms * 1e-3) / 1e12
+        roof = {'bound': 'tensor', 'kernel': 'job_kernel_tc (forward scan gate GEMMs, tables fwdA+fwdB)',
+                'achieved': achieved_tf, 'peak': pk['tf_sustained'], 'unit': 'TFLOP/s',
+                'frac': achieved_tf / pk['tf_sustained'], 'traffic': None,
+                'peak_source': pk['source'] + ' bf16 sustained (kernel timed inside a long step)',
+                'algorithmic_flops_per_launch': per_step_flops * T / max(1, (nA + nB) // P),
+                'avg_launch_us': scan_ms * 1e3 / max(1, (nA + nB) // P), 'launches_per_step': (nA + nB) // P,
+                'us_per_decoder_step': scan_ms * 1e3 / T}
+        msa, na = prof('attn_fwd')
+        H, Cc, A = cfg['rnn_h_dim'], 2 * cfg['encoder_dim'], cfg['attention_size']
+        att_bytes = 4.0 * (B * U * Cc + B * U + B * Cc + 3 * B * A)
+        att_us = msa * 1e3 / max(1, na)
+        extra['roofline_attention'] = {
+            'bound': 'hbm', 'kernel': 'attention_fwd_kernel (K7)', 'achieved': att_bytes / (att_us * 1e-6) / 1e9,
+            'peak': pk['hbm'], 'unit': 'GB/s', 'frac': att_bytes / (att_us * 1e-6) / 1e9 / pk['hbm'],
+            'traffic': None, 'algorithmic_bytes_per_launch': att_bytes, 'avg_launch_us': att_us}
+        sections = {}
+        for key in ('sec_pack_prep_encoder', 'sec_scan_fwd', 'sec_readout_emit_fwd', 'sec_readout_emit_bwd',
+                    'sec_scan_bwd', 'sec_grads_tail', 'fwdA', 'fwdB', 'attn_fwd', 'bwd1', 'bwd2', 'attn_bwd',
+                    'gru_bwd_pre', 'readout', 'output', 'dread', 'dh_readout', 'wgrad'):
+            ms, n = prof(key)
+            sections[key] = {'ms': round(ms / P, 3), 'launches': n // P}
+        extra['breakdown_ms_profiled_step'] = sections
+        lib.parrot_set_profiling(h.ptr, 0)
+
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        Ts = min(T, args.ref_frames)
+        sec = oracle_step_time(cfg, B, Ts, U, 2, 1, with_adam=False)
+        cpu = {'value': B * Ts / sec, 'unit': UNIT, 'cores': os.cpu_count(), 'kind': 'port',
+               'sample': 'numpy float32 restatement of the Theano CPU path (oracle), fwd+bwd, B=%d T=%d U=%d '
+                         '(per-step cost is T-independent), BLAS threads = host cores' % (B, Ts, U)}
+
+    if rank == 0:
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W,
+            'ms_per_step': ms_dev / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'bf16x3 (fp32 operands split hi+lo in bf16, 3 tcgen05 MMAs, fp32 accumulate)',
+            'data': 'synthetic',
+            'config': {'workload': 'Parrot base (BASELINE configs[1]): 1xBiGRU enc E=%d + 3xGRU dec H=%d, '
+                                   'batch=%d/GPU, T_text=%d, T_frames=%d, %s cost, weak feedback, fwd+bwd+Adam'
+                                   % (cfg['encoder_dim'], cfg['rnn_h_dim'], B, U, T, cfg['which_cost']),
+                       'global_batch': B * world, 'parallelism': 'dp%d' % world,
+                       'l2': 'working set (13 GB workspace) far exceeds the 126 MB L2; no explicit flush',
+                       'encoder_time_axis': 0},
+            'e2e': {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4,
+                    'ms_per_step': ms_e2e / K},
+            'gpu_launches': int(launches),
+            'clocks': sampler.summary(),
+            'roofline': roof,
+            'cpu_baseline': cpu,
+        }
+        line.update(extra)
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

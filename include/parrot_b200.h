@@ -85,6 +85,11 @@ int parrot_buffer_info(parrot_model* m, const char* name, int64_t* byte_offset, 
  * parrot_compute_cost does it automatically when parrot_mark_params_dirty was called). */
 int parrot_pack_weights(parrot_model* m, void* stream);
 int parrot_mark_params_dirty(parrot_model* m);
+/* per-launch CUDA-event timing of the engine / attention launches, aggregated by table name
+ * ("fwdA", "fwdB", "bwd1", "bwd2", "readout", "output", "dread", "dh_readout", "wgrad", "attn_fwd", "attn_bwd",
+ * "gru_bwd_pre", "sec_*" for whole sections).  parrot_get_profile synchronises the device. */
+int parrot_set_profiling(parrot_model* m, int enable);
+int parrot_get_profile(parrot_model* m, const char* key, double* total_ms, int64_t* launches);
 
 /* ---- the hot path, fine grained (SURVEY 8b "minimum surface") ---- */
 /* replaces Encoder.apply (model.py:233-247) + the context mask (model.py:645-646) */
@@ -122,11 +127,14 @@ int parrot_sample_scan(parrot_model* m, const int32_t* d_labels, const float* d_
                        void* stream);
 
 /* ---- optimizer: StepClipping(threshold) + Adam (train.py:100-108) on flat buffers ---- */
-/* grad_scale multiplies every gradient first (1/(sum(mask)+1e-5) after a data-parallel allreduce, else 1).
- * d_stats receives [global grad norm, clip multiplier]; d_scratch needs 1024 doubles. */
+/* Every gradient is first multiplied by grad_scale and, when d_mask_sum is not null, by
+ * 1/(d_mask_sum[0] + 1e-5) read on the device (data-parallel: the un-normalised gradients and sum(mask) are
+ * all-reduced together, model.py:784 is a masked mean over the global batch) -- no host synchronisation.
+ * d_stats receives [global grad norm, clip multiplier, total multiplier]; d_scratch needs 1024 doubles. */
 int parrot_adam_clip_step(float* d_params, const float* d_grads, float* d_m, float* d_v, int64_t n,
-                          float grad_scale, float threshold, float learning_rate, float beta1, float beta2,
-                          float epsilon, int64_t time_step, float* d_stats, double* d_scratch, void* stream);
+                          float grad_scale, const float* d_mask_sum, float threshold, float learning_rate,
+                          float beta1, float beta2, float epsilon, int64_t time_step, float* d_stats,
+                          double* d_scratch, void* stream);
 
 /* generic bf16x3 tensor-core GEMM used by the tests:  C[M][N] = A[M][K] * B[N][K]^T  (fp32 in/out) */
 int parrot_gemm_nt(const float* d_A, const float* d_B, float* d_C, int32_t M, int32_t N, int32_t K,

@@ -73,20 +73,18 @@ class GradientDescent(object):
         lib = _lib.load()
         model.backward(unnormalised=True)
         flat = parallel.allreduce_flat(model.flat_grads, self.group)
-        # 1/(sum(mask)+1e-5): computed on device, read back once per step (also the step's sync point)
-        msum = float(flat[-1])
-        scale = 1.0 / (msum + 1e-5)
+        # the divisor 1/(sum(mask)+1e-5) is read on the device from flat[-1]: no host sync in the step
         self.time += 1
         stream = torch.cuda.current_stream(model.device).cuda_stream
         thr = self.clip.threshold if self.clip.threshold is not None else float('inf')
         _lib.check(lib.parrot_adam_clip_step(
             C.c_void_p(model.flat_params.data_ptr()), C.c_void_p(flat.data_ptr()),
             C.c_void_p(self.m.data_ptr()), C.c_void_p(self.v.data_ptr()), model.num_floats,
-            scale, min(thr, 3.0e38), self.adam.learning_rate, self.adam.beta1, self.adam.beta2,
+            1.0, C.c_void_p(flat.data_ptr() + 4 * model.num_floats), min(thr, 3.0e38),
+            self.adam.learning_rate, self.adam.beta1, self.adam.beta2,
             self.adam.epsilon, self.time, C.c_void_p(self.stats.data_ptr()),
             C.c_void_p(self.scratch.data_ptr()), C.c_void_p(stream)))
         model.mark_dirty()
-        return msum
 
     def process_batch(self, batch, batch_size=None):
         """One training step on a batch dict with the reference's source names

@@ -271,6 +271,20 @@ struct parrot_model {
   bool dirty = true;
   float last_start_flag = 1.0f;
   bool have_fwd = false;
+  // optional per-launch timing (bench.py roofline): CUDA events around every tagged launch
+  bool profiling = false;
+  struct ProfRec { std::string key; cudaEvent_t e0, e1; };
+  std::vector<ProfRec> prof;
+  cudaEvent_t prof_begin(const std::string& key, cudaStream_t st) {
+    if (!profiling) return nullptr;
+    ProfRec r;
+    r.key = key;
+    cudaEventCreate(&r.e0); cudaEventCreate(&r.e1);
+    cudaEventRecord(r.e0, st);
+    prof.push_back(r);
+    return r.e1;
+  }
+  static void prof_end(cudaEvent_t e1, cudaStream_t st) { if (e1) cudaEventRecord(e1, st); }
 
   // ---- workspace ----
   void* alloc(const std::string& name, size_t bytes) {
@@ -448,6 +462,7 @@ static void run_table(parrot_model& M, const std::string& name, int tick, int T,
   EngineParams P;
   P.jobs = M.d_jobs + t.off; P.njobs = t.count; P.maps = M.d_maps; P.raws = M.d_raws; P.ctx = M.d_ctx;
   P.tick = tick; P.T = T; P.n_cols = t.n_cols; P.reverse = reverse;
+  cudaEvent_t pe = M.prof_begin(name, st);
   if (M.cfg.gemm_impl == 1) {
     const int grid = std::min(t.count, 148 * 8);
     LAUNCH(job_kernel_simt, grid, 128, 0, st, P);
@@ -455,6 +470,7 @@ static void run_table(parrot_model& M, const std::string& name, int tick, int T,
     const int grid = std::min(t.count, 148);
     LAUNCH(job_kernel_tc, grid, ENGINE_THREADS, SMEM_BYTES + 1024, st, P);
   }
+  parrot_model::prof_end(pe, st);
 }
 
 // ------------------------------------------------------------------ build
@@ -1126,7 +1142,9 @@ static void attention_step(parrot_model& M, int t, bool sampling, cudaStream_t s
   a.ab_out = M.fbuf("ab") + (long long)t * d.B * 2 * d.A;
   a.e_out = M.fbuf("att_e") + (long long)t * d.B * 3 * d.A;
   const size_t smem = (size_t)(d.H + 6 * d.A + d.U) * 4;
+  cudaEvent_t pe = M.prof_begin("attn_fwd", st);
   LAUNCH(attention_fwd_kernel, d.B, 256, smem, st, a);
+  parrot_model::prof_end(pe, st);
 }
 
 static void scan_fwd(parrot_model& M, const float* d_features, const float* d_noise, float level, float start_flag,
@@ -1236,7 +1254,9 @@ static void attention_bwd_step(parrot_model& M, int t, cudaStream_t st) {
   a.datt_hi = p.hi + (long long)t * d.Np * p.pitch;
   a.datt_lo = p.lo + (long long)t * d.Np * p.pitch;
   const size_t smem = (size_t)(d.C + d.U + 3 * d.A * 8 + 3 * d.A) * 4;
+  cudaEvent_t pe = M.prof_begin("attn_bwd", st);
   LAUNCH(attention_bwd_kernel, d.B, 256, smem, st, a);
+  parrot_model::prof_end(pe, st);
 }
 
 static void scan_bwd(parrot_model& M, cudaStream_t st) {
@@ -1249,7 +1269,11 @@ static void scan_bwd(parrot_model& M, cudaStream_t st) {
     if (s + 2 >= 0 && s + 2 < d.T) attention_bwd_step(M, s + 2, st);
     for (int l = 2; l >= 0; --l) {
       const int t = s + (2 - l);
-      if (t >= 0 && t < d.T) LAUNCH(gru_bwd_pre_kernel, blocks, 256, 0, st, M.d_ctx, l, t);
+      if (t >= 0 && t < d.T) {
+        cudaEvent_t pe = M.prof_begin("gru_bwd_pre", st);
+        LAUNCH(gru_bwd_pre_kernel, blocks, 256, 0, st, M.d_ctx, l, t);
+        parrot_model::prof_end(pe, st);
+      }
     }
     run_table(M, "bwd1", tick, d.T, 1, st);
     run_table(M, "bwd2", tick, d.T, 1, st);
@@ -1355,8 +1379,13 @@ static void backward(parrot_model& M, int unnormalised, cudaStream_t st) {
   const FwdInputs& in = g_inputs[&M];
   CK(cudaMemsetAsync(M.grads, 0, (size_t)(M.P.total + 1) * 4, st));
   CK(cudaMemcpyAsync(M.grads + M.P.total, M.fbuf("cost") + 2, 4, cudaMemcpyDeviceToDevice, st));
+  cudaEvent_t pe = M.prof_begin("sec_readout_emit_bwd", st);
   readout_emit_bwd(M, unnormalised, st);
+  parrot_model::prof_end(pe, st);
+  pe = M.prof_begin("sec_scan_bwd", st);
   scan_bwd(M, st);
+  parrot_model::prof_end(pe, st);
+  pe = M.prof_begin("sec_grads_tail", st);
   if (M.last_start_flag != 0.0f) {
     for (int l = 0; l < 3; ++l) colsum(st, M.ctx.L[l].dh, d.H, d.B, d.H, M.gp("/rnn" + LN(l) + ".initial_state"), 0);
     colsum(st, M.ctx.dw, d.C, d.B, d.C, M.gp(".initial_w"), 0);
@@ -1370,6 +1399,7 @@ static void backward(parrot_model& M, int unnormalised, cudaStream_t st) {
   encoder_bwd(M, in.lmask, st);
   weight_grads(M, st);
   speaker_grads(M, st);
+  parrot_model::prof_end(pe, st);
 }
 
 // ------------------------------------------------------------------ sampling
@@ -1503,6 +1533,29 @@ int parrot_mark_params_dirty(parrot_model* m) {
   m->dirty = true;
   return 0;
 }
+int parrot_set_profiling(parrot_model* m, int enable) {
+  return guard([&] {
+    m->profiling = enable != 0;
+    for (auto& r : m->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    m->prof.clear();
+  });
+}
+int parrot_get_profile(parrot_model* m, const char* key, double* total_ms, int64_t* launches) {
+  return guard([&] {
+    CK(cudaDeviceSynchronize());
+    double tot = 0.0;
+    int64_t n = 0;
+    for (auto& r : m->prof)
+      if (r.key == key) {
+        float ms = 0.0f;
+        CK(cudaEventElapsedTime(&ms, r.e0, r.e1));
+        tot += ms;
+        ++n;
+      }
+    *total_ms = tot;
+    *launches = n;
+  });
+}
 
 int parrot_encoder_fwd(parrot_model* m, const int32_t* d_labels, const float* d_labels_mask, void* stream) {
   return guard([&] {
@@ -1565,11 +1618,17 @@ int parrot_compute_cost(parrot_model* m, const float* d_features, const float* d
     FwdInputs& in = g_inputs[m];
     in.features = d_features; in.fmask = d_features_mask; in.labels = d_labels; in.lmask = d_labels_mask;
     in.speaker = d_speaker;
+    cudaEvent_t pe = M.prof_begin("sec_pack_prep_encoder", st);
     if (M.dirty) pack_weights(M, st);
     prep_base(M, d_speaker, st);
     encoder_fwd(M, d_labels, d_labels_mask, st);
+    parrot_model::prof_end(pe, st);
+    pe = M.prof_begin("sec_scan_fwd", st);
     scan_fwd(M, d_features, d_feedback_noise, noise_level, start_flag, st);
+    parrot_model::prof_end(pe, st);
+    pe = M.prof_begin("sec_readout_emit_fwd", st);
     readout_emit_fwd(M, d_features, d_features_mask, d_cost, st);
+    parrot_model::prof_end(pe, st);
     if (M.d.gmm && d_gmm_unis && d_gmm_normals) {
       // next_x = sample_gmm(mu, sigma, coeff) (model.py:782), all frames at once, no sampling bias
       SampleArgs a;
@@ -1594,19 +1653,20 @@ int parrot_sample_scan(parrot_model* m, const int32_t* d_labels, const float* d_
 }
 
 int parrot_adam_clip_step(float* d_params, const float* d_grads, float* d_m, float* d_v, int64_t n,
-                          float grad_scale, float threshold, float learning_rate, float beta1, float beta2,
-                          float epsilon, int64_t time_step, float* d_stats, double* d_scratch, void* stream) {
+                          float grad_scale, const float* d_mask_sum, float threshold, float learning_rate,
+                          float beta1, float beta2, float epsilon, int64_t time_step, float* d_stats,
+                          double* d_scratch, void* stream) {
   return guard([&] {
     cudaStream_t st = (cudaStream_t)stream;
     const int parts = 592;
     LAUNCH(sumsq_partial_kernel, parts, 1024, 0, st, d_grads, (long long)n, d_scratch);
-    LAUNCH(clip_finalize_kernel, 1, 32, 0, st, d_scratch, parts, grad_scale, threshold, d_stats);
+    LAUNCH(clip_finalize_kernel, 1, 32, 0, st, d_scratch, parts, grad_scale, d_mask_sum, threshold, d_stats);
     // blocks Adam: lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t)
     const double t1 = (double)time_step;
     const float lr_t = (float)(learning_rate * std::sqrt(1.0 - std::pow((double)beta2, t1)) /
                                (1.0 - std::pow((double)beta1, t1)));
-    LAUNCH(adam_kernel, 148 * 8, 256, 0, st, d_params, d_grads, d_m, d_v, (long long)n, d_stats, grad_scale, lr_t,
-           beta1, beta2, epsilon);
+    LAUNCH(adam_kernel, 148 * 8, 256, 0, st, d_params, d_grads, d_m, d_v, (long long)n, d_stats, lr_t, beta1, beta2,
+           epsilon);
   });
 }
 

@@ -824,21 +824,27 @@ __global__ void __launch_bounds__(1024) sumsq_partial_kernel(const float* __rest
     partial[blockIdx.x] = t;
   }
 }
-// stats[0] = grad norm (after scaling by gscale), stats[1] = clip multiplier
+// Effective gradient = g * gscale * (mask_sum ? 1/(mask_sum[0] + 1e-5) : 1)   (data-parallel: the all-reduced
+// gradients are un-normalised and the divisor is all-reduced with them).
+// stats[0] = grad norm (of the effective gradient), stats[1] = clip multiplier, stats[2] = total multiplier
 __global__ void clip_finalize_kernel(const double* __restrict__ partial, int nparts, float gscale,
-                                     float threshold, float* __restrict__ stats) {
+                                     const float* __restrict__ mask_sum, float threshold,
+                                     float* __restrict__ stats) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     double t = 0.0;
     for (int i = 0; i < nparts; ++i) t += partial[i];
-    const float norm = (float)sqrt(t) * fabsf(gscale);
+    float sc = gscale;
+    if (mask_sum) sc *= 1.0f / (mask_sum[0] + 1e-5f);
+    const float norm = (float)sqrt(t) * fabsf(sc);
     stats[0] = norm;
     stats[1] = (norm < threshold) ? 1.0f : threshold / norm;
+    stats[2] = stats[1] * sc;
   }
 }
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                            float* __restrict__ v, long long n, const float* __restrict__ stats, float gscale,
-                            float lr_t, float b1, float b2, float eps) {
-  const float mult = stats[1] * gscale;
+                            float* __restrict__ v, long long n, const float* __restrict__ stats, float lr_t,
+                            float b1, float b2, float eps) {
+  const float mult = stats[2];
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
     const float gi = g[i] * mult;

@@ -129,7 +129,7 @@ def test_adam_clip_matches_oracle():
         dg = torch.from_numpy(g).cuda()
         _lib.check(lib.parrot_adam_clip_step(
             C.c_void_p(dp.data_ptr()), C.c_void_p(dg.data_ptr()), C.c_void_p(dm.data_ptr()),
-            C.c_void_p(dv.data_ptr()), n, 1.0, 9.0, 1e-3, 0.9, 0.999, 1e-8, step,
+            C.c_void_p(dv.data_ptr()), n, 1.0, None, 9.0, 1e-3, 0.9, 0.999, 1e-8, step,
             C.c_void_p(stats.data_ptr()), C.c_void_p(scratch.data_ptr()),
             C.c_void_p(torch.cuda.current_stream().cuda_stream)))
         torch.cuda.synchronize()
