@@ -268,6 +268,10 @@ struct parrot_model {
   std::map<std::string, int> map_scan, map_plain, map_tA, map_tB;  // plane name -> hi map index
   std::map<std::string, Table> tables;
   std::vector<WGrad> wgrads;
+  int max_groups = 0;
+  size_t max_split_floats = 0;
+  float* d_split_scratch = nullptr;
+  unsigned int* d_split_count = nullptr;
   bool dirty = true;
   float last_start_flag = 1.0f;
   bool have_fwd = false;
@@ -444,12 +448,55 @@ static void build_plain_jobs(std::vector<Job>& out, int Mrows, int f0, long long
     }
 }
 
-static void push_table(parrot_model& M, const std::string& name, const std::vector<Job>& js, int n_cols) {
+static int job_kb(const Job& j) {
+  int n = 0;
+  for (int s = 0; s < j.nseg; ++s) n += j.seg[s].nkb;
+  return n;
+}
+// Split the K dimension of the jobs of a scan table so that one launch spreads over `target_ctas` CTAs
+// (each tile of a recurrent phase would otherwise stream its full K alone: per-SM bandwidth bound).
+static std::vector<Job> split_jobs(const std::vector<Job>& js, int target_ctas, int max_split, int* groups) {
+  long long total = 0;
+  for (auto& j : js) total += job_kb(j);
+  int per = (int)std::max<long long>(1, (total + target_ctas - 1) / target_ctas);
+  std::vector<Job> out;
+  for (;;) {
+    long long parts = 0;
+    for (auto& j : js) parts += std::min(max_split, std::max(1, (job_kb(j) + per - 1) / per));
+    if (parts <= target_ctas || per > total) break;
+    ++per;
+  }
+  int g = 0;
+  for (auto& j : js) {
+    const int sp = std::min(max_split, std::max(1, (job_kb(j) + per - 1) / per));
+    for (int p = 0; p < sp; ++p) {
+      Job c = j;
+      c.ksplit = sp; c.kpart = p; c.group = g;
+      out.push_back(c);
+    }
+    ++g;
+  }
+  *groups = g;
+  return out;
+}
+
+static void push_table(parrot_model& M, const std::string& name, const std::vector<Job>& js, int n_cols,
+                       int split_target = 0) {
   Table t;
   t.off = (int)M.jobs.size();
-  t.count = (int)js.size();
   t.n_cols = n_cols;
-  M.jobs.insert(M.jobs.end(), js.begin(), js.end());
+  if (split_target > 0) {
+    int groups = 0;
+    std::vector<Job> sp = split_jobs(js, split_target, MAX_KSPLIT, &groups);
+    // parts of one tile must run concurrently with distinct CTAs: order parts-major so that CTA i gets job i
+    t.count = (int)sp.size();
+    M.jobs.insert(M.jobs.end(), sp.begin(), sp.end());
+    M.max_groups = std::max(M.max_groups, groups);
+    M.max_split_floats = std::max(M.max_split_floats, (size_t)groups * MAX_KSPLIT * n_cols * TILE_M);
+  } else {
+    t.count = (int)js.size();
+    M.jobs.insert(M.jobs.end(), js.begin(), js.end());
+  }
   M.tables[name] = t;
 }
 
@@ -462,6 +509,7 @@ static void run_table(parrot_model& M, const std::string& name, int tick, int T,
   EngineParams P;
   P.jobs = M.d_jobs + t.off; P.njobs = t.count; P.maps = M.d_maps; P.raws = M.d_raws; P.ctx = M.d_ctx;
   P.tick = tick; P.T = T; P.n_cols = t.n_cols; P.reverse = reverse;
+  P.split_scratch = M.d_split_scratch; P.split_count = M.d_split_count;
   cudaEvent_t pe = M.prof_begin(name, st);
   if (M.cfg.gemm_impl == 1) {
     const int grid = std::min(t.count, 148 * 8);
@@ -478,7 +526,7 @@ static void build(parrot_model& M) {
   const Dims& d = M.d;
   M.ws_used = 0;
   M.bufs.clear(); M.maps.clear(); M.raws.clear(); M.jobs.clear(); M.packs.clear(); M.planes.clear();
-  M.tables.clear(); M.wgrads.clear();
+  M.tables.clear(); M.wgrads.clear(); M.max_groups = 0; M.max_split_floats = 0;
   const int T = d.T, B = d.B, H = d.H, Np = d.Np;
   const bool train = !d.sampling;
 
@@ -653,8 +701,8 @@ static void build(parrot_model& M) {
     std::vector<Job> A, Bj;
     for (int l = 0; l < 3; ++l) build_fwd_layer_jobs(M, A, l, true, l);
     for (int l = 0; l < 3; ++l) build_fwd_layer_jobs(M, Bj, l, false, l);
-    push_table(M, "fwdA", A, Np);
-    push_table(M, "fwdB", Bj, Np);
+    push_table(M, "fwdA", A, Np, 148);
+    push_table(M, "fwdB", Bj, Np, 148);
   } else {
     for (int l = 0; l < 3; ++l) {
       std::vector<Job> A, Bj;
@@ -775,7 +823,7 @@ static void build(parrot_model& M) {
                            0, 0, 0, d.Hp / 64);
           js.push_back(j);
         }
-      push_table(M, "bwd1", js, Np);
+      push_table(M, "bwd1", js, Np, 148);
     }
     // backward scan, product 2: dgrads into the carried state gradients.  Job time = step s of layer 3;
     // segments of layer 2 / layer 1 refer to steps s+1 / s+2 (reverse wavefront).
@@ -814,7 +862,7 @@ static void build(parrot_model& M) {
       add(d.C, 3, 1, {S("/inp_to_h3/fork_rnn3_inputs", {2, 0}), S("/inp_to_h3/fork_rnn3_gates", {2, 0})});
       add(d.C, 3, 2, {S("/inp_to_h2/fork_rnn2_inputs", {1, 1}), S("/inp_to_h2/fork_rnn2_gates", {1, 1}),
                       S("/inp_to_h1/fork_rnn1_inputs", {0, 2}), S("/inp_to_h1/fork_rnn1_gates", {0, 2})});
-      push_table(M, "bwd2", js, Np);
+      push_table(M, "bwd2", js, Np, 148);
     }
     // weight gradients: dW[in][out] = sum_samples X[s][in] * dY[s][out]
     {
@@ -867,6 +915,8 @@ static void build_device_tables(parrot_model& M) {
   M.d_raws = (MapRaw*)M.alloc("dev_raws", M.raws.size() * sizeof(MapRaw));
   M.d_jobs = (Job*)M.alloc("dev_jobs", M.jobs.size() * sizeof(Job));
   M.d_ctx = (ScanCtx*)M.alloc("dev_ctx", sizeof(ScanCtx));
+  M.d_split_scratch = (float*)M.alloc("split_scratch", std::max<size_t>(M.max_split_floats, 1) * 4);
+  M.d_split_count = (unsigned int*)M.alloc("split_count", (size_t)std::max(M.max_groups, 1) * 4);
 }
 
 static void upload_tables(parrot_model& M, cudaStream_t st) {
@@ -880,6 +930,8 @@ static void ensure_kernel_attrs() {
   static bool done = false;
   if (done) return;
   CK(cudaFuncSetAttribute(job_kernel_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES + 1024));
+  CK(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  CK(cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   done = true;
 }
 
@@ -1141,7 +1193,7 @@ static void attention_step(parrot_model& M, int t, bool sampling, cudaStream_t s
   a.phi_out = M.fbuf("phi") + (long long)t * d.B * d.U;
   a.ab_out = M.fbuf("ab") + (long long)t * d.B * 2 * d.A;
   a.e_out = M.fbuf("att_e") + (long long)t * d.B * 3 * d.A;
-  const size_t smem = (size_t)(d.H + 6 * d.A + d.U) * 4;
+  const size_t smem = (size_t)(rup(d.H, 4) + 2 * rup(3 * d.A, 4) + rup(d.U, 4) + 8 * d.C) * 4;
   cudaEvent_t pe = M.prof_begin("attn_fwd", st);
   LAUNCH(attention_fwd_kernel, d.B, 256, smem, st, a);
   parrot_model::prof_end(pe, st);
@@ -1262,18 +1314,21 @@ static void attention_bwd_step(parrot_model& M, int t, cudaStream_t st) {
 static void scan_bwd(parrot_model& M, cudaStream_t st) {
   const Dims& d = M.d;
   CK(cudaMemsetAsync(M.fbuf("dk_carry"), 0, (size_t)d.B * d.A * 4, st));
-  const int blocks = gs_blocks((long long)d.B * d.H);
+  const int blocks = std::min(gs_blocks((long long)d.B * d.H), 148);
   // reverse layer wavefront: tick tau -> layer 3 at s = T-1-tau, layer 2 at s+1, attention + layer 1 at s+2
   for (int tick = 0; tick < d.T + 2; ++tick) {
     const int s = d.T - 1 - tick;
     if (s + 2 >= 0 && s + 2 < d.T) attention_bwd_step(M, s + 2, st);
+    PreArgs pa;
+    pa.n = 0;
     for (int l = 2; l >= 0; --l) {
       const int t = s + (2 - l);
-      if (t >= 0 && t < d.T) {
-        cudaEvent_t pe = M.prof_begin("gru_bwd_pre", st);
-        LAUNCH(gru_bwd_pre_kernel, blocks, 256, 0, st, M.d_ctx, l, t);
-        parrot_model::prof_end(pe, st);
-      }
+      if (t >= 0 && t < d.T) { pa.layer[pa.n] = l; pa.t[pa.n] = t; ++pa.n; }
+    }
+    if (pa.n > 0) {
+      cudaEvent_t pe = M.prof_begin("gru_bwd_pre", st);
+      LAUNCH(gru_bwd_pre_kernel, dim3(blocks, pa.n), 256, 0, st, M.d_ctx, pa);
+      parrot_model::prof_end(pe, st);
     }
     run_table(M, "bwd1", tick, d.T, 1, st);
     run_table(M, "bwd2", tick, d.T, 1, st);
@@ -1602,7 +1657,8 @@ int parrot_attention_step(const parrot_config* cfg, const float* d_h1, const flo
     a.timing = training ? 1.0f : cfg->timing_coeff;
     a.h1 = d_h1; a.wT = d_wT; a.batt = d_batt; a.ctx = d_ctx; a.k_prev = d_k_prev; a.k_out = d_k_out;
     a.w_out = d_w_out; a.phi_out = d_phi_out; a.ab_out = d_ab_out; a.e_out = d_e_out;
-    const size_t smem = (size_t)(d.H + 6 * d.A + d.U) * 4;
+    const size_t smem = (size_t)(rup(d.H, 4) + 2 * rup(3 * d.A, 4) + rup(d.U, 4) + 8 * d.C) * 4;
+    ensure_kernel_attrs();
     LAUNCH(attention_fwd_kernel, d.B, 256, smem, (cudaStream_t)stream, a);
   });
 }

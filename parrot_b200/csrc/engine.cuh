@@ -35,6 +35,7 @@ constexpr int MAX_SEG = 6;
 constexpr int NO_SLOT = -(1 << 30);
 constexpr int ENGINE_THREADS = 192;
 constexpr int SMEM_BYTES = 200 * 1024;
+constexpr int MAX_KSPLIT = 8;   // scratch stride per split group
 
 enum Epi : int {
   EPI_PLAIN = 0,      // out = acc*scale (+bias) (+= out), optional hi/lo planes
@@ -78,6 +79,10 @@ struct Job {
   int m_valid;  // rows of the tile that exist
   int n0;       // first sample column
   int aux;      // epilogue specific
+  // split-K: `ksplit` jobs share one output tile (`group`); part `kpart` contracts its share of the
+  // k blocks, parks the partial tile in scratch, and the last part to arrive sums all parts in part
+  // order (deterministic) and runs the epilogue.
+  int ksplit, kpart, group, pad_;
   Seg seg[MAX_SEG];
   PlainArgs pa;
 };
@@ -122,6 +127,8 @@ struct EngineParams {
   int T;          // jobs whose t falls outside [0, T) are skipped
   int n_cols;     // UMMA N of every job in this launch (box rows of every B map used)
   int reverse;    // 0: t = tick - lag ; 1: t = (T - 1) - (tick - lag)
+  float* split_scratch;        // [group][part][n_cols][128] partial tiles
+  unsigned int* split_count;   // [group] arrival counters (zero between launches)
 };
 
 __device__ __forceinline__ int job_time(const EngineParams& P, const Job& jb) {
@@ -146,6 +153,13 @@ __device__ __forceinline__ int job_total_kb(const EngineParams& P, const Job& jb
   return n;
 }
 
+// k-block range [lo, hi) of the flattened (valid segment, block) sequence owned by this split part
+__device__ __forceinline__ void job_kb_range(const Job& jb, int total_kb, int& lo, int& hi) {
+  if (jb.ksplit <= 1) { lo = 0; hi = total_kb; return; }
+  lo = (int)(((long long)total_kb * jb.kpart) / jb.ksplit);
+  hi = (int)(((long long)total_kb * (jb.kpart + 1)) / jb.ksplit);
+}
+
 // ------------------------------------------------------------------ epilogues
 // Thread <-> output row (feature).  v[j] is the accumulator for sample n_base + j.
 __device__ __forceinline__ void epi_plain(const Job& jb, int t, int row, int n_base, int ncols,
@@ -155,8 +169,9 @@ __device__ __forceinline__ void epi_plain(const Job& jb, int t, int row, int n_b
   const int f = jb.row0 + row;
   const float bias = a.bias ? a.bias[f] : 0.0f;
   float* out = a.out ? a.out + (long long)t * a.out_tstride : nullptr;
-#pragma unroll 4
-  for (int j = 0; j < ncols; ++j) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    if (j >= ncols) break;
     const int n = jb.n0 + n_base + j;
     if (n >= a.n_total) break;
     long long srow = n;
@@ -182,6 +197,8 @@ __device__ __forceinline__ void epi_plain(const Job& jb, int t, int row, int n_b
 }
 
 // forward scan, gates tile: rows [0, 2H) of [update | reset]   (model.py:659-662)
+// All epilogues below are written as fully unrolled loops over the 32 columns of a TMEM chunk with the
+// global loads issued ahead of the arithmetic (32 independent requests in flight per thread).
 __device__ __forceinline__ void epi_gates(const Job& jb, const ScanCtx& c, int t, int row, int n_base,
                                           int ncols, const float* v) {
   if (row >= jb.m_valid) return;
@@ -189,24 +206,30 @@ __device__ __forceinline__ void epi_gates(const Job& jb, const ScanCtx& c, int t
   const int H = c.H, f = jb.row0 + row;
   const bool is_z = f < H;
   const int fr = is_z ? f : f - H;
-#pragma unroll 4
-  for (int j = 0; j < ncols; ++j) {
+  float pre[32], hp[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
     const int b = n_base + j;
-    if (b >= c.B) break;
-    float pre = L.base[(long long)b * 3 * H + H + f];
-    if (L.fb) pre += L.fb[((long long)t * c.B + b) * 3 * H + H + f];
-    const float g = sigmoidf_exact(v[j] + pre);
-    const long long o = ((long long)t * c.B + b) * H + fr;
-    if (is_z) {
-      L.z[o] = g;
-    } else {
-      L.r[o] = g;
-      const float hp = L.h[o];  // slot t == state before this step
-      bf16 hh, ll;
-      split_bf16(g * hp, hh, ll);
-      const long long po = ((long long)t * c.Np + b) * c.Hp + fr;
-      L.rh_hi[po] = hh;
-      L.rh_lo[po] = ll;
+    const bool ok = j < ncols && b < c.B;
+    pre[j] = ok ? __ldg(L.base + (long long)b * 3 * H + H + f) : 0.0f;
+    hp[j] = (ok && !is_z) ? L.h[((long long)t * c.B + b) * H + fr] : 0.0f;
+  }
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const int b = n_base + j;
+    if (j < ncols && b < c.B) {
+      const float g = sigmoidf_exact(v[j] + pre[j]);
+      const long long o = ((long long)t * c.B + b) * H + fr;
+      if (is_z) {
+        L.z[o] = g;
+      } else {
+        L.r[o] = g;
+        bf16 hh, ll;
+        split_bf16(g * hp[j], hh, ll);
+        const long long po = ((long long)t * c.Np + b) * c.Hp + fr;
+        L.rh_hi[po] = hh;
+        L.rh_lo[po] = ll;
+      }
     }
   }
 }
@@ -217,53 +240,69 @@ __device__ __forceinline__ void epi_cand(const Job& jb, const ScanCtx& c, int t,
   if (row >= jb.m_valid) return;
   const LayerBuf& L = c.L[jb.layer];
   const int H = c.H, f = jb.row0 + row;
-#pragma unroll 4
-  for (int j = 0; j < ncols; ++j) {
+  float pre[32], zz[32], hp[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
     const int b = n_base + j;
-    if (b >= c.B) break;
-    float pre = L.base[(long long)b * 3 * H + f];
-    if (L.fb) pre += L.fb[((long long)t * c.B + b) * 3 * H + f];
-    const float cc = tanhf(v[j] + pre);
+    const bool ok = j < ncols && b < c.B;
     const long long o = ((long long)t * c.B + b) * H + f;
-    const float zz = L.z[o];
-    const float hp = L.h[o];
-    const float hn = cc * zz + hp * (1.0f - zz);
-    L.c[o] = cc;
-    L.h[o + (long long)c.B * H] = hn;  // slot t + 1
-    bf16 hh, ll;
-    split_bf16(hn, hh, ll);
-    const long long po = ((long long)(t + 1) * c.Np + b) * c.Hp + f;
-    L.h_hi[po] = hh;
-    L.h_lo[po] = ll;
+    pre[j] = ok ? __ldg(L.base + (long long)b * 3 * H + f) : 0.0f;
+    zz[j] = ok ? L.z[o] : 0.0f;
+    hp[j] = ok ? L.h[o] : 0.0f;
+  }
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const int b = n_base + j;
+    if (j < ncols && b < c.B) {
+      const float cc = tanhf(v[j] + pre[j]);
+      const long long o = ((long long)t * c.B + b) * H + f;
+      const float hn = cc * zz[j] + hp[j] * (1.0f - zz[j]);
+      L.c[o] = cc;
+      L.h[o + (long long)c.B * H] = hn;  // slot t + 1
+      bf16 hh, ll;
+      split_bf16(hn, hh, ll);
+      const long long po = ((long long)(t + 1) * c.Np + b) * c.Hp + f;
+      L.h_hi[po] = hh;
+      L.h_lo[po] = ll;
+    }
   }
 }
 
 // backward scan: tile of d(r*h) = da_c * Ws^T, rows = state features [0, H).
 // Finishes the GRU step backward for those features:
-//   dr = drh * h_prev ; dh_prev += drh * r ; da_g = [dz z(1-z) | dr r(1-r)] -> planes + fp32
-// (dz part and da_c were produced by the elementwise pre-pass, scan_bwd.cu)
+//   dr = drh * h_prev ; dh_prev += drh * r ; da_g[reset half] = dr r (1-r) -> planes + fp32
+// (the update half of da_g and da_c come from the elementwise pre-pass, gru_bwd_pre_kernel)
 __device__ __forceinline__ void epi_bwd_rh(const Job& jb, const ScanCtx& c, int t, int row, int n_base,
                                            int ncols, const float* v) {
   if (row >= jb.m_valid) return;
   const LayerBuf& L = c.L[jb.layer];
   const int H = c.H, f = jb.row0 + row;
-#pragma unroll 4
-  for (int j = 0; j < ncols; ++j) {
+  float rr[32], hp[32], dh[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
     const int b = n_base + j;
-    if (b >= c.B) break;
+    const bool ok = j < ncols && b < c.B;
     const long long o = ((long long)t * c.B + b) * H + f;
-    const float drh = v[j];
-    const float r = L.r[o];
-    const float hp = L.h[o];
-    const float dr = drh * hp;
-    L.dh[o] += drh * r;  // slot t (state before the step)
-    const float dag = dr * r * (1.0f - r);
-    L.da[((long long)t * c.B + b) * 3 * H + 2 * H + f] = dag;
-    bf16 hh, ll;
-    split_bf16(dag, hh, ll);
-    const long long po = ((long long)t * c.Np + b) * (3 * c.Hp) + c.Hp + H + f;
-    L.da_hi[po] = hh;
-    L.da_lo[po] = ll;
+    rr[j] = ok ? L.r[o] : 0.0f;
+    hp[j] = ok ? L.h[o] : 0.0f;
+    dh[j] = ok ? L.dh[o] : 0.0f;
+  }
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const int b = n_base + j;
+    if (j < ncols && b < c.B) {
+      const long long o = ((long long)t * c.B + b) * H + f;
+      const float drh = v[j];
+      const float dr = drh * hp[j];
+      L.dh[o] = dh[j] + drh * rr[j];  // slot t (state before the step)
+      const float dag = dr * rr[j] * (1.0f - rr[j]);
+      L.da[((long long)t * c.B + b) * 3 * H + 2 * H + f] = dag;
+      bf16 hh, ll;
+      split_bf16(dag, hh, ll);
+      const long long po = ((long long)t * c.Np + b) * (3 * c.Hp) + c.Hp + H + f;
+      L.da_hi[po] = hh;
+      L.da_lo[po] = ll;
+    }
   }
 }
 
@@ -281,11 +320,16 @@ __device__ __forceinline__ void epi_bwd_state(const Job& jb, const ScanCtx& c, i
   } else {
     dst = c.L[jb.aux].dh; F = c.H;
   }
-#pragma unroll 4
-  for (int j = 0; j < ncols; ++j) {
+  float old[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
     const int b = n_base + j;
-    if (b >= c.B) break;
-    dst[((long long)slot * c.B + b) * F + f] += v[j];
+    old[j] = (j < ncols && b < c.B) ? dst[((long long)slot * c.B + b) * F + f] : 0.0f;
+  }
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const int b = n_base + j;
+    if (j < ncols && b < c.B) dst[((long long)slot * c.B + b) * F + f] = old[j] + v[j];
   }
 }
 
@@ -321,6 +365,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) job_kernel_tc(const EngineP
   uint64_t* tfull_bar = empty_bar + 8;   // [2] accumulator ready
   uint64_t* tempty_bar = tfull_bar + 2;  // [2] accumulator drained
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  volatile uint32_t* split_flag = tmem_slot + 1;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < nstages; ++s) {
@@ -351,13 +396,17 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) job_kernel_tc(const EngineP
       for (int j = blockIdx.x; j < P.njobs; j += gridDim.x) {
         const Job& jb = P.jobs[j];
         const int t = job_time(P, jb);
-        if (job_total_kb(P, jb, t) == 0) continue;
+        const int total_kb = job_total_kb(P, jb, t);
+        if (total_kb == 0) continue;
+        int klo, khi, kidx = 0;
+        job_kb_range(jb, total_kb, klo, khi);
         for (int s = 0; s < jb.nseg; ++s) {
           const Seg sg = jb.seg[s];
           if (!seg_valid(P, sg, t)) continue;
           const CUtensorMap* ma = P.maps + sg.a_map;
           const CUtensorMap* mb = P.maps + sg.b_map;
-          for (int kb = 0; kb < sg.nkb; ++kb) {
+          for (int kb = 0; kb < sg.nkb; ++kb, ++kidx) {
+            if (kidx < klo || kidx >= khi) continue;
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* st = tiles + (size_t)stage * stage_bytes;
             mbar_expect_tx(&full_bar[stage], stage_bytes);
@@ -385,10 +434,14 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) job_kernel_tc(const EngineP
     for (int j = blockIdx.x; j < P.njobs; j += gridDim.x) {
       const Job& jb = P.jobs[j];
       const int t = job_time(P, jb);
-      const int total_kb = job_total_kb(P, jb, t);
-      if (total_kb == 0) continue;
+      const int all_kb = job_total_kb(P, jb, t);
+      if (all_kb == 0) continue;
+      int klo, khi;
+      job_kb_range(jb, all_kb, klo, khi);
+      const int total_kb = khi - klo;
       const int buf = it & 1;
       const uint32_t use = (uint32_t)(it >> 1);
+      if (total_kb == 0) continue;   // empty split part: no accumulator is used, the epilogue contributes zeros
       mbar_wait(&tempty_bar[buf], (use & 1) ^ 1);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)buf * 256u;
@@ -424,24 +477,85 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) job_kernel_tc(const EngineP
     for (int j = blockIdx.x; j < P.njobs; j += gridDim.x) {
       const Job& jb = P.jobs[j];
       const int t = job_time(P, jb);
-      if (job_total_kb(P, jb, t) == 0) continue;
+      const int all_kb = job_total_kb(P, jb, t);
+      if (all_kb == 0) continue;
+      int klo, khi;
+      job_kb_range(jb, all_kb, klo, khi);
+      const bool have_acc = khi > klo;
       const int buf = it & 1;
       const uint32_t use = (uint32_t)(it >> 1);
-      mbar_wait(&tfull_bar[buf], use & 1);
-      tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t)buf * 256u + ((uint32_t)(q * 32) << 16);
-      for (int n0 = 0; n0 < n_cols; n0 += 32) {
-        float v[32];
-        const int nc = (n_cols - n0 >= 32) ? 32 : 16;
-        if (nc == 32) tmem_ld_32x32(taddr + n0, v);
-        else tmem_ld_32x16(taddr + n0, v);
-        tmem_ld_wait();
-        run_epilogue(jb, P.ctx, t, row, n0, nc, v);
+      if (have_acc) {
+        mbar_wait(&tfull_bar[buf], use & 1);
+        tc_fence_after();
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[buf]);
-      ++it;
+      if (jb.ksplit <= 1) {
+        for (int n0 = 0; n0 < n_cols; n0 += 32) {
+          float v[32];
+          const int nc = (n_cols - n0 >= 32) ? 32 : 16;
+          if (nc == 32) tmem_ld_32x32(taddr + n0, v);
+          else {
+            tmem_ld_32x16(taddr + n0, v);
+#pragma unroll
+            for (int i = 16; i < 32; ++i) v[i] = 0.0f;
+          }
+          tmem_ld_wait();
+          run_epilogue(jb, P.ctx, t, row, n0, nc, v);
+        }
+      } else {
+        // park the partial tile: scratch[group][part][col][row]  (row fastest -> coalesced)
+        float* part = P.split_scratch + ((size_t)jb.group * MAX_KSPLIT + jb.kpart) * (size_t)n_cols * TILE_M;
+        for (int n0 = 0; n0 < n_cols; n0 += 32) {
+          float v[32];
+          const int nc = (n_cols - n0 >= 32) ? 32 : 16;
+          if (have_acc) {
+            if (nc == 32) tmem_ld_32x32(taddr + n0, v);
+            else tmem_ld_32x16(taddr + n0, v);
+            tmem_ld_wait();
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = 0.0f;
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (i < nc) __stcg(part + (size_t)(n0 + i) * TILE_M + row, v[i]);
+        }
+      }
+      if (have_acc) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+      }
+      if (jb.ksplit > 1) {
+        __threadfence();
+        asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps
+        if (warp == 2 && lane == 0) {
+          const unsigned int old = atomicAdd(P.split_count + jb.group, 1u);
+          const bool last = old == (unsigned int)(jb.ksplit - 1);
+          if (last) P.split_count[jb.group] = 0u;   // ready for the next launch
+          *split_flag = last ? 1u : 0u;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (*split_flag) {
+          __threadfence();
+          const float* base = P.split_scratch + (size_t)jb.group * MAX_KSPLIT * (size_t)n_cols * TILE_M;
+          for (int n0 = 0; n0 < n_cols; n0 += 32) {
+            float v[32];
+            const int nc = (n_cols - n0 >= 32) ? 32 : 16;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = 0.0f;
+            for (int p = 0; p < jb.ksplit; ++p) {
+              const float* pp = base + (size_t)p * n_cols * TILE_M;
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (i < nc) v[i] += __ldcg(pp + (size_t)(n0 + i) * TILE_M + row);
+            }
+            run_epilogue(jb, P.ctx, t, row, n0, nc, v);
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");   // split_flag is reused by the next job
+      }
+      if (have_acc) ++it;   // accumulator buffers advance only when one was used (mirrors the MMA warp)
     }
   }
 
@@ -462,6 +576,7 @@ __global__ void __launch_bounds__(128) job_kernel_simt(const EngineParams P) {
     const Job& jb = P.jobs[j];
     const int t = job_time(P, jb);
     if (job_total_kb(P, jb, t) == 0) continue;
+    if (jb.ksplit > 1 && jb.kpart != 0) continue;   // the SIMT twin does not split: part 0 does the whole tile
     for (int n0 = 0; n0 < P.n_cols; n0 += 32) {
       const int nc = (P.n_cols - n0 >= 32) ? 32 : (P.n_cols - n0);
       float acc[32];

@@ -36,21 +36,31 @@ struct AttnFwdArgs {
 
 __global__ void __launch_bounds__(256) attention_fwd_kernel(const AttnFwdArgs a) {
   extern __shared__ float sh[];
-  float* sh_h = sh;                 // H
-  float* sh_hat = sh_h + a.H;       // 3A
-  float* sh_abk = sh_hat + 3 * a.A; // 3A : alpha, beta, kappa
-  float* sh_phi = sh_abk + 3 * a.A; // U
+  const int A3p = (3 * a.A + 3) & ~3;  // sections padded to 16 bytes (float4 accesses below)
+  float* sh_h = sh;                          // H
+  float* sh_hat = sh_h + ((a.H + 3) & ~3);   // 3A
+  float* sh_abk = sh_hat + A3p;              // 3A : alpha, beta, kappa
+  float* sh_phi = sh_abk + A3p;              // U
   const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int A = a.A;
   for (int i = tid; i < a.H; i += blockDim.x) sh_h[i] = a.h1[(long long)b * a.H + i];
   __syncthreads();
-  for (int j = warp; j < 3 * A; j += (blockDim.x >> 5)) {
-    const float* wr = a.wT + (long long)j * a.H;
-    float s = 0.0f;
-    for (int k = lane; k < a.H; k += 32) s = fmaf(sh_h[k], wr[k], s);
+  for (int j0 = warp * 4; j0 < 3 * A; j0 += (blockDim.x >> 5) * 4) {
+    float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+    for (int k = lane; k < a.H; k += 32) {
+      const float hv = sh_h[k];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) sh_hat[j] = s + a.batt[j];
+      for (int r = 0; r < 4; ++r)
+        if (j0 + r < 3 * A) s4[r] = fmaf(hv, __ldg(a.wT + (long long)(j0 + r) * a.H + k), s4[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      float sv = s4[r];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sv += __shfl_xor_sync(0xffffffffu, sv, o);
+      if (lane == 0 && j0 + r < 3 * A) sh_hat[j0 + r] = sv + a.batt[j0 + r];
+    }
   }
   __syncthreads();
   if (tid < A) {
@@ -101,11 +111,38 @@ __global__ void __launch_bounds__(256) attention_fwd_kernel(const AttnFwdArgs a)
     a.phi_out[(long long)b * a.U + u] = phi;
   }
   __syncthreads();
+  // w[c] = sum_u phi[u] * ctx[b][u][c]: warp w reduces its slice of text positions with 128-bit loads
+  // (all loads of a lane independent -> full memory-level parallelism), then the slices are summed in
+  // warp order.  (The reference sums over u serially; the reordering moves w by ~1e-7 relative and
+  // cannot affect argmax(phi), which is already fixed above.)
+  float* sh_part = sh_phi + ((a.U + 3) & ~3);   // [nwarp][C]
   const float* cb = a.ctx + (long long)b * a.U * a.C;
+  const int nwarp = blockDim.x >> 5;
+  const int per = (a.U + nwarp - 1) / nwarp;
+  const int u0 = warp * per, u1 = min(a.U, u0 + per);
+  if ((a.C & 3) == 0) {
+    for (int c = lane * 4; c < a.C; c += 128) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+      for (int u = u0; u < u1; ++u) {
+        const float4 x = __ldg(reinterpret_cast<const float4*>(cb + (long long)u * a.C + c));
+        const float p = sh_phi[u];
+        acc.x = fmaf(p, x.x, acc.x); acc.y = fmaf(p, x.y, acc.y);
+        acc.z = fmaf(p, x.z, acc.z); acc.w = fmaf(p, x.w, acc.w);
+      }
+      *reinterpret_cast<float4*>(sh_part + (long long)warp * a.C + c) = acc;
+    }
+  } else {
+    for (int c = lane; c < a.C; c += 32) {
+      float acc = 0.0f;
+      for (int u = u0; u < u1; ++u) acc = fmaf(sh_phi[u], cb[(long long)u * a.C + c], acc);
+      sh_part[(long long)warp * a.C + c] = acc;
+    }
+  }
+  __syncthreads();
   for (int c = tid; c < a.C; c += blockDim.x) {
     float w = 0.0f;
-#pragma unroll 8
-    for (int u = 0; u < a.U; ++u) w = __fadd_rn(w, __fmul_rn(sh_phi[u], cb[(long long)u * a.C + c]));
+    for (int q = 0; q < nwarp; ++q) w += sh_part[(long long)q * a.C + c];
     a.w_out[(long long)b * a.C + c] = w;
     if (a.w_hi) {
       bf16 hh, ll;
@@ -150,13 +187,31 @@ __global__ void __launch_bounds__(256) attention_bwd_kernel(const AttnBwdArgs a)
   for (int i = tid; i < a.C; i += blockDim.x) sh_dw[i] = a.dw[(long long)b * a.C + i];
   __syncthreads();
   const float* cb = a.ctx + (long long)b * a.U * a.C;
-  for (int u = warp; u < a.U; u += nwarp) {
-    const float* row = cb + (long long)u * a.C;
-    float s = 0.0f;
-    for (int c = lane; c < a.C; c += 32) s = fmaf(sh_dw[c], row[c], s);
+  for (int u = warp * 4; u < a.U; u += nwarp * 4) {
+    float s4[4] = {0.f, 0.f, 0.f, 0.f};
+    if ((a.C & 3) == 0) {
+      for (int c = lane * 4; c < a.C; c += 128) {
+        const float4 d = *reinterpret_cast<const float4*>(sh_dw + c);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) sh_dphi[u] = s;
+        for (int r = 0; r < 4; ++r)
+          if (u + r < a.U) {
+            const float4 x = __ldg(reinterpret_cast<const float4*>(cb + (long long)(u + r) * a.C + c));
+            s4[r] += d.x * x.x + d.y * x.y + d.z * x.z + d.w * x.w;
+          }
+      }
+    } else {
+      for (int c = lane; c < a.C; c += 32)
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+          if (u + r < a.U) s4[r] = fmaf(sh_dw[c], cb[(long long)(u + r) * a.C + c], s4[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      float sv = s4[r];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sv += __shfl_xor_sync(0xffffffffu, sv, o);
+      if (lane == 0 && u + r < a.U) sh_dphi[u + r] = sv;
+    }
   }
   __syncthreads();
   // per-component reductions over u
@@ -242,8 +297,11 @@ __global__ void __launch_bounds__(256) attention_bwd_kernel(const AttnBwdArgs a)
 // GRU backward pre-pass for one layer / step: everything that is elementwise in
 // dh_t (see oracle _gru_bwd).  Produces da_c and the update half of da_g.
 // =========================================================================
-__global__ void gru_bwd_pre_kernel(const ScanCtx* cp, int layer, int t) {
+struct PreArgs { int layer[3]; int t[3]; int n; };
+__global__ void gru_bwd_pre_kernel(const ScanCtx* cp, const PreArgs pa) {
   const ScanCtx& c = *cp;
+  if ((int)blockIdx.y >= pa.n) return;
+  const int layer = pa.layer[blockIdx.y], t = pa.t[blockIdx.y];
   const LayerBuf& L = c.L[layer];
   const int H = c.H;
   const long long n = (long long)c.B * H;
