@@ -270,6 +270,8 @@ struct parrot_model {
   std::vector<WGrad> wgrads;
   int max_groups = 0;
   size_t max_split_floats = 0;
+  unsigned long long* timeline = nullptr;
+  int sm_count = 0;
   float* d_split_scratch = nullptr;
   unsigned int* d_split_count = nullptr;
   bool dirty = true;
@@ -510,6 +512,8 @@ static void run_table(parrot_model& M, const std::string& name, int tick, int T,
   P.jobs = M.d_jobs + t.off; P.njobs = t.count; P.maps = M.d_maps; P.raws = M.d_raws; P.ctx = M.d_ctx;
   P.tick = tick; P.T = T; P.n_cols = t.n_cols; P.reverse = reverse;
   P.split_scratch = M.d_split_scratch; P.split_count = M.d_split_count;
+  P.timeline = M.timeline;
+  P.coop_epilogue = (t.count <= 148 && M.sm_count >= 148) ? 1 : 0;
   cudaEvent_t pe = M.prof_begin(name, st);
   if (M.cfg.gemm_impl == 1) {
     const int grid = std::min(t.count, 148 * 8);
@@ -932,6 +936,8 @@ static void ensure_kernel_attrs() {
   CK(cudaFuncSetAttribute(job_kernel_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES + 1024));
   CK(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
   CK(cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  CK(cudaFuncSetAttribute(encoder_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+  CK(cudaFuncSetAttribute(encoder_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
   done = true;
 }
 
@@ -1099,7 +1105,10 @@ static void encoder_fwd(parrot_model& M, const int32_t* d_labels, const float* d
          a.N, d.U, M.cfg.encoder_time_axis, d.E, (float*)a.xi[0], (float*)a.xg[0], (float*)a.xi[1], (float*)a.xg[1],
          (int*)M.fbuf("enc_lab"));
   dim3 grid(cdiv(a.N, ENC_ROWS), 2);
-  const size_t smem = (size_t)ENC_ROWS * d.E * 4 * 4;
+  size_t smem = (size_t)ENC_ROWS * d.E * 4 * 4;
+  const size_t wbytes = (size_t)3 * d.E * d.E * 4;
+  a.w_in_smem = (smem + wbytes <= 220 * 1024) ? 1 : 0;
+  if (a.w_in_smem) smem += wbytes;
   LAUNCH(encoder_fwd_kernel, grid, 256, smem, st, a);
   LAUNCH(context_mask_kernel, gs_blocks(n), 256, 0, st, M.fbuf("enc_out"), d_lmask, d.B, d.U, d.C,
          M.cfg.encoder_time_axis, M.fbuf("ctx"), 0);
@@ -1116,7 +1125,10 @@ static void encoder_bwd(parrot_model& M, const float* d_lmask, cudaStream_t st) 
   LAUNCH(context_mask_kernel, gs_blocks(n), 256, 0, st, M.fbuf("enc_dout"), d_lmask, d.B, d.U, d.C,
          M.cfg.encoder_time_axis, M.fbuf("dctx"), 1);
   dim3 grid(cdiv(a.N, ENC_ROWS), 2);
-  const size_t smem = (size_t)ENC_ROWS * E * 5 * 4;
+  size_t smem = (size_t)ENC_ROWS * E * 5 * 4;
+  const size_t wbytes = (size_t)3 * E * E * 4;
+  a.w_in_smem = (smem + wbytes <= 220 * 1024) ? 1 : 0;
+  if (a.w_in_smem) smem += wbytes;
   LAUNCH(encoder_bwd_kernel, grid, 256, smem, st, a);
   const long long LNn = (long long)a.L * a.N;
   const char* dn[2] = {"forward", "backward"};
@@ -1558,6 +1570,11 @@ int parrot_create(const parrot_config* cfg, float* d_params, float* d_grads, voi
       const float one = 1.0f;
       CK(cudaMemcpyAsync(M->fbuf("cost") + 4, &one, 4, cudaMemcpyHostToDevice, st));
       ensure_kernel_attrs();
+      {
+        int dev = 0;
+        CK(cudaGetDevice(&dev));
+        CK(cudaDeviceGetAttribute(&M->sm_count, cudaDevAttrMultiProcessorCount, dev));
+      }
       CK(cudaStreamSynchronize(st));  // host-side tables are read by the copies above
       M->dirty = true;
     } catch (...) {
@@ -1587,6 +1604,31 @@ int parrot_pack_weights(parrot_model* m, void* stream) {
 int parrot_mark_params_dirty(parrot_model* m) {
   m->dirty = true;
   return 0;
+}
+/* debug: launch table `name` `reps` times back to back at scan tick `tick`; returns the average milliseconds per
+ * launch.  If d_timeline is not null, the LAST launch writes [cta][16] globaltimer stamps there. */
+int parrot_debug_time_table(parrot_model* m, const char* name, int tick, int reverse, int reps, float* avg_ms,
+                            unsigned long long* d_timeline, void* stream) {
+  return guard([&] {
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    const bool plain = m->tables.at(name).n_cols == NT;
+    const int T = plain ? 1 : m->d.T;
+    run_table(*m, name, tick, T, reverse, st);
+    CK(cudaEventRecord(e0, st));
+    for (int i = 0; i < reps; ++i) {
+      if (i == reps - 1) m->timeline = d_timeline;
+      run_table(*m, name, tick, T, reverse, st);
+    }
+    m->timeline = nullptr;
+    CK(cudaEventRecord(e1, st));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    *avg_ms = ms / reps;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+  });
 }
 int parrot_set_profiling(parrot_model* m, int enable) {
   return guard([&] {

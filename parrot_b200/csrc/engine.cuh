@@ -129,7 +129,19 @@ struct EngineParams {
   int reverse;    // 0: t = tick - lag ; 1: t = (T - 1) - (tick - lag)
   float* split_scratch;        // [group][part][n_cols][128] partial tiles
   unsigned int* split_count;   // [group] arrival counters (zero between launches)
+  int coop_epilogue;           // 1: all parts of a split tile share the final epilogue (needs <= 1 job per CTA)
+  unsigned long long* timeline;  // debug: [cta][16] globaltimer stamps at pipeline milestones (or null)
 };
+
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define TL(slot)                                                              \
+  do {                                                                        \
+    if (P.timeline) P.timeline[(size_t)blockIdx.x * 16 + (slot)] = gtime();   \
+  } while (0)
 
 __device__ __forceinline__ int job_time(const EngineParams& P, const Job& jb) {
   int t = P.tick - jb.lag;
@@ -162,6 +174,7 @@ __device__ __forceinline__ void job_kb_range(const Job& jb, int total_kb, int& l
 
 // ------------------------------------------------------------------ epilogues
 // Thread <-> output row (feature).  v[j] is the accumulator for sample n_base + j.
+template <int W>
 __device__ __forceinline__ void epi_plain(const Job& jb, int t, int row, int n_base, int ncols,
                                           const float* v) {
   const PlainArgs& a = jb.pa;
@@ -170,7 +183,7 @@ __device__ __forceinline__ void epi_plain(const Job& jb, int t, int row, int n_b
   const float bias = a.bias ? a.bias[f] : 0.0f;
   float* out = a.out ? a.out + (long long)t * a.out_tstride : nullptr;
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
+  for (int j = 0; j < W; ++j) {
     if (j >= ncols) break;
     const int n = jb.n0 + n_base + j;
     if (n >= a.n_total) break;
@@ -199,6 +212,7 @@ __device__ __forceinline__ void epi_plain(const Job& jb, int t, int row, int n_b
 // forward scan, gates tile: rows [0, 2H) of [update | reset]   (model.py:659-662)
 // All epilogues below are written as fully unrolled loops over the 32 columns of a TMEM chunk with the
 // global loads issued ahead of the arithmetic (32 independent requests in flight per thread).
+template <int W>
 __device__ __forceinline__ void epi_gates(const Job& jb, const ScanCtx& c, int t, int row, int n_base,
                                           int ncols, const float* v) {
   if (row >= jb.m_valid) return;
@@ -206,16 +220,16 @@ __device__ __forceinline__ void epi_gates(const Job& jb, const ScanCtx& c, int t
   const int H = c.H, f = jb.row0 + row;
   const bool is_z = f < H;
   const int fr = is_z ? f : f - H;
-  float pre[32], hp[32];
+  float pre[W], hp[W];
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
+  for (int j = 0; j < W; ++j) {
     const int b = n_base + j;
     const bool ok = j < ncols && b < c.B;
     pre[j] = ok ? __ldg(L.base + (long long)b * 3 * H + H + f) : 0.0f;
     hp[j] = (ok && !is_z) ? L.h[((long long)t * c.B + b) * H + fr] : 0.0f;
   }
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
+  for (int j = 0; j < W; ++j) {
     const int b = n_base + j;
     if (j < ncols && b < c.B) {
       const float g = sigmoidf_exact(v[j] + pre[j]);
@@ -235,14 +249,15 @@ __device__ __forceinline__ void epi_gates(const Job& jb, const ScanCtx& c, int t
 }
 
 // forward scan, candidate tile: rows [0, H)
+template <int W>
 __device__ __forceinline__ void epi_cand(const Job& jb, const ScanCtx& c, int t, int row, int n_base,
                                          int ncols, const float* v) {
   if (row >= jb.m_valid) return;
   const LayerBuf& L = c.L[jb.layer];
   const int H = c.H, f = jb.row0 + row;
-  float pre[32], zz[32], hp[32];
+  float pre[W], zz[W], hp[W];
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
+  for (int j = 0; j < W; ++j) {
     const int b = n_base + j;
     const bool ok = j < ncols && b < c.B;
     const long long o = ((long long)t * c.B + b) * H + f;
@@ -251,7 +266,7 @@ __device__ __forceinline__ void epi_cand(const Job& jb, const ScanCtx& c, int t,
     hp[j] = ok ? L.h[o] : 0.0f;
   }
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
+  for (int j = 0; j < W; ++j) {
     const int b = n_base + j;
     if (j < ncols && b < c.B) {
       const float cc = tanhf(v[j] + pre[j]);
@@ -272,14 +287,15 @@ __device__ __forceinline__ void epi_cand(const Job& jb, const ScanCtx& c, int t,
 // Finishes the GRU step backward for those features:
 //   dr = drh * h_prev ; dh_prev += drh * r ; da_g[reset half] = dr r (1-r) -> planes + fp32
 // (the update half of da_g and da_c come from the elementwise pre-pass, gru_bwd_pre_kernel)
+template <int W>
 __device__ __forceinline__ void epi_bwd_rh(const Job& jb, const ScanCtx& c, int t, int row, int n_base,
                                            int ncols, const float* v) {
   if (row >= jb.m_valid) return;
   const LayerBuf& L = c.L[jb.layer];
   const int H = c.H, f = jb.row0 + row;
-  float rr[32], hp[32], dh[32];
+  float rr[W], hp[W], dh[W];
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
+  for (int j = 0; j < W; ++j) {
     const int b = n_base + j;
     const bool ok = j < ncols && b < c.B;
     const long long o = ((long long)t * c.B + b) * H + f;
@@ -288,7 +304,7 @@ __device__ __forceinline__ void epi_bwd_rh(const Job& jb, const ScanCtx& c, int 
     dh[j] = ok ? L.dh[o] : 0.0f;
   }
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
+  for (int j = 0; j < W; ++j) {
     const int b = n_base + j;
     if (j < ncols && b < c.B) {
       const long long o = ((long long)t * c.B + b) * H + f;
@@ -308,6 +324,7 @@ __device__ __forceinline__ void epi_bwd_rh(const Job& jb, const ScanCtx& c, int 
 
 // backward scan: accumulate a dgrad tile into a carried gradient buffer.
 //   aux = 0..2 : dh of layer aux, slot = t + jb.pa.n_pad(slot offset) ; aux = 3 : dw
+template <int W>
 __device__ __forceinline__ void epi_bwd_state(const Job& jb, const ScanCtx& c, int t, int row, int n_base,
                                               int ncols, const float* v) {
   if (row >= jb.m_valid) return;
@@ -320,27 +337,29 @@ __device__ __forceinline__ void epi_bwd_state(const Job& jb, const ScanCtx& c, i
   } else {
     dst = c.L[jb.aux].dh; F = c.H;
   }
-  float old[32];
+  float old[W];
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
+  for (int j = 0; j < W; ++j) {
     const int b = n_base + j;
     old[j] = (j < ncols && b < c.B) ? dst[((long long)slot * c.B + b) * F + f] : 0.0f;
   }
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
+  for (int j = 0; j < W; ++j) {
     const int b = n_base + j;
     if (j < ncols && b < c.B) dst[((long long)slot * c.B + b) * F + f] = old[j] + v[j];
   }
 }
 
+// W = number of columns held in v[] (compile time: the loops are fully unrolled over W)
+template <int W>
 __device__ __forceinline__ void run_epilogue(const Job& jb, const ScanCtx* ctx, int t, int row, int n_base,
                                              int ncols, const float* v) {
   switch (jb.epi) {
-    case EPI_PLAIN: epi_plain(jb, t, row, n_base, ncols, v); break;
-    case EPI_GATES: epi_gates(jb, *ctx, t, row, n_base, ncols, v); break;
-    case EPI_CAND: epi_cand(jb, *ctx, t, row, n_base, ncols, v); break;
-    case EPI_BWD_RH: epi_bwd_rh(jb, *ctx, t, row, n_base, ncols, v); break;
-    case EPI_BWD_STATE: epi_bwd_state(jb, *ctx, t, row, n_base, ncols, v); break;
+    case EPI_PLAIN: epi_plain<W>(jb, t, row, n_base, ncols, v); break;
+    case EPI_GATES: epi_gates<W>(jb, *ctx, t, row, n_base, ncols, v); break;
+    case EPI_CAND: epi_cand<W>(jb, *ctx, t, row, n_base, ncols, v); break;
+    case EPI_BWD_RH: epi_bwd_rh<W>(jb, *ctx, t, row, n_base, ncols, v); break;
+    case EPI_BWD_STATE: epi_bwd_state<W>(jb, *ctx, t, row, n_base, ncols, v); break;
   }
 }
 
@@ -353,6 +372,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) job_kernel_tc(const EngineP
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int n_cols = P.n_cols;
+  if (threadIdx.x == 0) TL(0);
   const uint32_t a_bytes = TILE_M * KB * 2;          // 16 KB
   const uint32_t b_bytes = (uint32_t)n_cols * KB * 2;
   const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
@@ -387,6 +407,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) job_kernel_tc(const EngineP
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) TL(1);
 
   if (warp == 0) {
     // ------------------------------------------------ TMA producer
@@ -424,6 +445,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) job_kernel_tc(const EngineP
           }
         }
       }
+      TL(2);
     }
   } else if (warp == 1) {
     // ------------------------------------------------ MMA issuer
@@ -469,6 +491,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) job_kernel_tc(const EngineP
       }
       ++it;
     }
+    if (lane == 0) TL(3);
   } else {
     // ------------------------------------------------ epilogue warps 2..5
     const int q = warp & 3;  // TMEM lane quarter this warp may access
@@ -489,18 +512,20 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) job_kernel_tc(const EngineP
         mbar_wait(&tfull_bar[buf], use & 1);
         tc_fence_after();
       }
+      if (threadIdx.x == 64) TL(4);
       if (jb.ksplit <= 1) {
         for (int n0 = 0; n0 < n_cols; n0 += 32) {
           float v[32];
           const int nc = (n_cols - n0 >= 32) ? 32 : 16;
-          if (nc == 32) tmem_ld_32x32(taddr + n0, v);
-          else {
+          if (nc == 32) {
+            tmem_ld_32x32(taddr + n0, v);
+            tmem_ld_wait();
+            run_epilogue<32>(jb, P.ctx, t, row, n0, nc, v);
+          } else {
             tmem_ld_32x16(taddr + n0, v);
-#pragma unroll
-            for (int i = 16; i < 32; ++i) v[i] = 0.0f;
+            tmem_ld_wait();
+            run_epilogue<16>(jb, P.ctx, t, row, n0, nc, v);
           }
-          tmem_ld_wait();
-          run_epilogue(jb, P.ctx, t, row, n0, nc, v);
         }
       } else {
         // park the partial tile: scratch[group][part][col][row]  (row fastest -> coalesced)
@@ -526,34 +551,70 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) job_kernel_tc(const EngineP
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty_bar[buf]);
       }
+      if (threadIdx.x == 64) TL(5);
       if (jb.ksplit > 1) {
         __threadfence();
         asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps
-        if (warp == 2 && lane == 0) {
-          const unsigned int old = atomicAdd(P.split_count + jb.group, 1u);
-          const bool last = old == (unsigned int)(jb.ksplit - 1);
-          if (last) P.split_count[jb.group] = 0u;   // ready for the next launch
-          *split_flag = last ? 1u : 0u;
-        }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (*split_flag) {
-          __threadfence();
-          const float* base = P.split_scratch + (size_t)jb.group * MAX_KSPLIT * (size_t)n_cols * TILE_M;
-          for (int n0 = 0; n0 < n_cols; n0 += 32) {
-            float v[32];
-            const int nc = (n_cols - n0 >= 32) ? 32 : 16;
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = 0.0f;
-            for (int p = 0; p < jb.ksplit; ++p) {
-              const float* pp = base + (size_t)p * n_cols * TILE_M;
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (i < nc) v[i] += __ldcg(pp + (size_t)(n0 + i) * TILE_M + row);
-            }
-            run_epilogue(jb, P.ctx, t, row, n0, nc, v);
+        const float* base = P.split_scratch + (size_t)jb.group * MAX_KSPLIT * (size_t)n_cols * TILE_M;
+        int c_lo = 0, c_hi = 0;
+        if (P.coop_epilogue) {
+          // Every part of the tile finishes a slice of its columns once all parts have arrived.  Safe because
+          // the launch has at most one job per CTA and all CTAs are co-resident (grid <= SM count).
+          if (warp == 2 && lane == 0) {
+            atomicAdd(P.split_count + jb.group, 1u);
+            unsigned int seen, spins = 0;
+            do {
+              asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(P.split_count + jb.group) : "memory");
+              if (++spins > (1u << 24)) { printf("parrot_b200: split-K arrival wait timed out\n"); __trap(); }
+            } while ((seen & 0xffffu) < (unsigned int)jb.ksplit);
           }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (threadIdx.x == 64) TL(6);
+          c_lo = (n_cols * jb.kpart) / jb.ksplit;
+          c_hi = (n_cols * (jb.kpart + 1)) / jb.ksplit;
+        } else {
+          if (warp == 2 && lane == 0) {
+            const unsigned int old = atomicAdd(P.split_count + jb.group, 1u);
+            const bool last = old == (unsigned int)(jb.ksplit - 1);
+            if (last) P.split_count[jb.group] = 0u;   // ready for the next launch
+            *split_flag = last ? 1u : 0u;
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (threadIdx.x == 64) TL(6);
+          if (*split_flag) { c_lo = 0; c_hi = n_cols; }
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");   // split_flag is reused by the next job
+        __threadfence();
+        for (int n0 = c_lo; n0 < c_hi; n0 += 8) {
+          float v[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = 0.0f;
+          const int nc = min(8, c_hi - n0);
+          // all parts in part order (deterministic); 8 columns x all parts of loads in flight
+          float x[MAX_KSPLIT][8];
+#pragma unroll
+          for (int pp = 0; pp < MAX_KSPLIT; ++pp) {
+            const float* src = base + (size_t)pp * n_cols * TILE_M;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              x[pp][i] = (pp < jb.ksplit && i < nc) ? __ldcg(src + (size_t)(n0 + i) * TILE_M + row) : 0.0f;
+          }
+#pragma unroll
+          for (int pp = 0; pp < MAX_KSPLIT; ++pp)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] += x[pp][i];
+          run_epilogue<8>(jb, P.ctx, t, row, n0, nc, v);
+        }
+        if (threadIdx.x == 64) TL(7);
+        if (P.coop_epilogue) {
+          // the last part to finish resets the arrival counter for the next launch
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (warp == 2 && lane == 0) {
+            const unsigned int old = atomicAdd(P.split_count + jb.group, 0x10000u);
+            if ((old >> 16) == (unsigned int)(jb.ksplit - 1)) P.split_count[jb.group] = 0u;
+          }
+        } else {
+          asm volatile("bar.sync 1, 128;" ::: "memory");   // split_flag is reused by the next job
+        }
       }
       if (have_acc) ++it;   // accumulator buffers advance only when one was used (mirrors the MMA warp)
     }
@@ -562,6 +623,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) job_kernel_tc(const EngineP
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, 512);
+  if (threadIdx.x == 0) TL(8);
 }
 
 // ------------------------------------------------------------------ SIMT twin
@@ -618,7 +680,7 @@ __global__ void __launch_bounds__(128) job_kernel_simt(const EngineParams P) {
           }
         }
       }
-      run_epilogue(jb, P.ctx, t, tid, n0, nc, acc);
+      run_epilogue<32>(jb, P.ctx, t, tid, n0, nc, acc);
     }
   }
 }

@@ -935,6 +935,7 @@ struct EncArgs {
   const float* dout;      // [L][N][2E]
   float* dxi[2]; float* dxg[2];
   float* ds0[2];          // [N][E] gradient wrt the initial state rows (summed later)
+  int w_in_smem;          // stage the recurrent weights in shared memory (they fit: 3 E^2 floats)
 };
 
 __global__ void __launch_bounds__(256) encoder_fwd_kernel(const EncArgs a) {
@@ -946,6 +947,16 @@ __global__ void __launch_bounds__(256) encoder_fwd_kernel(const EncArgs a) {
   float* rs = s + ENC_ROWS * E;     // [ENC_ROWS][E]
   float* g = rs + ENC_ROWS * E;     // [ENC_ROWS][2E]
   const int tid = threadIdx.x;
+  // recurrent weights staged in shared memory once (192 KB at E = 128) when they fit
+  const float* Wg = a.Wg[dir];
+  const float* Ws = a.Ws[dir];
+  if (a.w_in_smem) {
+    float* wg_s = g + ENC_ROWS * 2 * E;
+    float* ws_s = wg_s + 2 * E * E;
+    for (int i = tid; i < 2 * E * E; i += blockDim.x) wg_s[i] = Wg[i];
+    for (int i = tid; i < E * E; i += blockDim.x) ws_s[i] = Ws[i];
+    Wg = wg_s; Ws = ws_s;
+  }
   for (int i = tid; i < ENC_ROWS * E; i += blockDim.x) s[i] = a.s0[dir][i % E];
   __syncthreads();
   for (int step = 0; step < a.L; ++step) {
@@ -956,7 +967,7 @@ __global__ void __launch_bounds__(256) encoder_fwd_kernel(const EncArgs a) {
 #pragma unroll
       for (int n = 0; n < ENC_ROWS; ++n) acc[n] = 0.0f;
       for (int k = 0; k < E; ++k) {
-        const float w = a.Wg[dir][(long long)k * 2 * E + j];
+        const float w = Wg[(long long)k * 2 * E + j];
 #pragma unroll
         for (int n = 0; n < ENC_ROWS; ++n) acc[n] = fmaf(s[n * E + k], w, acc[n]);
       }
@@ -981,7 +992,7 @@ __global__ void __launch_bounds__(256) encoder_fwd_kernel(const EncArgs a) {
 #pragma unroll
       for (int n = 0; n < ENC_ROWS; ++n) acc[n] = 0.0f;
       for (int k = 0; k < E; ++k) {
-        const float w = a.Ws[dir][(long long)k * E + j];
+        const float w = Ws[(long long)k * E + j];
 #pragma unroll
         for (int n = 0; n < ENC_ROWS; ++n) acc[n] = fmaf(rs[n * E + k], w, acc[n]);
       }
@@ -1017,6 +1028,14 @@ __global__ void __launch_bounds__(256) encoder_bwd_kernel(const EncArgs a) {
   float* dag = dac + ENC_ROWS * E;     // [ENC_ROWS][2E]
   float* dsn = dag + ENC_ROWS * 2 * E; // [ENC_ROWS][E] next ds
   const int tid = threadIdx.x;
+  // transposed weights in shared memory: WsT[j][k] = Ws[k][j], WgT[j][k] = Wg[k][j]  (k fastest: the threads of
+  // a warp own consecutive k, so the reads below are conflict free; from global they were 32-way uncoalesced)
+  float* wsT = dsn + ENC_ROWS * E;
+  float* wgT = wsT + E * E;
+  if (a.w_in_smem) {
+    for (int i = tid; i < E * E; i += blockDim.x) { const int k = i / E, j = i % E; wsT[j * E + k] = a.Ws[dir][i]; }
+    for (int i = tid; i < 2 * E * E; i += blockDim.x) { const int k = i / (2 * E), j = i % (2 * E); wgT[j * E + k] = a.Wg[dir][i]; }
+  }
   for (int i = tid; i < ENC_ROWS * E; i += blockDim.x) ds[i] = 0.0f;
   __syncthreads();
   for (int step = a.L - 1; step >= 0; --step) {
@@ -1042,9 +1061,14 @@ __global__ void __launch_bounds__(256) encoder_bwd_kernel(const EncArgs a) {
     // d(rs)[n][k] = sum_j dac[n][j] * Ws[k][j]
     for (int e = tid; e < rows * E; e += blockDim.x) {
       const int n = e / E, k = e % E;
-      const float* wr = a.Ws[dir] + (long long)k * E;
       float acc = 0.0f;
-      for (int j = 0; j < E; ++j) acc = fmaf(dac[n * E + j], wr[j], acc);
+      if (a.w_in_smem) {
+#pragma unroll 8
+        for (int j = 0; j < E; ++j) acc = fmaf(dac[n * E + j], wsT[j * E + k], acc);
+      } else {
+        const float* wr = a.Ws[dir] + (long long)k * E;
+        for (int j = 0; j < E; ++j) acc = fmaf(dac[n * E + j], wr[j], acc);
+      }
       const long long o = ((long long)i * a.N + n0 + n) * E + k;
       const float r = a.r[dir][o], sp = a.sprev[dir][o];
       const float dr = acc * sp;
@@ -1057,9 +1081,14 @@ __global__ void __launch_bounds__(256) encoder_bwd_kernel(const EncArgs a) {
     // ds[n][k] += sum_j dag[n][j] * Wg[k][j]
     for (int e = tid; e < rows * E; e += blockDim.x) {
       const int n = e / E, k = e % E;
-      const float* wr = a.Wg[dir] + (long long)k * 2 * E;
       float acc = 0.0f;
-      for (int j = 0; j < 2 * E; ++j) acc = fmaf(dag[n * 2 * E + j], wr[j], acc);
+      if (a.w_in_smem) {
+#pragma unroll 8
+        for (int j = 0; j < 2 * E; ++j) acc = fmaf(dag[n * 2 * E + j], wgT[j * E + k], acc);
+      } else {
+        const float* wr = a.Wg[dir] + (long long)k * 2 * E;
+        for (int j = 0; j < 2 * E; ++j) acc = fmaf(dag[n * 2 * E + j], wr[j], acc);
+      }
       ds[e] = dsn[e] + acc;
     }
     __syncthreads();
