@@ -89,6 +89,8 @@ int parrot_mark_params_dirty(parrot_model* m);
  * ("fwdA", "fwdB", "bwd1", "bwd2", "readout", "output", "dread", "dh_readout", "wgrad", "attn_fwd", "attn_bwd",
  * "gru_bwd_pre", "sec_*" for whole sections).  parrot_get_profile synchronises the device. */
 int parrot_set_profiling(parrot_model* m, int enable);
+/* debug: the persistent forward scan writes [cta][bars][2] globaltimer stamps (barrier passed, arrival) */
+int parrot_debug_set_stamps(parrot_model* m, unsigned long long* d_stamps, int bars);
 /* debug / measurement: average time of one engine table launched back to back (optional per-CTA timeline) */
 int parrot_debug_time_table(parrot_model* m, const char* name, int tick, int reverse, int reps, float* avg_ms,
                             unsigned long long* d_timeline, void* stream);

@@ -31,7 +31,7 @@ class ParrotConfig(C.Structure):
 SYMBOLS = [
     'parrot_last_error', 'parrot_abi_version', 'parrot_param_count', 'parrot_param_info',
     'parrot_workspace_bytes', 'parrot_create', 'parrot_destroy', 'parrot_buffer_info',
-    'parrot_pack_weights', 'parrot_mark_params_dirty', 'parrot_set_profiling', 'parrot_get_profile', 'parrot_debug_time_table', 'parrot_encoder_fwd', 'parrot_encoder_bwd',
+    'parrot_pack_weights', 'parrot_mark_params_dirty', 'parrot_set_profiling', 'parrot_get_profile', 'parrot_debug_time_table', 'parrot_debug_set_stamps', 'parrot_encoder_fwd', 'parrot_encoder_bwd',
     'parrot_decoder_scan_fwd', 'parrot_decoder_scan_bwd', 'parrot_readout_emit_fwd',
     'parrot_readout_emit_bwd', 'parrot_attention_step', 'parrot_compute_cost', 'parrot_backward',
     'parrot_sample_scan', 'parrot_adam_clip_step', 'parrot_gemm_nt',
@@ -86,6 +86,7 @@ def load():
     lib.parrot_adam_clip_step.argtypes = [vp, vp, vp, vp, C.c_int64, C.c_float, vp, C.c_float, C.c_float,
                                           C.c_float, C.c_float, C.c_float, C.c_int64, vp, vp, vp]
     lib.parrot_debug_time_table.argtypes = [vp, C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), vp, vp]
+    lib.parrot_debug_set_stamps.argtypes = [vp, vp, C.c_int]
     lib.parrot_set_profiling.argtypes = [vp, C.c_int]
     lib.parrot_get_profile.argtypes = [vp, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     lib.parrot_gemm_nt.argtypes = [vp, vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, C.c_size_t, vp]

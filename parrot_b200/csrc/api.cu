@@ -271,18 +271,22 @@ struct parrot_model {
   int max_groups = 0;
   size_t max_split_floats = 0;
   unsigned long long* timeline = nullptr;
+  unsigned long long* stamps = nullptr;   // debug: persistent forward scan per-barrier stamps
+  int stamp_bars = 0;
   int sm_count = 0;
   float* d_split_scratch = nullptr;
   unsigned int* d_split_count = nullptr;
+  unsigned int* d_gridbar = nullptr;
   bool dirty = true;
   float last_start_flag = 1.0f;
   bool have_fwd = false;
   // optional per-launch timing (bench.py roofline): CUDA events around every tagged launch
-  bool profiling = false;
+  int profiling = 0;   // 0 off, 1 section events only (persistent kernels stay on), 2 per-launch events (per-phase launches)
   struct ProfRec { std::string key; cudaEvent_t e0, e1; };
   std::vector<ProfRec> prof;
   cudaEvent_t prof_begin(const std::string& key, cudaStream_t st) {
     if (!profiling) return nullptr;
+    if (profiling < 2 && key.compare(0, 4, "sec_") != 0) return nullptr;
     ProfRec r;
     r.key = key;
     cudaEventCreate(&r.e0); cudaEventCreate(&r.e1);
@@ -921,6 +925,7 @@ static void build_device_tables(parrot_model& M) {
   M.d_ctx = (ScanCtx*)M.alloc("dev_ctx", sizeof(ScanCtx));
   M.d_split_scratch = (float*)M.alloc("split_scratch", std::max<size_t>(M.max_split_floats, 1) * 4);
   M.d_split_count = (unsigned int*)M.alloc("split_count", (size_t)std::max(M.max_groups, 1) * 4);
+  M.d_gridbar = (unsigned int*)M.alloc("gridbar", 64);
 }
 
 static void upload_tables(parrot_model& M, cudaStream_t st) {
@@ -934,6 +939,8 @@ static void ensure_kernel_attrs() {
   static bool done = false;
   if (done) return;
   CK(cudaFuncSetAttribute(job_kernel_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES + 1024));
+  CK(cudaFuncSetAttribute(scan_fwd_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES + 1024 + ATT_SMEM_BYTES));
+  CK(cudaFuncSetAttribute(scan_bwd_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES + 1024 + ATT_SMEM_BYTES));
   CK(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
   CK(cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   CK(cudaFuncSetAttribute(encoder_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
@@ -1185,7 +1192,7 @@ static void init_slots(parrot_model& M, bool use_initial, cudaStream_t st) {
   else CK(cudaMemcpyAsync(M.fbuf("kappa"), M.fbuf("last_k"), (size_t)d.B * d.A * 4, cudaMemcpyDeviceToDevice, st));
 }
 
-static void attention_step(parrot_model& M, int t, bool sampling, cudaStream_t st) {
+static AttnFwdArgs attn_fwd_args(parrot_model& M, int t, bool sampling) {
   const Dims& d = M.d;
   AttnFwdArgs a;
   a.B = d.B; a.U = d.U; a.C = d.C; a.A = d.A; a.H = d.H; a.Np = d.Np;
@@ -1205,10 +1212,87 @@ static void attention_step(parrot_model& M, int t, bool sampling, cudaStream_t s
   a.phi_out = M.fbuf("phi") + (long long)t * d.B * d.U;
   a.ab_out = M.fbuf("ab") + (long long)t * d.B * 2 * d.A;
   a.e_out = M.fbuf("att_e") + (long long)t * d.B * 3 * d.A;
+  return a;
+}
+static void attention_step(parrot_model& M, int t, bool sampling, cudaStream_t st) {
+  const Dims& d = M.d;
+  AttnFwdArgs a = attn_fwd_args(M, t, sampling);
   const size_t smem = (size_t)(rup(d.H, 4) + 2 * rup(3 * d.A, 4) + rup(d.U, 4) + 8 * d.C) * 4;
   cudaEvent_t pe = M.prof_begin("attn_fwd", st);
   LAUNCH(attention_fwd_kernel, d.B, 256, smem, st, a);
   parrot_model::prof_end(pe, st);
+}
+
+static bool use_persistent(parrot_model& M) {
+  static int env = -1;
+  if (env < 0) {
+    const char* e = getenv("PARROT_NO_PERSISTENT");
+    env = (e && e[0] && e[0] != '0') ? 0 : 1;
+  }
+  const Dims& d = M.d;
+  if (!env || M.cfg.gemm_impl == 1 || M.profiling >= 2 || M.sm_count < 148) return false;
+  const size_t att_f = (size_t)rup(d.H, 4) + 2 * rup(3 * d.A, 4) + rup(d.U, 4) + 6 * (size_t)d.C;
+  const size_t att_b = (size_t)d.C + d.U + 3 * d.A * 8 + 3 * d.A;
+  if (std::max(att_f, att_b) * 4 > (size_t)ATT_SMEM_BYTES) return false;
+  for (const char* nm : {"fwdA", "fwdB", "bwd1", "bwd2"}) {
+    auto it = M.tables.find(nm);
+    if (it != M.tables.end() && it->second.count > 148) return false;
+  }
+  return true;
+}
+
+static EngineParams table_params(parrot_model& M, const std::string& name, int reverse) {
+  const Table& t = M.tables.at(name);
+  EngineParams P;
+  P.jobs = M.d_jobs + t.off; P.njobs = t.count; P.maps = M.d_maps; P.raws = M.d_raws; P.ctx = M.d_ctx;
+  P.tick = 0; P.T = M.d.T; P.n_cols = t.n_cols; P.reverse = reverse;
+  P.split_scratch = M.d_split_scratch; P.split_count = M.d_split_count;
+  P.timeline = nullptr; P.coop_epilogue = 1;
+  return P;
+}
+
+static AttnFwdArgs attn_fwd_args(parrot_model& M, int t, bool sampling);
+static AttnBwdArgs attn_bwd_args(parrot_model& M, int t);
+
+static void scan_fwd_persistent_launch(parrot_model& M, cudaStream_t st) {
+  const Dims& d = M.d;
+  ScanFwdParams S;
+  S.A = table_params(M, "fwdA", 0);
+  S.B = table_params(M, "fwdB", 0);
+  S.att = attn_fwd_args(M, 0, false);
+  S.s_h1 = (long long)d.B * d.H; S.s_k = (long long)d.B * d.A; S.s_w = (long long)d.B * d.C;
+  S.s_wp = (long long)d.Np * M.planes.at("w").pitch; S.s_phi = (long long)d.B * d.U;
+  S.s_ab = (long long)d.B * 2 * d.A; S.s_e = (long long)d.B * 3 * d.A;
+  S.T = d.T;
+  S.gridbar = M.d_gridbar;
+  S.stamps = M.stamps; S.stamp_bars = M.stamp_bars;
+  CK(cudaMemsetAsync(M.d_gridbar, 0, 4, st));
+  void* args[] = {&S};
+  g_ctx = "scan_fwd_persistent";
+  CK(cudaLaunchCooperativeKernel((void*)scan_fwd_persistent, dim3(148), dim3(ENGINE_THREADS), args,
+                                 SMEM_BYTES + 1024 + ATT_SMEM_BYTES, st));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (debug_sync()) CK(cudaStreamSynchronize(st));
+}
+
+static void scan_bwd_persistent_launch(parrot_model& M, cudaStream_t st) {
+  const Dims& d = M.d;
+  ScanBwdParams S;
+  S.B1 = table_params(M, "bwd1", 1);
+  S.B2 = table_params(M, "bwd2", 1);
+  S.att = attn_bwd_args(M, 0);
+  S.s_dw = (long long)d.B * d.C; S.s_ab = (long long)d.B * 2 * d.A; S.s_e = (long long)d.B * 3 * d.A;
+  S.s_k = (long long)d.B * d.A; S.s_dh1 = (long long)d.B * d.H; S.s_datt = (long long)d.B * 3 * d.A;
+  S.s_dattp = (long long)d.Np * M.planes.at("datt").pitch;
+  S.ctx = M.d_ctx; S.T = d.T; S.gridbar = M.d_gridbar;
+  S.stamps = nullptr; S.stamp_bars = 0;
+  CK(cudaMemsetAsync(M.d_gridbar, 0, 4, st));
+  void* args[] = {&S};
+  g_ctx = "scan_bwd_persistent";
+  CK(cudaLaunchCooperativeKernel((void*)scan_bwd_persistent, dim3(148), dim3(ENGINE_THREADS), args,
+                                 SMEM_BYTES + 1024 + ATT_SMEM_BYTES, st));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (debug_sync()) CK(cudaStreamSynchronize(st));
 }
 
 static void scan_fwd(parrot_model& M, const float* d_features, const float* d_noise, float level, float start_flag,
@@ -1223,6 +1307,10 @@ static void scan_fwd(parrot_model& M, const float* d_features, const float* d_no
   }
   init_slots(M, start_flag != 0.0f, st);
   M.last_start_flag = start_flag;
+  if (use_persistent(M)) {
+    scan_fwd_persistent_launch(M, st);
+    return;
+  }
   // layer wavefront: tick tau runs layer 1 at step tau, layer 2 at tau-1, layer 3 at tau-2
   for (int tick = 0; tick < d.T + 2; ++tick) {
     run_table(M, "fwdA", tick, d.T, 0, st);
@@ -1300,7 +1388,7 @@ static void readout_emit_bwd(parrot_model& M, int unnormalised, cudaStream_t st)
   run_table(M, "dh_readout", 0, 1, 0, st);
 }
 
-static void attention_bwd_step(parrot_model& M, int t, cudaStream_t st) {
+static AttnBwdArgs attn_bwd_args(parrot_model& M, int t) {
   const Dims& d = M.d;
   AttnBwdArgs a;
   a.B = d.B; a.U = d.U; a.C = d.C; a.A = d.A; a.H = d.H; a.Np = d.Np; a.Ap = d.Ap;
@@ -1317,6 +1405,11 @@ static void attention_bwd_step(parrot_model& M, int t, cudaStream_t st) {
   const Plane& p = M.planes.at("datt");
   a.datt_hi = p.hi + (long long)t * d.Np * p.pitch;
   a.datt_lo = p.lo + (long long)t * d.Np * p.pitch;
+  return a;
+}
+static void attention_bwd_step(parrot_model& M, int t, cudaStream_t st) {
+  const Dims& d = M.d;
+  AttnBwdArgs a = attn_bwd_args(M, t);
   const size_t smem = (size_t)(d.C + d.U + 3 * d.A * 8 + 3 * d.A) * 4;
   cudaEvent_t pe = M.prof_begin("attn_bwd", st);
   LAUNCH(attention_bwd_kernel, d.B, 256, smem, st, a);
@@ -1326,6 +1419,10 @@ static void attention_bwd_step(parrot_model& M, int t, cudaStream_t st) {
 static void scan_bwd(parrot_model& M, cudaStream_t st) {
   const Dims& d = M.d;
   CK(cudaMemsetAsync(M.fbuf("dk_carry"), 0, (size_t)d.B * d.A * 4, st));
+  if (use_persistent(M)) {
+    scan_bwd_persistent_launch(M, st);
+    return;
+  }
   const int blocks = std::min(gs_blocks((long long)d.B * d.H), 148);
   // reverse layer wavefront: tick tau -> layer 3 at s = T-1-tau, layer 2 at s+1, attention + layer 1 at s+2
   for (int tick = 0; tick < d.T + 2; ++tick) {
@@ -1630,9 +1727,13 @@ int parrot_debug_time_table(parrot_model* m, const char* name, int tick, int rev
     cudaEventDestroy(e0); cudaEventDestroy(e1);
   });
 }
+int parrot_debug_set_stamps(parrot_model* m, unsigned long long* d_stamps, int bars) {
+  m->stamps = d_stamps; m->stamp_bars = bars;
+  return 0;
+}
 int parrot_set_profiling(parrot_model* m, int enable) {
   return guard([&] {
-    m->profiling = enable != 0;
+    m->profiling = enable;
     for (auto& r : m->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
     m->prof.clear();
   });

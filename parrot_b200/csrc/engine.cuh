@@ -143,8 +143,8 @@ __device__ __forceinline__ unsigned long long gtime() {
     if (P.timeline) P.timeline[(size_t)blockIdx.x * 16 + (slot)] = gtime();   \
   } while (0)
 
-__device__ __forceinline__ int job_time(const EngineParams& P, const Job& jb) {
-  int t = P.tick - jb.lag;
+__device__ __forceinline__ int job_time(const EngineParams& P, const Job& jb, int tick) {
+  int t = tick - jb.lag;
   if (P.reverse) t = (P.T - 1) - t;
   return t;
 }
@@ -363,38 +363,47 @@ __device__ __forceinline__ void run_epilogue(const Job& jb, const ScanCtx* ctx, 
   }
 }
 
-// ---------------------------------------------------------- tensor-core kernel
-__global__ void __launch_bounds__(ENGINE_THREADS, 1) job_kernel_tc(const EngineParams P) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // 1024-byte alignment is required by the 128B swizzle atoms
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+// ---------------------------------------------------------- tensor-core pipeline
+// Shared-memory carve-up and the role-private running state.  The three role loops below are shared by
+// the one-launch-per-phase kernel (job_kernel_tc) and the persistent scan kernels (kernels.cuh), which keep
+// the pipeline state alive across phases and ticks.
+struct Pipe {
+  uint8_t* tiles;
+  uint64_t *full_bar, *empty_bar, *tfull_bar, *tempty_bar;
+  uint32_t tmem_base;
+  volatile uint32_t* split_flag;
+  int nstages, n_cols;
+  uint32_t a_bytes, b_bytes, stage_bytes;
+  int stage;       // producer / MMA: ring position
+  uint32_t phase;  // producer / MMA: ring parity
+  int it;          // MMA / epilogue: accumulator uses so far
+};
 
+// returns the first byte after the pipeline's shared memory (1024-aligned ring + barriers)
+__device__ __forceinline__ uint8_t* pipe_setup(Pipe& p, uint8_t* smem, int n_cols) {
   const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int n_cols = P.n_cols;
-  if (threadIdx.x == 0) TL(0);
-  const uint32_t a_bytes = TILE_M * KB * 2;          // 16 KB
-  const uint32_t b_bytes = (uint32_t)n_cols * KB * 2;
-  const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
-  int nstages = (SMEM_BYTES - 2048) / (int)stage_bytes;
-  if (nstages > 8) nstages = 8;
-
-  uint8_t* tiles = smem;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)nstages * stage_bytes);
-  uint64_t* empty_bar = full_bar + 8;
-  uint64_t* tfull_bar = empty_bar + 8;   // [2] accumulator ready
-  uint64_t* tempty_bar = tfull_bar + 2;  // [2] accumulator drained
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  volatile uint32_t* split_flag = tmem_slot + 1;
-
+  p.n_cols = n_cols;
+  p.a_bytes = TILE_M * KB * 2;  // 16 KB
+  p.b_bytes = (uint32_t)n_cols * KB * 2;
+  p.stage_bytes = 2 * p.a_bytes + 2 * p.b_bytes;
+  p.nstages = (SMEM_BYTES - 2048) / (int)p.stage_bytes;
+  if (p.nstages > 8) p.nstages = 8;
+  p.tiles = smem;
+  p.full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.nstages * p.stage_bytes);
+  p.empty_bar = p.full_bar + 8;
+  p.tfull_bar = p.empty_bar + 8;    // [2] accumulator ready
+  p.tempty_bar = p.tfull_bar + 2;   // [2] accumulator drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p.tempty_bar + 2);
+  p.split_flag = tmem_slot + 1;
+  p.stage = 0; p.phase = 0; p.it = 0;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < nstages; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+    for (int s = 0; s < p.nstages; ++s) {
+      mbar_init(&p.full_bar[s], 1);
+      mbar_init(&p.empty_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 4);  // one arrive per epilogue warp
+      mbar_init(&p.tfull_bar[s], 1);
+      mbar_init(&p.tempty_bar[s], 4);  // one arrive per epilogue warp
     }
     fence_barrier_init();
     fence_proxy_async_smem();
@@ -406,224 +415,264 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) job_kernel_tc(const EngineP
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  if (threadIdx.x == 0) TL(1);
+  p.tmem_base = *tmem_slot;
+  return smem + SMEM_BYTES;
+}
 
-  if (warp == 0) {
-    // ------------------------------------------------ TMA producer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int j = blockIdx.x; j < P.njobs; j += gridDim.x) {
-        const Job& jb = P.jobs[j];
-        const int t = job_time(P, jb);
-        const int total_kb = job_total_kb(P, jb, t);
-        if (total_kb == 0) continue;
-        int klo, khi, kidx = 0;
-        job_kb_range(jb, total_kb, klo, khi);
-        for (int s = 0; s < jb.nseg; ++s) {
-          const Seg sg = jb.seg[s];
-          if (!seg_valid(P, sg, t)) continue;
-          const CUtensorMap* ma = P.maps + sg.a_map;
-          const CUtensorMap* mb = P.maps + sg.b_map;
-          for (int kb = 0; kb < sg.nkb; ++kb, ++kidx) {
-            if (kidx < klo || kidx >= khi) continue;
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            uint8_t* st = tiles + (size_t)stage * stage_bytes;
-            mbar_expect_tx(&full_bar[stage], stage_bytes);
-            tma_load_2d(st, ma, &full_bar[stage], sg.a_k + kb * KB, sg.a_row);
-            tma_load_2d(st + a_bytes, ma + 1, &full_bar[stage], sg.a_k + kb * KB, sg.a_row);
-            if (sg.b_slot == NO_SLOT) {
-              tma_load_2d(st + 2 * a_bytes, mb, &full_bar[stage], sg.b_k + kb * KB, sg.b_row);
-              tma_load_2d(st + 2 * a_bytes + b_bytes, mb + 1, &full_bar[stage], sg.b_k + kb * KB, sg.b_row);
-            } else {
-              tma_load_3d(st + 2 * a_bytes, mb, &full_bar[stage], sg.b_k + kb * KB, sg.b_row, t + sg.b_slot);
-              tma_load_3d(st + 2 * a_bytes + b_bytes, mb + 1, &full_bar[stage], sg.b_k + kb * KB, sg.b_row,
-                          t + sg.b_slot);
-            }
-            if (++stage == nstages) { stage = 0; phase ^= 1; }
-          }
-        }
-      }
-      TL(2);
-    }
-  } else if (warp == 1) {
-    // ------------------------------------------------ MMA issuer
-    const uint32_t idesc = umma_idesc_bf16(TILE_M, n_cols);
-    int stage = 0;
-    uint32_t phase = 0;
-    int it = 0;
-    for (int j = blockIdx.x; j < P.njobs; j += gridDim.x) {
-      const Job& jb = P.jobs[j];
-      const int t = job_time(P, jb);
-      const int all_kb = job_total_kb(P, jb, t);
-      if (all_kb == 0) continue;
-      int klo, khi;
-      job_kb_range(jb, all_kb, klo, khi);
-      const int total_kb = khi - klo;
-      const int buf = it & 1;
-      const uint32_t use = (uint32_t)(it >> 1);
-      if (total_kb == 0) continue;   // empty split part: no accumulator is used, the epilogue contributes zeros
-      mbar_wait(&tempty_bar[buf], (use & 1) ^ 1);
-      tc_fence_after();
-      const uint32_t tmem_d = tmem_base + (uint32_t)buf * 256u;
-      for (int kbi = 0; kbi < total_kb; ++kbi) {
-        mbar_wait(&full_bar[stage], phase);
-        tc_fence_after();
-        if (lane == 0) {
-          const uint8_t* st = tiles + (size_t)stage * stage_bytes;
-          const uint64_t da_hi = umma_desc_sw128(st);
-          const uint64_t da_lo = umma_desc_sw128(st + a_bytes);
-          const uint64_t db_hi = umma_desc_sw128(st + 2 * a_bytes);
-          const uint64_t db_lo = umma_desc_sw128(st + 2 * a_bytes + b_bytes);
-#pragma unroll
-          for (int k = 0; k < KB / 16; ++k) {
-            const uint64_t adv = (uint64_t)((k * 16 * 2) >> 4);  // 32 bytes per k16 step
-            umma_bf16(tmem_d, da_hi + adv, db_hi + adv, idesc, (kbi | k) != 0);
-            umma_bf16(tmem_d, da_lo + adv, db_hi + adv, idesc, 1);
-            umma_bf16(tmem_d, da_hi + adv, db_lo + adv, idesc, 1);
-          }
-          umma_commit(&empty_bar[stage]);                       // frees the smem slot
-          if (kbi == total_kb - 1) umma_commit(&tfull_bar[buf]);  // accumulator complete
-        }
-        __syncwarp();
-        if (++stage == nstages) { stage = 0; phase ^= 1; }
-      }
-      ++it;
-    }
-    if (lane == 0) TL(3);
-  } else {
-    // ------------------------------------------------ epilogue warps 2..5
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
-    const int row = q * 32 + lane;
-    int it = 0;
-    for (int j = blockIdx.x; j < P.njobs; j += gridDim.x) {
-      const Job& jb = P.jobs[j];
-      const int t = job_time(P, jb);
-      const int all_kb = job_total_kb(P, jb, t);
-      if (all_kb == 0) continue;
-      int klo, khi;
-      job_kb_range(jb, all_kb, klo, khi);
-      const bool have_acc = khi > klo;
-      const int buf = it & 1;
-      const uint32_t use = (uint32_t)(it >> 1);
-      const uint32_t taddr = tmem_base + (uint32_t)buf * 256u + ((uint32_t)(q * 32) << 16);
-      if (have_acc) {
-        mbar_wait(&tfull_bar[buf], use & 1);
-        tc_fence_after();
-      }
-      if (threadIdx.x == 64) TL(4);
-      if (jb.ksplit <= 1) {
-        for (int n0 = 0; n0 < n_cols; n0 += 32) {
-          float v[32];
-          const int nc = (n_cols - n0 >= 32) ? 32 : 16;
-          if (nc == 32) {
-            tmem_ld_32x32(taddr + n0, v);
-            tmem_ld_wait();
-            run_epilogue<32>(jb, P.ctx, t, row, n0, nc, v);
-          } else {
-            tmem_ld_32x16(taddr + n0, v);
-            tmem_ld_wait();
-            run_epilogue<16>(jb, P.ctx, t, row, n0, nc, v);
-          }
-        }
-      } else {
-        // park the partial tile: scratch[group][part][col][row]  (row fastest -> coalesced)
-        float* part = P.split_scratch + ((size_t)jb.group * MAX_KSPLIT + jb.kpart) * (size_t)n_cols * TILE_M;
-        for (int n0 = 0; n0 < n_cols; n0 += 32) {
-          float v[32];
-          const int nc = (n_cols - n0 >= 32) ? 32 : 16;
-          if (have_acc) {
-            if (nc == 32) tmem_ld_32x32(taddr + n0, v);
-            else tmem_ld_32x16(taddr + n0, v);
-            tmem_ld_wait();
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = 0.0f;
-          }
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (i < nc) __stcg(part + (size_t)(n0 + i) * TILE_M + row, v[i]);
-        }
-      }
-      if (have_acc) {
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[buf]);
-      }
-      if (threadIdx.x == 64) TL(5);
-      if (jb.ksplit > 1) {
-        __threadfence();
-        asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps
-        const float* base = P.split_scratch + (size_t)jb.group * MAX_KSPLIT * (size_t)n_cols * TILE_M;
-        int c_lo = 0, c_hi = 0;
-        if (P.coop_epilogue) {
-          // Every part of the tile finishes a slice of its columns once all parts have arrived.  Safe because
-          // the launch has at most one job per CTA and all CTAs are co-resident (grid <= SM count).
-          if (warp == 2 && lane == 0) {
-            atomicAdd(P.split_count + jb.group, 1u);
-            unsigned int seen, spins = 0;
-            do {
-              asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(P.split_count + jb.group) : "memory");
-              if (++spins > (1u << 24)) { printf("parrot_b200: split-K arrival wait timed out\n"); __trap(); }
-            } while ((seen & 0xffffu) < (unsigned int)jb.ksplit);
-          }
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-          if (threadIdx.x == 64) TL(6);
-          c_lo = (n_cols * jb.kpart) / jb.ksplit;
-          c_hi = (n_cols * (jb.kpart + 1)) / jb.ksplit;
-        } else {
-          if (warp == 2 && lane == 0) {
-            const unsigned int old = atomicAdd(P.split_count + jb.group, 1u);
-            const bool last = old == (unsigned int)(jb.ksplit - 1);
-            if (last) P.split_count[jb.group] = 0u;   // ready for the next launch
-            *split_flag = last ? 1u : 0u;
-          }
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-          if (threadIdx.x == 64) TL(6);
-          if (*split_flag) { c_lo = 0; c_hi = n_cols; }
-        }
-        __threadfence();
-        for (int n0 = c_lo; n0 < c_hi; n0 += 8) {
-          float v[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = 0.0f;
-          const int nc = min(8, c_hi - n0);
-          // all parts in part order (deterministic); 8 columns x all parts of loads in flight
-          float x[MAX_KSPLIT][8];
-#pragma unroll
-          for (int pp = 0; pp < MAX_KSPLIT; ++pp) {
-            const float* src = base + (size_t)pp * n_cols * TILE_M;
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              x[pp][i] = (pp < jb.ksplit && i < nc) ? __ldcg(src + (size_t)(n0 + i) * TILE_M + row) : 0.0f;
-          }
-#pragma unroll
-          for (int pp = 0; pp < MAX_KSPLIT; ++pp)
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] += x[pp][i];
-          run_epilogue<8>(jb, P.ctx, t, row, n0, nc, v);
-        }
-        if (threadIdx.x == 64) TL(7);
-        if (P.coop_epilogue) {
-          // the last part to finish resets the arrival counter for the next launch
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-          if (warp == 2 && lane == 0) {
-            const unsigned int old = atomicAdd(P.split_count + jb.group, 0x10000u);
-            if ((old >> 16) == (unsigned int)(jb.ksplit - 1)) P.split_count[jb.group] = 0u;
-          }
-        } else {
-          asm volatile("bar.sync 1, 128;" ::: "memory");   // split_flag is reused by the next job
-        }
-      }
-      if (have_acc) ++it;   // accumulator buffers advance only when one was used (mirrors the MMA warp)
-    }
-  }
-
+__device__ __forceinline__ void pipe_teardown(Pipe& p) {
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 512);
+  if ((threadIdx.x >> 5) == 1) tmem_dealloc(p.tmem_base, 512);
+}
+
+// ------------------------------------------------ TMA producer (one thread: warp 0, lane 0)
+__device__ __forceinline__ void producer_run(Pipe& p, const EngineParams& P, int tick) {
+  for (int j = blockIdx.x; j < P.njobs; j += gridDim.x) {
+    const Job& jb = P.jobs[j];
+    const int t = job_time(P, jb, tick);
+    const int total_kb = job_total_kb(P, jb, t);
+    if (total_kb == 0) continue;
+    int klo, khi, kidx = 0;
+    job_kb_range(jb, total_kb, klo, khi);
+    for (int s = 0; s < jb.nseg; ++s) {
+      const Seg sg = jb.seg[s];
+      if (!seg_valid(P, sg, t)) continue;
+      const CUtensorMap* ma = P.maps + sg.a_map;
+      const CUtensorMap* mb = P.maps + sg.b_map;
+      for (int kb = 0; kb < sg.nkb; ++kb, ++kidx) {
+        if (kidx < klo || kidx >= khi) continue;
+        mbar_wait(&p.empty_bar[p.stage], p.phase ^ 1);
+        uint8_t* st = p.tiles + (size_t)p.stage * p.stage_bytes;
+        uint64_t* fb = &p.full_bar[p.stage];
+        mbar_expect_tx(fb, p.stage_bytes);
+        tma_load_2d(st, ma, fb, sg.a_k + kb * KB, sg.a_row);
+        tma_load_2d(st + p.a_bytes, ma + 1, fb, sg.a_k + kb * KB, sg.a_row);
+        if (sg.b_slot == NO_SLOT) {
+          tma_load_2d(st + 2 * p.a_bytes, mb, fb, sg.b_k + kb * KB, sg.b_row);
+          tma_load_2d(st + 2 * p.a_bytes + p.b_bytes, mb + 1, fb, sg.b_k + kb * KB, sg.b_row);
+        } else {
+          tma_load_3d(st + 2 * p.a_bytes, mb, fb, sg.b_k + kb * KB, sg.b_row, t + sg.b_slot);
+          tma_load_3d(st + 2 * p.a_bytes + p.b_bytes, mb + 1, fb, sg.b_k + kb * KB, sg.b_row, t + sg.b_slot);
+        }
+        if (++p.stage == p.nstages) { p.stage = 0; p.phase ^= 1; }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------ MMA issuer (warp 1; lane 0 issues)
+__device__ __forceinline__ void mma_run(Pipe& p, const EngineParams& P, int tick) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t idesc = umma_idesc_bf16(TILE_M, p.n_cols);
+  for (int j = blockIdx.x; j < P.njobs; j += gridDim.x) {
+    const Job& jb = P.jobs[j];
+    const int t = job_time(P, jb, tick);
+    const int all_kb = job_total_kb(P, jb, t);
+    if (all_kb == 0) continue;
+    int klo, khi;
+    job_kb_range(jb, all_kb, klo, khi);
+    const int total_kb = khi - klo;
+    if (total_kb == 0) continue;  // empty split part: no accumulator is used, the epilogue contributes zeros
+    const int buf = p.it & 1;
+    const uint32_t use = (uint32_t)(p.it >> 1);
+    mbar_wait(&p.tempty_bar[buf], (use & 1) ^ 1);
+    tc_fence_after();
+    const uint32_t tmem_d = p.tmem_base + (uint32_t)buf * 256u;
+    for (int kbi = 0; kbi < total_kb; ++kbi) {
+      mbar_wait(&p.full_bar[p.stage], p.phase);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint8_t* st = p.tiles + (size_t)p.stage * p.stage_bytes;
+        const uint64_t da_hi = umma_desc_sw128(st);
+        const uint64_t da_lo = umma_desc_sw128(st + p.a_bytes);
+        const uint64_t db_hi = umma_desc_sw128(st + 2 * p.a_bytes);
+        const uint64_t db_lo = umma_desc_sw128(st + 2 * p.a_bytes + p.b_bytes);
+#pragma unroll
+        for (int k = 0; k < KB / 16; ++k) {
+          const uint64_t adv = (uint64_t)((k * 16 * 2) >> 4);  // 32 bytes per k16 step
+          umma_bf16(tmem_d, da_hi + adv, db_hi + adv, idesc, (kbi | k) != 0);
+          umma_bf16(tmem_d, da_lo + adv, db_hi + adv, idesc, 1);
+          umma_bf16(tmem_d, da_hi + adv, db_lo + adv, idesc, 1);
+        }
+        umma_commit(&p.empty_bar[p.stage]);                        // frees the smem slot
+        if (kbi == total_kb - 1) umma_commit(&p.tfull_bar[buf]);   // accumulator complete
+      }
+      __syncwarp();
+      if (++p.stage == p.nstages) { p.stage = 0; p.phase ^= 1; }
+    }
+    ++p.it;
+  }
+}
+
+// ------------------------------------------------ epilogue (warps 2..5)
+__device__ __forceinline__ void epilogue_run(Pipe& p, const EngineParams& P, int tick) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_cols = p.n_cols;
+  const int q = warp & 3;  // TMEM lane quarter this warp may access
+  const int row = q * 32 + lane;
+  for (int j = blockIdx.x; j < P.njobs; j += gridDim.x) {
+    const Job& jb = P.jobs[j];
+    const int t = job_time(P, jb, tick);
+    const int all_kb = job_total_kb(P, jb, t);
+    if (all_kb == 0) continue;
+    int klo, khi;
+    job_kb_range(jb, all_kb, klo, khi);
+    const bool have_acc = khi > klo;
+    const int buf = p.it & 1;
+    const uint32_t use = (uint32_t)(p.it >> 1);
+    const uint32_t taddr = p.tmem_base + (uint32_t)buf * 256u + ((uint32_t)(q * 32) << 16);
+    if (have_acc) {
+      mbar_wait(&p.tfull_bar[buf], use & 1);
+      tc_fence_after();
+    }
+    if (threadIdx.x == 64) TL(4);
+    if (jb.ksplit <= 1) {
+      for (int n0 = 0; n0 < n_cols; n0 += 32) {
+        float v[32];
+        const int nc = (n_cols - n0 >= 32) ? 32 : 16;
+        if (nc == 32) {
+          tmem_ld_32x32(taddr + n0, v);
+          tmem_ld_wait();
+          run_epilogue<32>(jb, P.ctx, t, row, n0, nc, v);
+        } else {
+          tmem_ld_32x16(taddr + n0, v);
+          tmem_ld_wait();
+          run_epilogue<16>(jb, P.ctx, t, row, n0, nc, v);
+        }
+      }
+    } else {
+      // park the partial tile: scratch[group][part][col][row]  (row fastest -> coalesced)
+      float* part = P.split_scratch + ((size_t)jb.group * MAX_KSPLIT + jb.kpart) * (size_t)n_cols * TILE_M;
+      for (int n0 = 0; n0 < n_cols; n0 += 32) {
+        float v[32];
+        const int nc = (n_cols - n0 >= 32) ? 32 : 16;
+        if (have_acc) {
+          if (nc == 32) tmem_ld_32x32(taddr + n0, v);
+          else tmem_ld_32x16(taddr + n0, v);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = 0.0f;
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (i < nc) __stcg(part + (size_t)(n0 + i) * TILE_M + row, v[i]);
+      }
+    }
+    if (have_acc) {
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p.tempty_bar[buf]);
+    }
+    if (threadIdx.x == 64) TL(5);
+    if (jb.ksplit > 1) {
+      __threadfence();
+      asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps
+      const float* base = P.split_scratch + (size_t)jb.group * MAX_KSPLIT * (size_t)n_cols * TILE_M;
+      int c_lo = 0, c_hi = 0;
+      if (P.coop_epilogue) {
+        // Every part of the tile finishes a slice of its columns once all parts have arrived.  Safe because
+        // the launch has at most one job per CTA and all CTAs are co-resident (grid <= SM count).
+        if (warp == 2 && lane == 0) {
+          atomicAdd(P.split_count + jb.group, 1u);
+          unsigned int seen, spins = 0;
+          do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(P.split_count + jb.group) : "memory");
+            if (++spins > (1u << 24)) { printf("parrot_b200: split-K arrival wait timed out\n"); __trap(); }
+          } while ((seen & 0xffffu) < (unsigned int)jb.ksplit);
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (threadIdx.x == 64) TL(6);
+        c_lo = (n_cols * jb.kpart) / jb.ksplit;
+        c_hi = (n_cols * (jb.kpart + 1)) / jb.ksplit;
+      } else {
+        if (warp == 2 && lane == 0) {
+          const unsigned int old = atomicAdd(P.split_count + jb.group, 1u);
+          const bool last = old == (unsigned int)(jb.ksplit - 1);
+          if (last) P.split_count[jb.group] = 0u;   // ready for the next launch
+          *p.split_flag = last ? 1u : 0u;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (threadIdx.x == 64) TL(6);
+        if (*p.split_flag) { c_lo = 0; c_hi = n_cols; }
+      }
+      __threadfence();
+      for (int n0 = c_lo; n0 < c_hi; n0 += 8) {
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = 0.0f;
+        const int nc = min(8, c_hi - n0);
+        // all parts in part order (deterministic); 8 columns x all parts of loads in flight
+        float x[MAX_KSPLIT][8];
+#pragma unroll
+        for (int pp = 0; pp < MAX_KSPLIT; ++pp) {
+          const float* src = base + (size_t)pp * n_cols * TILE_M;
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            x[pp][i] = (pp < jb.ksplit && i < nc) ? __ldcg(src + (size_t)(n0 + i) * TILE_M + row) : 0.0f;
+        }
+#pragma unroll
+        for (int pp = 0; pp < MAX_KSPLIT; ++pp)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] += x[pp][i];
+        run_epilogue<8>(jb, P.ctx, t, row, n0, nc, v);
+      }
+      if (threadIdx.x == 64) TL(7);
+      if (P.coop_epilogue) {
+        // the last part to finish resets the arrival counter for the next use
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (warp == 2 && lane == 0) {
+          const unsigned int old = atomicAdd(P.split_count + jb.group, 0x10000u);
+          if ((old >> 16) == (unsigned int)(jb.ksplit - 1)) P.split_count[jb.group] = 0u;
+        }
+      } else {
+        asm volatile("bar.sync 1, 128;" ::: "memory");   // split_flag is reused by the next job
+      }
+    }
+    if (have_acc) ++p.it;   // accumulator buffers advance only when one was used (mirrors the MMA warp)
+  }
+}
+
+__device__ __forceinline__ uint8_t* align_smem(uint8_t* raw) {
+  // 1024-byte alignment is required by the 128B swizzle atoms
+  return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+}
+
+// ---------------------------------------------------------- one launch per phase
+__global__ void __launch_bounds__(ENGINE_THREADS, 1) job_kernel_tc(const EngineParams P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) TL(0);
+  Pipe p;
+  pipe_setup(p, align_smem(smem_raw), P.n_cols);
+  if (threadIdx.x == 0) TL(1);
+  if (warp == 0) {
+    if (lane == 0) { producer_run(p, P, P.tick); TL(2); }
+  } else if (warp == 1) {
+    mma_run(p, P, P.tick);
+    if (lane == 0) TL(3);
+  } else {
+    epilogue_run(p, P, P.tick);
+  }
+  pipe_teardown(p);
   if (threadIdx.x == 0) TL(8);
+}
+
+// ---------------------------------------------------------- grid barrier (persistent kernels)
+// Monotonic arrival counter, zeroed by the host before the launch; barrier k completes when the counter
+// reaches (k + 1) * gridDim.x.  All CTAs are co-resident (cooperative launch).
+__device__ __forceinline__ void grid_arrive(unsigned int* ctr) {
+  asm volatile("fence.proxy.async.global;" ::: "memory");   // generic-proxy stores -> later TMA (async proxy) reads
+  __threadfence();
+  atomicAdd(ctr, 1u);
+}
+__device__ __forceinline__ void grid_wait(const unsigned int* ctr, unsigned int target) {
+  unsigned int seen, spins = 0;
+  do {
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(ctr) : "memory");
+    if (++spins > (1u << 26)) { printf("parrot_b200: grid barrier timed out (block %d)\n", blockIdx.x); __trap(); }
+  } while (seen < target);
+  asm volatile("fence.proxy.async.global;" ::: "memory");
 }
 
 // ------------------------------------------------------------------ SIMT twin
@@ -636,7 +685,7 @@ __global__ void __launch_bounds__(128) job_kernel_simt(const EngineParams P) {
   const int tid = threadIdx.x;
   for (int j = blockIdx.x; j < P.njobs; j += gridDim.x) {
     const Job& jb = P.jobs[j];
-    const int t = job_time(P, jb);
+    const int t = job_time(P, jb, P.tick);
     if (job_total_kb(P, jb, t) == 0) continue;
     if (jb.ksplit > 1 && jb.kpart != 0) continue;   // the SIMT twin does not split: part 0 does the whole tile
     for (int n0 = 0; n0 < P.n_cols; n0 += 32) {

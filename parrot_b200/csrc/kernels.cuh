@@ -34,14 +34,15 @@ struct AttnFwdArgs {
   float* e_out;         // [B][3A]  exp(a_hat) (softmax: probabilities) | exp(b_hat) | exp(k_hat)
 };
 
-__global__ void __launch_bounds__(256) attention_fwd_kernel(const AttnFwdArgs a) {
-  extern __shared__ float sh[];
+// Executed by every thread of the CTA for batch row b; `sh` needs
+// rup(H,4) + 2*rup(3A,4) + rup(U,4) + nwarps*C floats.  Ends with a CTA barrier (sh may be reused).
+__device__ __forceinline__ void attention_fwd_body(const AttnFwdArgs& a, const int b, float* sh) {
   const int A3p = (3 * a.A + 3) & ~3;  // sections padded to 16 bytes (float4 accesses below)
   float* sh_h = sh;                          // H
   float* sh_hat = sh_h + ((a.H + 3) & ~3);   // 3A
   float* sh_abk = sh_hat + A3p;              // 3A : alpha, beta, kappa
   float* sh_phi = sh_abk + A3p;              // U
-  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int A = a.A;
   for (int i = tid; i < a.H; i += blockDim.x) sh_h[i] = a.h1[(long long)b * a.H + i];
   __syncthreads();
@@ -151,6 +152,12 @@ __global__ void __launch_bounds__(256) attention_fwd_kernel(const AttnFwdArgs a)
       a.w_lo[(long long)b * a.Cp + c] = ll;
     }
   }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) attention_fwd_kernel(const AttnFwdArgs a) {
+  extern __shared__ float sh[];
+  attention_fwd_body(a, blockIdx.x, sh);
 }
 
 // =========================================================================
@@ -176,13 +183,12 @@ struct AttnBwdArgs {
   bf16* datt_lo;
 };
 
-__global__ void __launch_bounds__(256) attention_bwd_kernel(const AttnBwdArgs a) {
-  extern __shared__ float sh[];
+__device__ __forceinline__ void attention_bwd_body(const AttnBwdArgs& a, const int b, float* sh) {
   float* sh_dw = sh;                    // C
   float* sh_dphi = sh_dw + a.C;         // U
   float* sh_red = sh_dphi + a.U;        // 3A * 8 warps
   float* sh_datt = sh_red + 3 * a.A * 8;// 3A
-  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int A = a.A, nwarp = blockDim.x >> 5;
   for (int i = tid; i < a.C; i += blockDim.x) sh_dw[i] = a.dw[(long long)b * a.C + i];
   __syncthreads();
@@ -291,6 +297,12 @@ __global__ void __launch_bounds__(256) attention_bwd_kernel(const AttnBwdArgs a)
     for (int j = 0; j < 3 * A; ++j) s = fmaf(sh_datt[j], a.watt[(long long)j * a.H + f], s);
     a.dh1[(long long)b * a.H + f] += s;
   }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) attention_bwd_kernel(const AttnBwdArgs a) {
+  extern __shared__ float sh[];
+  attention_bwd_body(a, blockIdx.x, sh);
 }
 
 // =========================================================================
@@ -298,10 +310,7 @@ __global__ void __launch_bounds__(256) attention_bwd_kernel(const AttnBwdArgs a)
 // dh_t (see oracle _gru_bwd).  Produces da_c and the update half of da_g.
 // =========================================================================
 struct PreArgs { int layer[3]; int t[3]; int n; };
-__global__ void gru_bwd_pre_kernel(const ScanCtx* cp, const PreArgs pa) {
-  const ScanCtx& c = *cp;
-  if ((int)blockIdx.y >= pa.n) return;
-  const int layer = pa.layer[blockIdx.y], t = pa.t[blockIdx.y];
+__device__ __forceinline__ void gru_bwd_pre_body(const ScanCtx& c, const int layer, const int t) {
   const LayerBuf& L = c.L[layer];
   const int H = c.H;
   const long long n = (long long)c.B * H;
@@ -328,6 +337,133 @@ __global__ void gru_bwd_pre_kernel(const ScanCtx* cp, const PreArgs pa) {
     L.da_hi[po + c.Hp + f] = hh;
     L.da_lo[po + c.Hp + f] = ll;
   }
+}
+__global__ void gru_bwd_pre_kernel(const ScanCtx* cp, const PreArgs pa) {
+  // grid (blocks, n): blockIdx.y selects the (layer, t) pair; the body strides over gridDim.x blocks
+  if ((int)blockIdx.y >= pa.n) return;
+  gru_bwd_pre_body(*cp, pa.layer[blockIdx.y], pa.t[blockIdx.y]);
+}
+
+// =========================================================================
+// Persistent scan kernels: ONE cooperative launch runs all T decoder steps (forward) / the whole reverse
+// sweep (backward).  Per tick the phases of the layer wavefront are separated by grid barriers instead of
+// kernel boundaries; the GEMM pipeline state (smem ring, TMEM accumulators) lives across phases.
+// =========================================================================
+constexpr int ATT_SMEM_BYTES = 24 * 1024;
+struct ScanFwdParams {
+  EngineParams A, B;   // tables fwdA (gates) / fwdB (candidates)
+  AttnFwdArgs att;     // pointers of step 0
+  long long s_h1, s_k, s_w, s_wp, s_phi, s_ab, s_e;   // per-step strides (elements)
+  int T;
+  unsigned int* gridbar;
+  unsigned long long* stamps;   // debug: [cta][bar][2] globaltimer at (barrier wait done, arrival) or null
+  int stamp_bars;
+};
+struct ScanBwdParams {
+  EngineParams B1, B2;  // tables bwd1 / bwd2
+  AttnBwdArgs att;      // pointers of step 0
+  long long s_dw, s_ab, s_e, s_k, s_dh1, s_datt, s_dattp;
+  const ScanCtx* ctx;
+  int T;
+  unsigned int* gridbar;
+  unsigned long long* stamps;
+  int stamp_bars;
+};
+#define STAMP(S, bar, k)                                                                                \
+  do {                                                                                                  \
+    if ((S).stamps && (int)(bar) < (S).stamp_bars)                                                      \
+      (S).stamps[((size_t)blockIdx.x * (S).stamp_bars + (bar)) * 2 + (k)] = gtime();                    \
+  } while (0)
+
+// one GEMM phase of a persistent kernel: wait for the previous grid barrier where data produced by other
+// CTAs is consumed (producer: TMA of activation planes; epilogue: stashes), run the roles, arrive.
+template <class SP>
+__device__ __forceinline__ void persistent_gemm_phase(Pipe& p, const EngineParams& P, int tick, const SP& S,
+                                                      unsigned int& bar) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned int* gridbar = S.gridbar;
+  const unsigned int target = bar * gridDim.x;
+  if (warp == 0) {
+    if (lane == 0) {
+      if (bar) grid_wait(gridbar, target);
+      producer_run(p, P, tick);
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    mma_run(p, P, tick);
+  } else {
+    if (lane == 0 && bar) grid_wait(gridbar, target);
+    __syncwarp();
+    if (threadIdx.x == 64) STAMP(S, bar, 0);
+    epilogue_run(p, P, tick);
+    asm volatile("fence.proxy.async.global;" ::: "memory");
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (threadIdx.x == 64) { STAMP(S, bar, 1); grid_arrive(gridbar); }
+  }
+  ++bar;
+}
+
+__global__ void __launch_bounds__(ENGINE_THREADS, 1) scan_fwd_persistent(const ScanFwdParams S) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  Pipe p;
+  float* att_sh = reinterpret_cast<float*>(pipe_setup(p, align_smem(smem_raw), S.A.n_cols));
+  unsigned int bar = 0;
+  for (int tick = 0; tick < S.T + 2; ++tick) {
+    persistent_gemm_phase(p, S.A, tick, S, bar);
+    persistent_gemm_phase(p, S.B, tick, S, bar);
+    if (tick < S.T) {
+      if (threadIdx.x == 0) { grid_wait(S.gridbar, bar * gridDim.x); STAMP(S, bar, 0); }
+      __syncthreads();
+      AttnFwdArgs a = S.att;
+      a.h1 += tick * S.s_h1; a.k_prev += tick * S.s_k; a.k_out += tick * S.s_k; a.w_out += tick * S.s_w;
+      a.w_hi += tick * S.s_wp; a.w_lo += tick * S.s_wp; a.phi_out += tick * S.s_phi; a.ab_out += tick * S.s_ab;
+      a.e_out += tick * S.s_e;
+      for (int b = blockIdx.x; b < a.B; b += gridDim.x) attention_fwd_body(a, b, att_sh);
+      asm volatile("fence.proxy.async.global;" ::: "memory");
+      __syncthreads();
+      if (threadIdx.x == 0) { STAMP(S, bar, 1); grid_arrive(S.gridbar); }
+      ++bar;
+    }
+  }
+  pipe_teardown(p);
+}
+
+__global__ void __launch_bounds__(ENGINE_THREADS, 1) scan_bwd_persistent(const ScanBwdParams S) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  Pipe p;
+  float* att_sh = reinterpret_cast<float*>(pipe_setup(p, align_smem(smem_raw), S.B1.n_cols));
+  unsigned int bar = 0;
+  const ScanCtx& c = *S.ctx;
+  for (int tick = 0; tick < S.T + 2; ++tick) {
+    const int s = S.T - 1 - tick;   // layer 3 at step s, layer 2 at s + 1, attention + layer 1 at s + 2
+    const int ta = s + 2;
+    if (ta >= 0 && ta < S.T) {
+      if (threadIdx.x == 0 && bar) grid_wait(S.gridbar, bar * gridDim.x);
+      __syncthreads();
+      AttnBwdArgs a = S.att;
+      a.dw += ta * S.s_dw; a.ab += ta * S.s_ab; a.e += ta * S.s_e; a.kappa += ta * S.s_k; a.dh1 += ta * S.s_dh1;
+      a.datt += ta * S.s_datt; a.datt_hi += ta * S.s_dattp; a.datt_lo += ta * S.s_dattp;
+      for (int b = blockIdx.x; b < a.B; b += gridDim.x) attention_bwd_body(a, b, att_sh);
+      __syncthreads();
+      if (threadIdx.x == 0) grid_arrive(S.gridbar);
+      ++bar;
+    }
+    {
+      if (threadIdx.x == 0 && bar) grid_wait(S.gridbar, bar * gridDim.x);
+      __syncthreads();
+      for (int l = 2; l >= 0; --l) {
+        const int t = s + (2 - l);
+        if (t >= 0 && t < S.T) gru_bwd_pre_body(c, l, t);
+      }
+      asm volatile("fence.proxy.async.global;" ::: "memory");
+      __syncthreads();
+      if (threadIdx.x == 0) grid_arrive(S.gridbar);
+      ++bar;
+    }
+    persistent_gemm_phase(p, S.B1, tick, S, bar);
+    persistent_gemm_phase(p, S.B2, tick, S, bar);
+  }
+  pipe_teardown(p);
 }
 
 // =========================================================================
