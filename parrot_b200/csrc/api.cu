@@ -225,6 +225,7 @@ struct Plane {
   int pitch = 0;      // elements per row (multiple of 64)
   int slots = 1;
   long long rows_alloc = 0;  // total rows allocated (slots*rows rounded up to 128)
+  int tiled_nkb = 0;         // > 0: tile-contiguous weight pack with this many k blocks per 128-row tile
 };
 struct WPack {
   std::string name;
@@ -273,6 +274,7 @@ struct parrot_model {
   unsigned long long* timeline = nullptr;
   unsigned long long* stamps = nullptr;   // debug: persistent forward scan per-barrier stamps
   int stamp_bars = 0;
+  int tl_tick = -1;
   int sm_count = 0;
   float* d_split_scratch = nullptr;
   unsigned int* d_split_count = nullptr;
@@ -338,6 +340,8 @@ struct parrot_model {
       r.row_pitch = p.pitch;
       r.box_rows = box_rows;
       r.cols = p.pitch;
+      r.tiled_nkb = p.tiled_nkb;
+      r.pad_ = 0;
       if (rank == 2) {
         r.slot_pitch = 0; r.rows = (int)p.rows_alloc; r.slots = 1;
       } else {
@@ -347,6 +351,12 @@ struct parrot_model {
         cuuint64_t dims[3] = {(cuuint64_t)p.pitch, (cuuint64_t)(rank == 2 ? p.rows_alloc : p.rows),
                               (cuuint64_t)p.slots};
         cuuint64_t strides[2] = {(cuuint64_t)p.pitch * 2, (cuuint64_t)p.rows * p.pitch * 2};
+        if (p.tiled_nkb > 0) {
+          // tile-contiguous pack seen as a [tiles*128][64] matrix: every 128 x 64 box is one contiguous 16 KB block
+          dims[0] = 64;
+          dims[1] = (cuuint64_t)(p.rows_alloc / 128) * p.tiled_nkb * 128;
+          strides[0] = 128;
+        }
         cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
         cuuint32_t es[3] = {1, 1, 1};
         CUresult res = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, (void*)r.base, dims,
@@ -369,9 +379,13 @@ struct parrot_model {
     WPack w;
     w.name = pname; w.in = pi.rows; w.out = pi.cols; w.need_bwd = need_bwd;
     w.fwd = make_plane("pack.f" + pname, rup(w.out, 128), w.in, 1);
+    w.fwd.tiled_nkb = w.fwd.pitch / 64;
+    planes["pack.f" + pname] = w.fwd;
     w.fwd_map = make_map(w.fwd, 2, 128);
     if (need_bwd) {
       w.bwd = make_plane("pack.b" + pname, rup(w.in, 128), w.out, 1);
+      w.bwd.tiled_nkb = w.bwd.pitch / 64;
+      planes["pack.b" + pname] = w.bwd;
       w.bwd_map = make_map(w.bwd, 2, 128);
     }
     packs[pname] = w;
@@ -385,7 +399,7 @@ static const int NT = 128;  // sample tile of the batched (outside-the-scan) pro
 static Seg mkseg(int a_map, int a_row, int a_k, int b_map, int b_row, int b_k, int b_slot, int nkb) {
   Seg s;
   s.a_map = a_map; s.a_row = a_row; s.a_k = a_k; s.b_map = b_map; s.b_row = b_row; s.b_k = b_k;
-  s.b_slot = b_slot; s.nkb = nkb;
+  s.b_slot = b_slot; s.nkb = nkb; s.a_nkb = 0; s.pad_ = 0;
   return s;
 }
 static Job blank_job() {
@@ -486,8 +500,11 @@ static std::vector<Job> split_jobs(const std::vector<Job>& js, int target_ctas, 
   return out;
 }
 
-static void push_table(parrot_model& M, const std::string& name, const std::vector<Job>& js, int n_cols,
+static void push_table(parrot_model& M, const std::string& name, const std::vector<Job>& js_in, int n_cols,
                        int split_target = 0) {
+  std::vector<Job> js = js_in;
+  for (auto& j : js)
+    for (int s = 0; s < j.nseg; ++s) j.seg[s].a_nkb = M.raws[j.seg[s].a_map].tiled_nkb;   // tile-contiguous packs
   Table t;
   t.off = (int)M.jobs.size();
   t.n_cols = n_cols;
@@ -966,7 +983,7 @@ static void pack_plane(cudaStream_t st, const float* src, long long src_ld, int 
   dim3 grid(cdiv(cols, 32), cdiv(rows, 32));
   dim3 block(32, 8);
   LAUNCH(pack_planes_kernel, grid, block, 0, st, src, src_ld, rows, cols, dst.hi, dst.lo, (long long)dst.pitch,
-         transpose);
+         transpose, dst.tiled_nkb);
 }
 static void transpose_planes(cudaStream_t st, const Plane& src, int feat_cols, const Plane& dst) {
   const long long rows = (long long)src.rows * src.slots;
@@ -1231,8 +1248,8 @@ static bool use_persistent(parrot_model& M) {
   }
   const Dims& d = M.d;
   if (!env || M.cfg.gemm_impl == 1 || M.profiling >= 2 || M.sm_count < 148) return false;
-  const size_t att_f = (size_t)rup(d.H, 4) + 2 * rup(3 * d.A, 4) + rup(d.U, 4) + 6 * (size_t)d.C;
-  const size_t att_b = (size_t)d.C + d.U + 3 * d.A * 8 + 3 * d.A;
+  const size_t att_f = (size_t)rup(d.H, 4) + 2 * rup(3 * d.A, 4) + rup(d.U, 4) + (ENGINE_THREADS / 32) * (size_t)d.C;
+  const size_t att_b = (size_t)d.C + d.U + 3 * d.A * 16 + 3 * d.A;
   if (std::max(att_f, att_b) * 4 > (size_t)ATT_SMEM_BYTES) return false;
   for (const char* nm : {"fwdA", "fwdB", "bwd1", "bwd2"}) {
     auto it = M.tables.find(nm);
@@ -1266,6 +1283,7 @@ static void scan_fwd_persistent_launch(parrot_model& M, cudaStream_t st) {
   S.T = d.T;
   S.gridbar = M.d_gridbar;
   S.stamps = M.stamps; S.stamp_bars = M.stamp_bars;
+  S.tl_buf = M.timeline; S.tl_tick = M.tl_tick;
   CK(cudaMemsetAsync(M.d_gridbar, 0, 4, st));
   void* args[] = {&S};
   g_ctx = "scan_fwd_persistent";
@@ -1285,7 +1303,7 @@ static void scan_bwd_persistent_launch(parrot_model& M, cudaStream_t st) {
   S.s_k = (long long)d.B * d.A; S.s_dh1 = (long long)d.B * d.H; S.s_datt = (long long)d.B * 3 * d.A;
   S.s_dattp = (long long)d.Np * M.planes.at("datt").pitch;
   S.ctx = M.d_ctx; S.T = d.T; S.gridbar = M.d_gridbar;
-  S.stamps = nullptr; S.stamp_bars = 0;
+  S.stamps = nullptr; S.stamp_bars = 0; S.tl_buf = nullptr; S.tl_tick = -1;
   CK(cudaMemsetAsync(M.d_gridbar, 0, 4, st));
   void* args[] = {&S};
   g_ctx = "scan_bwd_persistent";
@@ -1410,7 +1428,7 @@ static AttnBwdArgs attn_bwd_args(parrot_model& M, int t) {
 static void attention_bwd_step(parrot_model& M, int t, cudaStream_t st) {
   const Dims& d = M.d;
   AttnBwdArgs a = attn_bwd_args(M, t);
-  const size_t smem = (size_t)(d.C + d.U + 3 * d.A * 8 + 3 * d.A) * 4;
+  const size_t smem = (size_t)(d.C + d.U + 3 * d.A * 16 + 3 * d.A) * 4;
   cudaEvent_t pe = M.prof_begin("attn_bwd", st);
   LAUNCH(attention_bwd_kernel, d.B, 256, smem, st, a);
   parrot_model::prof_end(pe, st);
@@ -1728,6 +1746,8 @@ int parrot_debug_time_table(parrot_model* m, const char* name, int tick, int rev
   });
 }
 int parrot_debug_set_stamps(parrot_model* m, unsigned long long* d_stamps, int bars) {
+  // bars < 0: d_stamps is instead a [2][148][16] intra-phase timeline buffer for forward tick (-bars)
+  if (bars < 0) { m->timeline = d_stamps; m->tl_tick = -bars; return 0; }
   m->stamps = d_stamps; m->stamp_bars = bars;
   return 0;
 }

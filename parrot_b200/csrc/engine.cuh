@@ -33,7 +33,8 @@ constexpr int TILE_M = 128;
 constexpr int KB = 64;  // k elements per pipeline block (one 128-byte swizzle span)
 constexpr int MAX_SEG = 6;
 constexpr int NO_SLOT = -(1 << 30);
-constexpr int ENGINE_THREADS = 192;
+constexpr int ENGINE_THREADS = 384;   // warp 0 TMA, warp 1 MMA, warps 2-5 TMEM epilogue, warps 6-11 epilogue helpers
+constexpr int EPI_GROUP_THREADS = 320; // warps 2..11 share the post-reduction (split-K) epilogue
 constexpr int SMEM_BYTES = 200 * 1024;
 constexpr int MAX_KSPLIT = 8;   // scratch stride per split group
 
@@ -54,6 +55,9 @@ struct Seg {
   int b_k;     // first k column in B
   int b_slot;  // NO_SLOT: B map is 2-D; else 3-D and the slot coordinate is t + b_slot
   int nkb;     // number of 64-wide k blocks
+  int a_nkb;   // > 0: A is a tile-contiguous weight pack with a_nkb k blocks per 128-row tile: tile
+               // (row_tile, k_block) is rows [(row_tile*a_nkb + k_block)*128, +128) of a [.][64] matrix
+  int pad_;
 };
 
 struct PlainArgs {
@@ -92,9 +96,11 @@ struct MapRaw {
   const bf16* base;
   long long row_pitch;   // elements
   long long slot_pitch;  // elements (0 for 2-D)
-  int rows, cols;        // extents per slot
+  int rows, cols;        // extents per slot (logical, also for tiled packs)
   int slots;
   int box_rows;
+  int tiled_nkb;         // > 0: tile-contiguous weight pack (see Seg::a_nkb)
+  int pad_;
 };
 
 // ---- scan context (device resident; see scan.cu for the phase structure) ----
@@ -232,7 +238,7 @@ __device__ __forceinline__ void epi_gates(const Job& jb, const ScanCtx& c, int t
   for (int j = 0; j < W; ++j) {
     const int b = n_base + j;
     if (j < ncols && b < c.B) {
-      const float g = sigmoidf_exact(v[j] + pre[j]);
+      const float g = sigmoidf_fast(v[j] + pre[j]);
       const long long o = ((long long)t * c.B + b) * H + fr;
       if (is_z) {
         L.z[o] = g;
@@ -269,7 +275,7 @@ __device__ __forceinline__ void epi_cand(const Job& jb, const ScanCtx& c, int t,
   for (int j = 0; j < W; ++j) {
     const int b = n_base + j;
     if (j < ncols && b < c.B) {
-      const float cc = tanhf(v[j] + pre[j]);
+      const float cc = tanhf_fast(v[j] + pre[j]);
       const long long o = ((long long)t * c.B + b) * H + f;
       const float hn = cc * zz[j] + hp[j] * (1.0f - zz[j]);
       L.c[o] = cc;
@@ -427,6 +433,7 @@ __device__ __forceinline__ void pipe_teardown(Pipe& p) {
 
 // ------------------------------------------------ TMA producer (one thread: warp 0, lane 0)
 __device__ __forceinline__ void producer_run(Pipe& p, const EngineParams& P, int tick) {
+  const uint64_t pol_keep = l2_policy_evict_last();
   for (int j = blockIdx.x; j < P.njobs; j += gridDim.x) {
     const Job& jb = P.jobs[j];
     const int t = job_time(P, jb, tick);
@@ -445,8 +452,15 @@ __device__ __forceinline__ void producer_run(Pipe& p, const EngineParams& P, int
         uint8_t* st = p.tiles + (size_t)p.stage * p.stage_bytes;
         uint64_t* fb = &p.full_bar[p.stage];
         mbar_expect_tx(fb, p.stage_bytes);
-        tma_load_2d(st, ma, fb, sg.a_k + kb * KB, sg.a_row);
-        tma_load_2d(st + p.a_bytes, ma + 1, fb, sg.a_k + kb * KB, sg.a_row);
+        if (sg.a_nkb > 0) {
+          // tile-contiguous weight pack: one 16 KB contiguous block per plane, kept in L2 (re-read every step)
+          const int trow = ((sg.a_row >> 7) * sg.a_nkb + (sg.a_k >> 6) + kb) << 7;
+          tma_load_2d_hint(st, ma, fb, 0, trow, pol_keep);
+          tma_load_2d_hint(st + p.a_bytes, ma + 1, fb, 0, trow, pol_keep);
+        } else {
+          tma_load_2d(st, ma, fb, sg.a_k + kb * KB, sg.a_row);
+          tma_load_2d(st + p.a_bytes, ma + 1, fb, sg.a_k + kb * KB, sg.a_row);
+        }
         if (sg.b_slot == NO_SLOT) {
           tma_load_2d(st + 2 * p.a_bytes, mb, fb, sg.b_k + kb * KB, sg.b_row);
           tma_load_2d(st + 2 * p.a_bytes + p.b_bytes, mb + 1, fb, sg.b_k + kb * KB, sg.b_row);
@@ -458,6 +472,7 @@ __device__ __forceinline__ void producer_run(Pipe& p, const EngineParams& P, int
       }
     }
   }
+  TL(2);
 }
 
 // ------------------------------------------------ MMA issuer (warp 1; lane 0 issues)
@@ -502,14 +517,21 @@ __device__ __forceinline__ void mma_run(Pipe& p, const EngineParams& P, int tick
     }
     ++p.it;
   }
+  if (lane == 0) TL(3);
 }
 
-// ------------------------------------------------ epilogue (warps 2..5)
+// ------------------------------------------------ epilogue (warps 2..5 read TMEM; warps 6..11 help after split-K)
+// All ten warps run this loop.  Unsplit jobs: warps 2..5 read the accumulator (one TMEM lane quarter each) and
+// apply the epilogue; the helpers skip.  Split jobs: warps 2..5 park the partial tile in scratch, then ALL ten
+// warps share the post-reduction epilogue of this part's column slice as 4-column work items (the reduction
+// reads global memory, so any warp can do it; ten warps hide the load / MUFU latencies that four cannot).
 __device__ __forceinline__ void epilogue_run(Pipe& p, const EngineParams& P, int tick) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_cols = p.n_cols;
+  const bool tmem_warp = warp < 6;
   const int q = warp & 3;  // TMEM lane quarter this warp may access
   const int row = q * 32 + lane;
+  const int gtid = threadIdx.x - 64;   // 0..319 inside the epilogue group
   for (int j = blockIdx.x; j < P.njobs; j += gridDim.x) {
     const Job& jb = P.jobs[j];
     const int t = job_time(P, jb, tick);
@@ -520,54 +542,46 @@ __device__ __forceinline__ void epilogue_run(Pipe& p, const EngineParams& P, int
     const bool have_acc = khi > klo;
     const int buf = p.it & 1;
     const uint32_t use = (uint32_t)(p.it >> 1);
-    const uint32_t taddr = p.tmem_base + (uint32_t)buf * 256u + ((uint32_t)(q * 32) << 16);
-    if (have_acc) {
-      mbar_wait(&p.tfull_bar[buf], use & 1);
-      tc_fence_after();
-    }
-    if (threadIdx.x == 64) TL(4);
-    if (jb.ksplit <= 1) {
-      for (int n0 = 0; n0 < n_cols; n0 += 32) {
-        float v[32];
-        const int nc = (n_cols - n0 >= 32) ? 32 : 16;
-        if (nc == 32) {
-          tmem_ld_32x32(taddr + n0, v);
-          tmem_ld_wait();
-          run_epilogue<32>(jb, P.ctx, t, row, n0, nc, v);
-        } else {
+    if (tmem_warp) {
+      const uint32_t taddr = p.tmem_base + (uint32_t)buf * 256u + ((uint32_t)(q * 32) << 16);
+      if (have_acc) {
+        mbar_wait(&p.tfull_bar[buf], use & 1);
+        tc_fence_after();
+      }
+      if (threadIdx.x == 64) TL(4);
+      if (jb.ksplit <= 1) {
+        for (int n0 = 0; n0 < n_cols; n0 += 16) {
+          float v[16];
           tmem_ld_32x16(taddr + n0, v);
           tmem_ld_wait();
-          run_epilogue<16>(jb, P.ctx, t, row, n0, nc, v);
+          run_epilogue<16>(jb, P.ctx, t, row, n0, 16, v);
+        }
+      } else {
+        // park the partial tile: scratch[group][part][col][row]  (row fastest -> coalesced)
+        float* part = P.split_scratch + ((size_t)jb.group * MAX_KSPLIT + jb.kpart) * (size_t)n_cols * TILE_M;
+        for (int n0 = 0; n0 < n_cols; n0 += 16) {
+          float v[16];
+          if (have_acc) {
+            tmem_ld_32x16(taddr + n0, v);
+            tmem_ld_wait();
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = 0.0f;
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) __stcg(part + (size_t)(n0 + i) * TILE_M + row, v[i]);
         }
       }
-    } else {
-      // park the partial tile: scratch[group][part][col][row]  (row fastest -> coalesced)
-      float* part = P.split_scratch + ((size_t)jb.group * MAX_KSPLIT + jb.kpart) * (size_t)n_cols * TILE_M;
-      for (int n0 = 0; n0 < n_cols; n0 += 32) {
-        float v[32];
-        const int nc = (n_cols - n0 >= 32) ? 32 : 16;
-        if (have_acc) {
-          if (nc == 32) tmem_ld_32x32(taddr + n0, v);
-          else tmem_ld_32x16(taddr + n0, v);
-          tmem_ld_wait();
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = 0.0f;
-        }
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (i < nc) __stcg(part + (size_t)(n0 + i) * TILE_M + row, v[i]);
+      if (have_acc) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p.tempty_bar[buf]);
       }
+      if (threadIdx.x == 64) TL(5);
     }
-    if (have_acc) {
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&p.tempty_bar[buf]);
-    }
-    if (threadIdx.x == 64) TL(5);
     if (jb.ksplit > 1) {
-      __threadfence();
-      asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps
+      if (tmem_warp) __threadfence();
+      asm volatile("bar.sync 1, 320;" ::: "memory");   // partial tile written by warps 2..5
       const float* base = P.split_scratch + (size_t)jb.group * MAX_KSPLIT * (size_t)n_cols * TILE_M;
       int c_lo = 0, c_hi = 0;
       if (P.coop_epilogue) {
@@ -581,7 +595,7 @@ __device__ __forceinline__ void epilogue_run(Pipe& p, const EngineParams& P, int
             if (++spins > (1u << 24)) { printf("parrot_b200: split-K arrival wait timed out\n"); __trap(); }
           } while ((seen & 0xffffu) < (unsigned int)jb.ksplit);
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 320;" ::: "memory");
         if (threadIdx.x == 64) TL(6);
         c_lo = (n_cols * jb.kpart) / jb.ksplit;
         c_hi = (n_cols * (jb.kpart + 1)) / jb.ksplit;
@@ -592,41 +606,38 @@ __device__ __forceinline__ void epilogue_run(Pipe& p, const EngineParams& P, int
           if (last) P.split_count[jb.group] = 0u;   // ready for the next launch
           *p.split_flag = last ? 1u : 0u;
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 320;" ::: "memory");
         if (threadIdx.x == 64) TL(6);
         if (*p.split_flag) { c_lo = 0; c_hi = n_cols; }
       }
       __threadfence();
-      for (int n0 = c_lo; n0 < c_hi; n0 += 8) {
-        float v[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = 0.0f;
-        const int nc = min(8, c_hi - n0);
-        // all parts in part order (deterministic); 8 columns x all parts of loads in flight
-        float x[MAX_KSPLIT][8];
+      // work item = (row, group of 4 columns); consecutive threads take consecutive rows (coalesced)
+      const int ngroups = (c_hi - c_lo + 3) >> 2;
+      for (int e = gtid; e < ngroups * TILE_M; e += EPI_GROUP_THREADS) {
+        const int r = e & (TILE_M - 1);
+        const int n0 = c_lo + ((e >> 7) << 2);
+        const int nc = min(4, c_hi - n0);
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        float x[MAX_KSPLIT][4];
 #pragma unroll
         for (int pp = 0; pp < MAX_KSPLIT; ++pp) {
           const float* src = base + (size_t)pp * n_cols * TILE_M;
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            x[pp][i] = (pp < jb.ksplit && i < nc) ? __ldcg(src + (size_t)(n0 + i) * TILE_M + row) : 0.0f;
+          for (int i = 0; i < 4; ++i)
+            x[pp][i] = (pp < jb.ksplit && i < nc) ? __ldcg(src + (size_t)(n0 + i) * TILE_M + r) : 0.0f;
         }
 #pragma unroll
-        for (int pp = 0; pp < MAX_KSPLIT; ++pp)
+        for (int pp = 0; pp < MAX_KSPLIT; ++pp)   // part order: deterministic
 #pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] += x[pp][i];
-        run_epilogue<8>(jb, P.ctx, t, row, n0, nc, v);
+          for (int i = 0; i < 4; ++i) v[i] += x[pp][i];
+        run_epilogue<4>(jb, P.ctx, t, r, n0, nc, v);
       }
       if (threadIdx.x == 64) TL(7);
-      if (P.coop_epilogue) {
+      asm volatile("bar.sync 1, 320;" ::: "memory");
+      if (P.coop_epilogue && warp == 2 && lane == 0) {
         // the last part to finish resets the arrival counter for the next use
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (warp == 2 && lane == 0) {
-          const unsigned int old = atomicAdd(P.split_count + jb.group, 0x10000u);
-          if ((old >> 16) == (unsigned int)(jb.ksplit - 1)) P.split_count[jb.group] = 0u;
-        }
-      } else {
-        asm volatile("bar.sync 1, 128;" ::: "memory");   // split_flag is reused by the next job
+        const unsigned int old = atomicAdd(P.split_count + jb.group, 0x10000u);
+        if ((old >> 16) == (unsigned int)(jb.ksplit - 1)) P.split_count[jb.group] = 0u;
       }
     }
     if (have_acc) ++p.it;   // accumulator buffers advance only when one was used (mirrors the MMA warp)
@@ -647,10 +658,9 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) job_kernel_tc(const EngineP
   pipe_setup(p, align_smem(smem_raw), P.n_cols);
   if (threadIdx.x == 0) TL(1);
   if (warp == 0) {
-    if (lane == 0) { producer_run(p, P, P.tick); TL(2); }
+    if (lane == 0) producer_run(p, P, P.tick);
   } else if (warp == 1) {
     mma_run(p, P, P.tick);
-    if (lane == 0) TL(3);
   } else {
     epilogue_run(p, P, P.tick);
   }
@@ -706,7 +716,9 @@ __global__ void __launch_bounds__(128) job_kernel_simt(const EngineParams P) {
             const int gr = sg.a_row + r, gk = sg.a_k + kb * KB + k;
             float x = 0.0f;
             if (gr < ra.rows && gk < ra.cols) {
-              const long long o = (long long)gr * ra.row_pitch + gk;
+              long long o = (long long)gr * ra.row_pitch + gk;
+              if (ra.tiled_nkb > 0)
+                o = (((long long)(gr >> 7) * ra.tiled_nkb + (gk >> 6)) * TILE_M + (gr & 127)) * KB + (gk & 63);
               x = __bfloat162float(ra.base[o]) + __bfloat162float(ral.base[o]);
             }
             As[r][k] = x;

@@ -186,8 +186,8 @@ struct AttnBwdArgs {
 __device__ __forceinline__ void attention_bwd_body(const AttnBwdArgs& a, const int b, float* sh) {
   float* sh_dw = sh;                    // C
   float* sh_dphi = sh_dw + a.C;         // U
-  float* sh_red = sh_dphi + a.U;        // 3A * 8 warps
-  float* sh_datt = sh_red + 3 * a.A * 8;// 3A
+  float* sh_red = sh_dphi + a.U;        // 3A * 16 warps
+  float* sh_datt = sh_red + 3 * a.A * 16;// 3A
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int A = a.A, nwarp = blockDim.x >> 5;
   for (int i = tid; i < a.C; i += blockDim.x) sh_dw[i] = a.dw[(long long)b * a.C + i];
@@ -251,29 +251,29 @@ __device__ __forceinline__ void attention_bwd_body(const AttnBwdArgs& a, const i
       dk += __shfl_xor_sync(0xffffffffu, dk, o);
     }
     if (lane == 0) {
-      sh_red[(0 * A + i) * 8 + warp] = da;
-      sh_red[(1 * A + i) * 8 + warp] = db;
-      sh_red[(2 * A + i) * 8 + warp] = dk;
+      sh_red[(0 * A + i) * 16 + warp] = da;
+      sh_red[(1 * A + i) * 16 + warp] = db;
+      sh_red[(2 * A + i) * 16 + warp] = dk;
     }
   }
   __syncthreads();
   if (tid < 3 * A) {
     float s = 0.0f;
-    for (int w = 0; w < nwarp; ++w) s += sh_red[tid * 8 + w];
-    sh_red[tid * 8] = s;
+    for (int w = 0; w < nwarp; ++w) s += sh_red[tid * 16 + w];
+    sh_red[tid * 16] = s;
   }
   __syncthreads();
   if (tid < A) {
-    const float da = sh_red[(0 * A + tid) * 8];
-    const float db = sh_red[(1 * A + tid) * 8];
-    const float dk = sh_red[(2 * A + tid) * 8] + a.dk_carry[(long long)b * A + tid];
+    const float da = sh_red[(0 * A + tid) * 16];
+    const float db = sh_red[(1 * A + tid) * 16];
+    const float dk = sh_red[(2 * A + tid) * 16] + a.dk_carry[(long long)b * A + tid];
     const float ea = a.e[(long long)b * 3 * A + tid];
     const float eb = a.e[(long long)b * 3 * A + A + tid];
     const float ek = a.e[(long long)b * 3 * A + 2 * A + tid];
     float da_hat;
     if (a.type == 1) {
       float dot = 0.0f;
-      for (int i = 0; i < A; ++i) dot += sh_red[(0 * A + i) * 8] * a.e[(long long)b * 3 * A + i];
+      for (int i = 0; i < A; ++i) dot += sh_red[(0 * A + i) * 16] * a.e[(long long)b * 3 * A + i];
       da_hat = ea * (da - dot);
     } else {
       da_hat = da * ea;
@@ -358,6 +358,8 @@ struct ScanFwdParams {
   unsigned int* gridbar;
   unsigned long long* stamps;   // debug: [cta][bar][2] globaltimer at (barrier wait done, arrival) or null
   int stamp_bars;
+  unsigned long long* tl_buf;   // debug: [2 phases][cta][16] intra-phase milestones of tick tl_tick
+  int tl_tick;
 };
 struct ScanBwdParams {
   EngineParams B1, B2;  // tables bwd1 / bwd2
@@ -368,6 +370,8 @@ struct ScanBwdParams {
   unsigned int* gridbar;
   unsigned long long* stamps;
   int stamp_bars;
+  unsigned long long* tl_buf;
+  int tl_tick;
 };
 #define STAMP(S, bar, k)                                                                                \
   do {                                                                                                  \
@@ -378,26 +382,30 @@ struct ScanBwdParams {
 // one GEMM phase of a persistent kernel: wait for the previous grid barrier where data produced by other
 // CTAs is consumed (producer: TMA of activation planes; epilogue: stashes), run the roles, arrive.
 template <class SP>
-__device__ __forceinline__ void persistent_gemm_phase(Pipe& p, const EngineParams& P, int tick, const SP& S,
-                                                      unsigned int& bar) {
+__device__ __forceinline__ void persistent_gemm_phase(Pipe& p, const EngineParams& P0, int tick, const SP& S,
+                                                      unsigned int& bar, int which) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  EngineParams P = P0;
+  P.timeline = (S.tl_buf && tick == S.tl_tick) ? S.tl_buf + (size_t)which * gridDim.x * 16 : nullptr;
   unsigned int* gridbar = S.gridbar;
   const unsigned int target = bar * gridDim.x;
   if (warp == 0) {
     if (lane == 0) {
+      TL(0);
       if (bar) grid_wait(gridbar, target);
+      TL(1);
       producer_run(p, P, tick);
     }
     __syncwarp();
   } else if (warp == 1) {
     mma_run(p, P, tick);
   } else {
-    if (lane == 0 && bar) grid_wait(gridbar, target);
-    __syncwarp();
+    if (warp == 2 && lane == 0 && bar) grid_wait(gridbar, target);   // one poller for the ten epilogue warps
+    asm volatile("bar.sync 1, 320;" ::: "memory");
     if (threadIdx.x == 64) STAMP(S, bar, 0);
     epilogue_run(p, P, tick);
     asm volatile("fence.proxy.async.global;" ::: "memory");
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    asm volatile("bar.sync 1, 320;" ::: "memory");
     if (threadIdx.x == 64) { STAMP(S, bar, 1); grid_arrive(gridbar); }
   }
   ++bar;
@@ -409,8 +417,8 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) scan_fwd_persistent(const S
   float* att_sh = reinterpret_cast<float*>(pipe_setup(p, align_smem(smem_raw), S.A.n_cols));
   unsigned int bar = 0;
   for (int tick = 0; tick < S.T + 2; ++tick) {
-    persistent_gemm_phase(p, S.A, tick, S, bar);
-    persistent_gemm_phase(p, S.B, tick, S, bar);
+    persistent_gemm_phase(p, S.A, tick, S, bar, 0);
+    persistent_gemm_phase(p, S.B, tick, S, bar, 1);
     if (tick < S.T) {
       if (threadIdx.x == 0) { grid_wait(S.gridbar, bar * gridDim.x); STAMP(S, bar, 0); }
       __syncthreads();
@@ -460,8 +468,8 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) scan_bwd_persistent(const S
       if (threadIdx.x == 0) grid_arrive(S.gridbar);
       ++bar;
     }
-    persistent_gemm_phase(p, S.B1, tick, S, bar);
-    persistent_gemm_phase(p, S.B2, tick, S, bar);
+    persistent_gemm_phase(p, S.B1, tick, S, bar, 0);
+    persistent_gemm_phase(p, S.B2, tick, S, bar, 1);
   }
   pipe_teardown(p);
 }
@@ -471,9 +479,15 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) scan_bwd_persistent(const S
 // =========================================================================
 // dst planes [R_out][ld] ; src fp32 [rows][cols] row-major.
 // transpose=1: dst[c][r] = src[r][c] (dst rows = src cols)
+// tiled_nkb > 0: the destination is tile-contiguous: element (r, c) of the (possibly transposed) result goes to
+// ((r/128)*tiled_nkb + c/64)*128*64 + (r%128)*64 + c%64
+__device__ __forceinline__ long long pack_dst_index(long long r, long long c, long long dst_ld, int tiled_nkb) {
+  if (tiled_nkb <= 0) return r * dst_ld + c;
+  return (((r >> 7) * tiled_nkb + (c >> 6)) * 128 + (r & 127)) * 64 + (c & 63);
+}
 __global__ void pack_planes_kernel(const float* __restrict__ src, long long src_ld, int rows, int cols,
                                    bf16* __restrict__ hi, bf16* __restrict__ lo, long long dst_ld,
-                                   int transpose) {
+                                   int transpose, int tiled_nkb) {
   __shared__ float tile[32][33];
   const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
   const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
@@ -483,8 +497,9 @@ __global__ void pack_planes_kernel(const float* __restrict__ src, long long src_
       if (r < rows && c < cols) {
         bf16 hh, ll;
         split_bf16(src[(long long)r * src_ld + c], hh, ll);
-        hi[(long long)r * dst_ld + c] = hh;
-        lo[(long long)r * dst_ld + c] = ll;
+        const long long o = pack_dst_index(r, c, dst_ld, tiled_nkb);
+        hi[o] = hh;
+        lo[o] = ll;
       }
     }
   } else {
@@ -498,8 +513,9 @@ __global__ void pack_planes_kernel(const float* __restrict__ src, long long src_
       if (r < rows && c < cols) {
         bf16 hh, ll;
         split_bf16(tile[tx][j], hh, ll);
-        hi[(long long)c * dst_ld + r] = hh;
-        lo[(long long)c * dst_ld + r] = ll;
+        const long long o = pack_dst_index(c, r, dst_ld, tiled_nkb);
+        hi[o] = hh;
+        lo[o] = ll;
       }
     }
   }
