@@ -535,6 +535,7 @@ static void run_table(parrot_model& M, const std::string& name, int tick, int T,
   P.split_scratch = M.d_split_scratch; P.split_count = M.d_split_count;
   P.timeline = M.timeline;
   P.coop_epilogue = (t.count <= 148 && M.sm_count >= 148) ? 1 : 0;
+  P.debug_flags = 0;
   cudaEvent_t pe = M.prof_begin(name, st);
   if (M.cfg.gemm_impl == 1) {
     const int grid = std::min(t.count, 148 * 8);
@@ -1265,6 +1266,10 @@ static EngineParams table_params(parrot_model& M, const std::string& name, int r
   P.tick = 0; P.T = M.d.T; P.n_cols = t.n_cols; P.reverse = reverse;
   P.split_scratch = M.d_split_scratch; P.split_count = M.d_split_count;
   P.timeline = nullptr; P.coop_epilogue = 1;
+  {
+    const char* e = getenv("PARROT_DEBUG_FLAGS");
+    P.debug_flags = e ? atoi(e) : 0;
+  }
   return P;
 }
 

@@ -135,6 +135,7 @@ struct EngineParams {
   int reverse;    // 0: t = tick - lag ; 1: t = (T - 1) - (tick - lag)
   float* split_scratch;        // [group][part][n_cols][128] partial tiles
   unsigned int* split_count;   // [group] arrival counters (zero between launches)
+  int debug_flags;             // experiments: 1 skip partial loads, 2 skip epilogue body, 4 skip arrival wait fence
   int coop_epilogue;           // 1: all parts of a split tile share the final epilogue (needs <= 1 job per CTA)
   unsigned long long* timeline;  // debug: [cta][16] globaltimer stamps at pipeline milestones (or null)
 };
@@ -179,19 +180,48 @@ __device__ __forceinline__ void job_kb_range(const Job& jb, int total_kb, int& l
 }
 
 // ------------------------------------------------------------------ epilogues
+// Everything an epilogue needs, snapshotted into registers ONCE per job.  The job table and the scan context
+// live in global memory; reading them inside the store loops forces the compiler to reload pointers and
+// scalars after every store (possible aliasing), which serialises the epilogue into dependent L2 round trips.
+struct EpiLocal {
+  int epi, row0, m_valid, n0, aux, slot_off;
+  int B, H, Np, Hp, C;
+  LayerBuf L;     // layer jb.layer (forward) / unused
+  float* dst;     // EPI_BWD_STATE destination buffer
+  int dstF;
+  PlainArgs pa;
+};
+__device__ __forceinline__ EpiLocal make_epi_local(const Job& jb, const ScanCtx* ctx) {
+  EpiLocal E;
+  E.epi = jb.epi; E.row0 = jb.row0; E.m_valid = jb.m_valid; E.n0 = jb.n0; E.aux = jb.aux;
+  E.slot_off = jb.pa.n_pad;
+  E.pa = jb.pa;
+  E.B = E.H = E.Np = E.Hp = E.C = 0;
+  E.dst = nullptr; E.dstF = 0;
+  if (jb.epi != EPI_PLAIN) {
+    E.B = ctx->B; E.H = ctx->H; E.Np = ctx->Np; E.Hp = ctx->Hp; E.C = ctx->C;
+    E.L = ctx->L[jb.layer];
+    if (jb.epi == EPI_BWD_STATE) {
+      if (jb.aux == 3) { E.dst = ctx->dw; E.dstF = ctx->C; }
+      else { E.dst = ctx->L[jb.aux].dh; E.dstF = ctx->H; }
+    }
+  }
+  return E;
+}
+
 // Thread <-> output row (feature).  v[j] is the accumulator for sample n_base + j.
 template <int W>
-__device__ __forceinline__ void epi_plain(const Job& jb, int t, int row, int n_base, int ncols,
+__device__ __forceinline__ void epi_plain(const EpiLocal& E, int t, int row, int n_base, int ncols,
                                           const float* v) {
-  const PlainArgs& a = jb.pa;
-  if (row >= jb.m_valid) return;
-  const int f = jb.row0 + row;
-  const float bias = a.bias ? a.bias[f] : 0.0f;
+  const PlainArgs& a = E.pa;
+  if (row >= E.m_valid) return;
+  const int f = E.row0 + row;
+  const float bias = a.bias ? __ldg(a.bias + f) : 0.0f;
   float* out = a.out ? a.out + (long long)t * a.out_tstride : nullptr;
 #pragma unroll
   for (int j = 0; j < W; ++j) {
     if (j >= ncols) break;
-    const int n = jb.n0 + n_base + j;
+    const int n = E.n0 + n_base + j;
     if (n >= a.n_total) break;
     long long srow = n;
     if (a.n_pad > 0) {
@@ -216,39 +246,38 @@ __device__ __forceinline__ void epi_plain(const Job& jb, int t, int row, int n_b
 }
 
 // forward scan, gates tile: rows [0, 2H) of [update | reset]   (model.py:659-662)
-// All epilogues below are written as fully unrolled loops over the 32 columns of a TMEM chunk with the
-// global loads issued ahead of the arithmetic (32 independent requests in flight per thread).
+// The scan epilogues are fully unrolled over the W columns with the global loads issued ahead of the math.
 template <int W>
-__device__ __forceinline__ void epi_gates(const Job& jb, const ScanCtx& c, int t, int row, int n_base,
-                                          int ncols, const float* v) {
-  if (row >= jb.m_valid) return;
-  const LayerBuf& L = c.L[jb.layer];
-  const int H = c.H, f = jb.row0 + row;
+__device__ __forceinline__ void epi_gates(const EpiLocal& E, int t, int row, int n_base, int ncols,
+                                          const float* v) {
+  if (row >= E.m_valid) return;
+  const int H = E.H, B = E.B, f = E.row0 + row;
   const bool is_z = f < H;
   const int fr = is_z ? f : f - H;
+  const float* __restrict__ basep = E.L.base + H + f;
+  const float* __restrict__ hprev = E.L.h + (long long)t * B * H + fr;
+  float* __restrict__ outp = (is_z ? E.L.z : E.L.r) + (long long)t * B * H + fr;
+  bf16* __restrict__ phi = E.L.rh_hi + (long long)t * E.Np * E.Hp + fr;
+  bf16* __restrict__ plo = E.L.rh_lo + (long long)t * E.Np * E.Hp + fr;
   float pre[W], hp[W];
 #pragma unroll
   for (int j = 0; j < W; ++j) {
     const int b = n_base + j;
-    const bool ok = j < ncols && b < c.B;
-    pre[j] = ok ? __ldg(L.base + (long long)b * 3 * H + H + f) : 0.0f;
-    hp[j] = (ok && !is_z) ? L.h[((long long)t * c.B + b) * H + fr] : 0.0f;
+    const bool ok = j < ncols && b < B;
+    pre[j] = ok ? __ldg(basep + (long long)b * 3 * H) : 0.0f;
+    hp[j] = (ok && !is_z) ? hprev[(long long)b * H] : 0.0f;
   }
 #pragma unroll
   for (int j = 0; j < W; ++j) {
     const int b = n_base + j;
-    if (j < ncols && b < c.B) {
+    if (j < ncols && b < B) {
       const float g = sigmoidf_fast(v[j] + pre[j]);
-      const long long o = ((long long)t * c.B + b) * H + fr;
-      if (is_z) {
-        L.z[o] = g;
-      } else {
-        L.r[o] = g;
+      outp[(long long)b * H] = g;
+      if (!is_z) {
         bf16 hh, ll;
         split_bf16(g * hp[j], hh, ll);
-        const long long po = ((long long)t * c.Np + b) * c.Hp + fr;
-        L.rh_hi[po] = hh;
-        L.rh_lo[po] = ll;
+        phi[(long long)b * E.Hp] = hh;
+        plo[(long long)b * E.Hp] = ll;
       }
     }
   }
@@ -256,35 +285,38 @@ __device__ __forceinline__ void epi_gates(const Job& jb, const ScanCtx& c, int t
 
 // forward scan, candidate tile: rows [0, H)
 template <int W>
-__device__ __forceinline__ void epi_cand(const Job& jb, const ScanCtx& c, int t, int row, int n_base,
-                                         int ncols, const float* v) {
-  if (row >= jb.m_valid) return;
-  const LayerBuf& L = c.L[jb.layer];
-  const int H = c.H, f = jb.row0 + row;
+__device__ __forceinline__ void epi_cand(const EpiLocal& E, int t, int row, int n_base, int ncols,
+                                         const float* v) {
+  if (row >= E.m_valid) return;
+  const int H = E.H, B = E.B, f = E.row0 + row;
+  const long long tb = (long long)t * B * H + f;
+  const float* __restrict__ basep = E.L.base + f;
+  const float* __restrict__ zp = E.L.z + tb;
+  float* __restrict__ hp_ = E.L.h + tb;          // slot t (read) ; slot t + 1 = + B*H (write)
+  float* __restrict__ cp = E.L.c + tb;
+  bf16* __restrict__ phi = E.L.h_hi + (long long)(t + 1) * E.Np * E.Hp + f;
+  bf16* __restrict__ plo = E.L.h_lo + (long long)(t + 1) * E.Np * E.Hp + f;
   float pre[W], zz[W], hp[W];
 #pragma unroll
   for (int j = 0; j < W; ++j) {
     const int b = n_base + j;
-    const bool ok = j < ncols && b < c.B;
-    const long long o = ((long long)t * c.B + b) * H + f;
-    pre[j] = ok ? __ldg(L.base + (long long)b * 3 * H + f) : 0.0f;
-    zz[j] = ok ? L.z[o] : 0.0f;
-    hp[j] = ok ? L.h[o] : 0.0f;
+    const bool ok = j < ncols && b < B;
+    pre[j] = ok ? __ldg(basep + (long long)b * 3 * H) : 0.0f;
+    zz[j] = ok ? zp[(long long)b * H] : 0.0f;
+    hp[j] = ok ? hp_[(long long)b * H] : 0.0f;
   }
 #pragma unroll
   for (int j = 0; j < W; ++j) {
     const int b = n_base + j;
-    if (j < ncols && b < c.B) {
+    if (j < ncols && b < B) {
       const float cc = tanhf_fast(v[j] + pre[j]);
-      const long long o = ((long long)t * c.B + b) * H + f;
       const float hn = cc * zz[j] + hp[j] * (1.0f - zz[j]);
-      L.c[o] = cc;
-      L.h[o + (long long)c.B * H] = hn;  // slot t + 1
+      cp[(long long)b * H] = cc;
+      hp_[(long long)b * H + (long long)B * H] = hn;  // slot t + 1
       bf16 hh, ll;
       split_bf16(hn, hh, ll);
-      const long long po = ((long long)(t + 1) * c.Np + b) * c.Hp + f;
-      L.h_hi[po] = hh;
-      L.h_lo[po] = ll;
+      phi[(long long)b * E.Hp] = hh;
+      plo[(long long)b * E.Hp] = ll;
     }
   }
 }
@@ -294,78 +326,73 @@ __device__ __forceinline__ void epi_cand(const Job& jb, const ScanCtx& c, int t,
 //   dr = drh * h_prev ; dh_prev += drh * r ; da_g[reset half] = dr r (1-r) -> planes + fp32
 // (the update half of da_g and da_c come from the elementwise pre-pass, gru_bwd_pre_kernel)
 template <int W>
-__device__ __forceinline__ void epi_bwd_rh(const Job& jb, const ScanCtx& c, int t, int row, int n_base,
-                                           int ncols, const float* v) {
-  if (row >= jb.m_valid) return;
-  const LayerBuf& L = c.L[jb.layer];
-  const int H = c.H, f = jb.row0 + row;
+__device__ __forceinline__ void epi_bwd_rh(const EpiLocal& E, int t, int row, int n_base, int ncols,
+                                           const float* v) {
+  if (row >= E.m_valid) return;
+  const int H = E.H, B = E.B, f = E.row0 + row;
+  const long long tb = (long long)t * B * H + f;
+  const float* __restrict__ rp = E.L.r + tb;
+  const float* __restrict__ hpv = E.L.h + tb;
+  float* __restrict__ dhp = E.L.dh + tb;    // slot t (state before the step)
+  float* __restrict__ dap = E.L.da + (long long)t * B * 3 * H + 2 * H + f;
+  bf16* __restrict__ phi = E.L.da_hi + (long long)t * E.Np * (3 * E.Hp) + E.Hp + H + f;
+  bf16* __restrict__ plo = E.L.da_lo + (long long)t * E.Np * (3 * E.Hp) + E.Hp + H + f;
   float rr[W], hp[W], dh[W];
 #pragma unroll
   for (int j = 0; j < W; ++j) {
     const int b = n_base + j;
-    const bool ok = j < ncols && b < c.B;
-    const long long o = ((long long)t * c.B + b) * H + f;
-    rr[j] = ok ? L.r[o] : 0.0f;
-    hp[j] = ok ? L.h[o] : 0.0f;
-    dh[j] = ok ? L.dh[o] : 0.0f;
+    const bool ok = j < ncols && b < B;
+    rr[j] = ok ? rp[(long long)b * H] : 0.0f;
+    hp[j] = ok ? hpv[(long long)b * H] : 0.0f;
+    dh[j] = ok ? dhp[(long long)b * H] : 0.0f;
   }
 #pragma unroll
   for (int j = 0; j < W; ++j) {
     const int b = n_base + j;
-    if (j < ncols && b < c.B) {
-      const long long o = ((long long)t * c.B + b) * H + f;
+    if (j < ncols && b < B) {
       const float drh = v[j];
       const float dr = drh * hp[j];
-      L.dh[o] = dh[j] + drh * rr[j];  // slot t (state before the step)
+      dhp[(long long)b * H] = dh[j] + drh * rr[j];
       const float dag = dr * rr[j] * (1.0f - rr[j]);
-      L.da[((long long)t * c.B + b) * 3 * H + 2 * H + f] = dag;
+      dap[(long long)b * 3 * H] = dag;
       bf16 hh, ll;
       split_bf16(dag, hh, ll);
-      const long long po = ((long long)t * c.Np + b) * (3 * c.Hp) + c.Hp + H + f;
-      L.da_hi[po] = hh;
-      L.da_lo[po] = ll;
+      phi[(long long)b * 3 * E.Hp] = hh;
+      plo[(long long)b * 3 * E.Hp] = ll;
     }
   }
 }
 
-// backward scan: accumulate a dgrad tile into a carried gradient buffer.
-//   aux = 0..2 : dh of layer aux, slot = t + jb.pa.n_pad(slot offset) ; aux = 3 : dw
+// backward scan: accumulate a dgrad tile into a carried gradient buffer (dh of a layer or dw), slot t + slot_off
 template <int W>
-__device__ __forceinline__ void epi_bwd_state(const Job& jb, const ScanCtx& c, int t, int row, int n_base,
-                                              int ncols, const float* v) {
-  if (row >= jb.m_valid) return;
-  const int f = jb.row0 + row;
-  const int slot = t + jb.pa.n_pad;
-  float* dst;
-  int F;
-  if (jb.aux == 3) {
-    dst = c.dw; F = c.C;
-  } else {
-    dst = c.L[jb.aux].dh; F = c.H;
-  }
+__device__ __forceinline__ void epi_bwd_state(const EpiLocal& E, int t, int row, int n_base, int ncols,
+                                              const float* v) {
+  if (row >= E.m_valid) return;
+  const int F = E.dstF, B = E.B;
+  float* __restrict__ dst = E.dst + (long long)(t + E.slot_off) * B * F + (E.row0 + row);
   float old[W];
 #pragma unroll
   for (int j = 0; j < W; ++j) {
     const int b = n_base + j;
-    old[j] = (j < ncols && b < c.B) ? dst[((long long)slot * c.B + b) * F + f] : 0.0f;
+    old[j] = (j < ncols && b < B) ? dst[(long long)b * F] : 0.0f;
   }
 #pragma unroll
   for (int j = 0; j < W; ++j) {
     const int b = n_base + j;
-    if (j < ncols && b < c.B) dst[((long long)slot * c.B + b) * F + f] = old[j] + v[j];
+    if (j < ncols && b < B) dst[(long long)b * F] = old[j] + v[j];
   }
 }
 
 // W = number of columns held in v[] (compile time: the loops are fully unrolled over W)
 template <int W>
-__device__ __forceinline__ void run_epilogue(const Job& jb, const ScanCtx* ctx, int t, int row, int n_base,
-                                             int ncols, const float* v) {
-  switch (jb.epi) {
-    case EPI_PLAIN: epi_plain<W>(jb, t, row, n_base, ncols, v); break;
-    case EPI_GATES: epi_gates<W>(jb, *ctx, t, row, n_base, ncols, v); break;
-    case EPI_CAND: epi_cand<W>(jb, *ctx, t, row, n_base, ncols, v); break;
-    case EPI_BWD_RH: epi_bwd_rh<W>(jb, *ctx, t, row, n_base, ncols, v); break;
-    case EPI_BWD_STATE: epi_bwd_state<W>(jb, *ctx, t, row, n_base, ncols, v); break;
+__device__ __forceinline__ void run_epilogue(const EpiLocal& E, int t, int row, int n_base, int ncols,
+                                             const float* v) {
+  switch (E.epi) {
+    case EPI_PLAIN: epi_plain<W>(E, t, row, n_base, ncols, v); break;
+    case EPI_GATES: epi_gates<W>(E, t, row, n_base, ncols, v); break;
+    case EPI_CAND: epi_cand<W>(E, t, row, n_base, ncols, v); break;
+    case EPI_BWD_RH: epi_bwd_rh<W>(E, t, row, n_base, ncols, v); break;
+    case EPI_BWD_STATE: epi_bwd_state<W>(E, t, row, n_base, ncols, v); break;
   }
 }
 
@@ -542,6 +569,8 @@ __device__ __forceinline__ void epilogue_run(Pipe& p, const EngineParams& P, int
     const bool have_acc = khi > klo;
     const int buf = p.it & 1;
     const uint32_t use = (uint32_t)(p.it >> 1);
+    const EpiLocal E = make_epi_local(jb, P.ctx);
+    const int ksplit = jb.ksplit, kpart = jb.kpart, group = jb.group;
     if (tmem_warp) {
       const uint32_t taddr = p.tmem_base + (uint32_t)buf * 256u + ((uint32_t)(q * 32) << 16);
       if (have_acc) {
@@ -549,16 +578,16 @@ __device__ __forceinline__ void epilogue_run(Pipe& p, const EngineParams& P, int
         tc_fence_after();
       }
       if (threadIdx.x == 64) TL(4);
-      if (jb.ksplit <= 1) {
+      if (ksplit <= 1) {
         for (int n0 = 0; n0 < n_cols; n0 += 16) {
           float v[16];
           tmem_ld_32x16(taddr + n0, v);
           tmem_ld_wait();
-          run_epilogue<16>(jb, P.ctx, t, row, n0, 16, v);
+          run_epilogue<16>(E, t, row, n0, 16, v);
         }
       } else {
         // park the partial tile: scratch[group][part][col][row]  (row fastest -> coalesced)
-        float* part = P.split_scratch + ((size_t)jb.group * MAX_KSPLIT + jb.kpart) * (size_t)n_cols * TILE_M;
+        float* part = P.split_scratch + ((size_t)group * MAX_KSPLIT + kpart) * (size_t)n_cols * TILE_M;
         for (int n0 = 0; n0 < n_cols; n0 += 16) {
           float v[16];
           if (have_acc) {
@@ -579,31 +608,31 @@ __device__ __forceinline__ void epilogue_run(Pipe& p, const EngineParams& P, int
       }
       if (threadIdx.x == 64) TL(5);
     }
-    if (jb.ksplit > 1) {
+    if (ksplit > 1) {
       if (tmem_warp) __threadfence();
       asm volatile("bar.sync 1, 320;" ::: "memory");   // partial tile written by warps 2..5
-      const float* base = P.split_scratch + (size_t)jb.group * MAX_KSPLIT * (size_t)n_cols * TILE_M;
+      const float* base = P.split_scratch + (size_t)group * MAX_KSPLIT * (size_t)n_cols * TILE_M;
       int c_lo = 0, c_hi = 0;
       if (P.coop_epilogue) {
         // Every part of the tile finishes a slice of its columns once all parts have arrived.  Safe because
         // the launch has at most one job per CTA and all CTAs are co-resident (grid <= SM count).
         if (warp == 2 && lane == 0) {
-          atomicAdd(P.split_count + jb.group, 1u);
+          atomicAdd(P.split_count + group, 1u);
           unsigned int seen, spins = 0;
           do {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(P.split_count + jb.group) : "memory");
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(P.split_count + group) : "memory");
             if (++spins > (1u << 24)) { printf("parrot_b200: split-K arrival wait timed out\n"); __trap(); }
-          } while ((seen & 0xffffu) < (unsigned int)jb.ksplit);
+          } while ((seen & 0xffffu) < (unsigned int)ksplit);
         }
         asm volatile("bar.sync 1, 320;" ::: "memory");
         if (threadIdx.x == 64) TL(6);
-        c_lo = (n_cols * jb.kpart) / jb.ksplit;
-        c_hi = (n_cols * (jb.kpart + 1)) / jb.ksplit;
+        c_lo = (n_cols * kpart) / ksplit;
+        c_hi = (n_cols * (kpart + 1)) / ksplit;
       } else {
         if (warp == 2 && lane == 0) {
-          const unsigned int old = atomicAdd(P.split_count + jb.group, 1u);
-          const bool last = old == (unsigned int)(jb.ksplit - 1);
-          if (last) P.split_count[jb.group] = 0u;   // ready for the next launch
+          const unsigned int old = atomicAdd(P.split_count + group, 1u);
+          const bool last = old == (unsigned int)(ksplit - 1);
+          if (last) P.split_count[group] = 0u;   // ready for the next launch
           *p.split_flag = last ? 1u : 0u;
         }
         asm volatile("bar.sync 1, 320;" ::: "memory");
@@ -624,20 +653,21 @@ __device__ __forceinline__ void epilogue_run(Pipe& p, const EngineParams& P, int
           const float* src = base + (size_t)pp * n_cols * TILE_M;
 #pragma unroll
           for (int i = 0; i < 4; ++i)
-            x[pp][i] = (pp < jb.ksplit && i < nc) ? __ldcg(src + (size_t)(n0 + i) * TILE_M + r) : 0.0f;
+            x[pp][i] = (pp < ksplit && i < nc && !(P.debug_flags & 1)) ? __ldcg(src + (size_t)(n0 + i) * TILE_M + r) : 0.0f;
         }
 #pragma unroll
         for (int pp = 0; pp < MAX_KSPLIT; ++pp)   // part order: deterministic
 #pragma unroll
           for (int i = 0; i < 4; ++i) v[i] += x[pp][i];
-        run_epilogue<4>(jb, P.ctx, t, r, n0, nc, v);
+        if (!(P.debug_flags & 2)) run_epilogue<4>(E, t, r, n0, nc, v);
+        else if (v[0] == 123.456f) P.split_scratch[0] = v[1] + v[2] + v[3];
       }
       if (threadIdx.x == 64) TL(7);
       asm volatile("bar.sync 1, 320;" ::: "memory");
       if (P.coop_epilogue && warp == 2 && lane == 0) {
         // the last part to finish resets the arrival counter for the next use
-        const unsigned int old = atomicAdd(P.split_count + jb.group, 0x10000u);
-        if ((old >> 16) == (unsigned int)(jb.ksplit - 1)) P.split_count[jb.group] = 0u;
+        const unsigned int old = atomicAdd(P.split_count + group, 0x10000u);
+        if ((old >> 16) == (unsigned int)(ksplit - 1)) P.split_count[group] = 0u;
       }
     }
     if (have_acc) ++p.it;   // accumulator buffers advance only when one was used (mirrors the MMA warp)
@@ -698,6 +728,7 @@ __global__ void __launch_bounds__(128) job_kernel_simt(const EngineParams P) {
     const int t = job_time(P, jb, P.tick);
     if (job_total_kb(P, jb, t) == 0) continue;
     if (jb.ksplit > 1 && jb.kpart != 0) continue;   // the SIMT twin does not split: part 0 does the whole tile
+    const EpiLocal E = make_epi_local(jb, P.ctx);
     for (int n0 = 0; n0 < P.n_cols; n0 += 32) {
       const int nc = (P.n_cols - n0 >= 32) ? 32 : (P.n_cols - n0);
       float acc[32];
@@ -741,7 +772,7 @@ __global__ void __launch_bounds__(128) job_kernel_simt(const EngineParams P) {
           }
         }
       }
-      run_epilogue<32>(jb, P.ctx, t, tid, n0, nc, acc);
+      run_epilogue<32>(E, t, tid, n0, nc, acc);
     }
   }
 }

@@ -311,31 +311,38 @@ __global__ void __launch_bounds__(256) attention_bwd_kernel(const AttnBwdArgs a)
 // =========================================================================
 struct PreArgs { int layer[3]; int t[3]; int n; };
 __device__ __forceinline__ void gru_bwd_pre_body(const ScanCtx& c, const int layer, const int t) {
-  const LayerBuf& L = c.L[layer];
-  const int H = c.H;
-  const long long n = (long long)c.B * H;
+  // snapshot the context (it lives in global memory; see EpiLocal in engine.cuh)
+  const LayerBuf L = c.L[layer];
+  const int H = c.H, B = c.B, Np = c.Np, Hp = c.Hp;
+  const long long n = (long long)B * H;
+  const float* __restrict__ zp = L.z + (long long)t * n;
+  const float* __restrict__ cp = L.c + (long long)t * n;
+  const float* __restrict__ hp = L.h + (long long)t * n;
+  float* __restrict__ dhp = L.dh + (long long)t * n;         // slot t ; slot t + 1 = + n
+  float* __restrict__ dap = L.da + (long long)t * B * 3 * H;
+  bf16* __restrict__ phi = L.da_hi + (long long)t * Np * (3 * Hp);
+  bf16* __restrict__ plo = L.da_lo + (long long)t * Np * (3 * Hp);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
     const int b = (int)(i / H), f = (int)(i % H);
-    const long long o = ((long long)t * c.B + b) * H + f;
-    const float dh = L.dh[o + n];  // slot t + 1
-    const float z = L.z[o], cc = L.c[o], hp = L.h[o];
+    const float dh = dhp[i + n];  // slot t + 1
+    const float z = zp[i], cc = cp[i], hpv = hp[i];
     const float dc = dh * z;
-    const float dz = dh * (cc - hp);
-    L.dh[o] += dh * (1.0f - z);
+    const float dz = dh * (cc - hpv);
+    dhp[i] += dh * (1.0f - z);
     const float dac = dc * (1.0f - cc * cc);
     const float dagz = dz * z * (1.0f - z);
-    const long long ao = ((long long)t * c.B + b) * 3 * H;
-    L.da[ao + f] = dac;
-    L.da[ao + H + f] = dagz;
-    const long long po = ((long long)t * c.Np + b) * (3 * c.Hp);
+    const long long ao = (long long)b * 3 * H;
+    dap[ao + f] = dac;
+    dap[ao + H + f] = dagz;
+    const long long po = (long long)b * (3 * Hp);
     bf16 hh, ll;
     split_bf16(dac, hh, ll);
-    L.da_hi[po + f] = hh;
-    L.da_lo[po + f] = ll;
+    phi[po + f] = hh;
+    plo[po + f] = ll;
     split_bf16(dagz, hh, ll);
-    L.da_hi[po + c.Hp + f] = hh;
-    L.da_lo[po + c.Hp + f] = ll;
+    phi[po + Hp + f] = hh;
+    plo[po + Hp + f] = ll;
   }
 }
 __global__ void gru_bwd_pre_kernel(const ScanCtx* cp, const PreArgs pa) {
@@ -386,7 +393,7 @@ __device__ __forceinline__ void persistent_gemm_phase(Pipe& p, const EngineParam
                                                       unsigned int& bar, int which) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   EngineParams P = P0;
-  P.timeline = (S.tl_buf && tick == S.tl_tick) ? S.tl_buf + (size_t)which * gridDim.x * 16 : nullptr;
+  P.timeline = (S.tl_buf && tick == S.tl_tick) ? S.tl_buf + (size_t)(which + 1) * gridDim.x * 16 : nullptr;
   unsigned int* gridbar = S.gridbar;
   const unsigned int target = bar * gridDim.x;
   if (warp == 0) {

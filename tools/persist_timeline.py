@@ -41,12 +41,12 @@ tick_span = np.median(np.diff(s[0, 0::3, 0])[5:T - 3])
 print('tick period %.2f us' % tick_span)
 
 # ---- intra-phase milestones of one steady-state tick
-tl = torch.zeros(2 * 148 * 16, dtype=torch.int64, device='cuda')
+tl = torch.zeros(3 * 148 * 16, dtype=torch.int64, device='cuda')
 lib.parrot_debug_set_stamps(h.ptr, C.c_void_p(tl.data_ptr()), -20)
 m.compute_cost(bt['features'], bt['features_mask'], bt['labels'], bt['labels_mask'], None, 1.0, B)
 torch.cuda.synchronize()
 lib.parrot_debug_set_stamps(h.ptr, None, 0)
-tl = tl.cpu().numpy().reshape(2, 148, 16).astype(np.float64)
+tl = tl.cpu().numpy().reshape(3, 148, 16).astype(np.float64)[1:]
 names = {0: 'enter_phase', 1: 'barrier_passed', 2: 'tma_done', 3: 'mma_done', 4: 'acc_ready', 5: 'part_written',
          6: 'all_arrived', 7: 'epi_done'}
 for ph in range(2):
