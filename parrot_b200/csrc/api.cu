@@ -670,6 +670,7 @@ static void build(parrot_model& M) {
   M.falloc("phi", (long long)T * B * d.U);
   M.falloc("ab", (long long)T * B * 2 * d.A);
   M.falloc("att_e", (long long)T * B * 3 * d.A);
+  M.falloc("att_hat", (long long)B * 3 * d.A);
   if (d.weak) {
     Plane px = M.make_plane("xin", Np, d.D, d.sampling ? T + 1 : T);
     M.map_scan["xin"] = M.make_map(px, 3, Np);
@@ -1230,6 +1231,7 @@ static AttnFwdArgs attn_fwd_args(parrot_model& M, int t, bool sampling) {
   a.phi_out = M.fbuf("phi") + (long long)t * d.B * d.U;
   a.ab_out = M.fbuf("ab") + (long long)t * d.B * 2 * d.A;
   a.e_out = M.fbuf("att_e") + (long long)t * d.B * 3 * d.A;
+  a.hat = M.fbuf("att_hat");
   return a;
 }
 static void attention_step(parrot_model& M, int t, bool sampling, cudaStream_t st) {

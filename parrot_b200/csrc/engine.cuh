@@ -33,7 +33,9 @@ constexpr int TILE_M = 128;
 constexpr int KB = 64;  // k elements per pipeline block (one 128-byte swizzle span)
 constexpr int MAX_SEG = 6;
 constexpr int NO_SLOT = -(1 << 30);
-constexpr int ENGINE_THREADS = 384;   // warp 0 TMA, warp 1 MMA, warps 2-5 TMEM epilogue, warps 6-11 epilogue helpers
+// 12 warps: warp 0 TMA, warp 1 MMA, warps 2-5 TMEM epilogue, warps 6-11 epilogue helpers.  Register cap:
+// 3 warps per scheduler sub-partition -> 16384 / (3*32) = 168 registers per thread (same for 10..12 warps).
+constexpr int ENGINE_THREADS = 384;
 constexpr int EPI_GROUP_THREADS = 320; // warps 2..11 share the post-reduction (split-K) epilogue
 constexpr int SMEM_BYTES = 200 * 1024;
 constexpr int MAX_KSPLIT = 8;   // scratch stride per split group
@@ -183,28 +185,48 @@ __device__ __forceinline__ void job_kb_range(const Job& jb, int total_kb, int& l
 // Everything an epilogue needs, snapshotted into registers ONCE per job.  The job table and the scan context
 // live in global memory; reading them inside the store loops forces the compiler to reload pointers and
 // scalars after every store (possible aliasing), which serialises the epilogue into dependent L2 round trips.
+// Kept small (generic pointer slots) because the 12-warp CTA caps registers at 168 per thread:
+//   GATES      p0 base  p1 h   p2 z   p3 r    p4 rh_hi  p5 rh_lo
+//   CAND       p0 base  p1 h   p2 z   p3 c    p4 h_hi   p5 h_lo
+//   BWD_RH     p0 r     p1 h   p2 dh  p3 da   p4 da_hi  p5 da_lo
+//   BWD_STATE  p0 dst (F = dstF, slot offset = slot_off)
+//   PLAIN      p0 out   p1 bias p2 hi p3 lo ; l0 ldo, l1 ldp, l2 out_tstride ; n_pad n_valid n_total flags scale
 struct EpiLocal {
-  int epi, row0, m_valid, n0, aux, slot_off;
-  int B, H, Np, Hp, C;
-  LayerBuf L;     // layer jb.layer (forward) / unused
-  float* dst;     // EPI_BWD_STATE destination buffer
-  int dstF;
-  PlainArgs pa;
+  int epi, row0, m_valid, n0, slot_off;
+  int B, H, Np, Hp, dstF;
+  int n_pad, n_valid, n_total, flags;
+  float scale;
+  void *p0, *p1, *p2, *p3, *p4, *p5;
+  long long l0, l1, l2;
 };
 __device__ __forceinline__ EpiLocal make_epi_local(const Job& jb, const ScanCtx* ctx) {
   EpiLocal E;
-  E.epi = jb.epi; E.row0 = jb.row0; E.m_valid = jb.m_valid; E.n0 = jb.n0; E.aux = jb.aux;
+  E.epi = jb.epi; E.row0 = jb.row0; E.m_valid = jb.m_valid; E.n0 = jb.n0;
   E.slot_off = jb.pa.n_pad;
-  E.pa = jb.pa;
-  E.B = E.H = E.Np = E.Hp = E.C = 0;
-  E.dst = nullptr; E.dstF = 0;
-  if (jb.epi != EPI_PLAIN) {
-    E.B = ctx->B; E.H = ctx->H; E.Np = ctx->Np; E.Hp = ctx->Hp; E.C = ctx->C;
-    E.L = ctx->L[jb.layer];
-    if (jb.epi == EPI_BWD_STATE) {
-      if (jb.aux == 3) { E.dst = ctx->dw; E.dstF = ctx->C; }
-      else { E.dst = ctx->L[jb.aux].dh; E.dstF = ctx->H; }
-    }
+  E.B = E.H = E.Np = E.Hp = E.dstF = 0;
+  E.n_pad = E.n_valid = E.n_total = E.flags = 0; E.scale = 1.0f;
+  E.p0 = E.p1 = E.p2 = E.p3 = E.p4 = E.p5 = nullptr;
+  E.l0 = E.l1 = E.l2 = 0;
+  if (jb.epi == EPI_PLAIN) {
+    E.p0 = jb.pa.out; E.p1 = (void*)jb.pa.bias; E.p2 = jb.pa.hi; E.p3 = jb.pa.lo;
+    E.l0 = jb.pa.ldo; E.l1 = jb.pa.ldp; E.l2 = jb.pa.out_tstride;
+    E.n_pad = jb.pa.n_pad; E.n_valid = jb.pa.n_valid; E.n_total = jb.pa.n_total; E.flags = jb.pa.flags;
+    E.scale = jb.pa.scale;
+    return E;
+  }
+  E.B = ctx->B; E.H = ctx->H; E.Np = ctx->Np; E.Hp = ctx->Hp;
+  const LayerBuf& L = ctx->L[jb.layer];
+  switch (jb.epi) {
+    case EPI_GATES:
+      E.p0 = (void*)L.base; E.p1 = L.h; E.p2 = L.z; E.p3 = L.r; E.p4 = L.rh_hi; E.p5 = L.rh_lo; break;
+    case EPI_CAND:
+      E.p0 = (void*)L.base; E.p1 = L.h; E.p2 = L.z; E.p3 = L.c; E.p4 = L.h_hi; E.p5 = L.h_lo; break;
+    case EPI_BWD_RH:
+      E.p0 = L.r; E.p1 = L.h; E.p2 = L.dh; E.p3 = L.da; E.p4 = L.da_hi; E.p5 = L.da_lo; break;
+    case EPI_BWD_STATE:
+      if (jb.aux == 3) { E.p0 = ctx->dw; E.dstF = ctx->C; }
+      else { E.p0 = ctx->L[jb.aux].dh; E.dstF = ctx->H; }
+      break;
   }
   return E;
 }
@@ -213,69 +235,80 @@ __device__ __forceinline__ EpiLocal make_epi_local(const Job& jb, const ScanCtx*
 template <int W>
 __device__ __forceinline__ void epi_plain(const EpiLocal& E, int t, int row, int n_base, int ncols,
                                           const float* v) {
-  const PlainArgs& a = E.pa;
   if (row >= E.m_valid) return;
   const int f = E.row0 + row;
-  const float bias = a.bias ? __ldg(a.bias + f) : 0.0f;
-  float* out = a.out ? a.out + (long long)t * a.out_tstride : nullptr;
+  const float* biasp = (const float*)E.p1;
+  const float bias = biasp ? __ldg(biasp + f) : 0.0f;
+  float* out = E.p0 ? (float*)E.p0 + (long long)t * E.l2 : nullptr;
+  bf16* hi = (bf16*)E.p2;
+  bf16* lo = (bf16*)E.p3;
 #pragma unroll
   for (int j = 0; j < W; ++j) {
     if (j >= ncols) break;
     const int n = E.n0 + n_base + j;
-    if (n >= a.n_total) break;
+    if (n >= E.n_total) break;
     long long srow = n;
-    if (a.n_pad > 0) {
-      const int q = n / a.n_pad, r = n - q * a.n_pad;
-      if (r >= a.n_valid) continue;
-      srow = (long long)q * a.n_valid + r;
+    if (E.n_pad > 0) {
+      const int q = n / E.n_pad, r = n - q * E.n_pad;
+      if (r >= E.n_valid) continue;
+      srow = (long long)q * E.n_valid + r;
     }
-    float y = v[j] * a.scale + bias;
+    float y = v[j] * E.scale + bias;
     if (out) {
-      float* p = (a.flags & PF_TRANS) ? out + (long long)f * a.ldo + srow : out + srow * a.ldo + f;
-      if (a.flags & PF_ACC) y += *p;
+      float* p = (E.flags & PF_TRANS) ? out + (long long)f * E.l0 + srow : out + srow * E.l0 + f;
+      if (E.flags & PF_ACC) y += *p;
       *p = y;
     }
-    if (a.hi) {
-      const long long prow = (a.flags & PF_PLANE_PADDED) ? (long long)n : srow;
+    if (hi) {
+      const long long prow = (E.flags & PF_PLANE_PADDED) ? (long long)n : srow;
       bf16 h, l;
       split_bf16(y, h, l);
-      a.hi[prow * a.ldp + f] = h;
-      a.lo[prow * a.ldp + f] = l;
+      hi[prow * E.l1 + f] = h;
+      lo[prow * E.l1 + f] = l;
     }
   }
 }
 
-// forward scan, gates tile: rows [0, 2H) of [update | reset]   (model.py:659-662)
-// The scan epilogues are fully unrolled over the W columns with the global loads issued ahead of the math.
+// The scan epilogues are split in two stages so that callers can issue the operand loads BEFORE they consume
+// the accumulator (in-order issue: a load placed after the first use of an outstanding load cannot start).
 template <int W>
-__device__ __forceinline__ void epi_gates(const EpiLocal& E, int t, int row, int n_base, int ncols,
-                                          const float* v) {
+struct EpiOps { float a[W], b[W], c[W]; };
+
+// ---- forward scan, gates tile: rows [0, 2H) of [update | reset]   (model.py:659-662)
+template <int W>
+__device__ __forceinline__ void epi_gates_load(const EpiLocal& E, int t, int row, int n_base, int ncols, EpiOps<W>& o) {
+  const int H = E.H, B = E.B, f = E.row0 + row;
+  const bool is_z = f < H;
+  const int fr = is_z ? f : f - H;
+  const float* __restrict__ basep = (const float*)E.p0 + H + f;
+  const float* __restrict__ hprev = (const float*)E.p1 + (long long)t * B * H + fr;
+#pragma unroll
+  for (int j = 0; j < W; ++j) {
+    const int b = n_base + j;
+    const bool ok = row < E.m_valid && j < ncols && b < B;
+    o.a[j] = ok ? __ldg(basep + (long long)b * 3 * H) : 0.0f;
+    o.b[j] = (ok && !is_z) ? hprev[(long long)b * H] : 0.0f;
+  }
+}
+template <int W>
+__device__ __forceinline__ void epi_gates_apply(const EpiLocal& E, int t, int row, int n_base, int ncols,
+                                                const float* v, const EpiOps<W>& o) {
   if (row >= E.m_valid) return;
   const int H = E.H, B = E.B, f = E.row0 + row;
   const bool is_z = f < H;
   const int fr = is_z ? f : f - H;
-  const float* __restrict__ basep = E.L.base + H + f;
-  const float* __restrict__ hprev = E.L.h + (long long)t * B * H + fr;
-  float* __restrict__ outp = (is_z ? E.L.z : E.L.r) + (long long)t * B * H + fr;
-  bf16* __restrict__ phi = E.L.rh_hi + (long long)t * E.Np * E.Hp + fr;
-  bf16* __restrict__ plo = E.L.rh_lo + (long long)t * E.Np * E.Hp + fr;
-  float pre[W], hp[W];
-#pragma unroll
-  for (int j = 0; j < W; ++j) {
-    const int b = n_base + j;
-    const bool ok = j < ncols && b < B;
-    pre[j] = ok ? __ldg(basep + (long long)b * 3 * H) : 0.0f;
-    hp[j] = (ok && !is_z) ? hprev[(long long)b * H] : 0.0f;
-  }
+  float* __restrict__ outp = (float*)(is_z ? E.p2 : E.p3) + (long long)t * B * H + fr;
+  bf16* __restrict__ phi = (bf16*)E.p4 + (long long)t * E.Np * E.Hp + fr;
+  bf16* __restrict__ plo = (bf16*)E.p5 + (long long)t * E.Np * E.Hp + fr;
 #pragma unroll
   for (int j = 0; j < W; ++j) {
     const int b = n_base + j;
     if (j < ncols && b < B) {
-      const float g = sigmoidf_fast(v[j] + pre[j]);
+      const float g = sigmoidf_fast(v[j] + o.a[j]);
       outp[(long long)b * H] = g;
       if (!is_z) {
         bf16 hh, ll;
-        split_bf16(g * hp[j], hh, ll);
+        split_bf16(g * o.b[j], hh, ll);
         phi[(long long)b * E.Hp] = hh;
         plo[(long long)b * E.Hp] = ll;
       }
@@ -283,34 +316,39 @@ __device__ __forceinline__ void epi_gates(const EpiLocal& E, int t, int row, int
   }
 }
 
-// forward scan, candidate tile: rows [0, H)
+// ---- forward scan, candidate tile: rows [0, H)
 template <int W>
-__device__ __forceinline__ void epi_cand(const EpiLocal& E, int t, int row, int n_base, int ncols,
-                                         const float* v) {
-  if (row >= E.m_valid) return;
+__device__ __forceinline__ void epi_cand_load(const EpiLocal& E, int t, int row, int n_base, int ncols, EpiOps<W>& o) {
   const int H = E.H, B = E.B, f = E.row0 + row;
   const long long tb = (long long)t * B * H + f;
-  const float* __restrict__ basep = E.L.base + f;
-  const float* __restrict__ zp = E.L.z + tb;
-  float* __restrict__ hp_ = E.L.h + tb;          // slot t (read) ; slot t + 1 = + B*H (write)
-  float* __restrict__ cp = E.L.c + tb;
-  bf16* __restrict__ phi = E.L.h_hi + (long long)(t + 1) * E.Np * E.Hp + f;
-  bf16* __restrict__ plo = E.L.h_lo + (long long)(t + 1) * E.Np * E.Hp + f;
-  float pre[W], zz[W], hp[W];
+  const float* __restrict__ basep = (const float*)E.p0 + f;
+  const float* __restrict__ zp = (const float*)E.p2 + tb;
+  const float* __restrict__ hp_ = (const float*)E.p1 + tb;
 #pragma unroll
   for (int j = 0; j < W; ++j) {
     const int b = n_base + j;
-    const bool ok = j < ncols && b < B;
-    pre[j] = ok ? __ldg(basep + (long long)b * 3 * H) : 0.0f;
-    zz[j] = ok ? zp[(long long)b * H] : 0.0f;
-    hp[j] = ok ? hp_[(long long)b * H] : 0.0f;
+    const bool ok = row < E.m_valid && j < ncols && b < B;
+    o.a[j] = ok ? __ldg(basep + (long long)b * 3 * H) : 0.0f;
+    o.b[j] = ok ? zp[(long long)b * H] : 0.0f;
+    o.c[j] = ok ? hp_[(long long)b * H] : 0.0f;
   }
+}
+template <int W>
+__device__ __forceinline__ void epi_cand_apply(const EpiLocal& E, int t, int row, int n_base, int ncols,
+                                               const float* v, const EpiOps<W>& o) {
+  if (row >= E.m_valid) return;
+  const int H = E.H, B = E.B, f = E.row0 + row;
+  const long long tb = (long long)t * B * H + f;
+  float* __restrict__ hp_ = (float*)E.p1 + tb;          // slot t + 1 = + B*H
+  float* __restrict__ cp = (float*)E.p3 + tb;
+  bf16* __restrict__ phi = (bf16*)E.p4 + (long long)(t + 1) * E.Np * E.Hp + f;
+  bf16* __restrict__ plo = (bf16*)E.p5 + (long long)(t + 1) * E.Np * E.Hp + f;
 #pragma unroll
   for (int j = 0; j < W; ++j) {
     const int b = n_base + j;
     if (j < ncols && b < B) {
-      const float cc = tanhf_fast(v[j] + pre[j]);
-      const float hn = cc * zz[j] + hp[j] * (1.0f - zz[j]);
+      const float cc = tanhf_fast(v[j] + o.a[j]);
+      const float hn = cc * o.b[j] + o.c[j] * (1.0f - o.b[j]);
       cp[(long long)b * H] = cc;
       hp_[(long long)b * H + (long long)B * H] = hn;  // slot t + 1
       bf16 hh, ll;
@@ -321,39 +359,44 @@ __device__ __forceinline__ void epi_cand(const EpiLocal& E, int t, int row, int 
   }
 }
 
-// backward scan: tile of d(r*h) = da_c * Ws^T, rows = state features [0, H).
+// ---- backward scan: tile of d(r*h) = da_c * Ws^T, rows = state features [0, H).
 // Finishes the GRU step backward for those features:
 //   dr = drh * h_prev ; dh_prev += drh * r ; da_g[reset half] = dr r (1-r) -> planes + fp32
 // (the update half of da_g and da_c come from the elementwise pre-pass, gru_bwd_pre_kernel)
 template <int W>
-__device__ __forceinline__ void epi_bwd_rh(const EpiLocal& E, int t, int row, int n_base, int ncols,
-                                           const float* v) {
-  if (row >= E.m_valid) return;
+__device__ __forceinline__ void epi_bwd_rh_load(const EpiLocal& E, int t, int row, int n_base, int ncols, EpiOps<W>& o) {
   const int H = E.H, B = E.B, f = E.row0 + row;
   const long long tb = (long long)t * B * H + f;
-  const float* __restrict__ rp = E.L.r + tb;
-  const float* __restrict__ hpv = E.L.h + tb;
-  float* __restrict__ dhp = E.L.dh + tb;    // slot t (state before the step)
-  float* __restrict__ dap = E.L.da + (long long)t * B * 3 * H + 2 * H + f;
-  bf16* __restrict__ phi = E.L.da_hi + (long long)t * E.Np * (3 * E.Hp) + E.Hp + H + f;
-  bf16* __restrict__ plo = E.L.da_lo + (long long)t * E.Np * (3 * E.Hp) + E.Hp + H + f;
-  float rr[W], hp[W], dh[W];
+  const float* __restrict__ rp = (const float*)E.p0 + tb;
+  const float* __restrict__ hpv = (const float*)E.p1 + tb;
+  const float* __restrict__ dhp = (const float*)E.p2 + tb;
 #pragma unroll
   for (int j = 0; j < W; ++j) {
     const int b = n_base + j;
-    const bool ok = j < ncols && b < B;
-    rr[j] = ok ? rp[(long long)b * H] : 0.0f;
-    hp[j] = ok ? hpv[(long long)b * H] : 0.0f;
-    dh[j] = ok ? dhp[(long long)b * H] : 0.0f;
+    const bool ok = row < E.m_valid && j < ncols && b < B;
+    o.a[j] = ok ? rp[(long long)b * H] : 0.0f;
+    o.b[j] = ok ? hpv[(long long)b * H] : 0.0f;
+    o.c[j] = ok ? dhp[(long long)b * H] : 0.0f;
   }
+}
+template <int W>
+__device__ __forceinline__ void epi_bwd_rh_apply(const EpiLocal& E, int t, int row, int n_base, int ncols,
+                                                 const float* v, const EpiOps<W>& o) {
+  if (row >= E.m_valid) return;
+  const int H = E.H, B = E.B, f = E.row0 + row;
+  const long long tb = (long long)t * B * H + f;
+  float* __restrict__ dhp = (float*)E.p2 + tb;    // slot t (state before the step)
+  float* __restrict__ dap = (float*)E.p3 + (long long)t * B * 3 * H + 2 * H + f;
+  bf16* __restrict__ phi = (bf16*)E.p4 + (long long)t * E.Np * (3 * E.Hp) + E.Hp + H + f;
+  bf16* __restrict__ plo = (bf16*)E.p5 + (long long)t * E.Np * (3 * E.Hp) + E.Hp + H + f;
 #pragma unroll
   for (int j = 0; j < W; ++j) {
     const int b = n_base + j;
     if (j < ncols && b < B) {
       const float drh = v[j];
-      const float dr = drh * hp[j];
-      dhp[(long long)b * H] = dh[j] + drh * rr[j];
-      const float dag = dr * rr[j] * (1.0f - rr[j]);
+      const float dr = drh * o.b[j];
+      dhp[(long long)b * H] = o.c[j] + drh * o.a[j];
+      const float dag = dr * o.a[j] * (1.0f - o.a[j]);
       dap[(long long)b * 3 * H] = dag;
       bf16 hh, ll;
       split_bf16(dag, hh, ll);
@@ -363,37 +406,58 @@ __device__ __forceinline__ void epi_bwd_rh(const EpiLocal& E, int t, int row, in
   }
 }
 
-// backward scan: accumulate a dgrad tile into a carried gradient buffer (dh of a layer or dw), slot t + slot_off
+// ---- backward scan: accumulate a dgrad tile into a carried gradient buffer (dh of a layer or dw), slot t + slot_off
 template <int W>
-__device__ __forceinline__ void epi_bwd_state(const EpiLocal& E, int t, int row, int n_base, int ncols,
-                                              const float* v) {
+__device__ __forceinline__ void epi_bwd_state_load(const EpiLocal& E, int t, int row, int n_base, int ncols, EpiOps<W>& o) {
+  const int F = E.dstF, B = E.B;
+  const float* __restrict__ dst = (const float*)E.p0 + (long long)(t + E.slot_off) * B * F + (E.row0 + row);
+#pragma unroll
+  for (int j = 0; j < W; ++j) {
+    const int b = n_base + j;
+    o.a[j] = (row < E.m_valid && j < ncols && b < B) ? dst[(long long)b * F] : 0.0f;
+  }
+}
+template <int W>
+__device__ __forceinline__ void epi_bwd_state_apply(const EpiLocal& E, int t, int row, int n_base, int ncols,
+                                                    const float* v, const EpiOps<W>& o) {
   if (row >= E.m_valid) return;
   const int F = E.dstF, B = E.B;
-  float* __restrict__ dst = E.dst + (long long)(t + E.slot_off) * B * F + (E.row0 + row);
-  float old[W];
+  float* __restrict__ dst = (float*)E.p0 + (long long)(t + E.slot_off) * B * F + (E.row0 + row);
 #pragma unroll
   for (int j = 0; j < W; ++j) {
     const int b = n_base + j;
-    old[j] = (j < ncols && b < B) ? dst[(long long)b * F] : 0.0f;
-  }
-#pragma unroll
-  for (int j = 0; j < W; ++j) {
-    const int b = n_base + j;
-    if (j < ncols && b < B) dst[(long long)b * F] = old[j] + v[j];
+    if (j < ncols && b < B) dst[(long long)b * F] = o.a[j] + v[j];
   }
 }
 
 // W = number of columns held in v[] (compile time: the loops are fully unrolled over W)
 template <int W>
-__device__ __forceinline__ void run_epilogue(const EpiLocal& E, int t, int row, int n_base, int ncols,
-                                             const float* v) {
+__device__ __forceinline__ void epilogue_load(const EpiLocal& E, int t, int row, int n_base, int ncols, EpiOps<W>& o) {
+  switch (E.epi) {
+    case EPI_GATES: epi_gates_load<W>(E, t, row, n_base, ncols, o); break;
+    case EPI_CAND: epi_cand_load<W>(E, t, row, n_base, ncols, o); break;
+    case EPI_BWD_RH: epi_bwd_rh_load<W>(E, t, row, n_base, ncols, o); break;
+    case EPI_BWD_STATE: epi_bwd_state_load<W>(E, t, row, n_base, ncols, o); break;
+    default: break;
+  }
+}
+template <int W>
+__device__ __forceinline__ void epilogue_apply(const EpiLocal& E, int t, int row, int n_base, int ncols,
+                                               const float* v, const EpiOps<W>& o) {
   switch (E.epi) {
     case EPI_PLAIN: epi_plain<W>(E, t, row, n_base, ncols, v); break;
-    case EPI_GATES: epi_gates<W>(E, t, row, n_base, ncols, v); break;
-    case EPI_CAND: epi_cand<W>(E, t, row, n_base, ncols, v); break;
-    case EPI_BWD_RH: epi_bwd_rh<W>(E, t, row, n_base, ncols, v); break;
-    case EPI_BWD_STATE: epi_bwd_state<W>(E, t, row, n_base, ncols, v); break;
+    case EPI_GATES: epi_gates_apply<W>(E, t, row, n_base, ncols, v, o); break;
+    case EPI_CAND: epi_cand_apply<W>(E, t, row, n_base, ncols, v, o); break;
+    case EPI_BWD_RH: epi_bwd_rh_apply<W>(E, t, row, n_base, ncols, v, o); break;
+    case EPI_BWD_STATE: epi_bwd_state_apply<W>(E, t, row, n_base, ncols, v, o); break;
   }
+}
+template <int W>
+__device__ __forceinline__ void run_epilogue(const EpiLocal& E, int t, int row, int n_base, int ncols,
+                                             const float* v) {
+  EpiOps<W> o;
+  epilogue_load<W>(E, t, row, n_base, ncols, o);
+  epilogue_apply<W>(E, t, row, n_base, ncols, v, o);
 }
 
 // ---------------------------------------------------------- tensor-core pipeline
@@ -579,11 +643,13 @@ __device__ __forceinline__ void epilogue_run(Pipe& p, const EngineParams& P, int
       }
       if (threadIdx.x == 64) TL(4);
       if (ksplit <= 1) {
-        for (int n0 = 0; n0 < n_cols; n0 += 16) {
-          float v[16];
-          tmem_ld_32x16(taddr + n0, v);
+        for (int n0 = 0; n0 < n_cols; n0 += 8) {
+          float v[8];
+          EpiOps<8> ops;
+          tmem_ld_32x8(taddr + n0, v);
+          epilogue_load<8>(E, t, row, n0, 8, ops);
           tmem_ld_wait();
-          run_epilogue<16>(E, t, row, n0, 16, v);
+          epilogue_apply<8>(E, t, row, n0, 8, v, ops);
         }
       } else {
         // park the partial tile: scratch[group][part][col][row]  (row fastest -> coalesced)
@@ -648,6 +714,7 @@ __device__ __forceinline__ void epilogue_run(Pipe& p, const EngineParams& P, int
         const int nc = min(4, c_hi - n0);
         float v[4] = {0.f, 0.f, 0.f, 0.f};
         float x[MAX_KSPLIT][4];
+        EpiOps<4> ops;
 #pragma unroll
         for (int pp = 0; pp < MAX_KSPLIT; ++pp) {
           const float* src = base + (size_t)pp * n_cols * TILE_M;
@@ -655,11 +722,16 @@ __device__ __forceinline__ void epilogue_run(Pipe& p, const EngineParams& P, int
           for (int i = 0; i < 4; ++i)
             x[pp][i] = (pp < ksplit && i < nc && !(P.debug_flags & 1)) ? __ldcg(src + (size_t)(n0 + i) * TILE_M + r) : 0.0f;
         }
+        if (!(P.debug_flags & 4)) epilogue_load<4>(E, t, r, n0, nc, ops);   // operand loads in flight together with the partial-tile loads
+        else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { ops.a[i] = 0.5f; ops.b[i] = 0.5f; ops.c[i] = 0.5f; }
+        }
 #pragma unroll
         for (int pp = 0; pp < MAX_KSPLIT; ++pp)   // part order: deterministic
 #pragma unroll
           for (int i = 0; i < 4; ++i) v[i] += x[pp][i];
-        if (!(P.debug_flags & 2)) run_epilogue<4>(E, t, r, n0, nc, v);
+        if (!(P.debug_flags & 2)) epilogue_apply<4>(E, t, r, n0, nc, v, ops);
         else if (v[0] == 123.456f) P.split_scratch[0] = v[1] + v[2] + v[3];
       }
       if (threadIdx.x == 64) TL(7);

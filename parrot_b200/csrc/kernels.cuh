@@ -32,11 +32,40 @@ struct AttnFwdArgs {
   float* phi_out;       // [B][U]
   float* ab_out;        // [B][2A]  alpha | beta
   float* e_out;         // [B][3A]  exp(a_hat) (softmax: probabilities) | exp(b_hat) | exp(k_hat)
+  float* hat;           // [B][3A] scratch: pre-activations when the projection runs as its own stage (or null)
 };
 
 // Executed by every thread of the CTA for batch row b; `sh` needs
 // rup(H,4) + 2*rup(3A,4) + rup(U,4) + nwarps*C floats.  Ends with a CTA barrier (sh may be reused).
-__device__ __forceinline__ void attention_fwd_body(const AttnFwdArgs& a, const int b, float* sh) {
+// Projection stage of the attention step as a grid-wide pass: one (batch row, output) dot product of length H
+// per warp, all loads of a lane in flight at once.  hat[b][j] = h1[b] . wT[j] + batt[j].
+__device__ __forceinline__ void attention_proj_body(const AttnFwdArgs& a) {
+  const int lane = threadIdx.x & 31;
+  const int gw = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int nw = (int)((gridDim.x * blockDim.x) >> 5);
+  const int n = a.B * 3 * a.A;
+  for (int idx = gw; idx < n; idx += nw) {
+    const int b = idx / (3 * a.A), j = idx - b * 3 * a.A;
+    const float* __restrict__ hr = a.h1 + (long long)b * a.H;
+    const float* __restrict__ wr = a.wT + (long long)j * a.H;
+    float s = 0.0f;
+    if ((a.H & 127) == 0) {
+      for (int k = lane * 4; k < a.H; k += 128) {
+        const float4 h4 = __ldcg(reinterpret_cast<const float4*>(hr + k));
+        const float4 w4 = __ldg(reinterpret_cast<const float4*>(wr + k));
+        s += h4.x * w4.x + h4.y * w4.y + h4.z * w4.z + h4.w * w4.w;
+      }
+    } else {
+      for (int k = lane; k < a.H; k += 32) s = fmaf(__ldcg(hr + k), __ldg(wr + k), s);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) a.hat[idx] = s + __ldg(a.batt + j);
+  }
+}
+
+__device__ __forceinline__ void attention_fwd_body(const AttnFwdArgs& a, const int b, float* sh,
+                                                   const bool precomputed_hat = false) {
   const int A3p = (3 * a.A + 3) & ~3;  // sections padded to 16 bytes (float4 accesses below)
   float* sh_h = sh;                          // H
   float* sh_hat = sh_h + ((a.H + 3) & ~3);   // 3A
@@ -44,8 +73,13 @@ __device__ __forceinline__ void attention_fwd_body(const AttnFwdArgs& a, const i
   float* sh_phi = sh_abk + A3p;              // U
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int A = a.A;
+  if (precomputed_hat) {
+    if (tid < 3 * A) sh_hat[tid] = __ldcg(a.hat + (long long)b * 3 * A + tid);
+    __syncthreads();
+  } else {
   for (int i = tid; i < a.H; i += blockDim.x) sh_h[i] = a.h1[(long long)b * a.H + i];
   __syncthreads();
+  // h1 . Watt^T: 3A dot products of length H, four outputs per warp pass
   for (int j0 = warp * 4; j0 < 3 * A; j0 += (blockDim.x >> 5) * 4) {
     float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 4
@@ -64,6 +98,7 @@ __device__ __forceinline__ void attention_fwd_body(const AttnFwdArgs& a, const i
     }
   }
   __syncthreads();
+  }
   if (tid < A) {
     float ea;
     if (a.type == 1) {
@@ -433,9 +468,18 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) scan_fwd_persistent(const S
       a.h1 += tick * S.s_h1; a.k_prev += tick * S.s_k; a.k_out += tick * S.s_k; a.w_out += tick * S.s_w;
       a.w_hi += tick * S.s_wp; a.w_lo += tick * S.s_wp; a.phi_out += tick * S.s_phi; a.ab_out += tick * S.s_ab;
       a.e_out += tick * S.s_e;
-      for (int b = blockIdx.x; b < a.B; b += gridDim.x) attention_fwd_body(a, b, att_sh);
-      asm volatile("fence.proxy.async.global;" ::: "memory");
+      // stage 1 (all CTAs): h1 . Watt^T, one dot product per warp ; stage 2 (B CTAs): window + context
+      attention_proj_body(a);
       __syncthreads();
+      if (threadIdx.x == 0) { STAMP(S, bar, 1); grid_arrive(S.gridbar); }
+      ++bar;
+      if ((int)blockIdx.x < a.B) {
+        if (threadIdx.x == 0) { grid_wait(S.gridbar, bar * gridDim.x); STAMP(S, bar, 0); }
+        __syncthreads();
+        for (int b = blockIdx.x; b < a.B; b += gridDim.x) attention_fwd_body(a, b, att_sh, true);
+        asm volatile("fence.proxy.async.global;" ::: "memory");
+        __syncthreads();
+      }
       if (threadIdx.x == 0) { STAMP(S, bar, 1); grid_arrive(S.gridbar); }
       ++bar;
     }

@@ -17,7 +17,7 @@ for _ in range(2):
 torch.cuda.synchronize()
 h = m._last
 lib = _lib.load()
-bars = 3 * T + 4
+bars = 4 * T + 8
 st = torch.zeros(148 * bars * 2, dtype=torch.int64, device='cuda')
 lib.parrot_debug_set_stamps(h.ptr, C.c_void_p(st.data_ptr()), bars)
 m.compute_cost(bt['features'], bt['features_mask'], bt['labels'], bt['labels_mask'], None, 1.0, B)
@@ -26,10 +26,10 @@ lib.parrot_debug_set_stamps(h.ptr, None, 0)
 s = st.cpu().numpy().reshape(148, bars, 2).astype(np.float64)
 t0 = s[s > 0].min()
 s = (s - t0) / 1e3
-names = ['A(gates)', 'B(cand)', 'attention']
-# steady-state ticks 5..T-1: barrier index = 3*tick + k
-for k in range(3):
-    idx = [3 * t + k for t in range(5, T - 2)]
+names = ['A(gates)', 'B(cand)', 'att-proj', 'att-window']
+# steady-state ticks 5..T-1: barrier index = 4*tick + k
+for k in range(4):
+    idx = [4 * t + k for t in range(5, T - 2)]
     passed = s[:, idx, 0]; arr = s[:, idx, 1]
     work = arr - passed                       # this CTA's time inside the phase
     last_arr = arr.max(axis=0)                # when the slowest CTA arrived
@@ -37,7 +37,7 @@ for k in range(3):
     print('%-10s work median %.2f us  max-CTA median %.2f us ; barrier latency (last arrival -> first pass) %.2f us ; '
           'phase span %.2f us' % (names[k], np.median(work), np.median(work.max(axis=0)),
                                   np.median(nxt - last_arr), np.median(last_arr - passed.min(axis=0))))
-tick_span = np.median(np.diff(s[0, 0::3, 0])[5:T - 3])
+tick_span = np.median(np.diff(s[0, 0::4, 0])[5:T - 3])
 print('tick period %.2f us' % tick_span)
 
 # ---- intra-phase milestones of one steady-state tick
