@@ -296,7 +296,8 @@ def main():
         extra['sections_ms_persistent'] = sections
         diag = {}
         for key in ('sec_scan_fwd', 'sec_scan_bwd', 'fwdA', 'fwdB', 'attn_fwd', 'bwd1', 'bwd2', 'attn_bwd',
-                    'gru_bwd_pre', 'readout', 'output', 'dread', 'dh_readout', 'wgrad'):
+                    'gru_bwd_pre', 'readout', 'output', 'dread', 'dh_readout', 'wgrad', 'tail_dctx',
+                    'tail_encoder_bwd', 'tail_weight_grads', 'tail_bias_grads', 'tail_speaker'):
             ms, n = prof(key)
             diag[key] = {'ms': round(ms / P, 3), 'launches': n // P}
         extra['breakdown_ms_per_phase_launch_mode'] = diag

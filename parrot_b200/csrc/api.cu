@@ -1484,7 +1484,9 @@ static void weight_grads(parrot_model& M, cudaStream_t st) {
   tp("w", d.C);
   if (d.weak) tp("xin", d.D);
   tp("ro", d.R); tp("dread", d.R); tp("dpred", d.Dtp); tp("datt", 3 * d.A);
+  { cudaEvent_t p2 = M.prof_begin("tail_transposes_done", st); parrot_model::prof_end(p2, st); }
   run_table(M, "wgrad", 0, 1, 0, st);
+  cudaEvent_t pb = M.prof_begin("tail_bias_grads", st);
   // bias gradients: column sums of the pre-activation gradients
   float* scratch = M.fbuf("bias_scratch");
   for (int l = 0; l < 3; ++l) {
@@ -1523,6 +1525,7 @@ static void weight_grads(parrot_model& M, cudaStream_t st) {
   add_to(M, st, "/h1_to_att/fork_alpha.b", scratch, d.A);
   add_to(M, st, "/h1_to_att/fork_beta.b", scratch + d.A, d.A);
   add_to(M, st, "/h1_to_att/fork_kappa.b", scratch + 2 * d.A, d.A);
+  parrot_model::prof_end(pb, st);
 }
 
 static void speaker_grads(parrot_model& M, cudaStream_t st) {
@@ -1581,13 +1584,23 @@ static void backward(parrot_model& M, int unnormalised, cudaStream_t st) {
   }
   // dctx = sum_t phi_t (x) dw_t
   {
+    cudaEvent_t p2 = M.prof_begin("tail_dctx", st);
     dim3 grid(cdiv(d.C, 32), cdiv(d.U, 32), d.B);
     LAUNCH(dctx_kernel, grid, 256, 0, st, M.fbuf("phi"), M.ctx.dw + (long long)d.B * d.C, d.T, d.B, d.U, d.C,
            M.fbuf("dctx"));
+    parrot_model::prof_end(p2, st);
   }
-  encoder_bwd(M, in.lmask, st);
-  weight_grads(M, st);
-  speaker_grads(M, st);
+  {
+    cudaEvent_t p2 = M.prof_begin("tail_encoder_bwd", st);
+    encoder_bwd(M, in.lmask, st);
+    parrot_model::prof_end(p2, st);
+    p2 = M.prof_begin("tail_weight_grads", st);
+    weight_grads(M, st);
+    parrot_model::prof_end(p2, st);
+    p2 = M.prof_begin("tail_speaker", st);
+    speaker_grads(M, st);
+    parrot_model::prof_end(p2, st);
+  }
   parrot_model::prof_end(pe, st);
 }
 

@@ -207,6 +207,21 @@ class Parrot(object):
         return [('last_h1', (B, H)), ('last_h2', (B, H)), ('last_h3', (B, H)),
                 ('last_k', (B, A)), ('last_w', (B, Cc))]
 
+    def get_state(self):
+        """Copies of the carried TBPTT state (last_h1..3, last_k, last_w; model.py:534-546) or None."""
+        h = self._last
+        if h is None or h.sampling:
+            return None
+        return (h, [h.buffer(nm, shp).clone() for nm, shp in self._state_shapes(h.B)])
+
+    def set_state(self, state):
+        if state is None:
+            return
+        h, vals = state
+        for (nm, shp), v in zip(self._state_shapes(h.B), vals):
+            h.buffer(nm, shp).copy_(v)
+        self._last = h
+
     def _dev(self, x, dtype):
         if x is None:
             return None

@@ -91,6 +91,7 @@ def main(argv=None):
             # validation monitor (train.py:118-123): cost on a few batches, no update, no state carry
             vs = parrot_stream(args.dataset, args.use_speaker, ('valid',), args.batch_size, **valid_stream_args)
             vcost, vn = 0.0, 0
+            carried = parrot.get_state()          # the monitor must not disturb the TBPTT state
             for vt in vs.get_epoch_iterator():
                 vb = dict(zip(vs.sources, vt))
                 vb = parallel.shard_batch({('speaker' if k == 'speaker_index' else k): v for k, v in vb.items()},
@@ -102,6 +103,7 @@ def main(argv=None):
                 if vn >= 4:
                     break
             vcost /= max(vn, 1)
+            parrot.set_state(carried)
             if rank == 0:
                 print('iter %d  train_%s %.5f  valid_%s %.5f  (%.1f s)' %
                       (it + 1, cost_name, train_cost, cost_name, vcost, time.time() - t0))
