@@ -184,6 +184,7 @@ def main():
     from parrot_b200.algorithms import Adam, CompositeRule, GradientDescent, StepClipping
     import ctypes as C
 
+    os.environ['NCCL_DEBUG'] = os.environ.get('PARROT_NCCL_DEBUG', 'WARN')   # keep stdout to the one JSON line
     rank, world, local = parallel.init_from_env()
     assert world == args.gpus or world == 1 and args.gpus == 1, 'launch with torchrun for --gpus > 1'
     torch.cuda.set_device(local)
@@ -248,7 +249,9 @@ def main():
     # ---- profiled steps: per-launch durations of the dominant kernels (rank 0)
     roof = None
     extra = {}
-    if rank == 0:
+    # Profiled steps run on EVERY rank (they contain the gradient allreduce; a collective executed by rank 0
+    # alone would deadlock); only rank 0 reads the profile back.
+    if True:
         h = model._last
         P = max(1, args.profile_steps)
 
@@ -268,6 +271,7 @@ def main():
         for _ in range(P):
             step(devb)
         torch.cuda.synchronize()
+    if rank == 0:
 
         pk = peaks()
         per_step_flops, _ = algorithmic_flops(cfg, B, T)
@@ -331,7 +335,8 @@ def main():
             'cpu_baseline': cpu,
         }
         line.update(extra)
-        print(json.dumps(line))
+        sys.stdout.flush()
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
