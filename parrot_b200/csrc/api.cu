@@ -394,6 +394,7 @@ struct parrot_model {
 };
 
 static const int NT = 128;  // sample tile of the batched (outside-the-scan) products
+static const int COLSUM_CHUNKS = 64;
 
 // ------------------------------------------------------------------ job builders
 static Seg mkseg(int a_map, int a_row, int a_k, int b_map, int b_row, int b_k, int b_slot, int nkb) {
@@ -720,6 +721,7 @@ static void build(parrot_model& M) {
     tplane("datt", d.Ap, (long long)T * Np, false);
     M.alloc("opt_scratch", 1024 * 8);
     M.falloc("bias_scratch", (long long)std::max(3 * H, d.R) + d.Dtot + 128);
+    M.falloc("colsum_scratch", (long long)COLSUM_CHUNKS * 4096);
   }
   M.alloc("gemm_scratch", 1024 * 8);
 
@@ -977,7 +979,15 @@ static void sgemm(cudaStream_t st, const float* A, long long sam, long long sak,
   dim3 grid(cdiv(N, 32), cdiv(Mr, 32));
   LAUNCH(sgemm_kernel, grid, 256, 0, st, g);
 }
+static float* g_colsum_scratch = nullptr;   // set per model before use (workspace buffer "colsum_scratch")
 static void colsum(cudaStream_t st, const float* src, long long ld, long long rows, int cols, float* out, int acc) {
+  if (rows >= 4096 && g_colsum_scratch && cols <= 4096) {
+    const long long per = (rows + COLSUM_CHUNKS - 1) / COLSUM_CHUNKS;
+    dim3 grid(cdiv(cols, 32), COLSUM_CHUNKS);
+    LAUNCH(colsum_partial_kernel, grid, 256, 0, st, src, ld, rows, cols, per, g_colsum_scratch);
+    LAUNCH(colsum_final_kernel, cdiv(cols, 256), 256, 0, st, g_colsum_scratch, COLSUM_CHUNKS, cols, out, acc);
+    return;
+  }
   LAUNCH(colsum_kernel, cdiv(cols, 32), 256, 0, st, src, ld, rows, cols, out, acc);
 }
 static void pack_plane(cudaStream_t st, const float* src, long long src_ld, int rows, int cols, const Plane& dst,
@@ -989,8 +999,16 @@ static void pack_plane(cudaStream_t st, const float* src, long long src_ld, int 
 }
 static void transpose_planes(cudaStream_t st, const Plane& src, int feat_cols, const Plane& dst) {
   const long long rows = (long long)src.rows * src.slots;
-  dim3 grid(cdiv(feat_cols, 32), cdiv(rows, 32));
   dim3 block(32, 8);
+  if ((src.pitch & 1) == 0 && (dst.pitch & 1) == 0) {
+    dim3 grid(cdiv(feat_cols, 64), cdiv(rows, 64));
+    LAUNCH(transpose_plane64_kernel, grid, block, 0, st, src.hi, (long long)src.pitch, rows, feat_cols, dst.hi,
+           (long long)dst.pitch);
+    LAUNCH(transpose_plane64_kernel, grid, block, 0, st, src.lo, (long long)src.pitch, rows, feat_cols, dst.lo,
+           (long long)dst.pitch);
+    return;
+  }
+  dim3 grid(cdiv(feat_cols, 32), cdiv(rows, 32));
   LAUNCH(transpose_plane_kernel, grid, block, 0, st, src.hi, (long long)src.pitch, rows, feat_cols, dst.hi,
          (long long)dst.pitch);
   LAUNCH(transpose_plane_kernel, grid, block, 0, st, src.lo, (long long)src.pitch, rows, feat_cols, dst.lo,
@@ -1475,6 +1493,7 @@ static void add_to(parrot_model& M, cudaStream_t st, const std::string& pname, c
 
 static void weight_grads(parrot_model& M, cudaStream_t st) {
   const Dims& d = M.d;
+  g_colsum_scratch = M.fbuf("colsum_scratch");
   const int T = d.T, B = d.B, H = d.H;
   // operand transposes [samples][features] -> [features][samples]
   auto tp = [&](const std::string& nm, int feat) { transpose_planes(st, M.planes.at(nm), feat, M.planes.at("T." + nm)); };

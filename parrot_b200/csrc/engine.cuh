@@ -137,7 +137,7 @@ struct EngineParams {
   int reverse;    // 0: t = tick - lag ; 1: t = (T - 1) - (tick - lag)
   float* split_scratch;        // [group][part][n_cols][128] partial tiles
   unsigned int* split_count;   // [group] arrival counters (zero between launches)
-  int debug_flags;             // experiments: 1 skip partial loads, 2 skip epilogue body, 4 skip arrival wait fence
+  int debug_flags;             // reserved for experiments
   int coop_epilogue;           // 1: all parts of a split tile share the final epilogue (needs <= 1 job per CTA)
   unsigned long long* timeline;  // debug: [cta][16] globaltimer stamps at pipeline milestones (or null)
 };
@@ -706,7 +706,9 @@ __device__ __forceinline__ void epilogue_run(Pipe& p, const EngineParams& P, int
         if (*p.split_flag) { c_lo = 0; c_hi = n_cols; }
       }
       __threadfence();
-      // work item = (row, group of 4 columns); consecutive threads take consecutive rows (coalesced)
+      // work item = (row, group of 4 columns); consecutive threads take consecutive rows (coalesced).  All loads of
+      // an item (partial tiles + epilogue operands) are issued before the first use.  (8-column items halve the
+      // number of latency rounds but spill at the 168-register cap of the 12-warp CTA.)
       const int ngroups = (c_hi - c_lo + 3) >> 2;
       for (int e = gtid; e < ngroups * TILE_M; e += EPI_GROUP_THREADS) {
         const int r = e & (TILE_M - 1);
@@ -720,19 +722,14 @@ __device__ __forceinline__ void epilogue_run(Pipe& p, const EngineParams& P, int
           const float* src = base + (size_t)pp * n_cols * TILE_M;
 #pragma unroll
           for (int i = 0; i < 4; ++i)
-            x[pp][i] = (pp < ksplit && i < nc && !(P.debug_flags & 1)) ? __ldcg(src + (size_t)(n0 + i) * TILE_M + r) : 0.0f;
+            x[pp][i] = (pp < ksplit && i < nc) ? __ldcg(src + (size_t)(n0 + i) * TILE_M + r) : 0.0f;
         }
-        if (!(P.debug_flags & 4)) epilogue_load<4>(E, t, r, n0, nc, ops);   // operand loads in flight together with the partial-tile loads
-        else {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) { ops.a[i] = 0.5f; ops.b[i] = 0.5f; ops.c[i] = 0.5f; }
-        }
+        epilogue_load<4>(E, t, r, n0, nc, ops);   // operand loads in flight together with the partial-tile loads
 #pragma unroll
         for (int pp = 0; pp < MAX_KSPLIT; ++pp)   // part order: deterministic
 #pragma unroll
           for (int i = 0; i < 4; ++i) v[i] += x[pp][i];
-        if (!(P.debug_flags & 2)) epilogue_apply<4>(E, t, r, n0, nc, v, ops);
-        else if (v[0] == 123.456f) P.split_scratch[0] = v[1] + v[2] + v[3];
+        epilogue_apply<4>(E, t, r, n0, nc, v, ops);
       }
       if (threadIdx.x == 64) TL(7);
       asm volatile("bar.sync 1, 320;" ::: "memory");

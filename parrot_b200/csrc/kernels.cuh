@@ -424,18 +424,16 @@ struct ScanBwdParams {
 // one GEMM phase of a persistent kernel: wait for the previous grid barrier where data produced by other
 // CTAs is consumed (producer: TMA of activation planes; epilogue: stashes), run the roles, arrive.
 template <class SP>
-__device__ __forceinline__ void persistent_gemm_phase(Pipe& p, const EngineParams& P0, int tick, const SP& S,
+__device__ __forceinline__ void persistent_gemm_phase(Pipe& p, const EngineParams& P, int tick, const SP& S,
                                                       unsigned int& bar, int which) {
+  // P stays in kernel-parameter (constant) space: copying it would cost ~25 registers of a 168-register budget
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  EngineParams P = P0;
-  P.timeline = (S.tl_buf && tick == S.tl_tick) ? S.tl_buf + (size_t)(which + 1) * gridDim.x * 16 : nullptr;
+  (void)which;
   unsigned int* gridbar = S.gridbar;
   const unsigned int target = bar * gridDim.x;
   if (warp == 0) {
     if (lane == 0) {
-      TL(0);
       if (bar) grid_wait(gridbar, target);
-      TL(1);
       producer_run(p, P, tick);
     }
     __syncwarp();
@@ -573,6 +571,39 @@ __global__ void pack_planes_kernel(const float* __restrict__ src, long long src_
 }
 
 // bf16 plane transpose: dst[c][r] = src[r][c]   (for the weight-gradient operands)
+// 64 x 64 tiles, 4-byte (bf16x2) global accesses on both sides.  Requires even leading dimensions.
+__global__ void transpose_plane64_kernel(const bf16* __restrict__ src, long long src_ld, long long rows, int cols,
+                                         bf16* __restrict__ dst, long long dst_ld) {
+  __shared__ bf16 tile[64][66];
+  const long long by = (long long)blockIdx.y * 64;
+  const int bx = blockIdx.x * 64;
+  const int tx = threadIdx.x, ty = threadIdx.y;   // 32 x 8
+  for (int j = ty; j < 64; j += 8) {
+    const long long r = by + j;
+    const int c = bx + 2 * tx;
+    __nv_bfloat162 v = __floats2bfloat162_rn(0.0f, 0.0f);
+    if (r < rows && c + 1 < cols) v = *reinterpret_cast<const __nv_bfloat162*>(src + r * src_ld + c);
+    else if (r < rows && c < cols) v.x = src[r * src_ld + c];
+    tile[j][2 * tx] = v.x;
+    tile[j][2 * tx + 1] = v.y;
+  }
+  __syncthreads();
+  for (int j = ty; j < 64; j += 8) {
+    const int c = bx + j;              // dst row
+    const long long r = by + 2 * tx;   // dst column pair
+    if (c < cols) {
+      if (r + 1 < rows) {
+        __nv_bfloat162 v;
+        v.x = tile[2 * tx][j];
+        v.y = tile[2 * tx + 1][j];
+        *reinterpret_cast<__nv_bfloat162*>(dst + (long long)c * dst_ld + r) = v;
+      } else if (r < rows) {
+        dst[(long long)c * dst_ld + r] = tile[2 * tx][j];
+      }
+    }
+  }
+}
+
 __global__ void transpose_plane_kernel(const bf16* __restrict__ src, long long src_ld, long long rows, int cols,
                                        bf16* __restrict__ dst, long long dst_ld) {
   __shared__ bf16 tile[32][34];
@@ -705,6 +736,35 @@ __global__ void colsum_kernel(const float* __restrict__ src, long long ld, long 
     for (int j = 0; j < 8; ++j) t += red[j][tx];
     out[c] = accumulate ? out[c] + t : t;
   }
+}
+
+// Two-stage, deterministic column sums for tall matrices: stage 1 sums a chunk of rows per block into
+// partial[chunk][col]; stage 2 adds the chunks in chunk order.
+__global__ void colsum_partial_kernel(const float* __restrict__ src, long long ld, long long rows, int cols,
+                                      long long rows_per_chunk, float* __restrict__ partial) {
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  const long long r0 = (long long)blockIdx.y * rows_per_chunk;
+  const long long r1 = min(rows, r0 + rows_per_chunk);
+  float s = 0.0f;
+  if (c < cols)
+    for (long long r = r0 + ty; r < r1; r += 8) s += src[r * ld + c];
+  red[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && c < cols) {
+    float t = 0.0f;
+    for (int j = 0; j < 8; ++j) t += red[j][tx];
+    partial[(long long)blockIdx.y * cols + c] = t;
+  }
+}
+__global__ void colsum_final_kernel(const float* __restrict__ partial, int chunks, int cols, float* __restrict__ out,
+                                    int accumulate) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  float t = 0.0f;
+  for (int k = 0; k < chunks; ++k) t += partial[(long long)k * cols + c];
+  out[c] = accumulate ? out[c] + t : t;
 }
 
 __global__ void add_vec_kernel(float* __restrict__ dst, const float* __restrict__ src, long long n) {
