@@ -276,6 +276,7 @@ struct parrot_model {
   int stamp_bars = 0;
   int tl_tick = -1;
   int sm_count = 0;
+  bool persistent_ok = true;   // cleared when a cooperative launch is refused
   float* d_split_scratch = nullptr;
   unsigned int* d_split_count = nullptr;
   unsigned int* d_gridbar = nullptr;
@@ -1261,6 +1262,10 @@ static void attention_step(parrot_model& M, int t, bool sampling, cudaStream_t s
   parrot_model::prof_end(pe, st);
 }
 
+static int prefetch_enabled() {
+  const char* e = getenv("PARROT_NO_PREFETCH");
+  return (e && e[0] && e[0] != '0') ? 0 : 1;
+}
 static bool use_persistent(parrot_model& M) {
   static int env = -1;
   if (env < 0) {
@@ -1268,7 +1273,7 @@ static bool use_persistent(parrot_model& M) {
     env = (e && e[0] && e[0] != '0') ? 0 : 1;
   }
   const Dims& d = M.d;
-  if (!env || M.cfg.gemm_impl == 1 || M.profiling >= 2 || M.sm_count < 148) return false;
+  if (!env || !M.persistent_ok || M.cfg.gemm_impl == 1 || M.profiling >= 2 || M.sm_count < 148) return false;
   const size_t att_f = (size_t)rup(d.H, 4) + 2 * rup(3 * d.A, 4) + rup(d.U, 4) + (ENGINE_THREADS / 32) * (size_t)d.C;
   const size_t att_b = (size_t)d.C + d.U + 3 * d.A * 16 + 3 * d.A;
   if (std::max(att_f, att_b) * 4 > (size_t)ATT_SMEM_BYTES) return false;
@@ -1296,7 +1301,7 @@ static EngineParams table_params(parrot_model& M, const std::string& name, int r
 static AttnFwdArgs attn_fwd_args(parrot_model& M, int t, bool sampling);
 static AttnBwdArgs attn_bwd_args(parrot_model& M, int t);
 
-static void scan_fwd_persistent_launch(parrot_model& M, cudaStream_t st) {
+static bool scan_fwd_persistent_launch(parrot_model& M, cudaStream_t st) {
   const Dims& d = M.d;
   ScanFwdParams S;
   S.A = table_params(M, "fwdA", 0);
@@ -1309,16 +1314,24 @@ static void scan_fwd_persistent_launch(parrot_model& M, cudaStream_t st) {
   S.gridbar = M.d_gridbar;
   S.stamps = M.stamps; S.stamp_bars = M.stamp_bars;
   S.tl_buf = M.timeline; S.tl_tick = M.tl_tick;
+  S.prefetch = prefetch_enabled();
   CK(cudaMemsetAsync(M.d_gridbar, 0, 4, st));
   void* args[] = {&S};
   g_ctx = "scan_fwd_persistent";
-  CK(cudaLaunchCooperativeKernel((void*)scan_fwd_persistent, dim3(148), dim3(ENGINE_THREADS), args,
-                                 SMEM_BYTES + 1024 + ATT_SMEM_BYTES, st));
+  cudaError_t le = cudaLaunchCooperativeKernel((void*)scan_fwd_persistent, dim3(148), dim3(ENGINE_THREADS), args,
+                                               SMEM_BYTES + 1024 + ATT_SMEM_BYTES, st);
+  if (le != cudaSuccess) {
+    // co-residency of 148 CTAs refused (shared GPU, MPS limits ...): use one launch per phase from now on
+    cudaGetLastError();
+    M.persistent_ok = false;
+    return false;
+  }
   g_launches.fetch_add(1, std::memory_order_relaxed);
   if (debug_sync()) CK(cudaStreamSynchronize(st));
+  return true;
 }
 
-static void scan_bwd_persistent_launch(parrot_model& M, cudaStream_t st) {
+static bool scan_bwd_persistent_launch(parrot_model& M, cudaStream_t st) {
   const Dims& d = M.d;
   ScanBwdParams S;
   S.B1 = table_params(M, "bwd1", 1);
@@ -1329,13 +1342,20 @@ static void scan_bwd_persistent_launch(parrot_model& M, cudaStream_t st) {
   S.s_dattp = (long long)d.Np * M.planes.at("datt").pitch;
   S.ctx = M.d_ctx; S.T = d.T; S.gridbar = M.d_gridbar;
   S.stamps = nullptr; S.stamp_bars = 0; S.tl_buf = nullptr; S.tl_tick = -1;
+  S.prefetch = prefetch_enabled();
   CK(cudaMemsetAsync(M.d_gridbar, 0, 4, st));
   void* args[] = {&S};
   g_ctx = "scan_bwd_persistent";
-  CK(cudaLaunchCooperativeKernel((void*)scan_bwd_persistent, dim3(148), dim3(ENGINE_THREADS), args,
-                                 SMEM_BYTES + 1024 + ATT_SMEM_BYTES, st));
+  cudaError_t le = cudaLaunchCooperativeKernel((void*)scan_bwd_persistent, dim3(148), dim3(ENGINE_THREADS), args,
+                                               SMEM_BYTES + 1024 + ATT_SMEM_BYTES, st);
+  if (le != cudaSuccess) {
+    cudaGetLastError();
+    M.persistent_ok = false;
+    return false;
+  }
   g_launches.fetch_add(1, std::memory_order_relaxed);
   if (debug_sync()) CK(cudaStreamSynchronize(st));
+  return true;
 }
 
 static void scan_fwd(parrot_model& M, const float* d_features, const float* d_noise, float level, float start_flag,
@@ -1350,10 +1370,7 @@ static void scan_fwd(parrot_model& M, const float* d_features, const float* d_no
   }
   init_slots(M, start_flag != 0.0f, st);
   M.last_start_flag = start_flag;
-  if (use_persistent(M)) {
-    scan_fwd_persistent_launch(M, st);
-    return;
-  }
+  if (use_persistent(M) && scan_fwd_persistent_launch(M, st)) return;
   // layer wavefront: tick tau runs layer 1 at step tau, layer 2 at tau-1, layer 3 at tau-2
   for (int tick = 0; tick < d.T + 2; ++tick) {
     run_table(M, "fwdA", tick, d.T, 0, st);
@@ -1462,10 +1479,7 @@ static void attention_bwd_step(parrot_model& M, int t, cudaStream_t st) {
 static void scan_bwd(parrot_model& M, cudaStream_t st) {
   const Dims& d = M.d;
   CK(cudaMemsetAsync(M.fbuf("dk_carry"), 0, (size_t)d.B * d.A * 4, st));
-  if (use_persistent(M)) {
-    scan_bwd_persistent_launch(M, st);
-    return;
-  }
+  if (use_persistent(M) && scan_bwd_persistent_launch(M, st)) return;
   const int blocks = std::min(gs_blocks((long long)d.B * d.H), 148);
   // reverse layer wavefront: tick tau -> layer 3 at s = T-1-tau, layer 2 at s+1, attention + layer 1 at s+2
   for (int tick = 0; tick < d.T + 2; ++tick) {

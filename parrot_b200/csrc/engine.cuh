@@ -460,6 +460,9 @@ __device__ __forceinline__ void run_epilogue(const EpiLocal& E, int t, int row, 
   epilogue_apply<W>(E, t, row, n_base, ncols, v, o);
 }
 
+// grid barrier wait (defined with the persistent-kernel helpers below)
+__device__ __forceinline__ void grid_wait_ext(const unsigned int* ctr, unsigned int target);
+
 // ---------------------------------------------------------- tensor-core pipeline
 // Shared-memory carve-up and the role-private running state.  The three role loops below are shared by
 // the one-launch-per-phase kernel (job_kernel_tc) and the persistent scan kernels (kernels.cuh), which keep
@@ -523,15 +526,67 @@ __device__ __forceinline__ void pipe_teardown(Pipe& p) {
 }
 
 // ------------------------------------------------ TMA producer (one thread: warp 0, lane 0)
-__device__ __forceinline__ void producer_run(Pipe& p, const EngineParams& P, int tick) {
+__device__ __forceinline__ void producer_load_a(Pipe& p, const Seg& sg, int kb, const CUtensorMap* ma, uint8_t* st,
+                                                uint64_t* fb, uint64_t pol_keep) {
+  if (sg.a_nkb > 0) {
+    // tile-contiguous weight pack: one 16 KB contiguous block per plane, kept in L2 (re-read every step)
+    const int trow = ((sg.a_row >> 7) * sg.a_nkb + (sg.a_k >> 6) + kb) << 7;
+    tma_load_2d_hint(st, ma, fb, 0, trow, pol_keep);
+    tma_load_2d_hint(st + p.a_bytes, ma + 1, fb, 0, trow, pol_keep);
+  } else {
+    tma_load_2d(st, ma, fb, sg.a_k + kb * KB, sg.a_row);
+    tma_load_2d(st + p.a_bytes, ma + 1, fb, sg.a_k + kb * KB, sg.a_row);
+  }
+}
+__device__ __forceinline__ void producer_load_b(Pipe& p, const Seg& sg, int kb, int t, const CUtensorMap* mb,
+                                                uint8_t* st, uint64_t* fb) {
+  if (sg.b_slot == NO_SLOT) {
+    tma_load_2d(st + 2 * p.a_bytes, mb, fb, sg.b_k + kb * KB, sg.b_row);
+    tma_load_2d(st + 2 * p.a_bytes + p.b_bytes, mb + 1, fb, sg.b_k + kb * KB, sg.b_row);
+  } else {
+    tma_load_3d(st + 2 * p.a_bytes, mb, fb, sg.b_k + kb * KB, sg.b_row, t + sg.b_slot);
+    tma_load_3d(st + 2 * p.a_bytes + p.b_bytes, mb + 1, fb, sg.b_k + kb * KB, sg.b_row, t + sg.b_slot);
+  }
+}
+
+// gridbar != nullptr (persistent kernels): the activation (B) operands of this phase are produced by other CTAs
+// in the previous phase, so their loads must wait for grid barrier `target`; the WEIGHT (A) tiles do not depend
+// on it.  The producer therefore fills the free ring slots with weight tiles first (expect_tx without arrive),
+// waits for the barrier, and completes those slots with the activation tiles (arrive + expect_tx).
+__device__ __forceinline__ void producer_run(Pipe& p, const EngineParams& P, int tick,
+                                             const unsigned int* gridbar = nullptr, unsigned int target = 0) {
   const uint64_t pol_keep = l2_policy_evict_last();
+  bool waited = (gridbar == nullptr) || target == 0;
   for (int j = blockIdx.x; j < P.njobs; j += gridDim.x) {
     const Job& jb = P.jobs[j];
     const int t = job_time(P, jb, tick);
     const int total_kb = job_total_kb(P, jb, t);
     if (total_kb == 0) continue;
-    int klo, khi, kidx = 0;
+    int klo, khi;
     job_kb_range(jb, total_kb, klo, khi);
+    int early = 0;   // k blocks of this job whose weight tiles were issued before the barrier
+    if (!waited) {
+      // ---- pass 1: weight tiles of the first min(nstages, khi - klo) k blocks
+      int kidx = 0, st_i = p.stage;
+      uint32_t ph = p.phase;
+      for (int s = 0; s < jb.nseg && early < p.nstages; ++s) {
+        const Seg sg = jb.seg[s];
+        if (!seg_valid(P, sg, t)) continue;
+        for (int kb = 0; kb < sg.nkb && early < p.nstages; ++kb, ++kidx) {
+          if (kidx < klo || kidx >= khi) continue;
+          mbar_wait(&p.empty_bar[st_i], ph ^ 1);
+          uint8_t* st = p.tiles + (size_t)st_i * p.stage_bytes;
+          mbar_expect_tx_only(&p.full_bar[st_i], 2 * p.a_bytes);
+          producer_load_a(p, sg, kb, P.maps + sg.a_map, st, &p.full_bar[st_i], pol_keep);
+          ++early;
+          if (++st_i == p.nstages) { st_i = 0; ph ^= 1; }
+        }
+      }
+      grid_wait_ext(gridbar, target);
+      waited = true;
+    }
+    // ---- pass 2: everything else, in ring order
+    int kidx = 0, done = 0;
     for (int s = 0; s < jb.nseg; ++s) {
       const Seg sg = jb.seg[s];
       if (!seg_valid(P, sg, t)) continue;
@@ -539,30 +594,23 @@ __device__ __forceinline__ void producer_run(Pipe& p, const EngineParams& P, int
       const CUtensorMap* mb = P.maps + sg.b_map;
       for (int kb = 0; kb < sg.nkb; ++kb, ++kidx) {
         if (kidx < klo || kidx >= khi) continue;
-        mbar_wait(&p.empty_bar[p.stage], p.phase ^ 1);
         uint8_t* st = p.tiles + (size_t)p.stage * p.stage_bytes;
         uint64_t* fb = &p.full_bar[p.stage];
-        mbar_expect_tx(fb, p.stage_bytes);
-        if (sg.a_nkb > 0) {
-          // tile-contiguous weight pack: one 16 KB contiguous block per plane, kept in L2 (re-read every step)
-          const int trow = ((sg.a_row >> 7) * sg.a_nkb + (sg.a_k >> 6) + kb) << 7;
-          tma_load_2d_hint(st, ma, fb, 0, trow, pol_keep);
-          tma_load_2d_hint(st + p.a_bytes, ma + 1, fb, 0, trow, pol_keep);
+        if (done < early) {
+          mbar_expect_tx(fb, 2 * p.b_bytes);           // arrive + the activation bytes
+          producer_load_b(p, sg, kb, t, mb, st, fb);
         } else {
-          tma_load_2d(st, ma, fb, sg.a_k + kb * KB, sg.a_row);
-          tma_load_2d(st + p.a_bytes, ma + 1, fb, sg.a_k + kb * KB, sg.a_row);
+          mbar_wait(&p.empty_bar[p.stage], p.phase ^ 1);
+          mbar_expect_tx(fb, p.stage_bytes);
+          producer_load_a(p, sg, kb, ma, st, fb, pol_keep);
+          producer_load_b(p, sg, kb, t, mb, st, fb);
         }
-        if (sg.b_slot == NO_SLOT) {
-          tma_load_2d(st + 2 * p.a_bytes, mb, fb, sg.b_k + kb * KB, sg.b_row);
-          tma_load_2d(st + 2 * p.a_bytes + p.b_bytes, mb + 1, fb, sg.b_k + kb * KB, sg.b_row);
-        } else {
-          tma_load_3d(st + 2 * p.a_bytes, mb, fb, sg.b_k + kb * KB, sg.b_row, t + sg.b_slot);
-          tma_load_3d(st + 2 * p.a_bytes + p.b_bytes, mb + 1, fb, sg.b_k + kb * KB, sg.b_row, t + sg.b_slot);
-        }
+        ++done;
         if (++p.stage == p.nstages) { p.stage = 0; p.phase ^= 1; }
       }
     }
   }
+  if (!waited) grid_wait_ext(gridbar, target);   // no job this phase: still observe the barrier
   TL(2);
 }
 
@@ -775,6 +823,8 @@ __device__ __forceinline__ void grid_arrive(unsigned int* ctr) {
   __threadfence();
   atomicAdd(ctr, 1u);
 }
+__device__ __forceinline__ void grid_wait(const unsigned int* ctr, unsigned int target);
+__device__ __forceinline__ void grid_wait_ext(const unsigned int* ctr, unsigned int target) { grid_wait(ctr, target); }
 __device__ __forceinline__ void grid_wait(const unsigned int* ctr, unsigned int target) {
   unsigned int seen, spins = 0;
   do {

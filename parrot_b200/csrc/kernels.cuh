@@ -380,6 +380,41 @@ __device__ __forceinline__ void gru_bwd_pre_body(const ScanCtx& c, const int lay
     plo[po + Hp + f] = ll;
   }
 }
+// same as gru_bwd_pre_body restricted to batch rows [b0, b1), strided over an arbitrary worker set
+__device__ __forceinline__ void gru_bwd_pre_rows(const ScanCtx& c, const int layer, const int t, const int b0,
+                                                 const int b1, const int worker, const int nworkers) {
+  const LayerBuf L = c.L[layer];
+  const int H = c.H, B = c.B, Np = c.Np, Hp = c.Hp;
+  const long long n = (long long)B * H;
+  const float* __restrict__ zp = L.z + (long long)t * n;
+  const float* __restrict__ cp = L.c + (long long)t * n;
+  const float* __restrict__ hp = L.h + (long long)t * n;
+  float* __restrict__ dhp = L.dh + (long long)t * n;
+  float* __restrict__ dap = L.da + (long long)t * B * 3 * H;
+  bf16* __restrict__ phi = L.da_hi + (long long)t * Np * (3 * Hp);
+  bf16* __restrict__ plo = L.da_lo + (long long)t * Np * (3 * Hp);
+  for (long long i = (long long)b0 * H + worker; i < (long long)b1 * H; i += nworkers) {
+    const int b = (int)(i / H), f = (int)(i % H);
+    const float dh = dhp[i + n];
+    const float z = zp[i], cc = cp[i], hpv = hp[i];
+    const float dc = dh * z;
+    const float dz = dh * (cc - hpv);
+    dhp[i] += dh * (1.0f - z);
+    const float dac = dc * (1.0f - cc * cc);
+    const float dagz = dz * z * (1.0f - z);
+    const long long ao = (long long)b * 3 * H;
+    dap[ao + f] = dac;
+    dap[ao + H + f] = dagz;
+    const long long po = (long long)b * (3 * Hp);
+    bf16 hh, ll;
+    split_bf16(dac, hh, ll);
+    phi[po + f] = hh;
+    plo[po + f] = ll;
+    split_bf16(dagz, hh, ll);
+    phi[po + Hp + f] = hh;
+    plo[po + Hp + f] = ll;
+  }
+}
 __global__ void gru_bwd_pre_kernel(const ScanCtx* cp, const PreArgs pa) {
   // grid (blocks, n): blockIdx.y selects the (layer, t) pair; the body strides over gridDim.x blocks
   if ((int)blockIdx.y >= pa.n) return;
@@ -402,6 +437,7 @@ struct ScanFwdParams {
   int stamp_bars;
   unsigned long long* tl_buf;   // debug: [2 phases][cta][16] intra-phase milestones of tick tl_tick
   int tl_tick;
+  int prefetch;                 // 1: weight tiles of the next phase are issued before its grid barrier
 };
 struct ScanBwdParams {
   EngineParams B1, B2;  // tables bwd1 / bwd2
@@ -414,6 +450,7 @@ struct ScanBwdParams {
   int stamp_bars;
   unsigned long long* tl_buf;
   int tl_tick;
+  int prefetch;
 };
 #define STAMP(S, bar, k)                                                                                \
   do {                                                                                                  \
@@ -433,8 +470,11 @@ __device__ __forceinline__ void persistent_gemm_phase(Pipe& p, const EngineParam
   const unsigned int target = bar * gridDim.x;
   if (warp == 0) {
     if (lane == 0) {
-      if (bar) grid_wait(gridbar, target);
-      producer_run(p, P, tick);
+      if (S.prefetch) producer_run(p, P, tick, gridbar, target);   // weight tiles ahead of the barrier
+      else {
+        if (bar) grid_wait(gridbar, target);
+        producer_run(p, P, tick);
+      }
     }
     __syncwarp();
   } else if (warp == 1) {
@@ -494,23 +534,29 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) scan_bwd_persistent(const S
   for (int tick = 0; tick < S.T + 2; ++tick) {
     const int s = S.T - 1 - tick;   // layer 3 at step s, layer 2 at s + 1, attention + layer 1 at s + 2
     const int ta = s + 2;
-    if (ta >= 0 && ta < S.T) {
-      if (threadIdx.x == 0 && bar) grid_wait(S.gridbar, bar * gridDim.x);
-      __syncthreads();
-      AttnBwdArgs a = S.att;
-      a.dw += ta * S.s_dw; a.ab += ta * S.s_ab; a.e += ta * S.s_e; a.kappa += ta * S.s_k; a.dh1 += ta * S.s_dh1;
-      a.datt += ta * S.s_datt; a.datt_hi += ta * S.s_dattp; a.datt_lo += ta * S.s_dattp;
-      for (int b = blockIdx.x; b < a.B; b += gridDim.x) attention_bwd_body(a, b, att_sh);
-      __syncthreads();
-      if (threadIdx.x == 0) grid_arrive(S.gridbar);
-      ++bar;
-    }
+    // Phase 0: attention backward of step s+2 on the first B CTAs, each followed by the (row-local) GRU pre-pass of
+    // layer 1 for its batch row; meanwhile the other CTAs run the pre-pass of layers 3 (step s) and 2 (step s+1),
+    // which do not depend on the attention.
     {
       if (threadIdx.x == 0 && bar) grid_wait(S.gridbar, bar * gridDim.x);
       __syncthreads();
-      for (int l = 2; l >= 0; --l) {
-        const int t = s + (2 - l);
-        if (t >= 0 && t < S.T) gru_bwd_pre_body(c, l, t);
+      const bool att_valid = ta >= 0 && ta < S.T;
+      const int nB = att_valid ? min(S.att.B, (int)gridDim.x / 2) : 0;   // CTAs doing attention rows
+      if ((int)blockIdx.x < nB) {
+        AttnBwdArgs a = S.att;
+        a.dw += ta * S.s_dw; a.ab += ta * S.s_ab; a.e += ta * S.s_e; a.kappa += ta * S.s_k; a.dh1 += ta * S.s_dh1;
+        a.datt += ta * S.s_datt; a.datt_hi += ta * S.s_dattp; a.datt_lo += ta * S.s_dattp;
+        for (int b = blockIdx.x; b < a.B; b += nB) {
+          attention_bwd_body(a, b, att_sh);
+          gru_bwd_pre_rows(c, 0, ta, b, b + 1, threadIdx.x, blockDim.x);
+        }
+      } else {
+        const int nworkers = (int)gridDim.x - nB;
+        const int wid = (int)blockIdx.x - nB;
+        for (int l = 2; l >= 1; --l) {
+          const int t = s + (2 - l);
+          if (t >= 0 && t < S.T) gru_bwd_pre_rows(c, l, t, 0, c.B, wid * (int)blockDim.x + threadIdx.x, nworkers * (int)blockDim.x);
+        }
       }
       asm volatile("fence.proxy.async.global;" ::: "memory");
       __syncthreads();
