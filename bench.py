@@ -283,11 +283,24 @@ def main():
         roof = {'bound': 'tensor',
                 'kernel': 'scan_fwd_persistent (T decoder steps in one launch: tcgen05 gate GEMMs + attention)',
                 'achieved': achieved_tf, 'peak': pk['tf_sustained'], 'unit': 'TFLOP/s',
-                'frac': achieved_tf / pk['tf_sustained'], 'traffic': None,
+                'frac': achieved_tf / pk['tf_sustained'],
+                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full
+                # capture of the same command (profiles/r01_scan_fwd_persistent_ncu_T800.txt); base workload only
+                'traffic': (58.975116e9 + 9.330672e9) if (B, T, U, cfg['rnn_h_dim']) == (64, 800, 128, 1024) else None,
+                'traffic_source': 'profiles/r01_scan_fwd_persistent_ncu_T800.txt',
                 'peak_source': pk['source'] + ' bf16 sustained (kernel timed inside a long step)',
                 'algorithmic_flops_per_launch': per_step_flops * T,
                 'avg_launch_us': scan_ms * 1e3, 'launches_per_step': 1,
                 'us_per_decoder_step': scan_ms * 1e3 / T}
+        # why the tensor fraction is small: at batch 64 every decoder step re-streams the bf16x3 weight planes
+        # (hi+lo, 4 bytes per parameter on the recurrent path) -- report that stream against the HBM peak too
+        Hh, Cc2 = cfg['rnn_h_dim'], 2 * cfg['encoder_dim']
+        wbytes = 4.0 * (18 * Hh * Hh + 9 * Cc2 * Hh + 3 * cfg['output_dim'] * Hh)
+        extra['roofline_weight_stream'] = {
+            'bound': 'hbm', 'kernel': roof['kernel'], 'achieved': wbytes * T / (scan_ms * 1e-3) / 1e9,
+            'peak': pk['hbm'], 'unit': 'GB/s', 'frac': wbytes * T / (scan_ms * 1e-3) / 1e9 / pk['hbm'],
+            'algorithmic_bytes_per_decoder_step': wbytes,
+            'note': 'operand planes of the in-scan weights read once per decoder step (no reuse across steps yet)'}
         msa, na = prof('attn_fwd')
         H, Cc, A = cfg['rnn_h_dim'], 2 * cfg['encoder_dim'], cfg['attention_size']
         att_bytes = 4.0 * (B * U * Cc + B * U + B * Cc + 3 * B * A)
