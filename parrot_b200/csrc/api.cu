@@ -275,6 +275,7 @@ struct parrot_model {
   unsigned long long* stamps = nullptr;   // debug: persistent forward scan per-barrier stamps
   int stamp_bars = 0;
   int tl_tick = -1;
+  unsigned long long* stamps_bwd = nullptr;
   int sm_count = 0;
   bool persistent_ok = true;   // cleared when a cooperative launch is refused
   float* d_split_scratch = nullptr;
@@ -1258,7 +1259,8 @@ static void attention_step(parrot_model& M, int t, bool sampling, cudaStream_t s
   AttnFwdArgs a = attn_fwd_args(M, t, sampling);
   const size_t smem = (size_t)(rup(d.H, 4) + 2 * rup(3 * d.A, 4) + rup(d.U, 4) + 8 * d.C) * 4;
   cudaEvent_t pe = M.prof_begin("attn_fwd", st);
-  LAUNCH(attention_fwd_kernel, d.B, 256, smem, st, a);
+  LAUNCH(attention_proj_kernel, 148, 256, 0, st, a);          // h1 . Watt^T spread over the whole GPU
+  LAUNCH(attention_fwd_kernel, d.B, 256, smem, st, a, 1);     // window + context, one CTA per batch row
   parrot_model::prof_end(pe, st);
 }
 
@@ -1341,7 +1343,7 @@ static bool scan_bwd_persistent_launch(parrot_model& M, cudaStream_t st) {
   S.s_k = (long long)d.B * d.A; S.s_dh1 = (long long)d.B * d.H; S.s_datt = (long long)d.B * 3 * d.A;
   S.s_dattp = (long long)d.Np * M.planes.at("datt").pitch;
   S.ctx = M.d_ctx; S.T = d.T; S.gridbar = M.d_gridbar;
-  S.stamps = nullptr; S.stamp_bars = 0; S.tl_buf = nullptr; S.tl_tick = -1;
+  S.stamps = M.stamps_bwd; S.stamp_bars = M.stamps_bwd ? M.stamp_bars : 0; S.tl_buf = nullptr; S.tl_tick = -1;
   S.prefetch = prefetch_enabled();
   CK(cudaMemsetAsync(M.d_gridbar, 0, 4, st));
   void* args[] = {&S};
@@ -1801,7 +1803,8 @@ int parrot_debug_time_table(parrot_model* m, const char* name, int tick, int rev
 int parrot_debug_set_stamps(parrot_model* m, unsigned long long* d_stamps, int bars) {
   // bars < 0: d_stamps is instead a [2][148][16] intra-phase timeline buffer for forward tick (-bars)
   if (bars < 0) { m->timeline = d_stamps; m->tl_tick = -bars; return 0; }
-  m->stamps = d_stamps; m->stamp_bars = bars;
+  if (bars >= (1 << 20)) { m->stamps_bwd = d_stamps; m->stamp_bars = bars - (1 << 20); m->stamps = nullptr; return 0; }   // backward sweep
+  m->stamps = d_stamps; m->stamp_bars = bars; m->stamps_bwd = nullptr;
   return 0;
 }
 int parrot_set_profiling(parrot_model* m, int enable) {
@@ -1875,7 +1878,10 @@ int parrot_attention_step(const parrot_config* cfg, const float* d_h1, const flo
     a.w_out = d_w_out; a.phi_out = d_phi_out; a.ab_out = d_ab_out; a.e_out = d_e_out;
     const size_t smem = (size_t)(rup(d.H, 4) + 2 * rup(3 * d.A, 4) + rup(d.U, 4) + 8 * d.C) * 4;
     ensure_kernel_attrs();
-    LAUNCH(attention_fwd_kernel, d.B, 256, smem, (cudaStream_t)stream, a);
+    // the caller's e_out buffer ([B][3A]) doubles as the projection scratch: it is consumed before it is rewritten
+    a.hat = d_e_out;
+    LAUNCH(attention_proj_kernel, 148, 256, 0, (cudaStream_t)stream, a);
+    LAUNCH(attention_fwd_kernel, d.B, 256, smem, (cudaStream_t)stream, a, 1);
   });
 }
 

@@ -190,10 +190,12 @@ __device__ __forceinline__ void attention_fwd_body(const AttnFwdArgs& a, const i
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(256) attention_fwd_kernel(const AttnFwdArgs a) {
+__global__ void __launch_bounds__(256) attention_fwd_kernel(const AttnFwdArgs a, const int precomputed_hat) {
   extern __shared__ float sh[];
-  attention_fwd_body(a, blockIdx.x, sh);
+  attention_fwd_body(a, blockIdx.x, sh, precomputed_hat != 0);
 }
+// stage 1 of the two-kernel attention step: all 3A*B projections, one dot product per warp
+__global__ void __launch_bounds__(256) attention_proj_kernel(const AttnFwdArgs a) { attention_proj_body(a); }
 
 // =========================================================================
 // Attention window backward, one decoder step (training form: sharp = timing = 1).
@@ -539,6 +541,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) scan_bwd_persistent(const S
     // which do not depend on the attention.
     {
       if (threadIdx.x == 0 && bar) grid_wait(S.gridbar, bar * gridDim.x);
+      if (threadIdx.x == 0) STAMP(S, bar, 0);
       __syncthreads();
       const bool att_valid = ta >= 0 && ta < S.T;
       const int nB = att_valid ? min(S.att.B, (int)gridDim.x / 2) : 0;   // CTAs doing attention rows
@@ -560,7 +563,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) scan_bwd_persistent(const S
       }
       asm volatile("fence.proxy.async.global;" ::: "memory");
       __syncthreads();
-      if (threadIdx.x == 0) grid_arrive(S.gridbar);
+      if (threadIdx.x == 0) { STAMP(S, bar, 1); grid_arrive(S.gridbar); }
       ++bar;
     }
     persistent_gemm_phase(p, S.B1, tick, S, bar, 0);
