@@ -105,7 +105,7 @@ static EncodeTiledFn get_encode() {
 struct Dims {
   int H, R, D, A, C, U, B, T, E, S, K, Dtot, IN, NC;
   int Np, Hp, Cp, Rp, Dp, Dtp, Ap;
-  bool enc, spk, weak, full, gmm, sampling;
+  bool enc, spk, weak, full, gmm, sampling, ln;
 };
 static Dims make_dims(const parrot_config& c) {
   Dims d;
@@ -120,6 +120,7 @@ static Dims make_dims(const parrot_config& c) {
   d.full = c.full_feedback != 0;
   d.weak = c.weak_feedback != 0 || d.full;
   d.sampling = c.sampling != 0;
+  d.ln = c.layer_norm != 0;
   d.Np = rup(d.B, 16); d.Hp = rup(d.H, 64); d.Cp = rup(d.C, 64); d.Rp = rup(d.R, 64);
   d.Dp = rup(d.D, 64); d.Ap = 64;
   // planes of d(pred): the GMM blocks [mu | sigma | coeff] start at 64-aligned columns (TMA inner
@@ -128,7 +129,7 @@ static Dims make_dims(const parrot_config& c) {
   return d;
 }
 static void check_cfg(const parrot_config& c) {
-  REQUIRE(c.layer_norm == 0, "layer_norm=True is not implemented on the device path yet");
+  REQUIRE(!(c.layer_norm && c.sampling), "layer_norm=True is implemented for training only (no sample_model yet)");
   REQUIRE(c.batch_size >= 1 && c.batch_size <= 256, "batch_size per device must be in [1, 256]");
   REQUIRE(c.seq_len >= 1 && c.text_len >= 1, "seq_len / text_len must be positive");
   REQUIRE(3 * c.attention_size <= 64 && c.attention_size <= 32, "attention_size must be <= 21");
@@ -415,7 +416,8 @@ static Job blank_job() {
 static std::string LN(int l) { return std::to_string(l + 1); }
 
 // forward scan jobs of one layer (gates or candidate): model.py:655-662, 692-722
-static void build_fwd_layer_jobs(parrot_model& M, std::vector<Job>& out, int layer, bool gates, int lag) {
+static void build_fwd_layer_jobs(parrot_model& M, std::vector<Job>& out, int layer, bool gates, int lag,
+                                 bool ln = false) {
   const Dims& d = M.d;
   const int rows = gates ? 2 * d.H : d.H;
   const std::string l = LN(layer);
@@ -435,13 +437,13 @@ static void build_fwd_layer_jobs(parrot_model& M, std::vector<Job>& out, int lay
     // attention context: layer 1 consumes w_{t-1} (slot t), layers 2,3 consume w_t (slot t+1)
     j.seg[ns++] = mkseg(M.packs["/inp_to_h" + l + "/fork_rnn" + l + fk].fwd_map, mt * 128, 0, M.map_scan["w"], 0, 0,
                         layer == 0 ? 0 : 1, d.Cp / 64);
-    if (layer >= 1)
+    if (layer >= 1 && !ln)
       j.seg[ns++] = mkseg(M.packs["/h1_to_h" + l + "/fork_rnn" + l + fk].fwd_map, mt * 128, 0, M.map_scan["h1"], 0, 0,
                           1, d.Hp / 64);
-    if (layer == 2)
+    if (layer == 2 && !ln)
       j.seg[ns++] = mkseg(M.packs["/h2_to_h3/fork_rnn3" + fk].fwd_map, mt * 128, 0, M.map_scan["h2"], 0, 0, 1,
                           d.Hp / 64);
-    if ((layer == 0 && d.weak) || (layer > 0 && d.full))
+    if (!ln && ((layer == 0 && d.weak) || (layer > 0 && d.full)))
       j.seg[ns++] = mkseg(M.packs["/out_to_h" + l + "/fork_rnn" + l + fk].fwd_map, mt * 128, 0, M.map_scan["xin"], 0,
                           0, 0, d.Dp / 64);
     j.nseg = ns;
@@ -721,19 +723,60 @@ static void build(parrot_model& M) {
     tplane("dread", d.Rp, (long long)T * Np, false);
     tplane("dpred", d.Dtp, (long long)T * Np, false);
     tplane("datt", d.Ap, (long long)T * Np, false);
+    if (d.ln) {
+      // layer_norm=True: pre-norm Fork outputs (kept for the backward), per-step pre-activation terms, and the
+      // gradients wrt the pre-norm values with their operand planes
+      for (int l = 0; l < 3; ++l) {
+        M.falloc("preT" + LN(l), (long long)T * B * 3 * H);
+        M.falloc("ropre" + LN(l), (long long)T * B * d.R);
+        M.falloc("dro" + LN(l), (long long)T * B * d.R);
+        Plane pr = M.make_plane("dro" + LN(l), Np, d.R, T);
+        M.map_plain["dro" + LN(l)] = M.make_map(pr, 2, NT);
+        tplane("dro" + LN(l), d.Rp, (long long)T * Np, false);
+        if ((l == 0 && d.weak) || (l > 0 && d.full)) {
+          M.falloc("qfb" + LN(l), (long long)T * B * 3 * H);
+          M.falloc("dfb" + LN(l), (long long)T * B * 3 * H);
+          M.make_plane("dfb" + LN(l), Np, 3 * d.Hp, T);
+          tplane("dfb" + LN(l), 3 * d.Hp, (long long)T * Np, false);
+        }
+        if (d.spk) { M.falloc("spk_pre" + LN(l), (long long)B * 3 * H); }
+      }
+      if (d.spk) M.falloc("spk_tmp", (long long)B * 3 * H);
+      for (const char* nm : {"12", "13", "23"}) {
+        M.falloc(std::string("q") + nm, (long long)T * B * 3 * H);
+        M.falloc(std::string("dq") + nm, (long long)T * B * 3 * H);
+        Plane pq = M.make_plane(std::string("dq") + nm, Np, 3 * d.Hp, T);
+        M.map_scan[std::string("dq") + nm] = M.make_map(pq, 3, Np);
+        tplane(std::string("dq") + nm, 3 * d.Hp, (long long)T * Np, false);
+      }
+      if (d.weak) M.map_plain["xin"] = M.make_map(M.planes.at("xin"), 2, NT);
+    }
     M.alloc("opt_scratch", 1024 * 8);
     M.falloc("bias_scratch", (long long)std::max(3 * H, d.R) + d.Dtot + 128);
     M.falloc("colsum_scratch", (long long)COLSUM_CHUNKS * 4096);
   }
   M.alloc("gemm_scratch", 1024 * 8);
+  if (train && d.ln && !M.dry) {
+    for (int l = 0; l < 3; ++l) X.L[l].base = M.fbuf("preT" + LN(l));
+    X.base_tstride = (long long)B * 3 * H;
+  }
 
   // ============================ job tables ============================
-  if (train) {
+  if (train && !d.ln) {
     std::vector<Job> A, Bj;
     for (int l = 0; l < 3; ++l) build_fwd_layer_jobs(M, A, l, true, l);
     for (int l = 0; l < 3; ++l) build_fwd_layer_jobs(M, Bj, l, false, l);
     push_table(M, "fwdA", A, Np, 148);
     push_table(M, "fwdB", Bj, Np, 148);
+  } else if (train) {
+    // layer_norm: one layer at a time (lag 0); the normalised Fork outputs reach the epilogues through preT
+    for (int l = 0; l < 3; ++l) {
+      std::vector<Job> A, Bj;
+      build_fwd_layer_jobs(M, A, l, true, 0, true);
+      build_fwd_layer_jobs(M, Bj, l, false, 0, true);
+      push_table(M, "lnA" + LN(l), A, Np, 148);
+      push_table(M, "lnB" + LN(l), Bj, Np, 148);
+    }
   } else {
     for (int l = 0; l < 3; ++l) {
       std::vector<Job> A, Bj;
@@ -756,7 +799,29 @@ static void build(parrot_model& M) {
     pa.ldo = d.R; pa.ldp = planes_of("ro").pitch;
     pa.n_pad = Np; pa.n_valid = B;
     pa.flags = PF_PLANE_PADDED | (d.spk ? PF_ACC : 0);
-    if (train) {
+    if (train && d.ln) {
+      // layer_norm (model.py:743-746): the three state readouts are normalised one by one, so they are
+      // produced separately (pre-norm, with their own bias); the attention readout is added afterwards.
+      pa.n_total = T * Np;
+      std::vector<Job> pre;
+      for (int l = 0; l < 3; ++l) {
+        PlainArgs pl;
+        memset(&pl, 0, sizeof pl);
+        pl.scale = 1.0f;
+        pl.out = M.dry ? nullptr : M.fbuf("ropre" + LN(l));
+        pl.bias = M.dry ? nullptr : M.pp("/h" + LN(l) + "_to_readout.b");
+        pl.ldo = d.R; pl.n_pad = Np; pl.n_valid = B; pl.n_total = T * Np;
+        std::vector<PlainSeg> segs = {
+            {M.packs["/h" + LN(l) + "_to_readout"].fwd_map, 0, M.map_plain["h" + LN(l)], Np, 0, d.Hp / 64}};
+        build_plain_jobs(pre, d.R, 0, (long long)T * Np, segs, pl);
+      }
+      push_table(M, "ln_ro", pre, NT);
+      pa.bias = M.dry ? nullptr : M.pp("/att_to_readout.b");
+      pa.flags = PF_PLANE_PADDED | PF_ACC;
+      std::vector<PlainSeg> segs = {{M.packs["/att_to_readout"].fwd_map, 0, M.map_plain["w"], Np, 0, d.Cp / 64}};
+      build_plain_jobs(js, d.R, 0, (long long)T * Np, segs, pa);
+      push_table(M, "ln_ro_att", js, NT);
+    } else if (train) {
       pa.n_total = T * Np;
       std::vector<PlainSeg> segs;
       for (int l = 0; l < 3; ++l)
@@ -837,13 +902,116 @@ static void build(parrot_model& M) {
         pa.out = M.dry ? nullptr : (l < 3 ? M.ctx.L[l].dh + (long long)B * H : M.ctx.dw + (long long)B * d.C);
         pa.ldo = F; pa.n_pad = Np; pa.n_valid = B; pa.n_total = T * Np;
         const std::string pk = l < 3 ? "/h" + LN(l) + "_to_readout" : "/att_to_readout";
-        std::vector<PlainSeg> segs = {{M.packs[pk].bwd_map, 0, M.map_plain["dread"], 0, 0, d.Rp / 64}};
+        const std::string src = (d.ln && l < 3) ? "dro" + LN(l) : std::string("dread");
+        std::vector<PlainSeg> segs = {{M.packs[pk].bwd_map, 0, M.map_plain[src], 0, 0, d.Rp / 64}};
         build_plain_jobs(js, F, 0, (long long)T * Np, segs, pa);
       }
       push_table(M, "dh_readout", js, NT);
     }
+    if (d.ln) {
+      // layer_norm forward side products: q12/q13 (from h1_t), q23 (from h2_t) per step, the feedback Forks over
+      // all frames; backward: one table per layer and product (no wavefront: the norm sits between the layers)
+      auto qjobs = [&](std::vector<Job>& js, const std::string& fork, const std::string& fk_l, const std::string& src,
+                       const std::string& dst) {
+        for (int part = 0; part < 2; ++part) {
+          const std::string pk = fork + "/fork_rnn" + fk_l + (part == 0 ? "_inputs" : "_gates");
+          const int rows = part == 0 ? H : 2 * H, f0 = part == 0 ? 0 : H;
+          for (int mt = 0; mt < cdiv(rows, 128); ++mt) {
+            Job j = blank_job();
+            j.epi = EPI_PLAIN; j.row0 = f0 + mt * 128; j.m_valid = std::min(128, rows - mt * 128);
+            j.nseg = 1;
+            j.seg[0] = mkseg(M.packs[pk].fwd_map, mt * 128, 0, M.map_scan[src], 0, 0, 1, d.Hp / 64);
+            j.pa.out = M.dry ? nullptr : M.fbuf(dst);
+            j.pa.bias = M.dry ? nullptr : M.pp(pk + ".b") - f0;
+            j.pa.ldo = 3 * H; j.pa.out_tstride = (long long)B * 3 * H;
+            j.pa.n_pad = Np; j.pa.n_valid = B; j.pa.n_total = Np;
+            js.push_back(j);
+          }
+        }
+      };
+      {
+        std::vector<Job> js;
+        qjobs(js, "/h1_to_h2", "2", "h1", "q12");
+        qjobs(js, "/h1_to_h3", "3", "h1", "q13");
+        push_table(M, "lnQ1", js, Np);
+      }
+      {
+        std::vector<Job> js;
+        qjobs(js, "/h2_to_h3", "3", "h2", "q23");
+        push_table(M, "lnQ2", js, Np);
+      }
+      {
+        std::vector<Job> js;
+        for (int l = 0; l < 3; ++l) {
+          if (!((l == 0 && d.weak) || (l > 0 && d.full))) continue;
+          for (int part = 0; part < 2; ++part) {
+            const std::string pk = "/out_to_h" + LN(l) + "/fork_rnn" + LN(l) + (part == 0 ? "_inputs" : "_gates");
+            const int rows = part == 0 ? H : 2 * H, f0 = part == 0 ? 0 : H;
+            PlainArgs pa;
+            memset(&pa, 0, sizeof pa);
+            pa.scale = 1.0f;
+            pa.out = M.dry ? nullptr : M.fbuf("qfb" + LN(l));
+            pa.bias = M.dry ? nullptr : M.pp(pk + ".b") - f0;
+            pa.ldo = 3 * H; pa.n_pad = Np; pa.n_valid = B; pa.n_total = T * Np;
+            std::vector<PlainSeg> segs = {{M.packs[pk].fwd_map, 0, M.map_plain["xin"], 0, 0, d.Dp / 64}};
+            build_plain_jobs(js, rows, f0, (long long)T * Np, segs, pa);
+          }
+        }
+        push_table(M, "ln_fb", js, NT);
+      }
+      for (int l = 0; l < 3; ++l) {
+        std::vector<Job> js;
+        for (int mt = 0; mt < cdiv(H, 128); ++mt) {
+          Job j = blank_job();
+          j.epi = EPI_BWD_RH; j.layer = l; j.lag = 0; j.row0 = mt * 128; j.m_valid = std::min(128, H - mt * 128);
+          j.nseg = 1;
+          j.seg[0] = mkseg(M.packs["/rnn" + LN(l) + ".state_to_state"].bwd_map, mt * 128, 0, M.map_scan["da" + LN(l)],
+                           0, 0, 0, d.Hp / 64);
+          js.push_back(j);
+        }
+        push_table(M, "ln_bwd1_" + LN(l), js, Np, 148);
+      }
+      // (pack, plane holding dY, gate block?) -> destination (aux, slot offset)
+      struct Src { std::string pack, plane; };
+      auto add = [&](std::vector<Job>& js, int rows, int aux, int slot_off, const std::vector<Src>& src) {
+        for (int mt = 0; mt < cdiv(rows, 128); ++mt) {
+          Job j = blank_job();
+          j.epi = EPI_BWD_STATE; j.aux = aux; j.lag = 0; j.row0 = mt * 128; j.m_valid = std::min(128, rows - mt * 128);
+          j.pa.n_pad = slot_off;
+          int ns = 0;
+          for (auto& sname : src) {
+            const bool is_gate = sname.pack.find("_gates") != std::string::npos;
+            j.seg[ns++] = mkseg(M.packs[sname.pack].bwd_map, mt * 128, 0, M.map_scan[sname.plane], 0,
+                                is_gate ? d.Hp : 0, 0, (is_gate ? 2 : 1) * d.Hp / 64);
+          }
+          j.nseg = ns;
+          js.push_back(j);
+        }
+      };
+      {
+        std::vector<Job> js;
+        add(js, H, 2, 0, {{"/rnn3.state_to_gates", "da3"}});
+        add(js, d.C, 3, 1, {{"/inp_to_h3/fork_rnn3_inputs", "da3"}, {"/inp_to_h3/fork_rnn3_gates", "da3"}});
+        add(js, H, 1, 1, {{"/h2_to_h3/fork_rnn3_inputs", "dq23"}, {"/h2_to_h3/fork_rnn3_gates", "dq23"}});
+        add(js, H, 0, 1, {{"/h1_to_h3/fork_rnn3_inputs", "dq13"}, {"/h1_to_h3/fork_rnn3_gates", "dq13"}});
+        push_table(M, "ln_bwd2_3", js, Np, 148);
+      }
+      {
+        std::vector<Job> js;
+        add(js, H, 1, 0, {{"/rnn2.state_to_gates", "da2"}});
+        add(js, d.C, 3, 1, {{"/inp_to_h2/fork_rnn2_inputs", "da2"}, {"/inp_to_h2/fork_rnn2_gates", "da2"}});
+        add(js, H, 0, 1, {{"/h1_to_h2/fork_rnn2_inputs", "dq12"}, {"/h1_to_h2/fork_rnn2_gates", "dq12"}});
+        push_table(M, "ln_bwd2_2", js, Np, 148);
+      }
+      {
+        std::vector<Job> js;
+        add(js, H, 0, 0, {{"/rnn1.state_to_gates", "da1"}});
+        add(js, d.C, 3, 0, {{"/inp_to_h1/fork_rnn1_inputs", "da1"}, {"/inp_to_h1/fork_rnn1_gates", "da1"}});
+        push_table(M, "ln_bwd2_1", js, Np, 148);
+      }
+    }
     // backward scan, product 1: d(r*h) = da_c . Ws^T
-    {
+    if (!d.ln) {
       std::vector<Job> js;
       for (int l = 0; l < 3; ++l)
         for (int mt = 0; mt < cdiv(H, 128); ++mt) {
@@ -858,7 +1026,7 @@ static void build(parrot_model& M) {
     }
     // backward scan, product 2: dgrads into the carried state gradients.  Job time = step s of layer 3;
     // segments of layer 2 / layer 1 refer to steps s+1 / s+2 (reverse wavefront).
-    {
+    if (!d.ln) {
       std::vector<Job> js;
       const int gk = d.Hp;  // column offset of the gate block inside the da planes
       auto seg_c = [&](const std::string& pk, int mt, int layer, int slot) {
@@ -908,15 +1076,18 @@ static void build(parrot_model& M) {
         const int wshift = l == 0 ? 0 : Np;
         wg("w", wshift, "da" + s, 0, "/inp_to_h" + s + "/fork_rnn" + s + "_inputs");
         wg("w", wshift, "da" + s, d.Hp, "/inp_to_h" + s + "/fork_rnn" + s + "_gates");
-        wg("h" + s, Np, "dread", 0, "/h" + s + "_to_readout.W");
+        wg("h" + s, Np, d.ln ? "dro" + s : std::string("dread"), 0, "/h" + s + "_to_readout.W");
         if ((l == 0 && d.weak) || (l > 0 && d.full)) {
-          wg("xin", 0, "da" + s, 0, "/out_to_h" + s + "/fork_rnn" + s + "_inputs");
-          wg("xin", 0, "da" + s, d.Hp, "/out_to_h" + s + "/fork_rnn" + s + "_gates");
+          const std::string dfb = d.ln ? "dfb" + s : "da" + s;
+          wg("xin", 0, dfb, 0, "/out_to_h" + s + "/fork_rnn" + s + "_inputs");
+          wg("xin", 0, dfb, d.Hp, "/out_to_h" + s + "/fork_rnn" + s + "_gates");
         }
       }
-      wg("h1", Np, "da2", 0, "/h1_to_h2/fork_rnn2_inputs"); wg("h1", Np, "da2", d.Hp, "/h1_to_h2/fork_rnn2_gates");
-      wg("h1", Np, "da3", 0, "/h1_to_h3/fork_rnn3_inputs"); wg("h1", Np, "da3", d.Hp, "/h1_to_h3/fork_rnn3_gates");
-      wg("h2", Np, "da3", 0, "/h2_to_h3/fork_rnn3_inputs"); wg("h2", Np, "da3", d.Hp, "/h2_to_h3/fork_rnn3_gates");
+      // layer_norm: the gradient reaching a Fork is the one behind its own normalisation
+      const std::string g12 = d.ln ? "dq12" : "da2", g13 = d.ln ? "dq13" : "da3", g23 = d.ln ? "dq23" : "da3";
+      wg("h1", Np, g12, 0, "/h1_to_h2/fork_rnn2_inputs"); wg("h1", Np, g12, d.Hp, "/h1_to_h2/fork_rnn2_gates");
+      wg("h1", Np, g13, 0, "/h1_to_h3/fork_rnn3_inputs"); wg("h1", Np, g13, d.Hp, "/h1_to_h3/fork_rnn3_gates");
+      wg("h2", Np, g23, 0, "/h2_to_h3/fork_rnn3_inputs"); wg("h2", Np, g23, d.Hp, "/h2_to_h3/fork_rnn3_gates");
       wg("w", Np, "dread", 0, "/att_to_readout.W");
       for (size_t f = 0; f < out_forks.size(); ++f) wg("ro", 0, "dpred", out_poff[f], out_forks[f] + ".W");
       wg("h1", Np, "datt", 0, "/h1_to_att/fork_alpha.W");
@@ -1042,9 +1213,11 @@ static void pack_weights(parrot_model& M, cudaStream_t st) {
       const float* src[4] = {nullptr, nullptr, nullptr, nullptr};
       int ns = 0;
       src[ns++] = M.pp("/inp_to_h" + s + "/fork_rnn" + s + fk);
-      if (l >= 1) src[ns++] = M.pp("/h1_to_h" + s + "/fork_rnn" + s + fk);
-      if (l == 2) src[ns++] = M.pp("/h2_to_h3/fork_rnn3" + fk);
-      if ((l == 0 && d.weak) || (l > 0 && d.full)) src[ns++] = M.pp("/out_to_h" + s + "/fork_rnn" + s + fk);
+      // layer_norm: the other Forks are normalised together with their own bias (model.py:31-34)
+      if (l >= 1 && !d.ln) src[ns++] = M.pp("/h1_to_h" + s + "/fork_rnn" + s + fk);
+      if (l == 2 && !d.ln) src[ns++] = M.pp("/h2_to_h3/fork_rnn3" + fk);
+      if (!d.ln && ((l == 0 && d.weak) || (l > 0 && d.full)))
+        src[ns++] = M.pp("/out_to_h" + s + "/fork_rnn" + s + fk);
       const int n = part == 0 ? d.H : 2 * d.H;
       LAUNCH(vec_sum_kernel, gs_blocks(n), 256, 0, st, M.fbuf("bias_l" + s) + (part == 0 ? 0 : d.H), n, src[0], src[1],
              src[2], src[3]);
@@ -1076,6 +1249,22 @@ static void pack_weights(parrot_model& M, cudaStream_t st) {
   M.dirty = false;
 }
 
+// the two normalisation groups of a (., 3H) pre-activation row: cell block [0,H) and gate block [H,3H)
+static NormParts gru_parts(const Dims& d) {
+  NormParts P;
+  P.off[0] = 0; P.n[0] = d.H; P.poff[0] = 0;
+  P.off[1] = d.H; P.n[1] = 2 * d.H; P.poff[1] = d.Hp;
+  P.count = 2;
+  return P;
+}
+static NormParts row_parts(int n) {
+  NormParts P;
+  P.off[0] = 0; P.n[0] = n; P.poff[0] = 0;
+  P.off[1] = 0; P.n[1] = 0; P.poff[1] = 0;
+  P.count = 1;
+  return P;
+}
+
 // per-call time-constant inputs of the recurrent layers and of the readout (speaker conditioning)
 static void prep_base(parrot_model& M, const int32_t* d_speaker, cudaStream_t st) {
   const Dims& d = M.d;
@@ -1089,10 +1278,14 @@ static void prep_base(parrot_model& M, const int32_t* d_speaker, cudaStream_t st
          (long long)d.B, d.S, emb);
   for (int l = 0; l < 3; ++l) {
     const std::string s = LN(l), pre = "/speaker_to_h" + s + "/fork_rnn" + s;
-    sgemm(st, emb, d.S, 1, M.pp(pre + "_inputs.W"), d.H, 1, M.fbuf("base" + s), 3 * d.H, d.B, d.H, d.S,
-          M.pp(pre + "_inputs.b"), 1.0f);
-    sgemm(st, emb, d.S, 1, M.pp(pre + "_gates.W"), 2 * d.H, 1, M.fbuf("base" + s) + d.H, 3 * d.H, d.B, 2 * d.H, d.S,
-          M.pp(pre + "_gates.b"), 1.0f);
+    float* dst = d.ln ? M.fbuf("spk_pre" + s) : M.fbuf("base" + s);
+    const float beta = d.ln ? 0.0f : 1.0f;
+    sgemm(st, emb, d.S, 1, M.pp(pre + "_inputs.W"), d.H, 1, dst, 3 * d.H, d.B, d.H, d.S, M.pp(pre + "_inputs.b"), beta);
+    sgemm(st, emb, d.S, 1, M.pp(pre + "_gates.W"), 2 * d.H, 1, dst + d.H, 3 * d.H, d.B, 2 * d.H, d.S,
+          M.pp(pre + "_gates.b"), beta);
+    if (d.ln)   // model.py:619-627: norm(speaker projection), cell and gate halves separately
+      LAUNCH(rownorm_fwd_kernel, dim3(d.B, 2), 256, 0, st, dst, (long long)3 * d.H, M.fbuf("base" + s),
+             (long long)3 * d.H, gru_parts(d), 1);
   }
   sgemm(st, emb, d.S, 1, M.pp("/speaker_to_readout.W"), d.R, 1, M.fbuf("spk_ro"), d.R, d.B, d.R, d.S,
         M.pp("/speaker_to_readout.b"), 0.0f);
@@ -1269,6 +1462,7 @@ static int prefetch_enabled() {
   return (e && e[0] && e[0] != '0') ? 0 : 1;
 }
 static bool use_persistent(parrot_model& M) {
+  if (M.d.ln) return false;   // the normalisations sit between the layers: one launch per phase
   static int env = -1;
   if (env < 0) {
     const char* e = getenv("PARROT_NO_PERSISTENT");
@@ -1360,6 +1554,41 @@ static bool scan_bwd_persistent_launch(parrot_model& M, cudaStream_t st) {
   return true;
 }
 
+// layer_norm=True forward scan (model.py:571-603, 692-722 with _apply_norm active): every Fork output except
+// inp_to_h* is normalised before it is summed, so the layers cannot share one accumulator.  preT_l[t] collects
+// bias + norm(speaker) + norm(feedback) (+ norm(q12/q13/q23) as the lower layers finish step t).
+static void scan_fwd_ln(parrot_model& M, cudaStream_t st) {
+  const Dims& d = M.d;
+  const long long row = (long long)3 * d.H, step = (long long)d.B * row;
+  const NormParts gp = gru_parts(d);
+  run_table(M, "ln_fb", 0, 1, 0, st);
+  for (int l = 0; l < 3; ++l) {
+    LAUNCH(bcast_rows_kernel, gs_blocks((long long)d.T * step), 256, 0, st, M.fbuf("preT" + LN(l)),
+           M.fbuf("base" + LN(l)), d.T, step);
+    if ((l == 0 && d.weak) || (l > 0 && d.full))
+      LAUNCH(rownorm_fwd_kernel, dim3(d.T * d.B, 2), 256, 0, st, M.fbuf("qfb" + LN(l)), row,
+             M.fbuf("preT" + LN(l)), row, gp, 1);
+  }
+  auto norm_into = [&](const char* q, const char* pre, int t) {
+    LAUNCH(rownorm_fwd_kernel, dim3(d.B, 2), 256, 0, st, M.fbuf(q) + t * step, row, M.fbuf(pre) + t * step, row, gp,
+           1);
+  };
+  for (int t = 0; t < d.T; ++t) {
+    run_table(M, "lnA1", t, d.T, 0, st);
+    run_table(M, "lnB1", t, d.T, 0, st);
+    attention_step(M, t, false, st);
+    run_table(M, "lnQ1", t, d.T, 0, st);
+    norm_into("q12", "preT2", t);
+    norm_into("q13", "preT3", t);
+    run_table(M, "lnA2", t, d.T, 0, st);
+    run_table(M, "lnB2", t, d.T, 0, st);
+    run_table(M, "lnQ2", t, d.T, 0, st);
+    norm_into("q23", "preT3", t);
+    run_table(M, "lnA3", t, d.T, 0, st);
+    run_table(M, "lnB3", t, d.T, 0, st);
+  }
+}
+
 static void scan_fwd(parrot_model& M, const float* d_features, const float* d_noise, float level, float start_flag,
                      cudaStream_t st) {
   const Dims& d = M.d;
@@ -1372,6 +1601,7 @@ static void scan_fwd(parrot_model& M, const float* d_features, const float* d_no
   }
   init_slots(M, start_flag != 0.0f, st);
   M.last_start_flag = start_flag;
+  if (d.ln) { scan_fwd_ln(M, st); return; }
   if (use_persistent(M) && scan_fwd_persistent_launch(M, st)) return;
   // layer wavefront: tick tau runs layer 1 at step tau, layer 2 at tau-1, layer 3 at tau-2
   for (int tick = 0; tick < d.T + 2; ++tick) {
@@ -1410,7 +1640,16 @@ static void readout_emit_fwd(parrot_model& M, const float* d_features, const flo
     LAUNCH(bcast_rows_kernel, gs_blocks((long long)d.T * d.B * d.Dtot), 256, 0, st, M.fbuf("pred"), M.fbuf("spk_out"),
            d.T, (long long)d.B * d.Dtot);
   }
-  run_table(M, "readout", 0, 1, 0, st);
+  if (d.ln) {
+    // model.py:743-753: norm(h_l readout) summed, then speaker and attention readouts un-normalised
+    run_table(M, "ln_ro", 0, 1, 0, st);
+    for (int l = 0; l < 3; ++l)
+      LAUNCH(rownorm_fwd_kernel, dim3(d.T * d.B, 1), 256, 0, st, M.fbuf("ropre" + LN(l)), (long long)d.R,
+             M.fbuf("ro"), (long long)d.R, row_parts(d.R), (l > 0 || d.spk) ? 1 : 0);
+    run_table(M, "ln_ro_att", 0, 1, 0, st);
+  } else {
+    run_table(M, "readout", 0, 1, 0, st);
+  }
   run_table(M, "output", 0, 1, 0, st);
   EmitArgs e = emit_args(M, d_features, d_fmask, 0);
   LAUNCH(emit_cost_kernel, cdiv((long long)e.N * 32, 256), 256, 0, st, e);
@@ -1445,6 +1684,13 @@ static void readout_emit_bwd(parrot_model& M, int unnormalised, cudaStream_t st)
   EmitArgs e = emit_args(M, in.features, in.fmask, unnormalised);
   LAUNCH(emit_grad_kernel, cdiv((long long)e.N * 32, 256), 256, 0, st, e);
   run_table(M, "dread", 0, 1, 0, st);
+  if (d.ln)
+    for (int l = 0; l < 3; ++l) {
+      const Plane& pl = M.planes.at("dro" + LN(l));
+      LAUNCH(rownorm_bwd_kernel, dim3(d.T * d.B, 1), 256, 0, st, M.fbuf("dread"), (long long)d.R,
+             M.fbuf("ropre" + LN(l)), (long long)d.R, M.fbuf("dro" + LN(l)), (long long)d.R, pl.hi, pl.lo,
+             (long long)pl.pitch, d.B, d.Np, row_parts(d.R));
+    }
   for (int l = 0; l < 3; ++l) CK(cudaMemsetAsync(M.ctx.L[l].dh, 0, (size_t)d.B * d.H * 4, st));
   CK(cudaMemsetAsync(M.ctx.dw, 0, (size_t)d.B * d.C * 4, st));
   run_table(M, "dh_readout", 0, 1, 0, st);
@@ -1478,9 +1724,39 @@ static void attention_bwd_step(parrot_model& M, int t, cudaStream_t st) {
   parrot_model::prof_end(pe, st);
 }
 
+// layer_norm=True reverse sweep: per step, layer 3 -> layer 2 -> attention -> layer 1; the gradients that cross a
+// normalised Fork (q23, q13, q12) go through rownorm_bwd before the transposed products.
+static void scan_bwd_ln(parrot_model& M, cudaStream_t st) {
+  const Dims& d = M.d;
+  const int blocks = std::min(gs_blocks((long long)d.B * d.H), 148);
+  const long long row = (long long)3 * d.H, step = (long long)d.B * row;
+  const NormParts gp = gru_parts(d);
+  auto norm_bwd = [&](int layer, const char* q, const char* dq, int t) {
+    const Plane& pl = M.planes.at(dq);
+    const long long pstep = (long long)d.Np * pl.pitch;
+    LAUNCH(rownorm_bwd_kernel, dim3(d.B, 2), 256, 0, st, M.ctx.L[layer].da + t * step, row, M.fbuf(q) + t * step, row,
+           M.fbuf(dq) + t * step, row, pl.hi + t * pstep, pl.lo + t * pstep, (long long)pl.pitch, d.B, d.Np, gp);
+  };
+  for (int t = d.T - 1; t >= 0; --t) {
+    for (int l = 2; l >= 0; --l) {
+      if (l == 0) attention_bwd_step(M, t, st);
+      PreArgs pa;
+      pa.n = 1; pa.layer[0] = l; pa.t[0] = t;
+      cudaEvent_t pe = M.prof_begin("gru_bwd_pre", st);
+      LAUNCH(gru_bwd_pre_kernel, dim3(blocks, 1), 256, 0, st, M.d_ctx, pa);
+      parrot_model::prof_end(pe, st);
+      run_table(M, "ln_bwd1_" + LN(l), t, d.T, 0, st);
+      if (l == 2) { norm_bwd(2, "q23", "dq23", t); norm_bwd(2, "q13", "dq13", t); }
+      if (l == 1) norm_bwd(1, "q12", "dq12", t);
+      run_table(M, "ln_bwd2_" + LN(l), t, d.T, 0, st);
+    }
+  }
+}
+
 static void scan_bwd(parrot_model& M, cudaStream_t st) {
   const Dims& d = M.d;
   CK(cudaMemsetAsync(M.fbuf("dk_carry"), 0, (size_t)d.B * d.A * 4, st));
+  if (d.ln) { scan_bwd_ln(M, st); return; }
   if (use_persistent(M) && scan_bwd_persistent_launch(M, st)) return;
   const int blocks = std::min(gs_blocks((long long)d.B * d.H), 148);
   // reverse layer wavefront: tick tau -> layer 3 at s = T-1-tau, layer 2 at s+1, attention + layer 1 at s+2
@@ -1519,27 +1795,57 @@ static void weight_grads(parrot_model& M, cudaStream_t st) {
   tp("w", d.C);
   if (d.weak) tp("xin", d.D);
   tp("ro", d.R); tp("dread", d.R); tp("dpred", d.Dtp); tp("datt", 3 * d.A);
+  if (d.ln) {
+    const NormParts gp = gru_parts(d);
+    for (int l = 0; l < 3; ++l) {
+      tp("dro" + LN(l), d.R);
+      if ((l == 0 && d.weak) || (l > 0 && d.full)) {
+        // gradient behind the normalised feedback Fork (model.py:571-603)
+        const Plane& pl = M.planes.at("dfb" + LN(l));
+        LAUNCH(rownorm_bwd_kernel, dim3(T * B, 2), 256, 0, st, M.ctx.L[l].da, (long long)3 * H,
+               M.fbuf("qfb" + LN(l)), (long long)3 * H, M.fbuf("dfb" + LN(l)), (long long)3 * H, pl.hi, pl.lo,
+               (long long)pl.pitch, B, d.Np, gp);
+        tp("dfb" + LN(l), 3 * d.Hp);
+      }
+    }
+    tp("dq12", 3 * d.Hp); tp("dq13", 3 * d.Hp); tp("dq23", 3 * d.Hp);
+  }
   { cudaEvent_t p2 = M.prof_begin("tail_transposes_done", st); parrot_model::prof_end(p2, st); }
   run_table(M, "wgrad", 0, 1, 0, st);
   cudaEvent_t pb = M.prof_begin("tail_bias_grads", st);
   // bias gradients: column sums of the pre-activation gradients
   float* scratch = M.fbuf("bias_scratch");
+  auto fork_bias = [&](const float* src, const std::string& fork, const std::string& s) {
+    add_to(M, st, fork + "/fork_rnn" + s + "_inputs.b", src, H);
+    add_to(M, st, fork + "/fork_rnn" + s + "_gates.b", src + H, 2 * H);
+  };
   for (int l = 0; l < 3; ++l) {
     const std::string s = LN(l);
     colsum(st, M.ctx.L[l].da, 3 * H, (long long)T * B, 3 * H, scratch, 0);
-    for (int part = 0; part < 2; ++part) {
-      const std::string fk = part == 0 ? "_inputs.b" : "_gates.b";
-      const float* src = scratch + (part == 0 ? 0 : H);
-      const int n = part == 0 ? H : 2 * H;
-      add_to(M, st, "/inp_to_h" + s + "/fork_rnn" + s + fk, src, n);
-      if (l >= 1) add_to(M, st, "/h1_to_h" + s + "/fork_rnn" + s + fk, src, n);
-      if (l == 2) add_to(M, st, "/h2_to_h3/fork_rnn3" + fk, src, n);
-      if ((l == 0 && d.weak) || (l > 0 && d.full)) add_to(M, st, "/out_to_h" + s + "/fork_rnn" + s + fk, src, n);
-      if (d.spk) add_to(M, st, "/speaker_to_h" + s + "/fork_rnn" + s + fk, src, n);
+    fork_bias(scratch, "/inp_to_h" + s, s);
+    if (d.ln) continue;
+    if (l >= 1) fork_bias(scratch, "/h1_to_h" + s, s);
+    if (l == 2) fork_bias(scratch, "/h2_to_h3", s);
+    if ((l == 0 && d.weak) || (l > 0 && d.full)) fork_bias(scratch, "/out_to_h" + s, s);
+    if (d.spk) fork_bias(scratch, "/speaker_to_h" + s, s);
+  }
+  if (d.ln) {
+    // biases that sit inside a normalisation receive the column sums of the gradient behind it
+    auto through = [&](const char* dq, const std::string& fork, const std::string& s) {
+      colsum(st, M.fbuf(dq), 3 * H, (long long)T * B, 3 * H, scratch, 0);
+      fork_bias(scratch, fork, s);
+    };
+    through("dq12", "/h1_to_h2", "2"); through("dq13", "/h1_to_h3", "3"); through("dq23", "/h2_to_h3", "3");
+    for (int l = 0; l < 3; ++l)
+      if ((l == 0 && d.weak) || (l > 0 && d.full))
+        through(("dfb" + LN(l)).c_str(), "/out_to_h" + LN(l), LN(l));
+    for (int l = 0; l < 3; ++l) {
+      colsum(st, M.fbuf("dro" + LN(l)), d.R, (long long)T * B, d.R, scratch, 0);
+      add_to(M, st, "/h" + LN(l) + "_to_readout.b", scratch, d.R);
     }
   }
   colsum(st, M.fbuf("dread"), d.R, (long long)T * B, d.R, scratch, 0);
-  for (int l = 0; l < 3; ++l) add_to(M, st, "/h" + LN(l) + "_to_readout.b", scratch, d.R);
+  if (!d.ln) for (int l = 0; l < 3; ++l) add_to(M, st, "/h" + LN(l) + "_to_readout.b", scratch, d.R);
   add_to(M, st, "/att_to_readout.b", scratch, d.R);
   if (d.spk) add_to(M, st, "/speaker_to_readout.b", scratch, d.R);
   float* sc2 = scratch + std::max(3 * H, d.R);  // dpred sums
@@ -1580,6 +1886,16 @@ static void speaker_grads(parrot_model& M, cudaStream_t st) {
   for (int l = 0; l < 3; ++l) {
     const std::string s = LN(l), pre = "/speaker_to_h" + s + "/fork_rnn" + s;
     LAUNCH(timesum_kernel, gs_blocks((long long)B * 3 * H), 256, 0, st, M.ctx.L[l].da, T, (long long)B * 3 * H, dp);
+    if (d.ln) {
+      // norm(speaker projection) is constant over time: sum the gradient first, then one norm backward
+      float* tmp = M.fbuf("spk_tmp");
+      LAUNCH(rownorm_bwd_kernel, dim3(B, 2), 256, 0, st, dp, (long long)3 * H, M.fbuf("spk_pre" + s), (long long)3 * H,
+             tmp, (long long)3 * H, (bf16*)nullptr, (bf16*)nullptr, 0LL, B, d.Np, gru_parts(d));
+      CK(cudaMemcpyAsync(dp, tmp, (size_t)B * 3 * H * 4, cudaMemcpyDeviceToDevice, st));
+      colsum(st, dp, 3 * H, B, 3 * H, M.fbuf("bias_scratch"), 0);
+      add_to(M, st, pre + "_inputs.b", M.fbuf("bias_scratch"), H);
+      add_to(M, st, pre + "_gates.b", M.fbuf("bias_scratch") + H, 2 * H);
+    }
     through(dp, 3 * H, H, pre + "_inputs");
     through(dp + H, 3 * H, 2 * H, pre + "_gates");
   }

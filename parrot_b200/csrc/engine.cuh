@@ -121,6 +121,7 @@ struct LayerBuf {
 };
 struct ScanCtx {
   int T, B, Np, H, Hp, C, Cp, A, U;
+  long long base_tstride;   // 0: L.base is [B][3H] ; layer_norm mode: [T][B][3H] (per-step pre-activation terms)
   LayerBuf L[3];
   float* dw;           // [T+1][B][C] gradient wrt w slot s
 };
@@ -215,6 +216,7 @@ __device__ __forceinline__ EpiLocal make_epi_local(const Job& jb, const ScanCtx*
     return E;
   }
   E.B = ctx->B; E.H = ctx->H; E.Np = ctx->Np; E.Hp = ctx->Hp;
+  E.l0 = ctx->base_tstride;
   const LayerBuf& L = ctx->L[jb.layer];
   switch (jb.epi) {
     case EPI_GATES:
@@ -280,7 +282,7 @@ __device__ __forceinline__ void epi_gates_load(const EpiLocal& E, int t, int row
   const int H = E.H, B = E.B, f = E.row0 + row;
   const bool is_z = f < H;
   const int fr = is_z ? f : f - H;
-  const float* __restrict__ basep = (const float*)E.p0 + H + f;
+  const float* __restrict__ basep = (const float*)E.p0 + (long long)t * E.l0 + H + f;
   const float* __restrict__ hprev = (const float*)E.p1 + (long long)t * B * H + fr;
 #pragma unroll
   for (int j = 0; j < W; ++j) {
@@ -321,7 +323,7 @@ template <int W>
 __device__ __forceinline__ void epi_cand_load(const EpiLocal& E, int t, int row, int n_base, int ncols, EpiOps<W>& o) {
   const int H = E.H, B = E.B, f = E.row0 + row;
   const long long tb = (long long)t * B * H + f;
-  const float* __restrict__ basep = (const float*)E.p0 + f;
+  const float* __restrict__ basep = (const float*)E.p0 + (long long)t * E.l0 + f;
   const float* __restrict__ zp = (const float*)E.p2 + tb;
   const float* __restrict__ hp_ = (const float*)E.p1 + tb;
 #pragma unroll

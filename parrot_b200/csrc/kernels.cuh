@@ -857,6 +857,88 @@ __global__ void transpose_f32_kernel(const float* __restrict__ src, int rows, in
   }
 }
 
+// =========================================================================
+// _simple_norm (model.py:24-27): (x - mean) / (1e-5 + std) over a feature range, population std, no affine.
+// Used only with layer_norm=True.  One CTA per (row, part); a row may hold two independently normalised
+// parts (the [cell | gates] outputs of one Fork pair).
+// =========================================================================
+struct NormParts { int off[2]; int n[2]; int poff[2]; int count; };
+
+__device__ __forceinline__ float block_sum(float v, float* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float t = 0.0f;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+  return t;
+}
+
+// y[r][off + j] (= | +=) norm(x[r][off .. off + n))[j]
+__global__ void __launch_bounds__(256) rownorm_fwd_kernel(const float* __restrict__ x, long long xld,
+                                                          float* __restrict__ y, long long yld, NormParts P,
+                                                          int accumulate) {
+  __shared__ float red[8];
+  const long long r = blockIdx.x;
+  const int part = blockIdx.y;
+  const int off = P.off[part], n = P.n[part];
+  const float* xr = x + r * xld + off;
+  float* yr = y + r * yld + off;
+  float s = 0.0f;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) s += xr[j];
+  const float mean = block_sum(s, red) / n;
+  float v = 0.0f;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) { const float d = xr[j] - mean; v += d * d; }
+  const float sd = sqrtf(block_sum(v, red) / n);
+  const float inv = 1.0f / (1e-5f + sd);
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    const float o = (xr[j] - mean) * inv;
+    yr[j] = accumulate ? yr[j] + o : o;
+  }
+}
+
+// dx = d/dx of norm(x) applied to dy ; optional bf16 planes of dx at plane row (r / Bv) * Np + r % Bv, column
+// poff[part] + j
+__global__ void __launch_bounds__(256) rownorm_bwd_kernel(const float* __restrict__ dy, long long dyld,
+                                                          const float* __restrict__ x, long long xld,
+                                                          float* __restrict__ dx, long long dxld, bf16* hi,
+                                                          bf16* lo, long long pld, int Bv, int Np, NormParts P) {
+  __shared__ float red[8];
+  const long long r = blockIdx.x;
+  const int part = blockIdx.y;
+  const int off = P.off[part], n = P.n[part];
+  const float* xr = x + r * xld + off;
+  const float* dyr = dy + r * dyld + off;
+  float s = 0.0f;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) s += xr[j];
+  const float mean = block_sum(s, red) / n;
+  float v = 0.0f, sdy = 0.0f, dot = 0.0f;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    const float d = xr[j] - mean;
+    v += d * d;
+    sdy += dyr[j];
+    dot += dyr[j] * d;
+  }
+  const float sd = sqrtf(block_sum(v, red) / n);
+  const float mdy = block_sum(sdy, red) / n;
+  const float dotv = block_sum(dot, red);
+  const float sv = 1e-5f + sd;
+  const float k2 = (sd > 0.0f) ? dotv / ((float)n * sd * sv * sv) : 0.0f;
+  const long long prow = (r / Bv) * Np + (r % Bv);
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    const float g = (dyr[j] - mdy) / sv - (xr[j] - mean) * k2;
+    dx[r * dxld + off + j] = g;
+    if (hi) {
+      bf16 hh, ll;
+      split_bf16(g, hh, ll);
+      hi[prow * pld + P.poff[part] + j] = hh;
+      lo[prow * pld + P.poff[part] + j] = ll;
+    }
+  }
+}
+
 // dst[i] = sum_j src_j[i]  (null sources ignored)
 __global__ void vec_sum_kernel(float* __restrict__ dst, int n, const float* s0, const float* s1, const float* s2,
                                const float* s3) {

@@ -74,10 +74,13 @@ def test_workspace_query_and_config_errors():
     small = n.value
     cfg.seq_len = 100
     assert lib.parrot_workspace_bytes(C.byref(cfg), C.byref(n)) == 0 and n.value > small
-    cfg.layer_norm = 1
+    plain = n.value
+    cfg.layer_norm = 1; cfg.weak_feedback = 1
+    assert lib.parrot_workspace_bytes(C.byref(cfg), C.byref(n)) == 0 and n.value > plain   # pre-norm stashes
+    cfg.sampling = 1                                 # sample_model with layer_norm is not on the device yet
     assert lib.parrot_workspace_bytes(C.byref(cfg), C.byref(n)) != 0
     assert b'layer_norm' in lib.parrot_last_error()
-    cfg.layer_norm = 0; cfg.rnn_h_dim = 50
+    cfg.layer_norm = 0; cfg.sampling = 0; cfg.rnn_h_dim = 50
     assert lib.parrot_workspace_bytes(C.byref(cfg), C.byref(n)) != 0
 
 

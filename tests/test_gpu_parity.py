@@ -20,6 +20,8 @@ CASES = {
     'gmm_full_spk': dict(which_cost='GMM', full_feedback=True, use_speaker=True),
     'softmax_att_noise': dict(attention_type='softmax', weak_feedback=True, feedback_noise_level=0.3),
     'no_feedback': dict(),
+    'layer_norm_weak': dict(weak_feedback=True, layer_norm=True),
+    'layer_norm_gmm_full_spk': dict(which_cost='GMM', full_feedback=True, use_speaker=True, layer_norm=True),
 }
 
 
@@ -94,6 +96,12 @@ def test_init_scale_and_intended_encoder_axis():
     cfg = dict(util.TINY, weak_feedback=True, which_cost='GMM')
     orc_cfg = dict(cfg)
     _run_pair(orc_cfg, B=5, T=9, U=11, gain=None, impl='tcgen05', axis=1)
+
+
+def test_layer_norm_medium_two_segments():
+    """layer_norm=True (model.py:24-34, 571-603, 692-722, 743-746) at H=256, odd batch, carried state."""
+    cfg = dict(util.TINY, rnn_h_dim=256, readouts_dim=192, encoder_dim=32, weak_feedback=True, layer_norm=True)
+    _run_pair(cfg, B=20, T=12, U=24, gain=0.5, impl='tcgen05', start_flags=(1.0, 0.0), align=0.5)
 
 
 def test_medium_hidden_odd_batch():
