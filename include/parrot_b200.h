@@ -35,7 +35,7 @@ typedef struct parrot_config {
   int32_t readouts_dim;       /* model.py:256 */
   int32_t weak_feedback;      /* model.py:257 */
   int32_t full_feedback;      /* model.py:258 */
-  int32_t layer_norm;         /* model.py:260 (training handles only)             */
+  int32_t layer_norm;         /* model.py:260 */
   int32_t use_speaker;        /* model.py:261 */
   int32_t num_speakers;       /* model.py:262 */
   int32_t speaker_dim;        /* model.py:263 */

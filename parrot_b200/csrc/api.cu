@@ -129,7 +129,6 @@ static Dims make_dims(const parrot_config& c) {
   return d;
 }
 static void check_cfg(const parrot_config& c) {
-  REQUIRE(!(c.layer_norm && c.sampling), "layer_norm=True is implemented for training only (no sample_model yet)");
   REQUIRE(c.batch_size >= 1 && c.batch_size <= 256, "batch_size per device must be in [1, 256]");
   REQUIRE(c.seq_len >= 1 && c.text_len >= 1, "seq_len / text_len must be positive");
   REQUIRE(3 * c.attention_size <= 64 && c.attention_size <= 32, "attention_size must be <= 21");
@@ -756,9 +755,19 @@ static void build(parrot_model& M) {
     M.falloc("colsum_scratch", (long long)COLSUM_CHUNKS * 4096);
   }
   M.alloc("gemm_scratch", 1024 * 8);
-  if (train && d.ln && !M.dry) {
+  if (d.sampling && d.ln) {
+    // sampler with layer_norm: one step of pre-activation terms / pre-norm Fork outputs
+    for (int l = 0; l < 3; ++l) {
+      M.falloc("preT" + LN(l), (long long)B * 3 * H);
+      M.falloc("ropre" + LN(l), (long long)B * d.R);
+      if ((l == 0 && d.weak) || (l > 0 && d.full)) M.falloc("qfb" + LN(l), (long long)B * 3 * H);
+      if (d.spk) M.falloc("spk_pre" + LN(l), (long long)B * 3 * H);
+    }
+    for (const char* nm : {"q12", "q13", "q23"}) M.falloc(nm, (long long)B * 3 * H);
+  }
+  if (d.ln && !M.dry) {
     for (int l = 0; l < 3; ++l) X.L[l].base = M.fbuf("preT" + LN(l));
-    X.base_tstride = (long long)B * 3 * H;
+    X.base_tstride = train ? (long long)B * 3 * H : 0;
   }
 
   // ============================ job tables ============================
@@ -780,8 +789,8 @@ static void build(parrot_model& M) {
   } else {
     for (int l = 0; l < 3; ++l) {
       std::vector<Job> A, Bj;
-      build_fwd_layer_jobs(M, A, l, true, 0);
-      build_fwd_layer_jobs(M, Bj, l, false, 0);
+      build_fwd_layer_jobs(M, A, l, true, 0, d.ln);
+      build_fwd_layer_jobs(M, Bj, l, false, 0, d.ln);
       push_table(M, "sampA" + LN(l), A, Np);
       push_table(M, "sampB" + LN(l), Bj, Np);
     }
@@ -829,6 +838,34 @@ static void build(parrot_model& M) {
       segs.push_back({M.packs["/att_to_readout"].fwd_map, 0, M.map_plain["w"], Np, 0, d.Cp / 64});
       build_plain_jobs(js, d.R, 0, (long long)T * Np, segs, pa);
       push_table(M, "readout", js, NT);
+    } else if (d.ln) {
+      // sampler with layer_norm (model.py:992-1003): three pre-norm readouts, then the attention readout on top
+      pa.n_total = Np;
+      std::vector<Job> pre;
+      for (int l = 0; l < 3; ++l)
+        for (int mt = 0; mt < cdiv(d.R, 128); ++mt) {
+          Job j = blank_job();
+          j.epi = EPI_PLAIN; j.row0 = mt * 128; j.m_valid = std::min(128, d.R - mt * 128);
+          j.nseg = 1;
+          j.seg[0] = mkseg(M.packs["/h" + LN(l) + "_to_readout"].fwd_map, mt * 128, 0, M.map_scan["h" + LN(l)], 0, 0, 1,
+                           d.Hp / 64);
+          j.pa.out = M.dry ? nullptr : M.fbuf("ropre" + LN(l));
+          j.pa.bias = M.dry ? nullptr : M.pp("/h" + LN(l) + "_to_readout.b");
+          j.pa.ldo = d.R; j.pa.n_pad = Np; j.pa.n_valid = B; j.pa.n_total = Np;
+          pre.push_back(j);
+        }
+      push_table(M, "ln_ro", pre, Np);
+      pa.bias = M.dry ? nullptr : M.pp("/att_to_readout.b");
+      pa.flags = PF_PLANE_PADDED | PF_ACC;
+      for (int mt = 0; mt < cdiv(d.R, 128); ++mt) {
+        Job j = blank_job();
+        j.epi = EPI_PLAIN; j.row0 = mt * 128; j.m_valid = std::min(128, d.R - mt * 128);
+        j.nseg = 1;
+        j.seg[0] = mkseg(M.packs["/att_to_readout"].fwd_map, mt * 128, 0, M.map_scan["w"], 0, 0, 1, d.Cp / 64);
+        j.pa = pa;
+        js.push_back(j);
+      }
+      push_table(M, "ln_ro_att", js, Np);
     } else {
       // sampler: one step, operands taken from the scan maps at slot t+1
       pa.n_total = Np;
@@ -845,6 +882,64 @@ static void build(parrot_model& M) {
         js.push_back(j);
       }
       push_table(M, "readout", js, Np);
+    }
+  }
+  if (d.ln) {
+    // layer_norm forward side products, per step: q12/q13 (from h1_t), q23 (from h2_t) and, in the sampler, the
+    // feedback Forks of the frame just emitted (training: the feedback Forks run over all frames at once)
+    const long long tstride = train ? (long long)B * 3 * H : 0;
+    auto qjobs = [&](std::vector<Job>& js, const std::string& fork, const std::string& fk_l, const std::string& src,
+                     int slot, int nkb, const std::string& dst) {
+      for (int part = 0; part < 2; ++part) {
+        const std::string pk = fork + "/fork_rnn" + fk_l + (part == 0 ? "_inputs" : "_gates");
+        const int rows = part == 0 ? H : 2 * H, f0 = part == 0 ? 0 : H;
+        for (int mt = 0; mt < cdiv(rows, 128); ++mt) {
+          Job j = blank_job();
+          j.epi = EPI_PLAIN; j.row0 = f0 + mt * 128; j.m_valid = std::min(128, rows - mt * 128);
+          j.nseg = 1;
+          j.seg[0] = mkseg(M.packs[pk].fwd_map, mt * 128, 0, M.map_scan[src], 0, 0, slot, nkb);
+          j.pa.out = M.dry ? nullptr : M.fbuf(dst);
+          j.pa.bias = M.dry ? nullptr : M.pp(pk + ".b") - f0;
+          j.pa.ldo = 3 * H; j.pa.out_tstride = tstride;
+          j.pa.n_pad = Np; j.pa.n_valid = B; j.pa.n_total = Np;
+          js.push_back(j);
+        }
+      }
+    };
+    {
+      std::vector<Job> js;
+      qjobs(js, "/h1_to_h2", "2", "h1", 1, d.Hp / 64, "q12");
+      qjobs(js, "/h1_to_h3", "3", "h1", 1, d.Hp / 64, "q13");
+      push_table(M, "lnQ1", js, Np);
+    }
+    {
+      std::vector<Job> js;
+      qjobs(js, "/h2_to_h3", "3", "h2", 1, d.Hp / 64, "q23");
+      push_table(M, "lnQ2", js, Np);
+    }
+    if (!train) {
+      std::vector<Job> js;
+      for (int l = 0; l < 3; ++l)
+        if ((l == 0 && d.weak) || (l > 0 && d.full)) qjobs(js, "/out_to_h" + LN(l), LN(l), "xin", 0, d.Dp / 64, "qfb" + LN(l));
+      push_table(M, "ln_fb", js, Np);
+    } else {
+      std::vector<Job> js;
+      for (int l = 0; l < 3; ++l) {
+        if (!((l == 0 && d.weak) || (l > 0 && d.full))) continue;
+        for (int part = 0; part < 2; ++part) {
+          const std::string pk = "/out_to_h" + LN(l) + "/fork_rnn" + LN(l) + (part == 0 ? "_inputs" : "_gates");
+          const int rows = part == 0 ? H : 2 * H, f0 = part == 0 ? 0 : H;
+          PlainArgs pa;
+          memset(&pa, 0, sizeof pa);
+          pa.scale = 1.0f;
+          pa.out = M.dry ? nullptr : M.fbuf("qfb" + LN(l));
+          pa.bias = M.dry ? nullptr : M.pp(pk + ".b") - f0;
+          pa.ldo = 3 * H; pa.n_pad = Np; pa.n_valid = B; pa.n_total = T * Np;
+          std::vector<PlainSeg> segs = {{M.packs[pk].fwd_map, 0, M.map_plain["xin"], 0, 0, d.Dp / 64}};
+          build_plain_jobs(js, rows, f0, (long long)T * Np, segs, pa);
+        }
+      }
+      push_table(M, "ln_fb", js, NT);
     }
   }
   // output layer (model.py:755, 766)
@@ -909,56 +1004,7 @@ static void build(parrot_model& M) {
       push_table(M, "dh_readout", js, NT);
     }
     if (d.ln) {
-      // layer_norm forward side products: q12/q13 (from h1_t), q23 (from h2_t) per step, the feedback Forks over
-      // all frames; backward: one table per layer and product (no wavefront: the norm sits between the layers)
-      auto qjobs = [&](std::vector<Job>& js, const std::string& fork, const std::string& fk_l, const std::string& src,
-                       const std::string& dst) {
-        for (int part = 0; part < 2; ++part) {
-          const std::string pk = fork + "/fork_rnn" + fk_l + (part == 0 ? "_inputs" : "_gates");
-          const int rows = part == 0 ? H : 2 * H, f0 = part == 0 ? 0 : H;
-          for (int mt = 0; mt < cdiv(rows, 128); ++mt) {
-            Job j = blank_job();
-            j.epi = EPI_PLAIN; j.row0 = f0 + mt * 128; j.m_valid = std::min(128, rows - mt * 128);
-            j.nseg = 1;
-            j.seg[0] = mkseg(M.packs[pk].fwd_map, mt * 128, 0, M.map_scan[src], 0, 0, 1, d.Hp / 64);
-            j.pa.out = M.dry ? nullptr : M.fbuf(dst);
-            j.pa.bias = M.dry ? nullptr : M.pp(pk + ".b") - f0;
-            j.pa.ldo = 3 * H; j.pa.out_tstride = (long long)B * 3 * H;
-            j.pa.n_pad = Np; j.pa.n_valid = B; j.pa.n_total = Np;
-            js.push_back(j);
-          }
-        }
-      };
-      {
-        std::vector<Job> js;
-        qjobs(js, "/h1_to_h2", "2", "h1", "q12");
-        qjobs(js, "/h1_to_h3", "3", "h1", "q13");
-        push_table(M, "lnQ1", js, Np);
-      }
-      {
-        std::vector<Job> js;
-        qjobs(js, "/h2_to_h3", "3", "h2", "q23");
-        push_table(M, "lnQ2", js, Np);
-      }
-      {
-        std::vector<Job> js;
-        for (int l = 0; l < 3; ++l) {
-          if (!((l == 0 && d.weak) || (l > 0 && d.full))) continue;
-          for (int part = 0; part < 2; ++part) {
-            const std::string pk = "/out_to_h" + LN(l) + "/fork_rnn" + LN(l) + (part == 0 ? "_inputs" : "_gates");
-            const int rows = part == 0 ? H : 2 * H, f0 = part == 0 ? 0 : H;
-            PlainArgs pa;
-            memset(&pa, 0, sizeof pa);
-            pa.scale = 1.0f;
-            pa.out = M.dry ? nullptr : M.fbuf("qfb" + LN(l));
-            pa.bias = M.dry ? nullptr : M.pp(pk + ".b") - f0;
-            pa.ldo = 3 * H; pa.n_pad = Np; pa.n_valid = B; pa.n_total = T * Np;
-            std::vector<PlainSeg> segs = {{M.packs[pk].fwd_map, 0, M.map_plain["xin"], 0, 0, d.Dp / 64}};
-            build_plain_jobs(js, rows, f0, (long long)T * Np, segs, pa);
-          }
-        }
-        push_table(M, "ln_fb", js, NT);
-      }
+      // layer_norm backward: one table per layer and product (no wavefront: the norm sits between the layers)
       for (int l = 0; l < 3; ++l) {
         std::vector<Job> js;
         for (int mt = 0; mt < cdiv(H, 128); ++mt) {
@@ -1969,18 +2015,48 @@ static void sample_scan(parrot_model& M, const int32_t* d_labels, const float* d
     CK(cudaMemsetAsync(px->hi, 0, (size_t)d.Np * px->pitch * 2, st));  // x_0 = 0 (model.py:834-835)
     CK(cudaMemsetAsync(px->lo, 0, (size_t)d.Np * px->pitch * 2, st));
   }
+  const long long row = (long long)3 * d.H;
+  const NormParts gp = gru_parts(d);
+  auto norm_into = [&](const std::string& q, const std::string& pre) {   // layer_norm: pre += norm(q), one step
+    LAUNCH(rownorm_fwd_kernel, dim3(d.B, 2), 256, 0, st, M.fbuf(q), row, M.fbuf(pre), row, gp, 1);
+  };
   for (int t = 0; t < d.T; ++t) {
+    if (d.ln) {
+      for (int l = 0; l < 3; ++l)
+        CK(cudaMemcpyAsync(M.fbuf("preT" + LN(l)), M.fbuf("base" + LN(l)), (size_t)d.B * row * 4,
+                           cudaMemcpyDeviceToDevice, st));
+      if (d.weak) {   // model.py:899-924: norm(Fork(x_{t-1})) per layer
+        run_table(M, "ln_fb", t, d.T, 0, st);
+        for (int l = 0; l < 3; ++l)
+          if (l == 0 || d.full) norm_into("qfb" + LN(l), "preT" + LN(l));
+      }
+    }
     run_table(M, "sampA1", t, d.T, 0, st);
     run_table(M, "sampB1", t, d.T, 0, st);
     attention_step(M, t, true, st);
+    if (d.ln) {
+      run_table(M, "lnQ1", t, d.T, 0, st);
+      norm_into("q12", "preT2"); norm_into("q13", "preT3");
+    }
     run_table(M, "sampA2", t, d.T, 0, st);
     run_table(M, "sampB2", t, d.T, 0, st);
+    if (d.ln) {
+      run_table(M, "lnQ2", t, d.T, 0, st);
+      norm_into("q23", "preT3");
+    }
     run_table(M, "sampA3", t, d.T, 0, st);
     run_table(M, "sampB3", t, d.T, 0, st);
     if (d.spk) {
       CK(cudaMemcpyAsync(M.fbuf("ro"), M.fbuf("spk_ro"), (size_t)d.B * d.R * 4, cudaMemcpyDeviceToDevice, st));
       CK(cudaMemcpyAsync(M.fbuf("pred"), M.fbuf("spk_out"), (size_t)d.B * d.Dtot * 4, cudaMemcpyDeviceToDevice, st));
     }
+    if (d.ln) {
+      run_table(M, "ln_ro", t, d.T, 0, st);
+      for (int l = 0; l < 3; ++l)
+        LAUNCH(rownorm_fwd_kernel, dim3(d.B, 1), 256, 0, st, M.fbuf("ropre" + LN(l)), (long long)d.R, M.fbuf("ro"),
+               (long long)d.R, row_parts(d.R), (l > 0 || d.spk) ? 1 : 0);
+      run_table(M, "ln_ro_att", t, d.T, 0, st);
+    } else
     run_table(M, "readout", t, d.T, 0, st);
     run_table(M, "output", t, d.T, 0, st);
     SampleArgs a;

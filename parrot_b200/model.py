@@ -16,8 +16,7 @@ Differences a reference user has to know:
     tests; otherwise Philox streams are used (Theano's MRG31k3p streams are not
     reproduced, SURVEY hard part 7);
   * ``encoder_time_axis`` (0 = literal reference behaviour, SURVEY D4);
-  * ``layer_norm=True`` is implemented for training (``compute_cost`` / ``backward``); ``sample_model`` with
-    it and ``raw_output=True`` raise NotImplementedError.
+  * ``raw_output=True`` (sampleRNN coupling) raises NotImplementedError.
 """
 import ctypes as C
 from collections import OrderedDict, namedtuple
@@ -335,8 +334,6 @@ class Parrot(object):
                      num_samples, num_steps, gmm_noise=None, seed=0, as_numpy=True):
         """model.py:1061-1083.  Returns ``[x, k, w, pi, phi, pi_att]``, time-major.
         ``features_mask_tr`` is unused, as in the reference."""
-        if self.layer_norm:
-            raise NotImplementedError('sample_model with layer_norm=True is not implemented on the device path yet')
         lm = self._dev(labels_mask_tr, torch.float32)
         lab = self._dev(labels_tr, torch.float32 if self.encoder_type is None else torch.int32)
         spk = self._dev(speaker_tr, torch.int32) if self.use_speaker else None

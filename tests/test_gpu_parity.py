@@ -110,7 +110,7 @@ def test_medium_hidden_odd_batch():
     _run_pair(cfg, B=20, T=16, U=24, gain=0.5, impl='tcgen05', align=0.5)
 
 
-@pytest.mark.parametrize('case', ['mse_weak', 'gmm_full_spk'])
+@pytest.mark.parametrize('case', ['mse_weak', 'gmm_full_spk', 'layer_norm_weak', 'layer_norm_gmm_full_spk'])
 def test_sample_model_matches_oracle(case):
     """Free-running generation (model.py:827-1059) with injected GMM noise."""
     cfg = dict(util.TINY, **CASES[case])
