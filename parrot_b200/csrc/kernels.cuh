@@ -1031,6 +1031,7 @@ __global__ void __launch_bounds__(256) emit_cost_kernel(const EmitArgs a) {
   // lane j < k owns component j
   float inner = 0.0f, lw = -INFINITY;
   if (lane < k) {
+#pragma unroll 7   // independent loads in flight (63 = 9 x 7 output dimensions)
     for (int d = 0; d < D; ++d) {
       const float mu = p[d * k + lane];
       const float sg = expf(p[D * k + d * k + lane]) + a.eps;
@@ -1086,6 +1087,7 @@ __global__ void __launch_bounds__(256) emit_grad_kernel(const EmitArgs a) {
   const int k = a.k, D = a.D;
   float inner = 0.0f, lw = -INFINITY;
   if (lane < k) {
+#pragma unroll 7   // independent loads in flight (63 = 9 x 7 output dimensions)
     for (int d = 0; d < D; ++d) {
       const float mu = p[d * k + lane];
       const float sg = expf(p[D * k + d * k + lane]) + a.eps;
