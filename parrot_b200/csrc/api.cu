@@ -8,6 +8,7 @@
 #include "../../include/parrot_b200.h"
 #include "kernels.cuh"
 
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdio>
@@ -397,6 +398,7 @@ struct parrot_model {
 
 static const int NT = 128;  // sample tile of the batched (outside-the-scan) products
 static const int COLSUM_CHUNKS = 64;
+static const int SGEMM_SPLIT = 64;   // K chunks of the split SIMT GEMM (encoder weight gradients)
 
 // ------------------------------------------------------------------ job builders
 static Seg mkseg(int a_map, int a_row, int a_k, int b_map, int b_row, int b_k, int b_slot, int nkb) {
@@ -456,8 +458,10 @@ struct PlainSeg {
 };
 static void build_plain_jobs(std::vector<Job>& out, int Mrows, int f0, long long n_samples,
                              const std::vector<PlainSeg>& segs, const PlainArgs& pa) {
-  for (int mt = 0; mt < cdiv(Mrows, 128); ++mt)
-    for (int nt = 0; nt < cdiv(n_samples, NT); ++nt) {
+  // sample-tile major: the CTAs running at the same time share one activation tile (L2 hits) and walk the
+  // (small, L2-resident) weight tiles; feature-tile major would re-stream the activation planes per feature tile
+  for (int nt = 0; nt < cdiv(n_samples, NT); ++nt)
+    for (int mt = 0; mt < cdiv(Mrows, 128); ++mt) {
       Job j = blank_job();
       j.epi = EPI_PLAIN;
       j.row0 = f0 + mt * 128;
@@ -470,6 +474,11 @@ static void build_plain_jobs(std::vector<Job>& out, int Mrows, int f0, long long
       j.pa = pa;
       out.push_back(j);
     }
+}
+
+// tables assembled from several build_plain_jobs calls: keep all jobs of one sample tile adjacent
+static void sort_by_sample_tile(std::vector<Job>& js) {
+  std::stable_sort(js.begin(), js.end(), [](const Job& a, const Job& b) { return a.n0 < b.n0; });
 }
 
 static int job_kb(const Job& j) {
@@ -753,6 +762,7 @@ static void build(parrot_model& M) {
     M.alloc("opt_scratch", 1024 * 8);
     M.falloc("bias_scratch", (long long)std::max(3 * H, d.R) + d.Dtot + 128);
     M.falloc("colsum_scratch", (long long)COLSUM_CHUNKS * 4096);
+    if (d.enc) M.falloc("sgemm_scratch", (long long)SGEMM_SPLIT * d.E * 2 * d.E);
   }
   M.alloc("gemm_scratch", 1024 * 8);
   if (d.sampling && d.ln) {
@@ -824,6 +834,7 @@ static void build(parrot_model& M) {
             {M.packs["/h" + LN(l) + "_to_readout"].fwd_map, 0, M.map_plain["h" + LN(l)], Np, 0, d.Hp / 64}};
         build_plain_jobs(pre, d.R, 0, (long long)T * Np, segs, pl);
       }
+      sort_by_sample_tile(pre);
       push_table(M, "ln_ro", pre, NT);
       pa.bias = M.dry ? nullptr : M.pp("/att_to_readout.b");
       pa.flags = PF_PLANE_PADDED | PF_ACC;
@@ -939,6 +950,7 @@ static void build(parrot_model& M) {
           build_plain_jobs(js, rows, f0, (long long)T * Np, segs, pa);
         }
       }
+      sort_by_sample_tile(js);
       push_table(M, "ln_fb", js, NT);
     }
   }
@@ -967,6 +979,7 @@ static void build(parrot_model& M) {
         }
       }
     }
+    if (train) sort_by_sample_tile(js);
     push_table(M, "output", js, train ? NT : Np);
   }
   if (train) {
@@ -1001,6 +1014,7 @@ static void build(parrot_model& M) {
         std::vector<PlainSeg> segs = {{M.packs[pk].bwd_map, 0, M.map_plain[src], 0, 0, d.Rp / 64}};
         build_plain_jobs(js, F, 0, (long long)T * Np, segs, pa);
       }
+      sort_by_sample_tile(js);
       push_table(M, "dh_readout", js, NT);
     }
     if (d.ln) {
@@ -1189,13 +1203,30 @@ static void ensure_kernel_attrs() {
 }
 
 // ------------------------------------------------------------------ small helpers
+static float* g_sgemm_scratch = nullptr;    // set per model before use (workspace buffer "sgemm_scratch")
+static long long g_sgemm_scratch_floats = 0;
 static void sgemm(cudaStream_t st, const float* A, long long sam, long long sak, const float* B, long long sbk,
                   long long sbn, float* C, long long ldc, int Mr, int N, int K, const float* bias, float beta,
                   const int* gather = nullptr) {
   SGemm g;
   g.A = A; g.sam = sam; g.sak = sak; g.B = B; g.sbk = sbk; g.sbn = sbn; g.C = C; g.ldc = ldc;
   g.bias = bias; g.a_gather = gather; g.M = Mr; g.N = N; g.K = K; g.alpha = 1.0f; g.beta = beta;
+  g.k_chunk = K; g.c_zstride = 0;
   dim3 grid(cdiv(N, 32), cdiv(Mr, 32));
+  // long reductions with a small output (encoder weight gradients: K = B*U): split K over grid.z into partial
+  // products, then add them in chunk order (deterministic)
+  const long long mn = (long long)Mr * N;
+  if (K >= 2048 && g_sgemm_scratch && !bias && !gather && ldc == N && (beta == 0.0f || beta == 1.0f) &&
+      mn * SGEMM_SPLIT <= g_sgemm_scratch_floats) {
+    g.k_chunk = rup(cdiv(K, SGEMM_SPLIT), 32);
+    const int parts = cdiv(K, g.k_chunk);
+    g.C = g_sgemm_scratch; g.c_zstride = mn; g.beta = 0.0f;
+    grid.z = parts;
+    LAUNCH(sgemm_kernel, grid, 256, 0, st, g);
+    LAUNCH(colsum_kernel, cdiv(mn, 32), 256, 0, st, (const float*)g_sgemm_scratch, mn, (long long)parts, (int)mn, C,
+           beta != 0.0f ? 1 : 0);
+    return;
+  }
   LAUNCH(sgemm_kernel, grid, 256, 0, st, g);
 }
 static float* g_colsum_scratch = nullptr;   // set per model before use (workspace buffer "colsum_scratch")
@@ -1405,6 +1436,8 @@ static void encoder_bwd(parrot_model& M, const float* d_lmask, cudaStream_t st) 
   const int E = d.E;
   EncArgs a;
   enc_args(M, a);
+  g_sgemm_scratch = M.fbuf("sgemm_scratch");
+  g_sgemm_scratch_floats = (long long)SGEMM_SPLIT * E * 2 * E;
   const long long n = (long long)d.B * d.U * d.C;
   // enc_dout <- dctx * mask (in the encoder's own layout)
   LAUNCH(context_mask_kernel, gs_blocks(n), 256, 0, st, M.fbuf("enc_dout"), d_lmask, d.B, d.U, d.C,
@@ -1428,9 +1461,9 @@ static void encoder_bwd(parrot_model& M, const float* d_lmask, cudaStream_t st) 
     sgemm(st, a.sprev[dir], 1, E, a.dxg[dir], 2 * E, 1, M.gp(g + ".state_to_gates"), 2 * E, E, 2 * E, (int)LNn,
           nullptr, 0.0f);
     float* dp = M.fbuf("enc_dproj") + dir * 3 * E;
-    LAUNCH(scatter_rows_kernel, gs_blocks((long long)d.NC * E), 256, 0, st, a.dxi[dir], (long long)E,
+    LAUNCH(scatter_rows_kernel, dim3(cdiv(E, 32), d.NC), 1024, 0, st, a.dxi[dir], (long long)E,
            (const int*)M.fbuf("enc_lab"), (int)LNn, E, d.NC, dp, (long long)6 * E);
-    LAUNCH(scatter_rows_kernel, gs_blocks((long long)d.NC * 2 * E), 256, 0, st, a.dxg[dir], (long long)2 * E,
+    LAUNCH(scatter_rows_kernel, dim3(cdiv(2 * E, 32), d.NC), 1024, 0, st, a.dxg[dir], (long long)2 * E,
            (const int*)M.fbuf("enc_lab"), (int)LNn, 2 * E, d.NC, dp + E, (long long)6 * E);
   }
   const float* Wemb = M.pp("/encoder/embed_label.W");
@@ -1450,6 +1483,8 @@ static void encoder_bwd(parrot_model& M, const float* d_lmask, cudaStream_t st) 
             1.0f);
     }
   }
+  g_sgemm_scratch = nullptr;
+  g_sgemm_scratch_floats = 0;
 }
 
 // ------------------------------------------------------------------ decoder scan
@@ -1517,7 +1552,7 @@ static bool use_persistent(parrot_model& M) {
   const Dims& d = M.d;
   if (!env || !M.persistent_ok || M.cfg.gemm_impl == 1 || M.profiling >= 2 || M.sm_count < 148) return false;
   const size_t att_f = (size_t)rup(d.H, 4) + 2 * rup(3 * d.A, 4) + rup(d.U, 4) + (ENGINE_THREADS / 32) * (size_t)d.C;
-  const size_t att_b = (size_t)d.C + d.U + 3 * d.A * 16 + 3 * d.A;
+  const size_t att_b = (size_t)d.C + d.U + 3 * d.A * 16 + 10 * d.A;
   if (std::max(att_f, att_b) * 4 > (size_t)ATT_SMEM_BYTES) return false;
   for (const char* nm : {"fwdA", "fwdB", "bwd1", "bwd2"}) {
     auto it = M.tables.find(nm);
@@ -1764,7 +1799,7 @@ static AttnBwdArgs attn_bwd_args(parrot_model& M, int t) {
 static void attention_bwd_step(parrot_model& M, int t, cudaStream_t st) {
   const Dims& d = M.d;
   AttnBwdArgs a = attn_bwd_args(M, t);
-  const size_t smem = (size_t)(d.C + d.U + 3 * d.A * 16 + 3 * d.A) * 4;
+  const size_t smem = (size_t)(d.C + d.U + 3 * d.A * 16 + 10 * d.A) * 4;
   cudaEvent_t pe = M.prof_begin("attn_bwd", st);
   LAUNCH(attention_bwd_kernel, d.B, 256, smem, st, a);
   parrot_model::prof_end(pe, st);
@@ -1957,7 +1992,7 @@ static void speaker_grads(parrot_model& M, cudaStream_t st) {
     through(dout + DK, d.Dtot, DK, "/speaker_to_output/fork_gmm_sigma");
     through(dout + 2 * DK, d.Dtot, d.K, "/speaker_to_output/fork_gmm_coeff");
   }
-  LAUNCH(scatter_rows_kernel, gs_blocks((long long)M.cfg.num_speakers * S), 256, 0, st, demb, (long long)S, in.speaker,
+  LAUNCH(scatter_rows_kernel, dim3(cdiv(S, 32), M.cfg.num_speakers), 1024, 0, st, demb, (long long)S, in.speaker,
          B, S, M.cfg.num_speakers, M.gp("/lookuptable.W"), (long long)S);
 }
 

@@ -73,6 +73,8 @@ __device__ __forceinline__ void attention_fwd_body(const AttnFwdArgs& a, const i
   float* sh_phi = sh_abk + A3p;              // U
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int A = a.A;
+  // fetched before the projection so that its latency is off the dependent chain
+  const float k_prev_reg = (tid < A) ? a.k_prev[(long long)b * A + tid] : 0.0f;
   if (precomputed_hat) {
     if (tid < 3 * A) sh_hat[tid] = __ldcg(a.hat + (long long)b * 3 * A + tid);
     __syncthreads();
@@ -115,7 +117,7 @@ __device__ __forceinline__ void attention_fwd_body(const AttnFwdArgs& a, const i
     const float alpha = ea + a.eps;
     const float beta = (a.sharp == 1.0f ? eb : eb * a.sharp) + a.eps;
     const float step = (a.timing == 1.0f) ? a.align * ek : (a.align * ek) / a.timing;
-    const float kappa = a.k_prev[(long long)b * A + tid] + step;
+    const float kappa = k_prev_reg + step;
     sh_abk[tid] = alpha;
     sh_abk[A + tid] = beta;
     sh_abk[2 * A + tid] = kappa;
@@ -224,10 +226,20 @@ __device__ __forceinline__ void attention_bwd_body(const AttnBwdArgs& a, const i
   float* sh_dw = sh;                    // C
   float* sh_dphi = sh_dw + a.C;         // U
   float* sh_red = sh_dphi + a.U;        // 3A * 16 warps
-  float* sh_datt = sh_red + 3 * a.A * 16;// 3A
+  float* sh_datt = sh_red + 3 * a.A * 16;// 3A, then 7A of prefetched per-row vectors
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int A = a.A, nwarp = blockDim.x >> 5;
   for (int i = tid; i < a.C; i += blockDim.x) sh_dw[i] = a.dw[(long long)b * a.C + i];
+  // small per-row vectors needed after the reductions: fetch them now, off the dependent chain
+  float* sh_small = sh_datt + 3 * A;   // [ab 2A | kappa A | e 3A | dk_carry A]
+  for (int i = tid; i < 7 * A; i += blockDim.x) {
+    float v;
+    if (i < 2 * A) v = a.ab[(long long)b * 2 * A + i];
+    else if (i < 3 * A) v = a.kappa[(long long)b * A + (i - 2 * A)];
+    else if (i < 6 * A) v = a.e[(long long)b * 3 * A + (i - 3 * A)];
+    else v = a.dk_carry[(long long)b * A + (i - 6 * A)];
+    sh_small[i] = v;
+  }
   __syncthreads();
   const float* cb = a.ctx + (long long)b * a.U * a.C;
   for (int u = warp * 4; u < a.U; u += nwarp * 4) {
@@ -259,9 +271,9 @@ __device__ __forceinline__ void attention_bwd_body(const AttnBwdArgs& a, const i
   __syncthreads();
   // per-component reductions over u
   for (int i = 0; i < A; ++i) {
-    const float al = a.ab[(long long)b * 2 * A + i];
-    const float be = a.ab[(long long)b * 2 * A + A + i];
-    const float ka = a.kappa[(long long)b * A + i];
+    const float al = sh_small[i];
+    const float be = sh_small[A + i];
+    const float ka = sh_small[2 * A + i];
     float da = 0.0f, db = 0.0f, dk = 0.0f;
     for (int u = tid; u < a.U; u += blockDim.x) {
       const float d = ka - (float)u;
@@ -303,14 +315,14 @@ __device__ __forceinline__ void attention_bwd_body(const AttnBwdArgs& a, const i
   if (tid < A) {
     const float da = sh_red[(0 * A + tid) * 16];
     const float db = sh_red[(1 * A + tid) * 16];
-    const float dk = sh_red[(2 * A + tid) * 16] + a.dk_carry[(long long)b * A + tid];
-    const float ea = a.e[(long long)b * 3 * A + tid];
-    const float eb = a.e[(long long)b * 3 * A + A + tid];
-    const float ek = a.e[(long long)b * 3 * A + 2 * A + tid];
+    const float dk = sh_red[(2 * A + tid) * 16] + sh_small[6 * A + tid];
+    const float ea = sh_small[3 * A + tid];
+    const float eb = sh_small[4 * A + tid];
+    const float ek = sh_small[5 * A + tid];
     float da_hat;
     if (a.type == 1) {
       float dot = 0.0f;
-      for (int i = 0; i < A; ++i) dot += sh_red[(0 * A + i) * 16] * a.e[(long long)b * 3 * A + i];
+      for (int i = 0; i < A; ++i) dot += sh_red[(0 * A + i) * 16] * sh_small[3 * A + i];
       da_hat = ea * (da - dot);
     } else {
       da_hat = da * ea;
@@ -331,8 +343,10 @@ __device__ __forceinline__ void attention_bwd_body(const AttnBwdArgs& a, const i
   }
   for (int f = tid; f < a.H; f += blockDim.x) {
     float s = 0.0f;
-    for (int j = 0; j < 3 * A; ++j) s = fmaf(sh_datt[j], a.watt[(long long)j * a.H + f], s);
-    a.dh1[(long long)b * a.H + f] += s;
+    const float prev = a.dh1[(long long)b * a.H + f];
+#pragma unroll 10   // independent L2 loads in flight (3A = 30 rows of the transposed projection)
+    for (int j = 0; j < 3 * A; ++j) s = fmaf(sh_datt[j], __ldg(a.watt + (long long)j * a.H + f), s);
+    a.dh1[(long long)b * a.H + f] = prev + s;
   }
   __syncthreads();
 }
@@ -727,23 +741,26 @@ struct SGemm {
   const int* a_gather;
   int M, N, K;
   float alpha, beta;
+  int k_chunk;            // split-K: block z reduces k in [z*k_chunk, (z+1)*k_chunk) into C + z*c_zstride
+  long long c_zstride;
 };
 __global__ void __launch_bounds__(256) sgemm_kernel(const SGemm g) {
   __shared__ float As[32][33], Bs[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
   const int m0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+  const int kb = blockIdx.z * g.k_chunk, ke = min(g.K, kb + g.k_chunk);
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int k0 = 0; k0 < g.K; k0 += 32) {
+  for (int k0 = kb; k0 < ke; k0 += 32) {
     for (int j = ty; j < 32; j += 8) {
       const int m = m0 + j, k = k0 + tx;
       float x = 0.0f;
-      if (m < g.M && k < g.K) {
+      if (m < g.M && k < ke) {
         const long long mr = g.a_gather ? g.a_gather[m] : m;
         x = g.A[mr * g.sam + (long long)k * g.sak];
       }
       As[j][tx] = x;
       const int kk = k0 + j, n = n0 + tx;
-      Bs[j][tx] = (kk < g.K && n < g.N) ? g.B[(long long)kk * g.sbk + (long long)n * g.sbn] : 0.0f;
+      Bs[j][tx] = (kk < ke && n < g.N) ? g.B[(long long)kk * g.sbk + (long long)n * g.sbn] : 0.0f;
     }
     __syncthreads();
 #pragma unroll 8
@@ -761,7 +778,7 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const SGemm g) {
       if (m < g.M) {
         float y = g.alpha * acc[i];
         if (g.bias) y += g.bias[n];
-        float* p = g.C + (long long)m * g.ldc + n;
+        float* p = g.C + (long long)blockIdx.z * g.c_zstride + (long long)m * g.ldc + n;
         if (g.beta != 0.0f) y += g.beta * *p;
         *p = y;
       }
@@ -832,18 +849,24 @@ __global__ void timesum_kernel(const float* __restrict__ src, int T, long long b
   }
 }
 
-// scatter-add rows: dst[idx[m]][:] += src[m][:]   (lookup-table gradients; deterministic: one thread per
-// (table row, column) walks all m)
-__global__ void scatter_rows_kernel(const float* __restrict__ src, long long src_ld, const int* __restrict__ idx,
-                                    int M, int F, int rows, float* __restrict__ dst, long long dst_ld) {
-  const long long n = (long long)rows * F;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int r = (int)(i / F), f = (int)(i % F);
-    float s = 0.0f;
-    for (int m = 0; m < M; ++m)
-      if (idx[m] == r) s += src[(long long)m * src_ld + f];
-    dst[(long long)r * dst_ld + f] += s;
+// scatter-add rows: dst[idx[m]][:] += src[m][:]   (lookup-table gradients).  Deterministic: block (f-chunk, r)
+// scans all m, warp w taking m = w, w + nwarp, ...; the per-warp sums are added in warp order.
+__global__ void __launch_bounds__(1024) scatter_rows_kernel(const float* __restrict__ src, long long src_ld,
+                                                            const int* __restrict__ idx, int M, int F, int rows,
+                                                            float* __restrict__ dst, long long dst_ld) {
+  __shared__ float part[32][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const int r = blockIdx.y, f = blockIdx.x * 32 + lane;
+  float s = 0.0f;
+  if (f < F)
+    for (int m = warp; m < M; m += nwarp)
+      if (__ldg(idx + m) == r) s += src[(long long)m * src_ld + f];
+  part[warp][lane] = s;
+  __syncthreads();
+  if (warp == 0 && f < F && r < rows) {
+    float t = 0.0f;
+    for (int w = 0; w < nwarp; ++w) t += part[w][lane];
+    dst[(long long)r * dst_ld + f] += t;
   }
 }
 
