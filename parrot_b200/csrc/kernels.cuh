@@ -64,6 +64,9 @@ __device__ __forceinline__ void attention_proj_body(const AttnFwdArgs& a) {
   }
 }
 
+// WIDE: the window sum keeps 16 x 128-bit loads per lane in flight (fastest as a stand-alone 8-warp kernel; inside
+// the 12-warp persistent scan the narrower form measured faster, so that instantiation keeps it)
+template <bool WIDE>
 __device__ __forceinline__ void attention_fwd_body(const AttnFwdArgs& a, const int b, float* sh,
                                                    const bool precomputed_hat = false) {
   const int A3p = (3 * a.A + 3) & ~3;  // sections padded to 16 bytes (float4 accesses below)
@@ -158,7 +161,38 @@ __device__ __forceinline__ void attention_fwd_body(const AttnFwdArgs& a, const i
   const int nwarp = blockDim.x >> 5;
   const int per = (a.U + nwarp - 1) / nwarp;
   const int u0 = warp * per, u1 = min(a.U, u0 + per);
-  if ((a.C & 3) == 0) {
+  if (WIDE && (a.C & 3) == 0 && a.C <= 256) {
+    // both 128-column halves of 8 text positions in flight per lane (16 x 128 bit loads before the first use)
+    float4 acc[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
+    for (int ub = u0; ub < u1; ub += 8) {
+      float4 x[8][2];
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int c = lane * 4 + h * 128;
+          x[r][h] = (ub + r < u1 && c < a.C)
+                        ? __ldg(reinterpret_cast<const float4*>(cb + (long long)(ub + r) * a.C + c))
+                        : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        if (ub + r < u1) {
+          const float p = sh_phi[ub + r];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            acc[h].x = fmaf(p, x[r][h].x, acc[h].x); acc[h].y = fmaf(p, x[r][h].y, acc[h].y);
+            acc[h].z = fmaf(p, x[r][h].z, acc[h].z); acc[h].w = fmaf(p, x[r][h].w, acc[h].w);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int c = lane * 4 + h * 128;
+      if (c < a.C) *reinterpret_cast<float4*>(sh_part + (long long)warp * a.C + c) = acc[h];
+    }
+  } else if ((a.C & 3) == 0) {
     for (int c = lane * 4; c < a.C; c += 128) {
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 8
@@ -194,7 +228,7 @@ __device__ __forceinline__ void attention_fwd_body(const AttnFwdArgs& a, const i
 
 __global__ void __launch_bounds__(256) attention_fwd_kernel(const AttnFwdArgs a, const int precomputed_hat) {
   extern __shared__ float sh[];
-  attention_fwd_body(a, blockIdx.x, sh, precomputed_hat != 0);
+  attention_fwd_body<true>(a, blockIdx.x, sh, precomputed_hat != 0);
 }
 // stage 1 of the two-kernel attention step: all 3A*B projections, one dot product per warp
 __global__ void __launch_bounds__(256) attention_proj_kernel(const AttnFwdArgs a) { attention_proj_body(a); }
@@ -242,6 +276,37 @@ __device__ __forceinline__ void attention_bwd_body(const AttnBwdArgs& a, const i
   }
   __syncthreads();
   const float* cb = a.ctx + (long long)b * a.U * a.C;
+  if ((a.C & 3) == 0 && a.C <= 256) {
+    // 8 text positions per warp pass, all loads of a pass (<= 16 x 128 bit per lane) issued before the first use
+    for (int u = warp * 8; u < a.U; u += nwarp * 8) {
+      float4 x[8][2];
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int c = lane * 4 + h * 128;
+          x[r][h] = (u + r < a.U && c < a.C)
+                        ? __ldg(reinterpret_cast<const float4*>(cb + (long long)(u + r) * a.C + c))
+                        : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      float4 d[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c = lane * 4 + h * 128;
+        d[h] = (c < a.C) ? *reinterpret_cast<const float4*>(sh_dw + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        float sv = 0.0f;
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+          sv += d[h].x * x[r][h].x + d[h].y * x[r][h].y + d[h].z * x[r][h].z + d[h].w * x[r][h].w;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sv += __shfl_xor_sync(0xffffffffu, sv, o);
+        if (lane == 0 && u + r < a.U) sh_dphi[u + r] = sv;
+      }
+    }
+  } else
   for (int u = warp * 4; u < a.U; u += nwarp * 4) {
     float s4[4] = {0.f, 0.f, 0.f, 0.f};
     if ((a.C & 3) == 0) {
@@ -530,7 +595,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) scan_fwd_persistent(const S
       if ((int)blockIdx.x < a.B) {
         if (threadIdx.x == 0) { grid_wait(S.gridbar, bar * gridDim.x); STAMP(S, bar, 0); }
         __syncthreads();
-        for (int b = blockIdx.x; b < a.B; b += gridDim.x) attention_fwd_body(a, b, att_sh, true);
+        for (int b = blockIdx.x; b < a.B; b += gridDim.x) attention_fwd_body<false>(a, b, att_sh, true);
         asm volatile("fence.proxy.async.global;" ::: "memory");
         __syncthreads();
       }
