@@ -499,9 +499,30 @@ static std::vector<Job> split_jobs(const std::vector<Job>& js, int target_ctas, 
     if (parts <= target_ctas || per > total) break;
     ++per;
   }
+  // CTAs left over go to the least-split tiles: their post-reduction epilogue covers the widest column slice
+  // (n_cols / parts) and therefore sets the length of the phase's tail
+  std::vector<int> parts_of(js.size());
+  long long used = 0;
+  for (size_t i = 0; i < js.size(); ++i) {
+    parts_of[i] = std::min(max_split, std::max(1, (job_kb(js[i]) + per - 1) / per));
+    used += parts_of[i];
+  }
+  for (;;) {
+    int lo = max_split + 1;
+    for (size_t i = 0; i < js.size(); ++i)
+      if (parts_of[i] < job_kb(js[i])) lo = std::min(lo, parts_of[i]);
+    if (lo >= max_split) break;
+    int n_lo = 0;
+    for (size_t i = 0; i < js.size(); ++i)
+      if (parts_of[i] == lo && parts_of[i] < job_kb(js[i])) ++n_lo;
+    if (n_lo == 0 || used + n_lo > target_ctas) break;   // only whole levels: a partial upgrade leaves the tail as is
+    for (size_t i = 0; i < js.size(); ++i)
+      if (parts_of[i] == lo && parts_of[i] < job_kb(js[i])) { ++parts_of[i]; ++used; }
+  }
   int g = 0;
-  for (auto& j : js) {
-    const int sp = std::min(max_split, std::max(1, (job_kb(j) + per - 1) / per));
+  for (size_t ji = 0; ji < js.size(); ++ji) {
+    const Job& j = js[ji];
+    const int sp = parts_of[ji];
     for (int p = 0; p < sp; ++p) {
       Job c = j;
       c.ksplit = sp; c.kpart = p; c.group = g;
@@ -526,6 +547,14 @@ static void push_table(parrot_model& M, const std::string& name, const std::vect
     std::vector<Job> sp = split_jobs(js, split_target, MAX_KSPLIT, &groups);
     // parts of one tile must run concurrently with distinct CTAs: order parts-major so that CTA i gets job i
     t.count = (int)sp.size();
+    if (getenv("PARROT_DEBUG_SPLIT")) {
+      std::map<std::pair<int, int>, int> hist;   // (k blocks of the tile, parts) -> tiles
+      for (auto& j : sp)
+        if (j.kpart == 0) ++hist[{job_kb(j), j.ksplit}];
+      fprintf(stderr, "[split] %-10s %3d CTAs:", name.c_str(), t.count);
+      for (auto& kv : hist) fprintf(stderr, "  %dx(kb=%d parts=%d)", kv.second, kv.first.first, kv.first.second);
+      fprintf(stderr, "\n");
+    }
     M.jobs.insert(M.jobs.end(), sp.begin(), sp.end());
     M.max_groups = std::max(M.max_groups, groups);
     M.max_split_floats = std::max(M.max_split_floats, (size_t)groups * MAX_KSPLIT * n_cols * TILE_M);

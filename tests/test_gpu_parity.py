@@ -137,3 +137,47 @@ def test_sample_model_philox_runs():
     b = dev.sample_model(bt['labels'], bt['labels_mask'], None, None, 4, 8, seed=1)
     c = dev.sample_model(bt['labels'], bt['labels_mask'], None, None, 4, 8, seed=2)
     assert np.isfinite(a[0]).all() and (a[0] == b[0]).all() and not (a[0] == c[0]).all()
+
+
+@pytest.mark.parametrize('name', ['tiny_mse_graves', 'tiny_gmm_softmax_spk'])
+def test_device_matches_golden_fixtures(name):
+    """CUDA path vs the committed fixtures tests/golden/*.npz (no oracle execution: parameters, inputs and the
+    expected outputs all come from the file).  Two consecutive TBPTT segments: frames, alignment, carried state,
+    argmax(phi) bit-exact where the fixture's own top-2 gap is unambiguous, gradient signatures."""
+    import os
+    from tests.golden.make_golden import CASES, B
+    from parrot_b200.model import Parrot
+    z = np.load(os.path.join(os.path.dirname(__file__), 'golden', name + '.npz'))
+    cfg = CASES[name]['cfg']
+    dev = Parrot(**cfg)
+    dev.initialize()
+    names = [str(n) for n in z['grad_names']]
+    dev.set_parameter_values({n: z['param:' + n] for n in names})
+    for seg, sf in enumerate((1.0, 0.0)):
+        p = 'seg%d:' % seg
+        spk = z[p + 'in:speaker'] if cfg.get('use_speaker') else None
+        cost, updates, av, _ = dev.compute_cost(
+            z[p + 'in:features'], z[p + 'in:features_mask'], z[p + 'in:labels'], z[p + 'in:labels_mask'], spk,
+            sf, B, gmm_noise=(z[p + 'in:gmm_unis'], z[p + 'in:gmm_normals']))
+        assert abs(cost.item() - float(z[p + 'cost'])) / abs(float(z[p + 'cost'])) < FWD_TOL
+        for nm, v in zip(['next_x', 'k', 'w', 'coeff', 'phi', 'pi_att'], av):
+            key = p + 'out:' + nm
+            if key in z.files and v is not None:
+                assert util.rel_err(v.cpu().numpy(), z[key]) < FWD_TOL, nm
+        phi = z[p + 'out:phi']
+        top2 = np.sort(phi, -1)[..., -2:]
+        ok = (top2[..., 1] - top2[..., 0]) > 1e-4 * np.abs(top2[..., 1])
+        assert ok.mean() > 0.5
+        assert (av[4].cpu().numpy().argmax(-1)[ok] == z[p + 'argmax_phi'][ok]).all()
+        for nm, v in updates:
+            assert util.rel_err(v.cpu().numpy(), z[p + 'update:' + nm]) < FWD_TOL, nm
+        g = dev.backward()
+        torch.cuda.synchronize()
+        sig = z[p + 'grad_sig']
+        for i, n in enumerate(names):
+            l2 = float(np.sqrt((g[n].double() ** 2).sum().item()))
+            assert abs(l2 - sig[i, 1]) <= 5e-3 * sig[i, 1] + 1e-7, (n, l2, sig[i, 1])
+        for key in z.files:
+            if key.startswith(p + 'grad:'):
+                n = key[len(p + 'grad:'):]
+                assert util.rel_err(g[n].cpu().numpy(), z[key]) < GRAD_TOL, n
