@@ -377,22 +377,35 @@ struct parrot_model {
     }
     return idx;
   }
+  // Forward planes are allocated here, one after the other; finish_packs() then allocates all backward planes.
+  // Each set is one contiguous region of the workspace, so that one L2 access-policy window covers it.
+  std::vector<std::string> pack_order;
+  size_t fwd_region_off = 0, fwd_region_bytes = 0, bwd_region_off = 0, bwd_region_bytes = 0;
   WPack& add_pack(const std::string& pname, bool need_bwd) {
     const PInfo& pi = P.get("/parrot" + pname);
     WPack w;
     w.name = pname; w.in = pi.rows; w.out = pi.cols; w.need_bwd = need_bwd;
+    if (pack_order.empty()) fwd_region_off = ws_used;
     w.fwd = make_plane("pack.f" + pname, rup(w.out, 128), w.in, 1);
     w.fwd.tiled_nkb = w.fwd.pitch / 64;
     planes["pack.f" + pname] = w.fwd;
     w.fwd_map = make_map(w.fwd, 2, 128);
-    if (need_bwd) {
+    fwd_region_bytes = ws_used - fwd_region_off;
+    packs[pname] = w;
+    pack_order.push_back(pname);
+    return packs[pname];
+  }
+  void finish_packs() {
+    bwd_region_off = ws_used;
+    for (auto& pname : pack_order) {
+      WPack& w = packs[pname];
+      if (!w.need_bwd) continue;
       w.bwd = make_plane("pack.b" + pname, rup(w.in, 128), w.out, 1);
       w.bwd.tiled_nkb = w.bwd.pitch / 64;
       planes["pack.b" + pname] = w.bwd;
       w.bwd_map = make_map(w.bwd, 2, 128);
     }
-    packs[pname] = w;
-    return packs[pname];
+    bwd_region_bytes = ws_used - bwd_region_off;
   }
 };
 
@@ -594,7 +607,7 @@ static void build(parrot_model& M) {
   const Dims& d = M.d;
   M.ws_used = 0;
   M.bufs.clear(); M.maps.clear(); M.raws.clear(); M.jobs.clear(); M.packs.clear(); M.planes.clear();
-  M.tables.clear(); M.wgrads.clear(); M.max_groups = 0; M.max_split_floats = 0;
+  M.tables.clear(); M.wgrads.clear(); M.max_groups = 0; M.max_split_floats = 0; M.pack_order.clear();
   const int T = d.T, B = d.B, H = d.H, Np = d.Np;
   const bool train = !d.sampling;
 
@@ -628,6 +641,7 @@ static void build(parrot_model& M) {
     out_dim = {d.D * d.K, d.D * d.K, d.K};
   }
   for (auto& f : out_forks) M.add_pack(f, train);
+  M.finish_packs();
 
   // ---- fp32 staging of small derived quantities
   M.falloc("att_wT", (long long)3 * d.A * H);
@@ -1607,6 +1621,10 @@ static EngineParams table_params(parrot_model& M, const std::string& name, int r
 static AttnFwdArgs attn_fwd_args(parrot_model& M, int t, bool sampling);
 static AttnBwdArgs attn_bwd_args(parrot_model& M, int t);
 
+// (Measured and removed: a cudaAccessPolicyWindow with hitProp = persisting over the contiguous weight-plane
+// region, sized to the 79 MB persisting carve-out, left the DRAM traffic of the scan unchanged -- 75 MB per decoder
+// step with or without it, ncu -- and cost 3 % because the carve-out shrinks the L2 left for everything else;
+// per-instruction evict_last hints, full or fractional, are equally neutral.  DESIGN.md section 6.)
 static bool scan_fwd_persistent_launch(parrot_model& M, cudaStream_t st) {
   const Dims& d = M.d;
   ScanFwdParams S;

@@ -533,8 +533,13 @@ __device__ __forceinline__ void producer_load_a(Pipe& p, const Seg& sg, int kb, 
   if (sg.a_nkb > 0) {
     // tile-contiguous weight pack: one 16 KB contiguous block per plane, kept in L2 (re-read every step)
     const int trow = ((sg.a_row >> 7) * sg.a_nkb + (sg.a_k >> 6) + kb) << 7;
-    tma_load_2d_hint(st, ma, fb, 0, trow, pol_keep);
-    tma_load_2d_hint(st + p.a_bytes, ma + 1, fb, 0, trow, pol_keep);
+    if (pol_keep) {
+      tma_load_2d_hint(st, ma, fb, 0, trow, pol_keep);
+      tma_load_2d_hint(st + p.a_bytes, ma + 1, fb, 0, trow, pol_keep);
+    } else {   // no per-instruction hint: the stream's access-policy window decides
+      tma_load_2d(st, ma, fb, 0, trow);
+      tma_load_2d(st + p.a_bytes, ma + 1, fb, 0, trow);
+    }
   } else {
     tma_load_2d(st, ma, fb, sg.a_k + kb * KB, sg.a_row);
     tma_load_2d(st + p.a_bytes, ma + 1, fb, sg.a_k + kb * KB, sg.a_row);
@@ -557,7 +562,12 @@ __device__ __forceinline__ void producer_load_b(Pipe& p, const Seg& sg, int kb, 
 // waits for the barrier, and completes those slots with the activation tiles (arrive + expect_tx).
 __device__ __forceinline__ void producer_run(Pipe& p, const EngineParams& P, int tick,
                                              const unsigned int* gridbar = nullptr, unsigned int target = 0) {
-  const uint64_t pol_keep = l2_policy_evict_last();
+  // debug_flags bit 0: no per-instruction L2 hint on the weight tiles; bits 1-2: evict_last on a fraction of lines
+  uint64_t pol_keep = 0;
+  if (!(P.debug_flags & 1)) {
+    const int fr = (P.debug_flags >> 1) & 3;
+    pol_keep = fr == 0 ? l2_policy_evict_last() : (fr == 1 ? l2_policy_evict_last_075() : l2_policy_evict_last_050());
+  }
   bool waited = (gridbar == nullptr) || target == 0;
   for (int j = blockIdx.x; j < P.njobs; j += gridDim.x) {
     const Job& jb = P.jobs[j];
