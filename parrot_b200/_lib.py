@@ -48,12 +48,14 @@ def load():
     global _LIB
     if _LIB is not None:
         return _LIB
-    path = _build.LIB
-    try:
-        _build.build()
-    except Exception:
-        if not os.path.exists(path):
-            raise
+    path = os.environ.get('PARROT_B200_LIB')     # experiment hook: a variant build of the same sources
+    if not path:
+        path = _build.LIB
+        try:
+            _build.build()
+        except Exception:
+            if not os.path.exists(path):
+                raise
     if not os.path.exists(path):
         raise RuntimeError(
             'parrot_b200: %s not found. Run `python -c "import __graft_entry__ as g; g.build()"`; '

@@ -33,12 +33,25 @@ constexpr int TILE_M = 128;
 constexpr int KB = 64;  // k elements per pipeline block (one 128-byte swizzle span)
 constexpr int MAX_SEG = 6;
 constexpr int NO_SLOT = -(1 << 30);
-// 12 warps: warp 0 TMA, warp 1 MMA, warps 2-5 TMEM epilogue, warps 6-11 epilogue helpers.  Register cap:
-// 3 warps per scheduler sub-partition -> 16384 / (3*32) = 168 registers per thread (same for 10..12 warps).
-constexpr int ENGINE_THREADS = 384;
-constexpr int EPI_GROUP_THREADS = 320; // warps 2..11 share the post-reduction (split-K) epilogue
+// 8 warps: warp 0 TMA, warp 1 MMA, warps 2-5 TMEM epilogue, warps 6-7 epilogue helpers.  Two warps per scheduler
+// sub-partition leave the full 255 registers per thread: the epilogues keep every partial-tile / operand load of
+// a work item in flight, and ONE spilled load result serialises those L2 round trips.  Measured on one box, same
+// session (ms per training step at the base configuration): 12 warps (168-register cap, 430 B of spills) 138.9,
+// 10 warps 143.9, 16 warps 140.7, 8 warps 120.2, 8 warps + MAX_KSPLIT 6 115.4.
+// (PB_* are experiment knobs for variant builds, see tools/build_variants.sh)
+#ifndef PB_ENGINE_THREADS
+#define PB_ENGINE_THREADS 256
+#endif
+constexpr int ENGINE_THREADS = PB_ENGINE_THREADS;
+constexpr int EPI_GROUP_THREADS = ENGINE_THREADS - 64; // warps 2.. share the post-reduction (split-K) epilogue
+__device__ __forceinline__ void epi_group_sync() {
+  asm volatile("bar.sync 1, %0;" ::"r"(EPI_GROUP_THREADS) : "memory");
+}
 constexpr int SMEM_BYTES = 200 * 1024;
-constexpr int MAX_KSPLIT = 8;   // scratch stride per split group
+#ifndef PB_MAX_KSPLIT
+#define PB_MAX_KSPLIT 6   // 4: 121.5, 5: 119.9, 6: 115.4, 8: 120.2 ms/step (8 warps)
+#endif
+constexpr int MAX_KSPLIT = PB_MAX_KSPLIT;   // scratch stride per split group
 
 enum Epi : int {
   EPI_PLAIN = 0,      // out = acc*scale (+bias) (+= out), optional hi/lo planes
@@ -186,7 +199,7 @@ __device__ __forceinline__ void job_kb_range(const Job& jb, int total_kb, int& l
 // Everything an epilogue needs, snapshotted into registers ONCE per job.  The job table and the scan context
 // live in global memory; reading them inside the store loops forces the compiler to reload pointers and
 // scalars after every store (possible aliasing), which serialises the epilogue into dependent L2 round trips.
-// Kept small (generic pointer slots) because the 12-warp CTA caps registers at 168 per thread:
+// Kept small (generic pointer slots): register pressure in the epilogues is what limits the scan (see top):
 //   GATES      p0 base  p1 h   p2 z   p3 r    p4 rh_hi  p5 rh_lo
 //   CAND       p0 base  p1 h   p2 z   p3 c    p4 h_hi   p5 h_lo
 //   BWD_RH     p0 r     p1 h   p2 dh  p3 da   p4 da_hi  p5 da_lo
@@ -671,11 +684,80 @@ __device__ __forceinline__ void mma_run(Pipe& p, const EngineParams& P, int tick
   if (lane == 0) TL(3);
 }
 
-// ------------------------------------------------ epilogue (warps 2..5 read TMEM; warps 6..11 help after split-K)
-// All ten warps run this loop.  Unsplit jobs: warps 2..5 read the accumulator (one TMEM lane quarter each) and
+#ifndef PB_SPLIT_TEMPLATED
+#define PB_SPLIT_TEMPLATED 0
+#endif
+#ifndef PB_SPLIT_BATCH
+#define PB_SPLIT_BATCH 0
+#endif
+#ifndef PB_SPLIT_ITEM_W
+#define PB_SPLIT_ITEM_W 4
+#endif
+#ifndef PB_SPLIT_PAIR_MAX
+#define PB_SPLIT_PAIR_MAX 0
+#endif
+#if PB_SPLIT_TEMPLATED
+// Experiment (variant builds only): post-reduction epilogue with the number of parts known at compile time, so that
+// only KS x 4 partial values live in registers, and two items in flight per thread for KS <= PB_SPLIT_PAIR_MAX.
+template <int KS>
+struct SplitItem {
+  float x[KS][4];
+  EpiOps<4> ops;
+  int r, n0, nc;
+  __device__ __forceinline__ void load(const EpiLocal& E, int t, const float* __restrict__ base, int n_cols, int c_lo,
+                                       int c_hi, int e, int total, int ksplit) {
+    r = e & (TILE_M - 1);
+    n0 = c_lo + ((e >> 7) << 2);
+    nc = (e < total) ? min(4, c_hi - n0) : 0;
+#pragma unroll
+    for (int pp = 0; pp < KS; ++pp) {
+      const float* src = base + (size_t)pp * n_cols * TILE_M;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        x[pp][i] = (pp < ksplit && i < nc) ? __ldcg(src + (size_t)(n0 + i) * TILE_M + r) : 0.0f;
+    }
+    if (nc > 0) epilogue_load<4>(E, t, r, n0, nc, ops);
+  }
+  __device__ __forceinline__ void finish(const EpiLocal& E, int t) {
+    if (nc > 0) {
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int pp = 0; pp < KS; ++pp)   // part order: deterministic
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] += x[pp][i];
+      epilogue_apply<4>(E, t, r, n0, nc, v, ops);
+    }
+  }
+};
+template <int KS>
+__device__ __forceinline__ void split_items(const EpiLocal& E, const int t, const float* __restrict__ base,
+                                            const int n_cols, const int c_lo, const int c_hi, const int gtid,
+                                            const int ksplit) {
+  const int ngroups = (c_hi - c_lo + 3) >> 2;
+  const int total = ngroups * TILE_M;
+  if (KS <= PB_SPLIT_PAIR_MAX) {
+    for (int e0 = gtid; e0 < total; e0 += 2 * EPI_GROUP_THREADS) {
+      SplitItem<KS> i0, i1;
+      i0.load(E, t, base, n_cols, c_lo, c_hi, e0, total, ksplit);
+      i1.load(E, t, base, n_cols, c_lo, c_hi, e0 + EPI_GROUP_THREADS, total, ksplit);
+      i0.finish(E, t);
+      i1.finish(E, t);
+    }
+  } else {
+    for (int e0 = gtid; e0 < total; e0 += EPI_GROUP_THREADS) {
+      SplitItem<KS> i0;
+      i0.load(E, t, base, n_cols, c_lo, c_hi, e0, total, ksplit);
+      i0.finish(E, t);
+    }
+  }
+}
+#endif
+
+// ------------------------------------------------ epilogue (warps 2..5 read TMEM; warps 6.. help after split-K)
+// All epilogue warps run this loop.  Unsplit jobs: warps 2..5 read the accumulator (one TMEM lane quarter each) and
 // apply the epilogue; the helpers skip.  Split jobs: warps 2..5 park the partial tile in scratch, then ALL ten
 // warps share the post-reduction epilogue of this part's column slice as 4-column work items (the reduction
-// reads global memory, so any warp can do it; ten warps hide the load / MUFU latencies that four cannot).
+// reads global memory, so any warp can do it; the helpers hide load / MUFU latencies).
 __device__ __forceinline__ void epilogue_run(Pipe& p, const EngineParams& P, int tick) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_cols = p.n_cols;
@@ -736,7 +818,7 @@ __device__ __forceinline__ void epilogue_run(Pipe& p, const EngineParams& P, int
     }
     if (ksplit > 1) {
       if (tmem_warp) __threadfence();
-      asm volatile("bar.sync 1, 320;" ::: "memory");   // partial tile written by warps 2..5
+      epi_group_sync();   // partial tile written by warps 2..5
       const float* base = P.split_scratch + (size_t)group * MAX_KSPLIT * (size_t)n_cols * TILE_M;
       int c_lo = 0, c_hi = 0;
       if (P.coop_epilogue) {
@@ -750,7 +832,7 @@ __device__ __forceinline__ void epilogue_run(Pipe& p, const EngineParams& P, int
             if (++spins > (1u << 24)) { printf("parrot_b200: split-K arrival wait timed out\n"); __trap(); }
           } while ((seen & 0xffffu) < (unsigned int)ksplit);
         }
-        asm volatile("bar.sync 1, 320;" ::: "memory");
+        epi_group_sync();
         if (threadIdx.x == 64) TL(6);
         c_lo = (n_cols * kpart) / ksplit;
         c_hi = (n_cols * (kpart + 1)) / ksplit;
@@ -761,38 +843,73 @@ __device__ __forceinline__ void epilogue_run(Pipe& p, const EngineParams& P, int
           if (last) P.split_count[group] = 0u;   // ready for the next launch
           *p.split_flag = last ? 1u : 0u;
         }
-        asm volatile("bar.sync 1, 320;" ::: "memory");
+        epi_group_sync();
         if (threadIdx.x == 64) TL(6);
         if (*p.split_flag) { c_lo = 0; c_hi = n_cols; }
       }
       __threadfence();
+#if PB_SPLIT_TEMPLATED
+      switch (ksplit) {
+        case 2: split_items<2>(E, t, base, n_cols, c_lo, c_hi, gtid, ksplit); break;
+        case 3: split_items<3>(E, t, base, n_cols, c_lo, c_hi, gtid, ksplit); break;
+        case 4: split_items<4>(E, t, base, n_cols, c_lo, c_hi, gtid, ksplit); break;
+        default: split_items<MAX_KSPLIT>(E, t, base, n_cols, c_lo, c_hi, gtid, ksplit); break;
+      }
+#else
       // work item = (row, group of 4 columns); consecutive threads take consecutive rows (coalesced).  All loads of
       // an item (partial tiles + epilogue operands) are issued before the first use.  (8-column items halve the
-      // number of latency rounds but spill at the 168-register cap of the 12-warp CTA.)
-      const int ngroups = (c_hi - c_lo + 3) >> 2;
+      // number of latency rounds but measured slower: 118.6 vs 115.4 ms/step even without spills.)
+      constexpr int IW = PB_SPLIT_ITEM_W;   // columns per work item
+      const int ngroups = (c_hi - c_lo + IW - 1) / IW;
       for (int e = gtid; e < ngroups * TILE_M; e += EPI_GROUP_THREADS) {
         const int r = e & (TILE_M - 1);
-        const int n0 = c_lo + ((e >> 7) << 2);
-        const int nc = min(4, c_hi - n0);
-        float v[4] = {0.f, 0.f, 0.f, 0.f};
-        float x[MAX_KSPLIT][4];
-        EpiOps<4> ops;
+        const int n0 = c_lo + (e >> 7) * IW;
+        const int nc = min(IW, c_hi - n0);
+        float v[IW];
+#pragma unroll
+        for (int i = 0; i < IW; ++i) v[i] = 0.0f;
+        EpiOps<IW> ops;
+#if PB_SPLIT_BATCH
+        // partial tiles in batches of PB_SPLIT_BATCH parts: bounds the registers of the loads in flight (a spilled
+        // load result serialises the L2 round trips); the second batch only exists for tiles split more than that
+        epilogue_load<IW>(E, t, r, n0, nc, ops);
+#pragma unroll
+        for (int p0 = 0; p0 < MAX_KSPLIT; p0 += PB_SPLIT_BATCH) {
+          if (p0 < ksplit) {
+            float x[PB_SPLIT_BATCH][IW];
+#pragma unroll
+            for (int q = 0; q < PB_SPLIT_BATCH; ++q) {
+              const float* src = base + (size_t)(p0 + q) * n_cols * TILE_M;
+#pragma unroll
+              for (int i = 0; i < IW; ++i)
+                x[q][i] = (p0 + q < ksplit && i < nc) ? __ldcg(src + (size_t)(n0 + i) * TILE_M + r) : 0.0f;
+            }
+#pragma unroll
+            for (int q = 0; q < PB_SPLIT_BATCH; ++q)   // part order: deterministic
+#pragma unroll
+              for (int i = 0; i < IW; ++i) v[i] += x[q][i];
+          }
+        }
+#else
+        float x[MAX_KSPLIT][IW];
 #pragma unroll
         for (int pp = 0; pp < MAX_KSPLIT; ++pp) {
           const float* src = base + (size_t)pp * n_cols * TILE_M;
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
+          for (int i = 0; i < IW; ++i)
             x[pp][i] = (pp < ksplit && i < nc) ? __ldcg(src + (size_t)(n0 + i) * TILE_M + r) : 0.0f;
         }
-        epilogue_load<4>(E, t, r, n0, nc, ops);   // operand loads in flight together with the partial-tile loads
+        epilogue_load<IW>(E, t, r, n0, nc, ops);   // operand loads in flight together with the partial-tile loads
 #pragma unroll
         for (int pp = 0; pp < MAX_KSPLIT; ++pp)   // part order: deterministic
 #pragma unroll
-          for (int i = 0; i < 4; ++i) v[i] += x[pp][i];
-        epilogue_apply<4>(E, t, r, n0, nc, v, ops);
+          for (int i = 0; i < IW; ++i) v[i] += x[pp][i];
+#endif
+        epilogue_apply<IW>(E, t, r, n0, nc, v, ops);
       }
+#endif
       if (threadIdx.x == 64) TL(7);
-      asm volatile("bar.sync 1, 320;" ::: "memory");
+      epi_group_sync();
       if (P.coop_epilogue && warp == 2 && lane == 0) {
         // the last part to finish resets the arrival counter for the next use
         const unsigned int old = atomicAdd(P.split_count + group, 0x10000u);

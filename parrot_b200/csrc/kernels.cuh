@@ -64,8 +64,11 @@ __device__ __forceinline__ void attention_proj_body(const AttnFwdArgs& a) {
   }
 }
 
-// WIDE: the window sum keeps 16 x 128-bit loads per lane in flight (fastest as a stand-alone 8-warp kernel; inside
-// the 12-warp persistent scan the narrower form measured faster, so that instantiation keeps it)
+// WIDE: the window sum keeps 16 x 128-bit loads per lane in flight (measured faster with 8-warp CTAs, stand-alone
+// and inside the persistent scan; with the earlier 12-warp CTAs at the 168-register cap it was slower)
+#ifndef PB_ATT_WIDE
+#define PB_ATT_WIDE 1
+#endif
 template <bool WIDE>
 __device__ __forceinline__ void attention_fwd_body(const AttnFwdArgs& a, const int b, float* sh,
                                                    const bool precomputed_hat = false) {
@@ -544,7 +547,7 @@ struct ScanBwdParams {
 template <class SP>
 __device__ __forceinline__ void persistent_gemm_phase(Pipe& p, const EngineParams& P, int tick, const SP& S,
                                                       unsigned int& bar, int which) {
-  // P stays in kernel-parameter (constant) space: copying it would cost ~25 registers of a 168-register budget
+  // P stays in kernel-parameter (constant) space: copying it would cost ~25 registers
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   (void)which;
   unsigned int* gridbar = S.gridbar;
@@ -561,12 +564,12 @@ __device__ __forceinline__ void persistent_gemm_phase(Pipe& p, const EngineParam
   } else if (warp == 1) {
     mma_run(p, P, tick);
   } else {
-    if (warp == 2 && lane == 0 && bar) grid_wait(gridbar, target);   // one poller for the ten epilogue warps
-    asm volatile("bar.sync 1, 320;" ::: "memory");
+    if (warp == 2 && lane == 0 && bar) grid_wait(gridbar, target);   // one poller for the epilogue warps
+    epi_group_sync();
     if (threadIdx.x == 64) STAMP(S, bar, 0);
     epilogue_run(p, P, tick);
     asm volatile("fence.proxy.async.global;" ::: "memory");
-    asm volatile("bar.sync 1, 320;" ::: "memory");
+    epi_group_sync();
     if (threadIdx.x == 64) { STAMP(S, bar, 1); grid_arrive(gridbar); }
   }
   ++bar;
@@ -595,7 +598,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) scan_fwd_persistent(const S
       if ((int)blockIdx.x < a.B) {
         if (threadIdx.x == 0) { grid_wait(S.gridbar, bar * gridDim.x); STAMP(S, bar, 0); }
         __syncthreads();
-        for (int b = blockIdx.x; b < a.B; b += gridDim.x) attention_fwd_body<false>(a, b, att_sh, true);
+        for (int b = blockIdx.x; b < a.B; b += gridDim.x) attention_fwd_body<PB_ATT_WIDE != 0>(a, b, att_sh, true);
         asm volatile("fence.proxy.async.global;" ::: "memory");
         __syncthreads();
       }
