@@ -257,16 +257,18 @@ __device__ __forceinline__ void epi_plain(const EpiLocal& E, int t, int row, int
   float* out = E.p0 ? (float*)E.p0 + (long long)t * E.l2 : nullptr;
   bf16* hi = (bf16*)E.p2;
   bf16* lo = (bf16*)E.p3;
+  // sample index -> (block q of n_pad padded rows, row r inside it): one division per call, then increments
+  int n = E.n0 + n_base, q = 0, r = n;
+  if (E.n_pad > 0) { q = n / E.n_pad; r = n - q * E.n_pad; }
 #pragma unroll
-  for (int j = 0; j < W; ++j) {
-    if (j >= ncols) break;
-    const int n = E.n0 + n_base + j;
-    if (n >= E.n_total) break;
+  for (int j = 0; j < W; ++j, ++n) {
+    if (j >= ncols || n >= E.n_total) break;
     long long srow = n;
     if (E.n_pad > 0) {
-      const int q = n / E.n_pad, r = n - q * E.n_pad;
-      if (r >= E.n_valid) continue;
-      srow = (long long)q * E.n_valid + r;
+      const int rr = r;
+      srow = (long long)q * E.n_valid + rr;
+      if (++r == E.n_pad) { r = 0; ++q; }
+      if (rr >= E.n_valid) continue;
     }
     float y = v[j] * E.scale + bias;
     if (out) {
@@ -693,6 +695,9 @@ __device__ __forceinline__ void mma_run(Pipe& p, const EngineParams& P, int tick
 #ifndef PB_SPLIT_ITEM_W
 #define PB_SPLIT_ITEM_W 4
 #endif
+#ifndef PB_TMEM_W
+#define PB_TMEM_W 8   // columns per tcgen05.ld chunk of the unsplit (TMEM) epilogue path
+#endif
 #ifndef PB_SPLIT_PAIR_MAX
 #define PB_SPLIT_PAIR_MAX 0
 #endif
@@ -785,6 +790,16 @@ __device__ __forceinline__ void epilogue_run(Pipe& p, const EngineParams& P, int
       }
       if (threadIdx.x == 64) TL(4);
       if (ksplit <= 1) {
+#if PB_TMEM_W == 16
+        for (int n0 = 0; n0 < n_cols; n0 += 16) {
+          float v[16];
+          EpiOps<16> ops;
+          tmem_ld_32x16(taddr + n0, v);
+          epilogue_load<16>(E, t, row, n0, 16, ops);
+          tmem_ld_wait();
+          epilogue_apply<16>(E, t, row, n0, 16, v, ops);
+        }
+#else
         for (int n0 = 0; n0 < n_cols; n0 += 8) {
           float v[8];
           EpiOps<8> ops;
@@ -793,6 +808,7 @@ __device__ __forceinline__ void epilogue_run(Pipe& p, const EngineParams& P, int
           tmem_ld_wait();
           epilogue_apply<8>(E, t, row, n0, 8, v, ops);
         }
+#endif
       } else {
         // park the partial tile: scratch[group][part][col][row]  (row fastest -> coalesced)
         float* part = P.split_scratch + ((size_t)group * MAX_KSPLIT + kpart) * (size_t)n_cols * TILE_M;
