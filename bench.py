@@ -285,9 +285,9 @@ def main():
                 'achieved': achieved_tf, 'peak': pk['tf_sustained'], 'unit': 'TFLOP/s',
                 'frac': achieved_tf / pk['tf_sustained'],
                 # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full
-                # capture of the same command (profiles/r01_scan_fwd_persistent_ncu_T800.txt); base workload only
-                'traffic': (58.975116e9 + 9.330672e9) if (B, T, U, cfg['rnn_h_dim']) == (64, 800, 128, 1024) else None,
-                'traffic_source': 'profiles/r01_scan_fwd_persistent_ncu_T800.txt',
+                # capture of the same command (profiles/r01_scan_persistent_ncu_T800_final.txt); base workload only
+                'traffic': (56.268694e9 + 7.882148e9) if (B, T, U, cfg['rnn_h_dim']) == (64, 800, 128, 1024) else None,
+                'traffic_source': 'profiles/r01_scan_persistent_ncu_T800_final.txt',
                 'peak_source': pk['source'] + ' bf16 sustained (kernel timed inside a long step)',
                 'algorithmic_flops_per_launch': per_step_flops * T,
                 'avg_launch_us': scan_ms * 1e3, 'launches_per_step': 1,
