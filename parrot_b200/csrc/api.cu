@@ -411,6 +411,9 @@ struct parrot_model {
 
 static const int NT = 128;  // sample tile of the batched (outside-the-scan) products
 static const int COLSUM_CHUNKS = 64;
+#ifndef PB_SPLIT_TARGET
+#define PB_SPLIT_TARGET 148   // CTAs one scan phase is split over (experiment knob)
+#endif
 static const int SGEMM_SPLIT = 64;   // K chunks of the split SIMT GEMM (encoder weight gradients)
 
 // ------------------------------------------------------------------ job builders
@@ -828,8 +831,8 @@ static void build(parrot_model& M) {
     std::vector<Job> A, Bj;
     for (int l = 0; l < 3; ++l) build_fwd_layer_jobs(M, A, l, true, l);
     for (int l = 0; l < 3; ++l) build_fwd_layer_jobs(M, Bj, l, false, l);
-    push_table(M, "fwdA", A, Np, 148);
-    push_table(M, "fwdB", Bj, Np, 148);
+    push_table(M, "fwdA", A, Np, PB_SPLIT_TARGET);
+    push_table(M, "fwdB", Bj, Np, PB_SPLIT_TARGET);
   } else if (train) {
     // layer_norm: one layer at a time (lag 0); the normalised Fork outputs reach the epilogues through preT
     for (int l = 0; l < 3; ++l) {
@@ -1125,7 +1128,7 @@ static void build(parrot_model& M) {
                            0, 0, 0, d.Hp / 64);
           js.push_back(j);
         }
-      push_table(M, "bwd1", js, Np, 148);
+      push_table(M, "bwd1", js, Np, PB_SPLIT_TARGET);
     }
     // backward scan, product 2: dgrads into the carried state gradients.  Job time = step s of layer 3;
     // segments of layer 2 / layer 1 refer to steps s+1 / s+2 (reverse wavefront).
@@ -1164,7 +1167,7 @@ static void build(parrot_model& M) {
       add(d.C, 3, 1, {S("/inp_to_h3/fork_rnn3_inputs", {2, 0}), S("/inp_to_h3/fork_rnn3_gates", {2, 0})});
       add(d.C, 3, 2, {S("/inp_to_h2/fork_rnn2_inputs", {1, 1}), S("/inp_to_h2/fork_rnn2_gates", {1, 1}),
                       S("/inp_to_h1/fork_rnn1_inputs", {0, 2}), S("/inp_to_h1/fork_rnn1_gates", {0, 2})});
-      push_table(M, "bwd2", js, Np, 148);
+      push_table(M, "bwd2", js, Np, PB_SPLIT_TARGET);
     }
     // weight gradients: dW[in][out] = sum_samples X[s][in] * dY[s][out]
     {
