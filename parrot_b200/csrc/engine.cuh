@@ -686,9 +686,6 @@ __device__ __forceinline__ void mma_run(Pipe& p, const EngineParams& P, int tick
   if (lane == 0) TL(3);
 }
 
-#ifndef PB_SPLIT_TEMPLATED
-#define PB_SPLIT_TEMPLATED 0
-#endif
 #ifndef PB_SPLIT_BATCH
 #define PB_SPLIT_BATCH 3   // partial tiles summed in batches of 3 parts: 111.5 vs 115.0 ms/step unbatched (8 warps)
 #endif
@@ -701,66 +698,6 @@ __device__ __forceinline__ void mma_run(Pipe& p, const EngineParams& P, int tick
 #ifndef PB_TMEM_W
 #define PB_TMEM_W 8   // columns per tcgen05.ld chunk of the unsplit (TMEM) epilogue path
 #endif
-#ifndef PB_SPLIT_PAIR_MAX
-#define PB_SPLIT_PAIR_MAX 0
-#endif
-#if PB_SPLIT_TEMPLATED
-// Experiment (variant builds only): post-reduction epilogue with the number of parts known at compile time, so that
-// only KS x 4 partial values live in registers, and two items in flight per thread for KS <= PB_SPLIT_PAIR_MAX.
-template <int KS>
-struct SplitItem {
-  float x[KS][4];
-  EpiOps<4> ops;
-  int r, n0, nc;
-  __device__ __forceinline__ void load(const EpiLocal& E, int t, const float* __restrict__ base, int n_cols, int c_lo,
-                                       int c_hi, int e, int total, int ksplit) {
-    r = e & (TILE_M - 1);
-    n0 = c_lo + ((e >> 7) << 2);
-    nc = (e < total) ? min(4, c_hi - n0) : 0;
-#pragma unroll
-    for (int pp = 0; pp < KS; ++pp) {
-      const float* src = base + (size_t)pp * n_cols * TILE_M;
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-        x[pp][i] = (pp < ksplit && i < nc) ? __ldcg(src + (size_t)(n0 + i) * TILE_M + r) : 0.0f;
-    }
-    if (nc > 0) epilogue_load<4>(E, t, r, n0, nc, ops);
-  }
-  __device__ __forceinline__ void finish(const EpiLocal& E, int t) {
-    if (nc > 0) {
-      float v[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int pp = 0; pp < KS; ++pp)   // part order: deterministic
-#pragma unroll
-        for (int i = 0; i < 4; ++i) v[i] += x[pp][i];
-      epilogue_apply<4>(E, t, r, n0, nc, v, ops);
-    }
-  }
-};
-template <int KS>
-__device__ __forceinline__ void split_items(const EpiLocal& E, const int t, const float* __restrict__ base,
-                                            const int n_cols, const int c_lo, const int c_hi, const int gtid,
-                                            const int ksplit) {
-  const int ngroups = (c_hi - c_lo + 3) >> 2;
-  const int total = ngroups * TILE_M;
-  if (KS <= PB_SPLIT_PAIR_MAX) {
-    for (int e0 = gtid; e0 < total; e0 += 2 * EPI_GROUP_THREADS) {
-      SplitItem<KS> i0, i1;
-      i0.load(E, t, base, n_cols, c_lo, c_hi, e0, total, ksplit);
-      i1.load(E, t, base, n_cols, c_lo, c_hi, e0 + EPI_GROUP_THREADS, total, ksplit);
-      i0.finish(E, t);
-      i1.finish(E, t);
-    }
-  } else {
-    for (int e0 = gtid; e0 < total; e0 += EPI_GROUP_THREADS) {
-      SplitItem<KS> i0;
-      i0.load(E, t, base, n_cols, c_lo, c_hi, e0, total, ksplit);
-      i0.finish(E, t);
-    }
-  }
-}
-#endif
-
 // ------------------------------------------------ epilogue (warps 2..5 read TMEM; warps 6.. help after split-K)
 // All epilogue warps run this loop.  Unsplit jobs: warps 2..5 read the accumulator (one TMEM lane quarter each) and
 // apply the epilogue; the helpers skip.  Split jobs: warps 2..5 park the partial tile in scratch, then ALL ten
@@ -883,14 +820,6 @@ __device__ __forceinline__ void epilogue_run(Pipe& p, const EngineParams& P, int
         if (*p.split_flag) { c_lo = 0; c_hi = n_cols; }
       }
       __threadfence();
-#if PB_SPLIT_TEMPLATED
-      switch (ksplit) {
-        case 2: split_items<2>(E, t, base, n_cols, c_lo, c_hi, gtid, ksplit); break;
-        case 3: split_items<3>(E, t, base, n_cols, c_lo, c_hi, gtid, ksplit); break;
-        case 4: split_items<4>(E, t, base, n_cols, c_lo, c_hi, gtid, ksplit); break;
-        default: split_items<MAX_KSPLIT>(E, t, base, n_cols, c_lo, c_hi, gtid, ksplit); break;
-      }
-#else
       // work item = (row, group of 4 columns); consecutive threads take consecutive rows (coalesced).  All loads of
       // an item (partial tiles + epilogue operands) are issued before the first use.  (8-column items halve the
       // number of latency rounds but measured slower: 118.6 vs 115.4 ms/step even without spills.)
@@ -942,7 +871,6 @@ __device__ __forceinline__ void epilogue_run(Pipe& p, const EngineParams& P, int
 #endif
         epilogue_apply<IW>(E, t, r, n0, nc, v, ops);
       }
-#endif
       if (threadIdx.x == 64) TL(7);
       epi_group_sync();
       if (P.coop_epilogue && warp == 2 && lane == 0) {
