@@ -1,0 +1,81 @@
+"""Host-side contract of the reference entry points, on CPU: flag surface (utils.py:173-327), the sampling stop
+heuristic (sample.py:147-163) and the batch / TBPTT layout of the data stream (datasets.py:206-298)."""
+import json
+import os
+
+import numpy as np
+
+from oracle import parrot_oracle as O
+from parrot_b200 import datasets, utils
+
+GOLD = os.path.join(os.path.dirname(__file__), 'golden')
+
+
+def test_flag_surface_matches_the_reference_table():
+    """tests/golden/cli_flags.json is extracted from the reference's parsers by tests/golden/make_cli_fixture.py:
+    same flag names, same literal defaults; additions are the documented three."""
+    table = json.load(open(os.path.join(GOLD, 'cli_flags.json')))
+    extra = {'train_parse': {'synthetic', 'steps', 'seed'}, 'sample_parse': {'seed'}}
+    for fn, ref in table.items():
+        ours = vars(getattr(utils, fn)([]))
+        assert set(ref) - set(ours) == set(), fn
+        assert set(ours) - set(ref) == extra[fn], fn
+        for k, v in ref.items():
+            if v['default'] != '<expr>':
+                assert ours[k] == v['default'], (fn, k)
+            if v['type'] == 'bool':                      # reference: type=bool (any non-empty string is True)
+                assert isinstance(ours[k], bool)
+
+
+def test_boolean_flags_parse_false_strings_as_false():
+    a = utils.train_parse(['--layer_norm', 'False', '--weak_feedback', 'true', '--use_speaker', '0'])
+    assert a.layer_norm is False and a.weak_feedback is True and a.use_speaker is False
+    assert utils.train_parse(['--encoder_type', 'none']).encoder_type is None
+    a = utils.train_parse(['--dataset', 'blizzard', '--save_dir', '/tmp/x'])
+    assert a.save_dir == os.path.join('/tmp/x', 'blizzard')                  # utils.py:250-251
+
+
+def test_stop_heuristic_matches_oracle_and_known_case():
+    rng = np.random.default_rng(0)
+    for _ in range(20):
+        T, U = 60, 12
+        phi = rng.random((T, U + 2)).astype(np.float32)
+        L = int(rng.integers(3, U))
+        assert utils.stop_heuristic(phi, L, T) == O.stop_heuristic(phi, L, T)
+    phi = np.zeros((30, 8), np.float32)
+    phi[:, 1] = 1.0
+    phi[7:, 5] = 2.0                                   # position 5 (= labels_length) wins from frame 7 on
+    assert utils.stop_heuristic(phi, 5, 100) == 47     # first frame + 40 frames of slack
+    assert utils.stop_heuristic(phi, 5, 20) == 20      # clamped to num_steps
+    assert utils.stop_heuristic(np.zeros((4, 8), np.float32), 5, 9) == 9   # never ends -> num_steps
+
+
+def test_stream_layout_sorting_and_segments():
+    ds = datasets.SyntheticVoice(num_examples=40, seed=3)
+    st = datasets.parrot_stream('synthetic', use_speaker=True, batch_size=4, seq_size=20, sorting_mult=2,
+                                noise_level=0.3, dataset=ds, seed=1)
+    assert st.sources == ('features', 'features_mask', 'labels', 'labels_mask', 'speaker_index', 'start_flag',
+                          'feedback_noise_level')
+    batches = list(st.get_epoch_iterator(as_dict=True))
+    assert batches
+    n_first = 0
+    prev_tail = None
+    for b in batches:
+        f, m, lab, lm = b['features'], b['features_mask'], b['labels'], b['labels_mask']
+        assert f.ndim == 3 and f.shape[1] == 4 and f.shape[2] == 63 and f.dtype == np.float32   # time-major
+        assert m.shape == f.shape[:2] and lab.shape == lm.shape and lab.shape[0] == 4
+        assert f.shape[0] <= 21                                     # seq_size + 1 frames per segment
+        assert b['speaker_index'].shape == (4, 1) and b['feedback_noise_level'] == 0.3
+        assert ((f != 0).any(-1) <= (m > 0)).all()                  # padding is zero where the mask is zero
+        if b['start_flag'] == 1:
+            n_first += 1
+            # lengths inside a batch come from one sorted chunk: masks are nested (sorted by length)
+            lens = m.sum(0) if f.shape[0] < 21 else None
+        else:
+            assert np.array_equal(prev_tail, f[0])                  # consecutive segments share one frame
+        prev_tail = f[-1]
+    assert n_first == 40 // 4                                        # every full batch starts exactly once
+    # ragged last batch is dropped (datasets.py:259-260): 42 examples -> still 10 batches
+    ds2 = datasets.SyntheticVoice(num_examples=42, seed=3)
+    st2 = datasets.parrot_stream('synthetic', batch_size=4, seq_size=20, sorting_mult=2, dataset=ds2, seed=1)
+    assert sum(1 for t in st2 if t[-1] == 1) == 10
