@@ -181,3 +181,45 @@ def test_device_matches_golden_fixtures(name):
             if key.startswith(p + 'grad:'):
                 n = key[len(p + 'grad:'):]
                 assert util.rel_err(g[n].cpu().numpy(), z[key]) < GRAD_TOL, n
+
+
+@pytest.mark.parametrize('name', ['mse_weak', 'gmm_full_spk_softmax', 'layer_norm_noise', 'layer_norm_gmm_full_spk'])
+def test_device_matches_reference_source_fixtures(name):
+    """CUDA path vs tests/golden/ref_model_*.npz: the outputs of the reference's OWN Parrot.compute_cost /
+    sample_model_fun code executed in float64 on the eager Theano/Blocks stand-in (tests/golden/ref_shim.py,
+    make_ref_model_fixtures.py).  No oracle in the loop: parameters, inputs and expectations come from the file."""
+    import os
+    from tests.golden.make_ref_model_fixtures import CASES as RCASES, B, T, SAMP
+    from parrot_b200.model import Parrot
+    z = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'ref_model_%s.npz' % name))
+    cfg = dict(util.TINY, **RCASES[name])
+    params = {k[len('param:'):]: z[k].astype(np.float32) for k in z.files if k.startswith('param:')}
+    dev = Parrot(**cfg)
+    dev.initialize()
+    dev.set_parameter_values(params)
+    f32 = lambda k: z[k].astype(np.float32)
+    for seg, sf in enumerate((1.0, 0.0)):
+        p = 'seg%d:' % seg
+        spk = z[p + 'in:speaker'] if cfg.get('use_speaker') else None
+        cost, updates, av, _ = dev.compute_cost(
+            f32(p + 'in:features'), f32(p + 'in:features_mask'), z[p + 'in:labels'], f32(p + 'in:labels_mask'), spk,
+            sf, B, feedback_noise=f32(p + 'in:feedback_noise'), noise_level=cfg.get('feedback_noise_level'),
+            gmm_noise=(f32(p + 'in:gmm_unis'), f32(p + 'in:gmm_normals')))
+        assert abs(cost.item() - float(z[p + 'cost'])) / abs(float(z[p + 'cost'])) < FWD_TOL
+        for nm, v in zip(['next_x', 'k', 'w', 'coeff', 'phi', 'pi_att'], av):
+            assert util.rel_err(v.cpu().numpy(), z[p + 'out:' + nm]) < FWD_TOL, (nm, seg)
+        phi = z[p + 'out:phi']
+        top2 = np.sort(phi, -1)[..., -2:]
+        ok = (top2[..., 1] - top2[..., 0]) > 1e-4 * np.abs(top2[..., 1])
+        assert ok.mean() > 0.5
+        assert (av[4].cpu().numpy().argmax(-1)[ok] == phi.argmax(-1)[ok]).all()
+        for nm, v in updates:
+            assert util.rel_err(v.cpu().numpy(), z[p + 'update:' + nm]) < FWD_TOL, nm
+    smp = Parrot(**dict(cfg, **SAMP))
+    smp.initialize()
+    smp.set_parameter_values(params)
+    spk = z['samp:in:speaker'] if cfg.get('use_speaker') else None
+    out = smp.sample_model(z['samp:in:labels'], f32('samp:in:labels_mask'), None, spk, B, T,
+                           gmm_noise=(f32('samp:in:gmm_unis'), f32('samp:in:gmm_normals')))
+    for nm, a in zip(['x', 'k', 'w', 'pi', 'phi', 'pi_att'], out):
+        assert util.rel_err(a, z['samp:out:' + nm]) < FWD_TOL, nm

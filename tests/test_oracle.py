@@ -165,3 +165,55 @@ def test_mma_emulator_ordering():
     ref = x.astype(np.float64) @ W.astype(np.float64)
     e = {m: np.abs(O.emulate_mma(x, W, m) - ref).max() / np.abs(ref).max() for m in ('bf16', 'tf32', 'fp16', 'bf16x3')}
     assert e['bf16'] > 5 * e['tf32'] and e['tf32'] > 5 * e['bf16x3'] and e['bf16x3'] < 2e-5
+
+
+REF_MODEL_CASES = ['mse_weak', 'gmm_full_spk_softmax', 'layer_norm_noise', 'layer_norm_gmm_full_spk']
+
+
+def test_free_functions_match_the_reference_source():
+    """tests/golden/ref_functions.npz holds outputs of the reference's own _simple_norm / logsumexp / cost_gmm /
+    sample_gmm (model.py:24-118), executed unmodified on a numpy stand-in (make_ref_function_fixtures.py)."""
+    z = np.load(os.path.join(GOLD, 'ref_functions.npz'))
+    for k in ('norm_a', 'norm_b'):
+        assert np.abs(O.simple_norm(z[k + ':x']) - z[k + ':y']).max() < 1e-12
+    assert np.abs(O.logsumexp(z['lse:x'], axis=-1) - z['lse:y']).max() < 1e-12
+    nll = O.cost_gmm(z['gmm:y'], z['gmm:mu'], z['gmm:sig'], z['gmm:weight'])
+    assert nll.shape == z['gmm:nll'].shape and np.abs(nll - z['gmm:nll']).max() < 1e-12
+    x = O.sample_gmm(z['samp:mu'], z['samp:sigma'], z['samp:weight'], z['samp:unis'], z['samp:normals'])
+    assert np.abs(x - z['samp:x']).max() < 1e-12
+
+
+@pytest.mark.parametrize('name', REF_MODEL_CASES)
+def test_oracle_matches_the_reference_parrot_class(name):
+    """tests/golden/ref_model_*.npz: outputs of the reference's own Parrot.compute_cost (two TBPTT segments) and
+    Parrot.sample_model_fun, executed unmodified on the eager Theano/Blocks stand-in tests/golden/ref_shim.py
+    (make_ref_model_fixtures.py).  The oracle must reproduce them to rounding in float64 and to 1e-4 in float32:
+    this pins its wiring to the reference's code (only the brick arithmetic of Blocks stays restated)."""
+    from tests.golden.make_ref_model_fixtures import CASES, B, T, SAMP
+    z = np.load(os.path.join(GOLD, 'ref_model_%s.npz' % name))
+    cfg = dict(util.TINY, **CASES[name])
+    for dtype, tol in ((np.float64, 1e-10), (np.float32, 2e-4)):
+        orc = O.OracleParrot(dtype=dtype, **cfg)
+        orc.set_params({n: z['param:' + n].astype(dtype) for n in orc.shapes})
+        for seg, sf in enumerate((1.0, 0.0)):
+            p = 'seg%d:' % seg
+            spk = z[p + 'in:speaker'] if cfg.get('use_speaker') else None
+            cost, updates, av, _ = orc.compute_cost(
+                z[p + 'in:features'].astype(dtype), z[p + 'in:features_mask'].astype(dtype), z[p + 'in:labels'],
+                z[p + 'in:labels_mask'].astype(dtype), spk, sf, B, gmm_unis=z[p + 'in:gmm_unis'],
+                gmm_normals=z[p + 'in:gmm_normals'], feedback_noise=z[p + 'in:feedback_noise'].astype(dtype),
+                noise_level=cfg.get('feedback_noise_level'))
+            assert abs(cost - z[p + 'cost']) / abs(z[p + 'cost']) < tol
+            for nm, v in zip(['next_x', 'k', 'w', 'coeff', 'phi', 'pi_att'], av):
+                assert util.rel_err(v, z[p + 'out:' + nm]) < tol, (nm, seg)
+            for nm, v in updates:
+                assert util.rel_err(v, z[p + 'update:' + nm]) < tol, (nm, seg)
+            if dtype == np.float64:
+                assert (av[4].argmax(-1) == z[p + 'out:phi'].argmax(-1)).all()
+        so = O.OracleParrot(dtype=dtype, **dict(cfg, **SAMP))
+        so.set_params({n: z['param:' + n].astype(dtype) for n in so.shapes})
+        spk = z['samp:in:speaker'] if cfg.get('use_speaker') else None
+        res = so.sample_model(z['samp:in:labels'], z['samp:in:labels_mask'].astype(dtype), None, spk, B, T,
+                              gmm_unis=z['samp:in:gmm_unis'], gmm_normals=z['samp:in:gmm_normals'])
+        for nm, v in zip(['x', 'k', 'w', 'pi', 'phi', 'pi_att'], res):
+            assert util.rel_err(v, z['samp:out:' + nm]) < (tol if dtype == np.float64 else 2e-3), nm
