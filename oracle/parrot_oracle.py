@@ -6,26 +6,40 @@ This file is a numpy restatement of the reference algorithm (sotelo/parrot,
 ``--impl reference`` legs may import it.  The product (``parrot_b200``) never
 does, and fails loudly when its CUDA library is missing.
 
-PARITY UNPINNED.  The reference is Python-2 / Theano / Blocks; none of those can
-be imported in the build container, the reference tree holds no tests, no golden
-vectors and no fixtures for this path, and the
-arithmetic of ``GatedRecurrent`` / ``Linear`` / ``Fork`` / ``LookupTable`` /
-``Bidirectional`` / ``Adam`` / ``StepClipping`` lives in the third-party package
-``mila-iqia/blocks`` which is not vendored and not version-pinned by the
-reference.  Those semantics are restated here from the published Blocks source
-(blocks/bricks/recurrent/simple.py ``GatedRecurrent.apply``,
-blocks/bricks/recurrent/misc.py ``Bidirectional.apply``,
-blocks/algorithms ``Adam`` / ``StepClipping``) and anchored on the reference's
-own call sites, each cited below as ``model.py:LINE``.
+PARITY: PINNED TO THE REFERENCE'S SOURCE FOR THE MODEL CODE, UNPINNED FOR THE BLOCKS BRICKS.
+The reference is Python-2 / Theano / Blocks; none of those can be imported in the
+build container and the reference tree holds no tests, golden vectors or fixtures
+for this path.  Two things stand in for them:
 
-What pins this oracle instead (see tests/test_oracle.py):
-  * its hand-derived backward pass agrees with central finite differences of
-    its own forward pass in float64 (every parameter tensor, every option);
+  * model.py itself is executed.  tests/golden/make_ref_function_fixtures.py and
+    tests/golden/make_ref_model_fixtures.py read the source of the free functions
+    (model.py:24-118) and of RecurrentWithFork / Encoder / Parrot
+    (model.py:171-1083) from the read-only reference mount and run it, unmodified,
+    on an eager numpy stand-in for the Theano / Blocks names it uses
+    (tests/golden/ref_shim.py).  Parrot.compute_cost (two TBPTT segments) and
+    Parrot.sample_model_fun outputs for four configurations are committed under
+    tests/golden/ref_*.npz; this oracle reproduces them to 1e-15 relative in
+    float64 (tests/test_oracle.py), and the CUDA path is tested against the same
+    files (tests/test_gpu_parity.py).  That pins every executed line of model.py:
+    Fork wiring, attention window, masks, readouts, GMM head, cost, carried-state
+    updates, sampler.
+  * What stays UNPINNED: the arithmetic inside ``GatedRecurrent`` / ``Linear`` /
+    ``Fork`` / ``LookupTable`` / ``Bidirectional`` and ``Adam`` / ``StepClipping``.
+    It lives in the third-party package ``mila-iqia/blocks``, which the reference
+    neither vendors nor version-pins; it is restated (here and in ref_shim.py) from
+    the published Blocks source (blocks/bricks/recurrent/simple.py
+    ``GatedRecurrent.apply``, blocks/bricks/recurrent/misc.py
+    ``Bidirectional.apply``, blocks/algorithms ``Adam`` / ``StepClipping``),
+    anchored on the reference's call sites, each cited below as ``model.py:LINE``.
+
+Further self-consistency pins (tests/test_oracle.py):
+  * the hand-derived backward pass agrees with central finite differences of the
+    forward pass in float64 (every parameter tensor, every option);
   * float32 and float64 evaluations agree to float32 round-off;
   * the free-running sampler reproduces the teacher-forced graph when it is fed
     its own samples;
-  * frozen golden vectors under tests/golden/ (generated by
-    tests/golden/make_golden.py) detect any later drift.
+  * frozen golden vectors under tests/golden/ (tests/golden/make_golden.py)
+    detect any later drift, gradients included.
 
 Layout conventions (reference): frame tensors are time-major (T, B, .)
 (datasets.py:274-275); text tensors are batch-major (B, U) (model.py:645-649).
