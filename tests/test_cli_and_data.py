@@ -79,3 +79,17 @@ def test_stream_layout_sorting_and_segments():
     ds2 = datasets.SyntheticVoice(num_examples=42, seed=3)
     st2 = datasets.parrot_stream('synthetic', batch_size=4, seq_size=20, sorting_mult=2, dataset=ds2, seed=1)
     assert sum(1 for t in st2 if t[-1] == 1) == 10
+
+
+def test_segmentation_matches_the_reference_transformer():
+    """tests/golden/segments.json: windows emitted by the reference's own SegmentSequence (datasets.py:41-138,
+    executed by tests/golden/make_segment_fixture.py with parrot_stream's arguments) for 61 utterance lengths."""
+    table = json.load(open(os.path.join(GOLD, 'segments.json')))
+    assert len(table) > 50
+    for key, wins in table.items():
+        seq, L = map(int, key.split(':'))
+        f = np.arange(L)[:, None, None].repeat(2, 1)
+        m = np.ones((L, 2))
+        ours = [[int(a[0, 0, 0]), int(a[-1, 0, 0]) + 1, int(flag)]
+                for a, _, flag in datasets.segment_sequence(f, m, seq + 1, share_value=1, return_last=False)]
+        assert ours == wins, key
