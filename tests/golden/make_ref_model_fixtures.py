@@ -9,7 +9,8 @@ repository) against tests/golden/ref_shim.py, loads seeded parameters, and runs
     the compiled function's updates do), and
   * Parrot.sample_model_fun (free-running generation),
 
-in float64 with the random draws injected.  Inputs, parameters and every output go to
+in float64 with the random draws injected, plus central finite differences of the reference cost (segment 0) at
+two entries of every parameter tensor.  Inputs, parameters and every output go to
 tests/golden/ref_model_<case>.npz; tests/test_oracle.py holds oracle/parrot_oracle.py to them.  This pins the
 oracle's wiring (which Fork feeds what, attention window, masks, readouts, cost, updates, sampler) to the
 reference's code; the brick arithmetic inside the stand-in is the published Blocks semantics (see ref_shim.py).
@@ -102,6 +103,36 @@ def run_case(name, extra, ns):
         out[p + 'cost'] = np.float64(cost)
         for nm, v in zip(['next_x', 'k', 'w', 'coeff', 'phi', 'pi_att'], av):
             out[p + 'out:' + nm] = np.asarray(v)
+        if seg == 0:
+            # derivative of the REFERENCE cost (this very code path) by central differences, two entries per
+            # parameter tensor: pins the oracle's hand-derived backward pass to the reference's forward code
+            slots = model.named_parameters()
+            rng = np.random.default_rng(7)
+
+            def ref_cost():
+                model.theano_rng = S.FakeRng(unis=[bt['gmm_unis'].reshape(-1)],
+                                             normals=[bt['gmm_normals'].reshape(T * B, -1)],
+                                             feedback_noise=bt['feedback_noise'] if cfg.get('feedback_noise_level') else None)
+                c, _, _, _ = model.compute_cost(S.A(bt['features'].copy()), S.A(bt['features_mask']), S.A(bt['labels']),
+                                                S.A(bt['labels_mask']), spk, sf, B)
+                return float(c)
+            for n in sorted(slots):
+                brick, key = slots[n]
+                arr = getattr(brick, key[1:]) if key.startswith('@') else brick.params[key]
+                flat = np.asarray(arr).reshape(-1)          # view: perturbing it perturbs the brick's parameter
+                idx = rng.choice(flat.size, size=min(2, flat.size), replace=False)
+                fd = []
+                for i in idx:
+                    old = flat[i]
+                    h = 1e-6 * max(1.0, abs(old))
+                    flat[i] = old + h
+                    cp = ref_cost()
+                    flat[i] = old - h
+                    cm = ref_cost()
+                    flat[i] = old
+                    fd.append((cp - cm) / (2 * h))
+                out['fd:idx:' + n] = idx.astype(np.int64)
+                out['fd:val:' + n] = np.asarray(fd)
         carried = [np.asarray(v) for _, v in updates]
         for nm, v in zip(['last_h1', 'last_h2', 'last_h3', 'last_k', 'last_w'], carried):
             out[p + 'update:' + nm] = v

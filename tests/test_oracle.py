@@ -217,3 +217,28 @@ def test_oracle_matches_the_reference_parrot_class(name):
                               gmm_unis=z['samp:in:gmm_unis'], gmm_normals=z['samp:in:gmm_normals'])
         for nm, v in zip(['x', 'k', 'w', 'pi', 'phi', 'pi_att'], res):
             assert util.rel_err(v, z['samp:out:' + nm]) < (tol if dtype == np.float64 else 2e-3), nm
+
+
+@pytest.mark.parametrize('name', REF_MODEL_CASES)
+def test_oracle_backward_matches_finite_differences_of_the_reference_cost(name):
+    """ref_model_*.npz also hold central finite differences of the REFERENCE's compute_cost (executed on the
+    stand-in, float64) at two entries of every parameter tensor: the oracle's hand-derived BPTT is the derivative of
+    the reference's forward code, tensor by tensor."""
+    from tests.golden.make_ref_model_fixtures import CASES, B
+    z = np.load(os.path.join(GOLD, 'ref_model_%s.npz' % name))
+    cfg = dict(util.TINY, **CASES[name])
+    orc = O.OracleParrot(dtype=np.float64, **cfg)
+    orc.set_params({n: z['param:' + n] for n in orc.shapes})
+    p = 'seg0:'
+    spk = z[p + 'in:speaker'] if cfg.get('use_speaker') else None
+    orc.compute_cost(z[p + 'in:features'], z[p + 'in:features_mask'], z[p + 'in:labels'], z[p + 'in:labels_mask'], spk,
+                     1.0, B, gmm_unis=z[p + 'in:gmm_unis'], gmm_normals=z[p + 'in:gmm_normals'],
+                     feedback_noise=z[p + 'in:feedback_noise'], noise_level=cfg.get('feedback_noise_level'))
+    g = orc.backward()
+    checked = 0
+    for n in orc.shapes:
+        idx, fd = z['fd:idx:' + n], z['fd:val:' + n]
+        scale = max(np.abs(g[n]).max(), 1e-12)
+        assert np.abs(g[n].reshape(-1)[idx] - fd).max() / scale < 2e-5, n
+        checked += int((np.abs(fd) > 0).sum())
+    assert checked > 100
