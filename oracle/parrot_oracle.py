@@ -20,7 +20,9 @@ for this path.  Two things stand in for them:
     Parrot.sample_model_fun outputs for four configurations are committed under
     tests/golden/ref_*.npz; this oracle reproduces them to 1e-15 relative in
     float64 (tests/test_oracle.py), and the CUDA path is tested against the same
-    files (tests/test_gpu_parity.py).  That pins every executed line of model.py:
+    files (tests/test_gpu_parity.py).  The fixtures also carry central finite
+    differences of the reference cost for every parameter tensor, which the
+    hand-derived backward pass below matches.  That pins every executed line of model.py:
     Fork wiring, attention window, masks, readouts, GMM head, cost, carried-state
     updates, sampler.
   * What stays UNPINNED: the arithmetic inside ``GatedRecurrent`` / ``Linear`` /
