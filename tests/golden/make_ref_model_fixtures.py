@@ -73,7 +73,9 @@ def build(ns, cfg, params):
 def run_case(name, extra, ns):
     cfg = dict(util.TINY, **extra)
     orc = util.make_oracle(cfg, gain=0.5, dtype=np.float64)
-    out = {'param:' + n: v for n, v in orc.params.items()}
+    # float32-representable parameters: stored as float32 (half the file), identical on the float32 device path
+    orc.params = {n: v.astype(np.float32).astype(np.float64) for n, v in orc.params.items()}
+    out = {'param:' + n: v.astype(np.float32) for n, v in orc.params.items()}
     ref_cfg = {k: v for k, v in cfg.items()}
     model = build(ns, ref_cfg, orc.params)
     carried = None
