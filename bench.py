@@ -56,9 +56,8 @@ def workload_config(args, world):
 
 
 def make_batch(cfg, B, T, U, seed):
-    from tests import util
-    bt = util.make_batch(cfg, B, T, U, seed=seed)
-    return bt
+    from parrot_b200.synthetic import make_batch as mk      # product module: no tests / oracle import on the GPU arm
+    return mk(cfg, B, T, U, seed=seed)
 
 
 def algorithmic_flops(cfg, B, T):
@@ -222,7 +221,9 @@ def main():
     from parrot_b200.algorithms import Adam, CompositeRule, GradientDescent, StepClipping
     import ctypes as C
 
-    os.environ['NCCL_DEBUG'] = os.environ.get('PARROT_NCCL_DEBUG', 'WARN')   # keep stdout to the one JSON line
+    # NCCL_DEBUG is left as the launcher set it (the driver reads the communicator's INFO lines).  NCCL logs to
+    # stdout by default: route them to stderr unless the launcher chose a file, so that stdout carries one JSON line
+    os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
     rank, world, local = parallel.init_from_env()
     assert world == args.gpus or world == 1 and args.gpus == 1, 'launch with torchrun for --gpus > 1'
     torch.cuda.set_device(local)

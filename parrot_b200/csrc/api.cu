@@ -237,6 +237,7 @@ struct WPack {
 };
 struct Table {
   int off = 0, count = 0, n_cols = 0;
+  int chunk_samples = 0;   // > 0: chunk table (engine.cuh chunk_window)
 };
 struct Buf {
   size_t off;
@@ -272,6 +273,8 @@ struct parrot_model {
   std::vector<WGrad> wgrads;
   int max_groups = 0;
   size_t max_split_floats = 0;
+  int Tc = 0;              // chunk length of the chunk-lagged layer wavefront (0: not used)
+  int att_slices = 0;      // K slices of the attention projection (persistent scan)
   unsigned long long* timeline = nullptr;
   unsigned long long* stamps = nullptr;   // debug: persistent forward scan per-barrier stamps
   int stamp_bars = 0;
@@ -433,8 +436,11 @@ static Job blank_job() {
 static std::string LN(int l) { return std::to_string(l + 1); }
 
 // forward scan jobs of one layer (gates or candidate): model.py:655-662, 692-722
+// hoisted: only the products that depend on the layer's own recurrence stay in the scan (state_to_gates /
+// state_to_state, and for layer 1 the attention context w_{t-1}); everything else reaches the epilogue through
+// LayerBuf::pre (chunk-lagged wavefront, kernels.cuh).
 static void build_fwd_layer_jobs(parrot_model& M, std::vector<Job>& out, int layer, bool gates, int lag,
-                                 bool ln = false) {
+                                 bool ln = false, bool hoisted = false) {
   const Dims& d = M.d;
   const int rows = gates ? 2 * d.H : d.H;
   const std::string l = LN(layer);
@@ -452,15 +458,16 @@ static void build_fwd_layer_jobs(parrot_model& M, std::vector<Job>& out, int lay
       j.seg[ns++] = mkseg(M.packs["/rnn" + l + ".state_to_state"].fwd_map, mt * 128, 0, M.map_scan["rh" + l], 0, 0,
                           0, d.Hp / 64);
     // attention context: layer 1 consumes w_{t-1} (slot t), layers 2,3 consume w_t (slot t+1)
-    j.seg[ns++] = mkseg(M.packs["/inp_to_h" + l + "/fork_rnn" + l + fk].fwd_map, mt * 128, 0, M.map_scan["w"], 0, 0,
-                        layer == 0 ? 0 : 1, d.Cp / 64);
-    if (layer >= 1 && !ln)
+    if (!hoisted || layer == 0)
+      j.seg[ns++] = mkseg(M.packs["/inp_to_h" + l + "/fork_rnn" + l + fk].fwd_map, mt * 128, 0, M.map_scan["w"], 0, 0,
+                          layer == 0 ? 0 : 1, d.Cp / 64);
+    if (layer >= 1 && !ln && !hoisted)
       j.seg[ns++] = mkseg(M.packs["/h1_to_h" + l + "/fork_rnn" + l + fk].fwd_map, mt * 128, 0, M.map_scan["h1"], 0, 0,
                           1, d.Hp / 64);
-    if (layer == 2 && !ln)
+    if (layer == 2 && !ln && !hoisted)
       j.seg[ns++] = mkseg(M.packs["/h2_to_h3/fork_rnn3" + fk].fwd_map, mt * 128, 0, M.map_scan["h2"], 0, 0, 1,
                           d.Hp / 64);
-    if (!ln && ((layer == 0 && d.weak) || (layer > 0 && d.full)))
+    if (!ln && !hoisted && ((layer == 0 && d.weak) || (layer > 0 && d.full)))
       j.seg[ns++] = mkseg(M.packs["/out_to_h" + l + "/fork_rnn" + l + fk].fwd_map, mt * 128, 0, M.map_scan["xin"], 0,
                           0, 0, d.Dp / 64);
     j.nseg = ns;
@@ -551,13 +558,14 @@ static std::vector<Job> split_jobs(const std::vector<Job>& js, int target_ctas, 
 }
 
 static void push_table(parrot_model& M, const std::string& name, const std::vector<Job>& js_in, int n_cols,
-                       int split_target = 0) {
+                       int split_target = 0, int chunk_samples = 0) {
   std::vector<Job> js = js_in;
   for (auto& j : js)
     for (int s = 0; s < j.nseg; ++s) j.seg[s].a_nkb = M.raws[j.seg[s].a_map].tiled_nkb;   // tile-contiguous packs
   Table t;
   t.off = (int)M.jobs.size();
   t.n_cols = n_cols;
+  t.chunk_samples = chunk_samples;
   if (split_target > 0) {
     int groups = 0;
     std::vector<Job> sp = split_jobs(js, split_target, MAX_KSPLIT, &groups);
@@ -590,8 +598,9 @@ static void run_table(parrot_model& M, const std::string& name, int tick, int T,
   EngineParams P;
   P.jobs = M.d_jobs + t.off; P.njobs = t.count; P.maps = M.d_maps; P.raws = M.d_raws; P.ctx = M.d_ctx;
   P.tick = tick; P.T = T; P.n_cols = t.n_cols; P.reverse = reverse;
+  P.chunk_samples = t.chunk_samples;
   P.split_scratch = M.d_split_scratch; P.split_count = M.d_split_count;
-  P.timeline = M.timeline;
+  P.timeline = M.timeline; P.tl_tick = -1;
   P.coop_epilogue = (t.count <= 148 && M.sm_count >= 148) ? 1 : 0;
   P.debug_flags = 0;
   cudaEvent_t pe = M.prof_begin(name, st);
@@ -719,8 +728,16 @@ static void build(parrot_model& M) {
       Plane pd = M.make_plane("da" + s, Np, 3 * d.Hp, T);
       L.da_hi = pd.hi; L.da_lo = pd.lo;
       M.map_scan["da" + s] = M.make_map(pd, 3, Np);
+      if (!d.ln) {
+        M.map_plain["da" + s] = M.make_map(pd, 2, NT);
+        // hoisted pre-activation terms of the chunk-lagged wavefront (layer 1: only the teacher-forced feedback)
+        if (l > 0 || d.weak) L.pre = M.falloc("pre" + s, (long long)T * B * 3 * H);
+      }
     }
   }
+  M.Tc = (train && !d.ln) ? (T >= 64 ? 16 : 8) : 0;
+  M.att_slices = H / ATT_KS;
+  M.falloc("att_hat_part", (long long)M.att_slices * B * 3 * d.A);
   M.falloc("w", (long long)(T + 1) * B * d.C);
   Plane pw = M.make_plane("w", Np, d.C, T + 1);
   M.map_scan["w"] = M.make_map(pw, 3, Np);
@@ -733,6 +750,7 @@ static void build(parrot_model& M) {
   if (d.weak) {
     Plane px = M.make_plane("xin", Np, d.D, d.sampling ? T + 1 : T);
     M.map_scan["xin"] = M.make_map(px, 3, Np);
+    if (train && !d.ln) M.map_plain["xin"] = M.make_map(px, 2, NT);
   }
   if (train) {
     X.dw = M.falloc("dw", (long long)(T + 1) * B * d.C);
@@ -828,11 +846,54 @@ static void build(parrot_model& M) {
 
   // ============================ job tables ============================
   if (train && !d.ln) {
+    // chunk-lagged wavefront (kernels.cuh): layer l runs l * Tc steps behind layer 1
+    const int Tc = M.Tc;
     std::vector<Job> A, Bj;
-    for (int l = 0; l < 3; ++l) build_fwd_layer_jobs(M, A, l, true, l);
-    for (int l = 0; l < 3; ++l) build_fwd_layer_jobs(M, Bj, l, false, l);
+    for (int l = 0; l < 3; ++l) build_fwd_layer_jobs(M, A, l, true, l * Tc, false, true);
+    for (int l = 0; l < 3; ++l) build_fwd_layer_jobs(M, Bj, l, false, l * Tc, false, true);
     push_table(M, "fwdA", A, Np, PB_SPLIT_TARGET);
     push_table(M, "fwdB", Bj, Np, PB_SPLIT_TARGET);
+    // hoisted products -> pre_l[t][b][3H] (plain stores, biases stay in base_l).  (source plane, first plane row,
+    // pack prefix, k blocks); "_inputs" packs fill features [0, H), "_gates" packs [H, 3H).
+    struct HSrc { std::string plane; int row0; std::string pack; int nkb; };
+    auto hoist = [&](std::vector<Job>& js, int layer, long long n_samples, const std::vector<HSrc>& src, int lag) {
+      const std::string l = LN(layer);
+      for (int part = 0; part < 2; ++part) {
+        const int rows = part == 0 ? H : 2 * H, f0 = part == 0 ? 0 : H;
+        PlainArgs pa;
+        memset(&pa, 0, sizeof pa);
+        pa.scale = 1.0f;
+        pa.out = M.dry ? nullptr : M.fbuf("pre" + l);
+        pa.ldo = 3 * H; pa.n_pad = Np; pa.n_valid = B; pa.n_total = T * Np;
+        std::vector<PlainSeg> segs;
+        for (auto& sc : src)
+          segs.push_back({M.packs[sc.pack + "/fork_rnn" + l + (part == 0 ? "_inputs" : "_gates")].fwd_map, 0,
+                          M.map_plain[sc.plane], sc.row0, 0, sc.nkb});
+        const size_t first = js.size();
+        build_plain_jobs(js, rows, f0, n_samples, segs, pa);
+        for (size_t i = first; i < js.size(); ++i) js[i].lag = lag;
+      }
+    };
+    if (d.weak) {   // layer 1: x_{t-1} . out_to_h1, all frames at once before the scan
+      std::vector<Job> js;
+      hoist(js, 0, (long long)T * Np, {{"xin", 0, "/out_to_h1", d.Dp / 64}}, 0);
+      sort_by_sample_tile(js);
+      push_table(M, "hoist1", js, NT);
+    }
+    {
+      // one chunk of Tc steps: pre2 from (h1_t, w_t) of chunk e, pre3 from (h1_t, h2_t, w_t) of chunk e - 1
+      std::vector<Job> js;
+      std::vector<HSrc> s3 = {{"h1", Np, "/h1_to_h3", d.Hp / 64}, {"h2", Np, "/h2_to_h3", d.Hp / 64},
+                              {"w", Np, "/inp_to_h3", d.Cp / 64}};
+      std::vector<HSrc> s2 = {{"h1", Np, "/h1_to_h2", d.Hp / 64}, {"w", Np, "/inp_to_h2", d.Cp / 64}};
+      if (d.full) {
+        s3.push_back({"xin", 0, "/out_to_h3", d.Dp / 64});
+        s2.push_back({"xin", 0, "/out_to_h2", d.Dp / 64});
+      }
+      hoist(js, 2, (long long)Tc * Np, s3, 1);   // the longer jobs first
+      hoist(js, 1, (long long)Tc * Np, s2, 0);
+      push_table(M, "chunkF", js, NT, 0, Tc * Np);
+    }
   } else if (train) {
     // layer_norm: one layer at a time (lag 0); the normalised Fork outputs reach the epilogues through preT
     for (int l = 0; l < 3; ++l) {
@@ -1116,13 +1177,15 @@ static void build(parrot_model& M) {
         push_table(M, "ln_bwd2_1", js, Np, 148);
       }
     }
-    // backward scan, product 1: d(r*h) = da_c . Ws^T
+    // backward scan, product 1: d(r*h) = da_c . Ws^T.  Reverse chunk-lagged wavefront: layer 3 leads, layer l runs
+    // (2 - l) * Tc steps behind it.
     if (!d.ln) {
+      const int Tc = M.Tc;
       std::vector<Job> js;
       for (int l = 0; l < 3; ++l)
         for (int mt = 0; mt < cdiv(H, 128); ++mt) {
           Job j = blank_job();
-          j.epi = EPI_BWD_RH; j.layer = l; j.lag = 2 - l; j.row0 = mt * 128; j.m_valid = std::min(128, H - mt * 128);
+          j.epi = EPI_BWD_RH; j.layer = l; j.lag = (2 - l) * Tc; j.row0 = mt * 128; j.m_valid = std::min(128, H - mt * 128);
           j.nseg = 1;
           j.seg[0] = mkseg(M.packs["/rnn" + LN(l) + ".state_to_state"].bwd_map, mt * 128, 0, M.map_scan["da" + LN(l)],
                            0, 0, 0, d.Hp / 64);
@@ -1130,44 +1193,59 @@ static void build(parrot_model& M) {
         }
       push_table(M, "bwd1", js, Np, PB_SPLIT_TARGET);
     }
-    // backward scan, product 2: dgrads into the carried state gradients.  Job time = step s of layer 3;
-    // segments of layer 2 / layer 1 refer to steps s+1 / s+2 (reverse wavefront).
+    // backward scan, product 2: the dgrads that stay in the recurrence -- da_g . Wg^T into dh_l[slot t] (the state
+    // entering step t) and, for layer 1, da_1 . Wi1^T into dw[slot t] (layer 1 consumes w_{t-1}).
     if (!d.ln) {
+      const int Tc = M.Tc;
       std::vector<Job> js;
       const int gk = d.Hp;  // column offset of the gate block inside the da planes
-      auto seg_c = [&](const std::string& pk, int mt, int layer, int slot) {
-        return mkseg(M.packs[pk].bwd_map, mt * 128, 0, M.map_scan["da" + LN(layer)], 0, 0, slot, d.Hp / 64);
-      };
-      auto seg_g = [&](const std::string& pk, int mt, int layer, int slot) {
-        return mkseg(M.packs[pk].bwd_map, mt * 128, 0, M.map_scan["da" + LN(layer)], 0, gk, slot, 2 * d.Hp / 64);
-      };
-      auto add = [&](int rows, int aux, int slot_off, const std::vector<std::pair<std::string, std::pair<int, int>>>& src) {
-        // src: (pack name, (layer, slot)) ; "_inputs" packs pair with the cell block, "_gates"/state_to_gates with gates
+      auto add = [&](int rows, int aux, int layer, const std::vector<std::string>& packs_) {
         for (int mt = 0; mt < cdiv(rows, 128); ++mt) {
           Job j = blank_job();
-          j.epi = EPI_BWD_STATE; j.aux = aux; j.lag = 0; j.row0 = mt * 128; j.m_valid = std::min(128, rows - mt * 128);
-          j.pa.n_pad = slot_off;
+          j.epi = EPI_BWD_STATE; j.aux = aux; j.layer = layer; j.lag = (2 - layer) * Tc;
+          j.row0 = mt * 128; j.m_valid = std::min(128, rows - mt * 128);
+          j.pa.n_pad = 0;   // destination slot = t
           int ns = 0;
-          for (auto& s : src) {
-            const bool is_gate = s.first.find("_gates") != std::string::npos;
-            j.seg[ns++] = is_gate ? seg_g(s.first, mt, s.second.first, s.second.second)
-                                  : seg_c(s.first, mt, s.second.first, s.second.second);
+          for (auto& pk : packs_) {
+            const bool is_gate = pk.find("_gates") != std::string::npos;
+            j.seg[ns++] = mkseg(M.packs[pk].bwd_map, mt * 128, 0, M.map_scan["da" + LN(layer)], 0, is_gate ? gk : 0, 0,
+                                (is_gate ? 2 : 1) * d.Hp / 64);
           }
           j.nseg = ns;
           js.push_back(j);
         }
       };
-      typedef std::pair<std::string, std::pair<int, int>> S;
-      add(H, 2, 0, {S("/rnn3.state_to_gates", {2, 0})});
-      add(H, 1, 1, {S("/h2_to_h3/fork_rnn3_inputs", {2, 0}), S("/h2_to_h3/fork_rnn3_gates", {2, 0}),
-                    S("/rnn2.state_to_gates", {1, 1})});
-      add(H, 0, 1, {S("/h1_to_h3/fork_rnn3_inputs", {2, 0}), S("/h1_to_h3/fork_rnn3_gates", {2, 0})});
-      add(H, 0, 2, {S("/h1_to_h2/fork_rnn2_inputs", {1, 1}), S("/h1_to_h2/fork_rnn2_gates", {1, 1}),
-                    S("/rnn1.state_to_gates", {0, 2})});
-      add(d.C, 3, 1, {S("/inp_to_h3/fork_rnn3_inputs", {2, 0}), S("/inp_to_h3/fork_rnn3_gates", {2, 0})});
-      add(d.C, 3, 2, {S("/inp_to_h2/fork_rnn2_inputs", {1, 1}), S("/inp_to_h2/fork_rnn2_gates", {1, 1}),
-                      S("/inp_to_h1/fork_rnn1_inputs", {0, 2}), S("/inp_to_h1/fork_rnn1_gates", {0, 2})});
+      add(H, 2, 2, {"/rnn3.state_to_gates"});
+      add(H, 1, 1, {"/rnn2.state_to_gates"});
+      add(H, 0, 0, {"/rnn1.state_to_gates"});
+      add(d.C, 3, 0, {"/inp_to_h1/fork_rnn1_inputs", "/inp_to_h1/fork_rnn1_gates"});
       push_table(M, "bwd2", js, Np, PB_SPLIT_TARGET);
+      // hoisted dgrads, one range of Tc steps at a time (accumulated into slot t + 1 of the consumer's gradient):
+      // event e: from da3 of range e into dh2 / dh1 / dw ; from da2 of range e - 1 into dh1 / dw
+      std::vector<Job> cj;
+      auto chunk = [&](int rows, float* out, int F, int layer, const std::string& fork, int lag) {
+        PlainArgs pa;
+        memset(&pa, 0, sizeof pa);
+        pa.scale = 1.0f;
+        pa.out = out;
+        pa.ldo = F; pa.n_pad = Np; pa.n_valid = B; pa.n_total = T * Np; pa.flags = PF_ACC;
+        const std::string l = LN(layer);
+        std::vector<PlainSeg> segs = {
+            {M.packs[fork + "/fork_rnn" + l + "_inputs"].bwd_map, 0, M.map_plain["da" + l], 0, 0, d.Hp / 64},
+            {M.packs[fork + "/fork_rnn" + l + "_gates"].bwd_map, 0, M.map_plain["da" + l], 0, gk, 2 * d.Hp / 64}};
+        const size_t first = cj.size();
+        build_plain_jobs(cj, rows, 0, (long long)Tc * Np, segs, pa);
+        for (size_t i = first; i < cj.size(); ++i) cj[i].lag = lag;
+      };
+      float* dh1s = M.dry ? nullptr : M.ctx.L[0].dh + (long long)B * H;
+      float* dh2s = M.dry ? nullptr : M.ctx.L[1].dh + (long long)B * H;
+      float* dws = M.dry ? nullptr : M.ctx.dw + (long long)B * d.C;
+      chunk(H, dh2s, H, 2, "/h2_to_h3", 0);
+      chunk(H, dh1s, H, 2, "/h1_to_h3", 0);
+      chunk(d.C, dws, d.C, 2, "/inp_to_h3", 0);
+      chunk(H, dh1s, H, 1, "/h1_to_h2", 1);
+      chunk(d.C, dws, d.C, 1, "/inp_to_h2", 1);
+      push_table(M, "chunkB", cj, NT, 0, Tc * Np);
     }
     // weight gradients: dW[in][out] = sum_samples X[s][in] * dY[s][out]
     {
@@ -1242,6 +1320,8 @@ static void ensure_kernel_attrs() {
   CK(cudaFuncSetAttribute(scan_fwd_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES + 1024 + ATT_SMEM_BYTES));
   CK(cudaFuncSetAttribute(scan_bwd_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES + 1024 + ATT_SMEM_BYTES));
   CK(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  CK(cudaFuncSetAttribute(attention_proj_slice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  CK(cudaFuncSetAttribute(attention_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
   CK(cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   CK(cudaFuncSetAttribute(encoder_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
   CK(cudaFuncSetAttribute(encoder_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
@@ -1572,15 +1652,21 @@ static AttnFwdArgs attn_fwd_args(parrot_model& M, int t, bool sampling) {
   a.ab_out = M.fbuf("ab") + (long long)t * d.B * 2 * d.A;
   a.e_out = M.fbuf("att_e") + (long long)t * d.B * 3 * d.A;
   a.hat = M.fbuf("att_hat");
+  a.hat_part = M.fbuf("att_hat_part");
   return a;
+}
+static size_t att_proj_smem(const Dims& d) { return (size_t)(d.B + 3 * d.A) * (ATT_KS + 1) * 4; }
+static size_t att_window_smem(const Dims& d, int nparts) {
+  return (size_t)(2 * rup(3 * d.A, 4) + rup(d.U, 4) + 8 * (d.C / nparts)) * 4;
 }
 static void attention_step(parrot_model& M, int t, bool sampling, cudaStream_t st) {
   const Dims& d = M.d;
   AttnFwdArgs a = attn_fwd_args(M, t, sampling);
-  const size_t smem = (size_t)(rup(d.H, 4) + 2 * rup(3 * d.A, 4) + rup(d.U, 4) + 8 * d.C) * 4;
   cudaEvent_t pe = M.prof_begin("attn_fwd", st);
-  LAUNCH(attention_proj_kernel, 148, 256, 0, st, a);          // h1 . Watt^T spread over the whole GPU
-  LAUNCH(attention_fwd_kernel, d.B, 256, smem, st, a, 1);     // window + context, one CTA per batch row
+  // stage 1: K-sliced partial projections h1 . Watt^T ; stage 2: window + context, nparts CTAs per batch row
+  const int nparts = attention_nparts(d.B, d.C, 148);
+  LAUNCH(attention_proj_slice_kernel, M.att_slices, 256, att_proj_smem(d), st, a);
+  LAUNCH(attention_window_kernel, d.B * nparts, 256, att_window_smem(d, nparts), st, a, nparts, M.att_slices);
   parrot_model::prof_end(pe, st);
 }
 
@@ -1597,9 +1683,9 @@ static bool use_persistent(parrot_model& M) {
   }
   const Dims& d = M.d;
   if (!env || !M.persistent_ok || M.cfg.gemm_impl == 1 || M.profiling >= 2 || M.sm_count < 148) return false;
-  const size_t att_f = (size_t)rup(d.H, 4) + 2 * rup(3 * d.A, 4) + rup(d.U, 4) + (ENGINE_THREADS / 32) * (size_t)d.C;
-  const size_t att_b = (size_t)d.C + d.U + 3 * d.A * 16 + 10 * d.A;
-  if (std::max(att_f, att_b) * 4 > (size_t)ATT_SMEM_BYTES) return false;
+  const size_t att_f = std::max(att_proj_smem(d), att_window_smem(d, attention_nparts(d.B, d.C, 148)));
+  const size_t att_b = ((size_t)d.C + d.U + 3 * d.A * 16 + 10 * d.A) * 4;
+  if (std::max(att_f, att_b) > (size_t)ATT_SMEM_BYTES) return false;
   for (const char* nm : {"fwdA", "fwdB", "bwd1", "bwd2"}) {
     auto it = M.tables.find(nm);
     if (it != M.tables.end() && it->second.count > 148) return false;
@@ -1607,13 +1693,17 @@ static bool use_persistent(parrot_model& M) {
   return true;
 }
 
-static EngineParams table_params(parrot_model& M, const std::string& name, int reverse) {
+static EngineParams table_params(parrot_model& M, const std::string& name, int reverse, int tl_slot = -1) {
   const Table& t = M.tables.at(name);
   EngineParams P;
   P.jobs = M.d_jobs + t.off; P.njobs = t.count; P.maps = M.d_maps; P.raws = M.d_raws; P.ctx = M.d_ctx;
   P.tick = 0; P.T = M.d.T; P.n_cols = t.n_cols; P.reverse = reverse;
+  P.chunk_samples = t.chunk_samples;
   P.split_scratch = M.d_split_scratch; P.split_count = M.d_split_count;
-  P.timeline = nullptr; P.coop_epilogue = 1;
+  // debug: intra-phase milestones of persistent tick M.tl_tick, one [148][16] block per phase
+  P.timeline = (M.timeline && tl_slot >= 0) ? M.timeline + (size_t)tl_slot * 148 * 16 : nullptr;
+  P.tl_tick = M.tl_tick;
+  P.coop_epilogue = 1;
   {
     const char* e = getenv("PARROT_DEBUG_FLAGS");
     P.debug_flags = e ? atoi(e) : 0;
@@ -1631,8 +1721,11 @@ static AttnBwdArgs attn_bwd_args(parrot_model& M, int t);
 static bool scan_fwd_persistent_launch(parrot_model& M, cudaStream_t st) {
   const Dims& d = M.d;
   ScanFwdParams S;
-  S.A = table_params(M, "fwdA", 0);
-  S.B = table_params(M, "fwdB", 0);
+  S.A = table_params(M, "fwdA", 0, 0);
+  S.B = table_params(M, "fwdB", 0, 1);
+  S.G = table_params(M, "chunkF", 0);
+  S.Tc = M.Tc; S.nticks = d.T + 2 * M.Tc;
+  S.att_parts = attention_nparts(d.B, d.C, 148); S.att_slices = M.att_slices;
   S.att = attn_fwd_args(M, 0, false);
   S.s_h1 = (long long)d.B * d.H; S.s_k = (long long)d.B * d.A; S.s_w = (long long)d.B * d.C;
   S.s_wp = (long long)d.Np * M.planes.at("w").pitch; S.s_phi = (long long)d.B * d.U;
@@ -1661,8 +1754,10 @@ static bool scan_fwd_persistent_launch(parrot_model& M, cudaStream_t st) {
 static bool scan_bwd_persistent_launch(parrot_model& M, cudaStream_t st) {
   const Dims& d = M.d;
   ScanBwdParams S;
-  S.B1 = table_params(M, "bwd1", 1);
-  S.B2 = table_params(M, "bwd2", 1);
+  S.B1 = table_params(M, "bwd1", 1, 0);
+  S.B2 = table_params(M, "bwd2", 1, 1);
+  S.G = table_params(M, "chunkB", 1);
+  S.Tc = M.Tc; S.nticks = d.T + 2 * M.Tc;
   S.att = attn_bwd_args(M, 0);
   S.s_dw = (long long)d.B * d.C; S.s_ab = (long long)d.B * 2 * d.A; S.s_e = (long long)d.B * 3 * d.A;
   S.s_k = (long long)d.B * d.A; S.s_dh1 = (long long)d.B * d.H; S.s_datt = (long long)d.B * 3 * d.A;
@@ -1733,12 +1828,16 @@ static void scan_fwd(parrot_model& M, const float* d_features, const float* d_no
   init_slots(M, start_flag != 0.0f, st);
   M.last_start_flag = start_flag;
   if (d.ln) { scan_fwd_ln(M, st); return; }
+  if (d.weak) run_table(M, "hoist1", 0, 1, 0, st);   // pre1 = x_{t-1} . out_to_h1 for all frames
   if (use_persistent(M) && scan_fwd_persistent_launch(M, st)) return;
-  // layer wavefront: tick tau runs layer 1 at step tau, layer 2 at tau-1, layer 3 at tau-2
-  for (int tick = 0; tick < d.T + 2; ++tick) {
+  // chunk-lagged layer wavefront, one launch per phase: tick tau runs layer 1 at step tau, layer 2 at tau - Tc,
+  // layer 3 at tau - 2 Tc; every Tc ticks the hoisted products of the chunk just finished
+  const int Tc = M.Tc;
+  for (int tick = 0; tick < d.T + 2 * Tc; ++tick) {
     run_table(M, "fwdA", tick, d.T, 0, st);
     run_table(M, "fwdB", tick, d.T, 0, st);
     if (tick < d.T) attention_step(M, tick, false, st);
+    if ((tick + 1) % Tc == 0) run_table(M, "chunkF", (tick + 1) / Tc - 1, d.T, 0, st);
   }
 }
 
@@ -1890,14 +1989,16 @@ static void scan_bwd(parrot_model& M, cudaStream_t st) {
   if (d.ln) { scan_bwd_ln(M, st); return; }
   if (use_persistent(M) && scan_bwd_persistent_launch(M, st)) return;
   const int blocks = std::min(gs_blocks((long long)d.B * d.H), 148);
-  // reverse layer wavefront: tick tau -> layer 3 at s = T-1-tau, layer 2 at s+1, attention + layer 1 at s+2
-  for (int tick = 0; tick < d.T + 2; ++tick) {
+  // reverse chunk-lagged wavefront: tick tau -> layer 3 at s = T-1-tau, layer 2 at s + Tc, attention + layer 1 at
+  // s + 2 Tc; every Tc ticks the hoisted dgrads of the ranges just finished
+  const int Tc = M.Tc;
+  for (int tick = 0; tick < d.T + 2 * Tc; ++tick) {
     const int s = d.T - 1 - tick;
-    if (s + 2 >= 0 && s + 2 < d.T) attention_bwd_step(M, s + 2, st);
+    if (s + 2 * Tc >= 0 && s + 2 * Tc < d.T) attention_bwd_step(M, s + 2 * Tc, st);
     PreArgs pa;
     pa.n = 0;
     for (int l = 2; l >= 0; --l) {
-      const int t = s + (2 - l);
+      const int t = s + (2 - l) * Tc;
       if (t >= 0 && t < d.T) { pa.layer[pa.n] = l; pa.t[pa.n] = t; ++pa.n; }
     }
     if (pa.n > 0) {
@@ -1907,6 +2008,7 @@ static void scan_bwd(parrot_model& M, cudaStream_t st) {
     }
     run_table(M, "bwd1", tick, d.T, 1, st);
     run_table(M, "bwd2", tick, d.T, 1, st);
+    if ((tick + 1) % Tc == 0) run_table(M, "chunkB", (tick + 1) / Tc - 1, d.T, 1, st);
   }
 }
 
@@ -2279,6 +2381,7 @@ int parrot_debug_time_table(parrot_model* m, const char* name, int tick, int rev
 }
 int parrot_debug_set_stamps(parrot_model* m, unsigned long long* d_stamps, int bars) {
   // bars < 0: d_stamps is instead a [2][148][16] intra-phase timeline buffer for forward tick (-bars)
+  if (!d_stamps) { m->timeline = nullptr; m->tl_tick = -1; m->stamps = nullptr; m->stamps_bwd = nullptr; m->stamp_bars = 0; return 0; }
   if (bars < 0) { m->timeline = d_stamps; m->tl_tick = -bars; return 0; }
   if (bars >= (1 << 20)) { m->stamps_bwd = d_stamps; m->stamp_bars = bars - (1 << 20); m->stamps = nullptr; return 0; }   // backward sweep
   m->stamps = d_stamps; m->stamp_bars = bars; m->stamps_bwd = nullptr;
@@ -2357,8 +2460,10 @@ int parrot_attention_step(const parrot_config* cfg, const float* d_h1, const flo
     ensure_kernel_attrs();
     // the caller's e_out buffer ([B][3A]) doubles as the projection scratch: it is consumed before it is rewritten
     a.hat = d_e_out;
+    (void)smem;
+    const int nparts = attention_nparts(d.B, d.C, 148);
     LAUNCH(attention_proj_kernel, 148, 256, 0, (cudaStream_t)stream, a);
-    LAUNCH(attention_fwd_kernel, d.B, 256, smem, (cudaStream_t)stream, a, 1);
+    LAUNCH(attention_window_kernel, d.B * nparts, 256, att_window_smem(d, nparts), (cudaStream_t)stream, a, nparts, 0);
   });
 }
 

@@ -72,7 +72,7 @@ struct Seg {
   int nkb;     // number of 64-wide k blocks
   int a_nkb;   // > 0: A is a tile-contiguous weight pack with a_nkb k blocks per 128-row tile: tile
                // (row_tile, k_block) is rows [(row_tile*a_nkb + k_block)*128, +128) of a [.][64] matrix
-  int pad_;
+  int b_slots; // slots of the B plane (copied from MapRaw at table build: no dependent global load in seg_valid)
 };
 
 struct PlainArgs {
@@ -88,7 +88,7 @@ struct PlainArgs {
   int n_total;         // samples >= n_total are not stored
   int flags;           // 1 accumulate, 2 store transposed (out[row*ldo + n]), 4 planes indexed by padded n
   float scale;
-  int pad_;
+  int rowbias_ld;      // > 0: `bias` is a [n_pad rows][rowbias_ld] matrix indexed by (sample % n_pad, feature)
 };
 enum { PF_ACC = 1, PF_TRANS = 2, PF_PLANE_PADDED = 4 };
 
@@ -126,6 +126,8 @@ struct LayerBuf {
   float *z, *r, *c;    // [T][B][H]
   const float* base;   // [B][3H]  time-constant input: summed Fork biases (+ speaker), [cell | gates]
   const float* fb;     // [T][B][3H] teacher-forcing feedback term or null
+  const float* pre;    // [T][B][3H] hoisted pre-activation terms (products whose inputs do not depend on this
+                       // layer's own recurrence: teacher-forced feedback, lower layers, attention context), or null
   // backward
   float* dh;           // [T+1][B][H]  gradient wrt h slot s (accumulated)
   float* drh;          // [B][H] scratch: d(r*h) of the current step
@@ -149,11 +151,14 @@ struct EngineParams {
   int T;          // jobs whose t falls outside [0, T) are skipped
   int n_cols;     // UMMA N of every job in this launch (box rows of every B map used)
   int reverse;    // 0: t = tick - lag ; 1: t = (T - 1) - (tick - lag)
+  int chunk_samples;  // > 0: EPI_PLAIN jobs of this table cover ONE chunk of `chunk_samples` consecutive samples; the
+                      // launch's `tick` is the chunk event e, job j works on chunk e - j.lag (see chunk_window)
   float* split_scratch;        // [group][part][n_cols][128] partial tiles
   unsigned int* split_count;   // [group] arrival counters (zero between launches)
   int debug_flags;             // reserved for experiments
   int coop_epilogue;           // 1: all parts of a split tile share the final epilogue (needs <= 1 job per CTA)
   unsigned long long* timeline;  // debug: [cta][16] globaltimer stamps at pipeline milestones (or null)
+  int tl_tick;                   // debug: only the launch / persistent tick with this value writes the timeline (-1: any)
 };
 
 __device__ __forceinline__ unsigned long long gtime() {
@@ -161,15 +166,39 @@ __device__ __forceinline__ unsigned long long gtime() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-#define TL(slot)                                                              \
-  do {                                                                        \
-    if (P.timeline) P.timeline[(size_t)blockIdx.x * 16 + (slot)] = gtime();   \
+#define TL(slot)                                                                                 \
+  do {                                                                                           \
+    if (P.timeline && (P.tl_tick < 0 || P.tl_tick == tick))                                      \
+      P.timeline[(size_t)blockIdx.x * 16 + (slot)] = gtime();                                    \
   } while (0)
 
 __device__ __forceinline__ int job_time(const EngineParams& P, const Job& jb, int tick) {
   int t = tick - jb.lag;
+  if (P.chunk_samples > 0 && jb.epi == EPI_PLAIN) return t;   // chunk index, see chunk_window
   if (P.reverse) t = (P.T - 1) - t;
   return t;
+}
+// Sample window [shift, limit) of a plain job.  Ordinary tables: the whole sample axis.  Chunk tables (products whose
+// operands become available one chunk of time steps at a time inside the persistent scans): chunk ce = event - lag
+// covers samples [ce * cs, (ce + 1) * cs) forward, [n_total - (ce + 1) * cs, n_total - ce * cs) in the reverse sweep,
+// clipped to [0, n_total); the job's own sample tile n0 is relative to `shift`.
+__device__ __forceinline__ bool chunk_window(const EngineParams& P, const Job& jb, int ce, int& shift, int& limit) {
+  shift = 0; limit = jb.pa.n_total;
+  if (P.chunk_samples <= 0) return true;
+  if (ce < 0) return false;
+  const long long cs = P.chunk_samples, nt = jb.pa.n_total;
+  if (!P.reverse) {
+    if (ce * cs >= nt) return false;
+    shift = (int)(ce * cs);
+    limit = (int)((ce + 1) * cs < nt ? (ce + 1) * cs : nt);
+  } else {
+    const long long hi = nt - ce * cs;
+    if (hi <= 0) return false;
+    const long long lo = hi - cs;
+    shift = (int)(lo > 0 ? lo : 0);
+    limit = (int)hi;
+  }
+  return true;
 }
 
 // A segment whose B operand is slot-indexed is skipped when its slot falls outside the plane
@@ -177,11 +206,16 @@ __device__ __forceinline__ int job_time(const EngineParams& P, const Job& jb, in
 __device__ __forceinline__ bool seg_valid(const EngineParams& P, const Seg& sg, int t) {
   if (sg.b_slot == NO_SLOT) return true;
   const int s = t + sg.b_slot;
-  return s >= 0 && s < P.raws[sg.b_map].slots;
+  return s >= 0 && s < sg.b_slots;
 }
 // total number of k blocks of the job at time t; 0 means "skip this job"
 __device__ __forceinline__ int job_total_kb(const EngineParams& P, const Job& jb, int t) {
   if (jb.epi != EPI_BWD_STATE && (t < 0 || t >= P.T)) return 0;
+  if (jb.epi == EPI_BWD_STATE && jb.lag != 0 && (t < 0 || t >= P.T)) return 0;   // single-time state jobs
+  if (jb.epi == EPI_PLAIN) {
+    int shift, limit;
+    if (!chunk_window(P, jb, t, shift, limit) || jb.n0 + shift >= limit) return 0;
+  }
   int n = 0;
   for (int s = 0; s < jb.nseg; ++s)
     if (seg_valid(P, jb.seg[s], t)) n += jb.seg[s].nkb;
@@ -209,23 +243,30 @@ struct EpiLocal {
   int epi, row0, m_valid, n0, slot_off;
   int B, H, Np, Hp, dstF;
   int n_pad, n_valid, n_total, flags;
+  int rowbias_ld;
   float scale;
   void *p0, *p1, *p2, *p3, *p4, *p5;
+  const float* pre;   // GATES / CAND: hoisted pre-activation terms [T][B][3H] (or null), added to base
   long long l0, l1, l2;
 };
-__device__ __forceinline__ EpiLocal make_epi_local(const Job& jb, const ScanCtx* ctx) {
+__device__ __forceinline__ EpiLocal make_epi_local(const Job& jb, const ScanCtx* ctx, int n_shift = 0,
+                                                   int n_limit = 0) {
   EpiLocal E;
   E.epi = jb.epi; E.row0 = jb.row0; E.m_valid = jb.m_valid; E.n0 = jb.n0;
   E.slot_off = jb.pa.n_pad;
   E.B = E.H = E.Np = E.Hp = E.dstF = 0;
-  E.n_pad = E.n_valid = E.n_total = E.flags = 0; E.scale = 1.0f;
+  E.n_pad = E.n_valid = E.n_total = E.flags = 0; E.scale = 1.0f; E.rowbias_ld = 0;
   E.p0 = E.p1 = E.p2 = E.p3 = E.p4 = E.p5 = nullptr;
+  E.pre = nullptr;
   E.l0 = E.l1 = E.l2 = 0;
   if (jb.epi == EPI_PLAIN) {
     E.p0 = jb.pa.out; E.p1 = (void*)jb.pa.bias; E.p2 = jb.pa.hi; E.p3 = jb.pa.lo;
     E.l0 = jb.pa.ldo; E.l1 = jb.pa.ldp; E.l2 = jb.pa.out_tstride;
     E.n_pad = jb.pa.n_pad; E.n_valid = jb.pa.n_valid; E.n_total = jb.pa.n_total; E.flags = jb.pa.flags;
     E.scale = jb.pa.scale;
+    E.rowbias_ld = jb.pa.rowbias_ld;
+    E.n0 = jb.n0 + n_shift;
+    if (n_limit > 0) E.n_total = n_limit;
     return E;
   }
   E.B = ctx->B; E.H = ctx->H; E.Np = ctx->Np; E.Hp = ctx->Hp;
@@ -233,9 +274,9 @@ __device__ __forceinline__ EpiLocal make_epi_local(const Job& jb, const ScanCtx*
   const LayerBuf& L = ctx->L[jb.layer];
   switch (jb.epi) {
     case EPI_GATES:
-      E.p0 = (void*)L.base; E.p1 = L.h; E.p2 = L.z; E.p3 = L.r; E.p4 = L.rh_hi; E.p5 = L.rh_lo; break;
+      E.p0 = (void*)L.base; E.p1 = L.h; E.p2 = L.z; E.p3 = L.r; E.p4 = L.rh_hi; E.p5 = L.rh_lo; E.pre = L.pre; break;
     case EPI_CAND:
-      E.p0 = (void*)L.base; E.p1 = L.h; E.p2 = L.z; E.p3 = L.c; E.p4 = L.h_hi; E.p5 = L.h_lo; break;
+      E.p0 = (void*)L.base; E.p1 = L.h; E.p2 = L.z; E.p3 = L.c; E.p4 = L.h_hi; E.p5 = L.h_lo; E.pre = L.pre; break;
     case EPI_BWD_RH:
       E.p0 = L.r; E.p1 = L.h; E.p2 = L.dh; E.p3 = L.da; E.p4 = L.da_hi; E.p5 = L.da_lo; break;
     case EPI_BWD_STATE:
@@ -247,13 +288,45 @@ __device__ __forceinline__ EpiLocal make_epi_local(const Job& jb, const ScanCtx*
 }
 
 // Thread <-> output row (feature).  v[j] is the accumulator for sample n_base + j.
+// sample index -> destination row: n = q * n_pad + r (block q of n_pad padded rows, row r) is stored at row
+// q * n_valid + r when r < n_valid.
+template <int W>
+struct EpiOps { float a[W], b[W], c[W]; };
+
+// operands of the plain epilogue that come from memory (old value for PF_ACC, row bias): requested for all W columns
+// before the accumulator is consumed, so that a tile costs one L2 round trip per W columns instead of one per element
+template <int W>
+__device__ __forceinline__ void epi_plain_load(const EpiLocal& E, int t, int row, int n_base, int ncols, EpiOps<W>& o) {
+  const bool acc = (E.flags & PF_ACC) != 0, rb = E.rowbias_ld > 0;
+  if (!acc && !rb) return;
+  const int f = E.row0 + row;
+  const float* out = E.p0 ? (const float*)E.p0 + (long long)t * E.l2 : nullptr;
+  const float* biasp = (const float*)E.p1;
+  int n = E.n0 + n_base, q = 0, r = n;
+  if (E.n_pad > 0) { q = n / E.n_pad; r = n - q * E.n_pad; }
+#pragma unroll
+  for (int j = 0; j < W; ++j, ++n) {
+    o.a[j] = 0.0f; o.b[j] = 0.0f;
+    const bool live = row < E.m_valid && j < ncols && n < E.n_total;
+    long long srow = n;
+    int rr = r;
+    if (E.n_pad > 0) {
+      srow = (long long)q * E.n_valid + rr;
+      if (++r == E.n_pad) { r = 0; ++q; }
+    }
+    if (!live || (E.n_pad > 0 && rr >= E.n_valid)) continue;
+    if (acc && out) o.a[j] = __ldcg((E.flags & PF_TRANS) ? out + (long long)f * E.l0 + srow : out + srow * E.l0 + f);
+    if (rb) o.b[j] = __ldg(biasp + (long long)rr * E.rowbias_ld + f);
+  }
+}
 template <int W>
 __device__ __forceinline__ void epi_plain(const EpiLocal& E, int t, int row, int n_base, int ncols,
-                                          const float* v) {
+                                          const float* v, const EpiOps<W>& o) {
   if (row >= E.m_valid) return;
   const int f = E.row0 + row;
   const float* biasp = (const float*)E.p1;
-  const float bias = biasp ? __ldg(biasp + f) : 0.0f;
+  const bool acc = (E.flags & PF_ACC) != 0, rb = E.rowbias_ld > 0;
+  const float bias = (biasp && !rb) ? __ldg(biasp + f) : 0.0f;
   float* out = E.p0 ? (float*)E.p0 + (long long)t * E.l2 : nullptr;
   bf16* hi = (bf16*)E.p2;
   bf16* lo = (bf16*)E.p3;
@@ -271,9 +344,10 @@ __device__ __forceinline__ void epi_plain(const EpiLocal& E, int t, int row, int
       if (rr >= E.n_valid) continue;
     }
     float y = v[j] * E.scale + bias;
+    if (rb) y += o.b[j];
     if (out) {
       float* p = (E.flags & PF_TRANS) ? out + (long long)f * E.l0 + srow : out + srow * E.l0 + f;
-      if (E.flags & PF_ACC) y += *p;
+      if (acc) y += o.a[j];
       *p = y;
     }
     if (hi) {
@@ -288,9 +362,6 @@ __device__ __forceinline__ void epi_plain(const EpiLocal& E, int t, int row, int
 
 // The scan epilogues are split in two stages so that callers can issue the operand loads BEFORE they consume
 // the accumulator (in-order issue: a load placed after the first use of an outstanding load cannot start).
-template <int W>
-struct EpiOps { float a[W], b[W], c[W]; };
-
 // ---- forward scan, gates tile: rows [0, 2H) of [update | reset]   (model.py:659-662)
 template <int W>
 __device__ __forceinline__ void epi_gates_load(const EpiLocal& E, int t, int row, int n_base, int ncols, EpiOps<W>& o) {
@@ -298,12 +369,14 @@ __device__ __forceinline__ void epi_gates_load(const EpiLocal& E, int t, int row
   const bool is_z = f < H;
   const int fr = is_z ? f : f - H;
   const float* __restrict__ basep = (const float*)E.p0 + (long long)t * E.l0 + H + f;
+  const float* __restrict__ prep = E.pre ? E.pre + (long long)t * B * 3 * H + H + f : nullptr;
   const float* __restrict__ hprev = (const float*)E.p1 + (long long)t * B * H + fr;
 #pragma unroll
   for (int j = 0; j < W; ++j) {
     const int b = n_base + j;
     const bool ok = row < E.m_valid && j < ncols && b < B;
     o.a[j] = ok ? __ldg(basep + (long long)b * 3 * H) : 0.0f;
+    if (prep && ok) o.a[j] += __ldcg(prep + (long long)b * 3 * H);
     o.b[j] = (ok && !is_z) ? hprev[(long long)b * H] : 0.0f;
   }
 }
@@ -339,6 +412,7 @@ __device__ __forceinline__ void epi_cand_load(const EpiLocal& E, int t, int row,
   const int H = E.H, B = E.B, f = E.row0 + row;
   const long long tb = (long long)t * B * H + f;
   const float* __restrict__ basep = (const float*)E.p0 + (long long)t * E.l0 + f;
+  const float* __restrict__ prep = E.pre ? E.pre + (long long)t * B * 3 * H + f : nullptr;
   const float* __restrict__ zp = (const float*)E.p2 + tb;
   const float* __restrict__ hp_ = (const float*)E.p1 + tb;
 #pragma unroll
@@ -346,6 +420,7 @@ __device__ __forceinline__ void epi_cand_load(const EpiLocal& E, int t, int row,
     const int b = n_base + j;
     const bool ok = row < E.m_valid && j < ncols && b < B;
     o.a[j] = ok ? __ldg(basep + (long long)b * 3 * H) : 0.0f;
+    if (prep && ok) o.a[j] += __ldcg(prep + (long long)b * 3 * H);
     o.b[j] = ok ? zp[(long long)b * H] : 0.0f;
     o.c[j] = ok ? hp_[(long long)b * H] : 0.0f;
   }
@@ -455,14 +530,14 @@ __device__ __forceinline__ void epilogue_load(const EpiLocal& E, int t, int row,
     case EPI_CAND: epi_cand_load<W>(E, t, row, n_base, ncols, o); break;
     case EPI_BWD_RH: epi_bwd_rh_load<W>(E, t, row, n_base, ncols, o); break;
     case EPI_BWD_STATE: epi_bwd_state_load<W>(E, t, row, n_base, ncols, o); break;
-    default: break;
+    default: epi_plain_load<W>(E, t, row, n_base, ncols, o); break;
   }
 }
 template <int W>
 __device__ __forceinline__ void epilogue_apply(const EpiLocal& E, int t, int row, int n_base, int ncols,
                                                const float* v, const EpiOps<W>& o) {
   switch (E.epi) {
-    case EPI_PLAIN: epi_plain<W>(E, t, row, n_base, ncols, v); break;
+    case EPI_PLAIN: epi_plain<W>(E, t, row, n_base, ncols, v, o); break;
     case EPI_GATES: epi_gates_apply<W>(E, t, row, n_base, ncols, v, o); break;
     case EPI_CAND: epi_cand_apply<W>(E, t, row, n_base, ncols, v, o); break;
     case EPI_BWD_RH: epi_bwd_rh_apply<W>(E, t, row, n_base, ncols, v, o); break;
@@ -475,6 +550,183 @@ __device__ __forceinline__ void run_epilogue(const EpiLocal& E, int t, int row, 
   EpiOps<W> o;
   epilogue_load<W>(E, t, row, n_base, ncols, o);
   epilogue_apply<W>(E, t, row, n_base, ncols, v, o);
+}
+
+
+// ------------------------------------------------------------------ quad epilogues (split-K finish)
+// Thread <-> FOUR consecutive output rows (features) of ONE sample column: every global access of the finish is a
+// 128-bit access (fp32 stashes [.][b][f], partial tiles [col][row], operand planes 4 x bf16 = 8 bytes), and all
+// loads of a thread's items are issued together: ONE L2 round trip per finish instead of one per 4-column item.
+// Data produced earlier in the same persistent launch is read with ld.global.cg (L2), never through L1.
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 f4zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ float4 f4add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+// 4 floats -> 4 bf16 hi + 4 bf16 lo (same rounding as split_bf16), packed for one 8-byte store each
+__device__ __forceinline__ void split4(float4 x, uint2& hi, uint2& lo) {
+  const __nv_bfloat162 h01 = __floats2bfloat162_rn(x.x, x.y), h23 = __floats2bfloat162_rn(x.z, x.w);
+  const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+  const __nv_bfloat162 l01 = __floats2bfloat162_rn(x.x - f01.x, x.y - f01.y);
+  const __nv_bfloat162 l23 = __floats2bfloat162_rn(x.z - f23.x, x.w - f23.y);
+  hi.x = *reinterpret_cast<const uint32_t*>(&h01); hi.y = *reinterpret_cast<const uint32_t*>(&h23);
+  lo.x = *reinterpret_cast<const uint32_t*>(&l01); lo.y = *reinterpret_cast<const uint32_t*>(&l23);
+}
+struct QOps { float4 a, b, c, d; };
+
+// can this job's split-K finish use the quad path?  (feature counts divisible by 4, aligned stashes)
+__device__ __forceinline__ bool quad_ok(const EpiLocal& E) {
+  if (E.epi == EPI_PLAIN) return false;
+  if ((E.m_valid & 3) || (E.row0 & 3)) return false;
+  if (E.epi == EPI_BWD_STATE) return (E.dstF & 3) == 0;
+  return (E.H & 3) == 0 && (E.Hp & 3) == 0;
+}
+
+__device__ __forceinline__ void q_load(const EpiLocal& E, int t, int rq, int b, QOps& o) {
+  const int H = E.H, B = E.B, f = E.row0 + 4 * rq;
+  o.a = o.b = o.c = o.d = f4zero();
+  if (4 * rq >= E.m_valid || b >= B) return;
+  switch (E.epi) {
+    case EPI_GATES: {
+      const bool is_z = f < H;
+      const int fr = is_z ? f : f - H;
+      o.a = ldg4((const float*)E.p0 + (long long)t * E.l0 + (long long)b * 3 * H + H + f);
+      if (E.pre) o.d = ldcg4(E.pre + ((long long)t * B + b) * 3 * H + H + f);
+      if (!is_z) o.b = ldcg4((const float*)E.p1 + ((long long)t * B + b) * H + fr);
+    } break;
+    case EPI_CAND: {
+      const long long tb = ((long long)t * B + b) * H + f;
+      o.a = ldg4((const float*)E.p0 + (long long)t * E.l0 + (long long)b * 3 * H + f);
+      if (E.pre) o.d = ldcg4(E.pre + ((long long)t * B + b) * 3 * H + f);
+      o.b = ldcg4((const float*)E.p2 + tb);
+      o.c = ldcg4((const float*)E.p1 + tb);
+    } break;
+    case EPI_BWD_RH: {
+      const long long tb = ((long long)t * B + b) * H + f;
+      o.a = ldcg4((const float*)E.p0 + tb);
+      o.b = ldcg4((const float*)E.p1 + tb);
+      o.c = ldcg4((const float*)E.p2 + tb);
+    } break;
+    case EPI_BWD_STATE:
+      o.a = ldcg4((const float*)E.p0 + ((long long)(t + E.slot_off) * B + b) * E.dstF + f);
+      break;
+    default: break;
+  }
+}
+
+// after ALL loads of a batch have been issued: fold the hoisted term into the base term (frees o.d)
+__device__ __forceinline__ void q_merge(QOps& o) { o.a = f4add(o.a, o.d); }
+
+__device__ __forceinline__ void q_apply(const EpiLocal& E, int t, int rq, int b, float4 v, const QOps& o) {
+  const int H = E.H, B = E.B, f = E.row0 + 4 * rq;
+  if (4 * rq >= E.m_valid || b >= B) return;
+  switch (E.epi) {
+    case EPI_GATES: {
+      const bool is_z = f < H;
+      const int fr = is_z ? f : f - H;
+      float4 g;
+      g.x = sigmoidf_fast(v.x + o.a.x); g.y = sigmoidf_fast(v.y + o.a.y);
+      g.z = sigmoidf_fast(v.z + o.a.z); g.w = sigmoidf_fast(v.w + o.a.w);
+      *reinterpret_cast<float4*>((float*)(is_z ? E.p2 : E.p3) + ((long long)t * B + b) * H + fr) = g;
+      if (!is_z) {
+        uint2 hh, ll;
+        split4(make_float4(g.x * o.b.x, g.y * o.b.y, g.z * o.b.z, g.w * o.b.w), hh, ll);
+        const long long po = ((long long)t * E.Np + b) * E.Hp + fr;
+        *reinterpret_cast<uint2*>((bf16*)E.p4 + po) = hh;
+        *reinterpret_cast<uint2*>((bf16*)E.p5 + po) = ll;
+      }
+    } break;
+    case EPI_CAND: {
+      const long long tb = ((long long)t * B + b) * H + f;
+      float4 cc, hn;
+      cc.x = tanhf_fast(v.x + o.a.x); cc.y = tanhf_fast(v.y + o.a.y);
+      cc.z = tanhf_fast(v.z + o.a.z); cc.w = tanhf_fast(v.w + o.a.w);
+      hn.x = cc.x * o.b.x + o.c.x * (1.0f - o.b.x); hn.y = cc.y * o.b.y + o.c.y * (1.0f - o.b.y);
+      hn.z = cc.z * o.b.z + o.c.z * (1.0f - o.b.z); hn.w = cc.w * o.b.w + o.c.w * (1.0f - o.b.w);
+      *reinterpret_cast<float4*>((float*)E.p3 + tb) = cc;
+      *reinterpret_cast<float4*>((float*)E.p1 + tb + (long long)B * H) = hn;   // slot t + 1
+      uint2 hh, ll;
+      split4(hn, hh, ll);
+      const long long po = ((long long)(t + 1) * E.Np + b) * E.Hp + f;
+      *reinterpret_cast<uint2*>((bf16*)E.p4 + po) = hh;
+      *reinterpret_cast<uint2*>((bf16*)E.p5 + po) = ll;
+    } break;
+    case EPI_BWD_RH: {
+      const long long tb = ((long long)t * B + b) * H + f;
+      float4 dhn, dag;
+      dhn.x = o.c.x + v.x * o.a.x; dhn.y = o.c.y + v.y * o.a.y; dhn.z = o.c.z + v.z * o.a.z; dhn.w = o.c.w + v.w * o.a.w;
+      dag.x = (v.x * o.b.x) * o.a.x * (1.0f - o.a.x); dag.y = (v.y * o.b.y) * o.a.y * (1.0f - o.a.y);
+      dag.z = (v.z * o.b.z) * o.a.z * (1.0f - o.a.z); dag.w = (v.w * o.b.w) * o.a.w * (1.0f - o.a.w);
+      *reinterpret_cast<float4*>((float*)E.p2 + tb) = dhn;
+      *reinterpret_cast<float4*>((float*)E.p3 + ((long long)t * B + b) * 3 * H + 2 * H + f) = dag;
+      uint2 hh, ll;
+      split4(dag, hh, ll);
+      const long long po = ((long long)t * E.Np + b) * (3 * E.Hp) + E.Hp + H + f;
+      *reinterpret_cast<uint2*>((bf16*)E.p4 + po) = hh;
+      *reinterpret_cast<uint2*>((bf16*)E.p5 + po) = ll;
+    } break;
+    case EPI_BWD_STATE:
+      *reinterpret_cast<float4*>((float*)E.p0 + ((long long)(t + E.slot_off) * B + b) * E.dstF + f) = f4add(o.a, v);
+      break;
+    default: break;
+  }
+}
+
+// Finish of one split-K part, flat layout: per batch a thread handles CB = min(QC, QS / ksplit) columns and keeps
+// ksplit * CB <= QS partial-tile quads in flight (slot i <-> column i / ksplit, part i % ksplit), so the register
+// footprint does not depend on how a table happens to be split.  Column sums run in part order (deterministic).
+constexpr int QC = 4;    // columns per batch (operand registers)
+constexpr int QS = 12;   // partial-tile slots per batch
+struct QBatch { float4 a[QC], b[QC], c[QC]; };
+
+__device__ __forceinline__ int q_cols_per_batch(int ksplit) { return ksplit <= 3 ? QC : (QS / ksplit < QC ? QS / ksplit : QC); }
+
+// request the operands of batch k0 (columns c_lo + ew + nwarps * (k0 + k), k < cb); all loads first, merges after
+__device__ __forceinline__ void q_batch_load(const EpiLocal& E, int t, int lane, int ew, int nwarps, int c_lo, int c_hi,
+                                             int cb, int k0, QBatch& q) {
+  float4 d[QC];
+#pragma unroll
+  for (int k = 0; k < QC; ++k) {
+    const int c = c_lo + ew + nwarps * (k0 + k);
+    QOps o;
+    q_load(E, t, lane, (k < cb && c < c_hi) ? c : (1 << 30), o);
+    q.a[k] = o.a; q.b[k] = o.b; q.c[k] = o.c; d[k] = o.d;
+  }
+#pragma unroll
+  for (int k = 0; k < QC; ++k) q.a[k] = f4add(q.a[k], d[k]);
+}
+
+__device__ __forceinline__ void q_finish(const EpiLocal& E, int t, int lane, int ew, int nwarps, int c_lo, int c_hi,
+                                         int ksplit, int n_cols, const float* base, QBatch& q) {
+  const int cb = q_cols_per_batch(ksplit);
+  for (int k0 = 0; c_lo + ew + nwarps * k0 < c_hi; k0 += cb) {
+    float4 x[QS];
+    {
+      int kk = 0, pp = 0;
+#pragma unroll
+      for (int i = 0; i < QS; ++i) {
+        const int c = c_lo + ew + nwarps * (k0 + kk);
+        x[i] = (kk < cb && c < c_hi) ? ldcg4(base + ((size_t)pp * n_cols + c) * TILE_M + 4 * lane) : f4zero();
+        if (++pp == ksplit) { pp = 0; ++kk; }
+      }
+    }
+    if (k0 > 0) q_batch_load(E, t, lane, ew, nwarps, c_lo, c_hi, cb, k0, q);   // first batch: requested at phase start
+#pragma unroll
+    for (int k = 0; k < QC; ++k) {
+      float4 v = f4zero();
+      int kk = 0, pp = 0;
+#pragma unroll
+      for (int i = 0; i < QS; ++i) {
+        if (kk == k) v = f4add(v, x[i]);
+        if (++pp == ksplit) { pp = 0; ++kk; }
+      }
+      const int c = c_lo + ew + nwarps * (k0 + k);
+      if (k < cb && c < c_hi) {
+        QOps o;
+        o.a = q.a[k]; o.b = q.b[k]; o.c = q.c[k]; o.d = f4zero();
+        q_apply(E, t, lane, c, v, o);
+      }
+    }
+  }
 }
 
 // grid barrier wait (defined with the persistent-kernel helpers below)
@@ -561,10 +813,10 @@ __device__ __forceinline__ void producer_load_a(Pipe& p, const Seg& sg, int kb, 
   }
 }
 __device__ __forceinline__ void producer_load_b(Pipe& p, const Seg& sg, int kb, int t, const CUtensorMap* mb,
-                                                uint8_t* st, uint64_t* fb) {
+                                                uint8_t* st, uint64_t* fb, int n_shift) {
   if (sg.b_slot == NO_SLOT) {
-    tma_load_2d(st + 2 * p.a_bytes, mb, fb, sg.b_k + kb * KB, sg.b_row);
-    tma_load_2d(st + 2 * p.a_bytes + p.b_bytes, mb + 1, fb, sg.b_k + kb * KB, sg.b_row);
+    tma_load_2d(st + 2 * p.a_bytes, mb, fb, sg.b_k + kb * KB, sg.b_row + n_shift);
+    tma_load_2d(st + 2 * p.a_bytes + p.b_bytes, mb + 1, fb, sg.b_k + kb * KB, sg.b_row + n_shift);
   } else {
     tma_load_3d(st + 2 * p.a_bytes, mb, fb, sg.b_k + kb * KB, sg.b_row, t + sg.b_slot);
     tma_load_3d(st + 2 * p.a_bytes + p.b_bytes, mb + 1, fb, sg.b_k + kb * KB, sg.b_row, t + sg.b_slot);
@@ -584,6 +836,7 @@ __device__ __forceinline__ void producer_run(Pipe& p, const EngineParams& P, int
     pol_keep = fr == 0 ? l2_policy_evict_last() : (fr == 1 ? l2_policy_evict_last_075() : l2_policy_evict_last_050());
   }
   bool waited = (gridbar == nullptr) || target == 0;
+  const uint32_t tx_bytes = 2 * p.a_bytes + 2 * p.b_bytes;   // <= stage_bytes (the ring is sized for the widest phase)
   for (int j = blockIdx.x; j < P.njobs; j += gridDim.x) {
     const Job& jb = P.jobs[j];
     const int t = job_time(P, jb, tick);
@@ -591,6 +844,8 @@ __device__ __forceinline__ void producer_run(Pipe& p, const EngineParams& P, int
     if (total_kb == 0) continue;
     int klo, khi;
     job_kb_range(jb, total_kb, klo, khi);
+    int n_shift = 0;
+    if (jb.epi == EPI_PLAIN && P.chunk_samples > 0) { int lim; chunk_window(P, jb, t, n_shift, lim); }
     int early = 0;   // k blocks of this job whose weight tiles were issued before the barrier
     if (!waited) {
       // ---- pass 1: weight tiles of the first min(nstages, khi - klo) k blocks
@@ -610,6 +865,7 @@ __device__ __forceinline__ void producer_run(Pipe& p, const EngineParams& P, int
         }
       }
       grid_wait_ext(gridbar, target);
+      TL(10);
       waited = true;
     }
     // ---- pass 2: everything else, in ring order
@@ -625,12 +881,12 @@ __device__ __forceinline__ void producer_run(Pipe& p, const EngineParams& P, int
         uint64_t* fb = &p.full_bar[p.stage];
         if (done < early) {
           mbar_expect_tx(fb, 2 * p.b_bytes);           // arrive + the activation bytes
-          producer_load_b(p, sg, kb, t, mb, st, fb);
+          producer_load_b(p, sg, kb, t, mb, st, fb, n_shift);
         } else {
           mbar_wait(&p.empty_bar[p.stage], p.phase ^ 1);
-          mbar_expect_tx(fb, p.stage_bytes);
+          mbar_expect_tx(fb, tx_bytes);
           producer_load_a(p, sg, kb, ma, st, fb, pol_keep);
-          producer_load_b(p, sg, kb, t, mb, st, fb);
+          producer_load_b(p, sg, kb, t, mb, st, fb, n_shift);
         }
         ++done;
         if (++p.stage == p.nstages) { p.stage = 0; p.phase ^= 1; }
@@ -695,6 +951,9 @@ __device__ __forceinline__ void mma_run(Pipe& p, const EngineParams& P, int tick
 #ifndef PB_PART_W
 #define PB_PART_W 16   // columns per tcgen05.ld when a split-K partial tile is parked
 #endif
+#ifndef PB_QMAX
+#define PB_QMAX 4     // columns per warp whose loads are in flight together in the quad split-K finish
+#endif
 #ifndef PB_TMEM_W
 #define PB_TMEM_W 8   // columns per tcgen05.ld chunk of the unsplit (TMEM) epilogue path
 #endif
@@ -720,8 +979,21 @@ __device__ __forceinline__ void epilogue_run(Pipe& p, const EngineParams& P, int
     const bool have_acc = khi > klo;
     const int buf = p.it & 1;
     const uint32_t use = (uint32_t)(p.it >> 1);
-    const EpiLocal E = make_epi_local(jb, P.ctx);
+    int cw_shift = 0, cw_limit = 0;
+    if (jb.epi == EPI_PLAIN && P.chunk_samples > 0) chunk_window(P, jb, t, cw_shift, cw_limit);
+    const EpiLocal E = make_epi_local(jb, P.ctx, cw_shift, cw_limit);
     const int ksplit = jb.ksplit, kpart = jb.kpart, group = jb.group;
+    // Quad finish (cooperative split-K only): this part finishes columns [qc_lo, qc_hi) of the tile; warp ew takes
+    // columns qc_lo + ew, + NEW, ...; lane = row quad.  The epilogue operands of the first QMAX columns are requested
+    // NOW, before the accumulator is complete: they only depend on the previous phase (already behind the grid
+    // barrier), so their latency hides under the MMAs and the partial-tile exchange.
+    const bool quad = ksplit > 1 && P.coop_epilogue && quad_ok(E);
+    constexpr int NEW = EPI_GROUP_THREADS / 32;
+    const int ew = warp - 2;
+    const int qc_lo = (n_cols * kpart) / ksplit, qc_hi = (n_cols * (kpart + 1)) / ksplit;
+    QBatch qb;
+    if (quad) q_batch_load(E, t, lane, ew, NEW, qc_lo, qc_hi, q_cols_per_batch(ksplit), 0, qb);
+    if (threadIdx.x == 64) TL(9);
     if (tmem_warp) {
       const uint32_t taddr = p.tmem_base + (uint32_t)buf * 256u + ((uint32_t)(q * 32) << 16);
       if (have_acc) {
@@ -819,6 +1091,9 @@ __device__ __forceinline__ void epilogue_run(Pipe& p, const EngineParams& P, int
         if (threadIdx.x == 64) TL(6);
         if (*p.split_flag) { c_lo = 0; c_hi = n_cols; }
       }
+      if (quad) {
+        q_finish(E, t, lane, ew, NEW, qc_lo, qc_hi, ksplit, n_cols, base, qb);
+      } else {
       __threadfence();
       // work item = (row, group of 4 columns); consecutive threads take consecutive rows (coalesced).  All loads of
       // an item (partial tiles + epilogue operands) are issued before the first use.  (8-column items halve the
@@ -871,6 +1146,7 @@ __device__ __forceinline__ void epilogue_run(Pipe& p, const EngineParams& P, int
 #endif
         epilogue_apply<IW>(E, t, r, n0, nc, v, ops);
       }
+      }   // !quad
       if (threadIdx.x == 64) TL(7);
       epi_group_sync();
       if (P.coop_epilogue && warp == 2 && lane == 0) {
@@ -892,6 +1168,7 @@ __device__ __forceinline__ uint8_t* align_smem(uint8_t* raw) {
 __global__ void __launch_bounds__(ENGINE_THREADS, 1) job_kernel_tc(const EngineParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tick = P.tick;
   if (threadIdx.x == 0) TL(0);
   Pipe p;
   pipe_setup(p, align_smem(smem_raw), P.n_cols);
@@ -939,7 +1216,9 @@ __global__ void __launch_bounds__(128) job_kernel_simt(const EngineParams P) {
     const int t = job_time(P, jb, P.tick);
     if (job_total_kb(P, jb, t) == 0) continue;
     if (jb.ksplit > 1 && jb.kpart != 0) continue;   // the SIMT twin does not split: part 0 does the whole tile
-    const EpiLocal E = make_epi_local(jb, P.ctx);
+    int cw_shift = 0, cw_limit = 0;
+    if (jb.epi == EPI_PLAIN && P.chunk_samples > 0) chunk_window(P, jb, t, cw_shift, cw_limit);
+    const EpiLocal E = make_epi_local(jb, P.ctx, cw_shift, cw_limit);
     for (int n0 = 0; n0 < P.n_cols; n0 += 32) {
       const int nc = (P.n_cols - n0 >= 32) ? 32 : (P.n_cols - n0);
       float acc[32];
@@ -967,7 +1246,7 @@ __global__ void __launch_bounds__(128) job_kernel_simt(const EngineParams P) {
           }
           for (int e = tid; e < 32 * KB; e += 128) {
             const int r = e / KB, k = e % KB;
-            const int gr = sg.b_row + n0 + r, gk = sg.b_k + kb * KB + k;
+            const int gr = sg.b_row + (sg.b_slot == NO_SLOT ? cw_shift : 0) + n0 + r, gk = sg.b_k + kb * KB + k;
             float x = 0.0f;
             if (r < nc && gr < rb.rows && gk < rb.cols) {
               const long long o = bslot + (long long)gr * rb.row_pitch + gk;

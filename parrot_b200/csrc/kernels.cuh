@@ -33,7 +33,9 @@ struct AttnFwdArgs {
   float* ab_out;        // [B][2A]  alpha | beta
   float* e_out;         // [B][3A]  exp(a_hat) (softmax: probabilities) | exp(b_hat) | exp(k_hat)
   float* hat;           // [B][3A] scratch: pre-activations when the projection runs as its own stage (or null)
+  float* hat_part;      // [H/32][B][3A] scratch: K-sliced partial projections (persistent scan / stand-alone step)
 };
+constexpr int ATT_KS = 32;   // features per projection slice
 
 // Executed by every thread of the CTA for batch row b; `sh` needs
 // rup(H,4) + 2*rup(3A,4) + rup(U,4) + nwarps*C floats.  Ends with a CTA barrier (sh may be reused).
@@ -227,6 +229,180 @@ __device__ __forceinline__ void attention_fwd_body(const AttnFwdArgs& a, const i
     }
   }
   __syncthreads();
+}
+
+
+// ---- projection stage, K-sliced (persistent scan and stand-alone step): CTA `slice` owns ATT_KS consecutive
+// features of h1 and produces hat_part[slice][b][j] = sum_{k in slice} h1[b][k] * wT[j][k] for all rows / outputs.
+// The window stage adds the slices in slice order (deterministic).  sh: (B + 3A) * (ATT_KS + 1) floats.
+__device__ __forceinline__ void attention_proj_slice(const AttnFwdArgs& a, const int slice, float* sh) {
+  const int A3 = 3 * a.A, k0 = slice * ATT_KS;
+  float* sh_h = sh;                              // [B][ATT_KS + 1]
+  float* sh_w = sh + a.B * (ATT_KS + 1);         // [3A][ATT_KS + 1]
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int i = tid; i < a.B * ATT_KS; i += nt) {
+    const int b = i / ATT_KS, k = i % ATT_KS;
+    sh_h[b * (ATT_KS + 1) + k] = __ldcg(a.h1 + (long long)b * a.H + k0 + k);
+  }
+  for (int i = tid; i < A3 * ATT_KS; i += nt) {
+    const int j = i / ATT_KS, k = i % ATT_KS;
+    sh_w[j * (ATT_KS + 1) + k] = __ldg(a.wT + (long long)j * a.H + k0 + k);
+  }
+  __syncthreads();
+  float* out = a.hat_part + (long long)slice * a.B * A3;
+  for (int i = tid; i < a.B * A3; i += nt) {
+    const int b = i / A3, j = i % A3;
+    const float* hr = sh_h + b * (ATT_KS + 1);
+    const float* wr = sh_w + j * (ATT_KS + 1);
+    float s = 0.0f;
+#pragma unroll
+    for (int k = 0; k < ATT_KS; ++k) s = fmaf(hr[k], wr[k], s);
+    out[i] = s;
+  }
+  __syncthreads();
+}
+
+// ---- window stage: CTA (b, part) of `nparts` CTAs per batch row.  Every part recomputes the (cheap) mixture
+// parameters and phi for the row -- identical bits -- and reduces its own slice of the context columns; part 0
+// writes kappa / alpha / beta / phi.  hat comes from the K-sliced partials (nslices > 0) or from a.hat.
+// sh: 2*rup(3A,4) + rup(U,4) + nwarps*Cs floats (Cs = C / nparts).
+template <bool WIDE>
+__device__ __forceinline__ void attention_window_part(const AttnFwdArgs& a, const int b, const int part,
+                                                      const int nparts, const int nslices, float* sh) {
+  const int A3p = (3 * a.A + 3) & ~3;
+  float* sh_hat = sh;               // 3A
+  float* sh_abk = sh_hat + A3p;     // 3A : alpha, beta, kappa
+  float* sh_phi = sh_abk + A3p;     // U
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int A = a.A;
+  const float k_prev_reg = (tid < A) ? __ldcg(a.k_prev + (long long)b * A + tid) : 0.0f;
+  if (tid < 3 * A) {
+    float s;
+    if (nslices > 0) {
+      s = 0.0f;
+      const float* src = a.hat_part + (long long)b * 3 * A + tid;
+      const long long sstride = (long long)a.B * 3 * A;
+#pragma unroll 8
+      for (int q = 0; q < nslices; ++q) s += __ldcg(src + q * sstride);   // slice order
+      s += __ldg(a.batt + tid);
+    } else {
+      s = __ldcg(a.hat + (long long)b * 3 * A + tid);
+    }
+    sh_hat[tid] = s;
+  }
+  __syncthreads();
+  if (tid < A) {
+    float ea;
+    if (a.type == 1) {
+      float m = sh_hat[0];
+      for (int i = 1; i < A; ++i) m = fmaxf(m, sh_hat[i]);
+      float sum = 0.0f;
+      for (int i = 0; i < A; ++i) sum += expf(sh_hat[i] - m);
+      ea = expf(sh_hat[tid] - m) / sum;
+    } else {
+      ea = expf(sh_hat[tid]);
+    }
+    const float eb = expf(sh_hat[A + tid]);
+    const float ek = expf(sh_hat[2 * A + tid]);
+    const float alpha = ea + a.eps;
+    const float beta = (a.sharp == 1.0f ? eb : eb * a.sharp) + a.eps;
+    const float step = (a.timing == 1.0f) ? a.align * ek : (a.align * ek) / a.timing;
+    const float kappa = k_prev_reg + step;
+    sh_abk[tid] = alpha;
+    sh_abk[A + tid] = beta;
+    sh_abk[2 * A + tid] = kappa;
+    if (part == 0) {
+      a.k_out[(long long)b * A + tid] = kappa;
+      a.ab_out[(long long)b * 2 * A + tid] = alpha;
+      a.ab_out[(long long)b * 2 * A + A + tid] = beta;
+      a.e_out[(long long)b * 3 * A + tid] = ea;
+      a.e_out[(long long)b * 3 * A + A + tid] = eb;
+      a.e_out[(long long)b * 3 * A + 2 * A + tid] = ek;
+    }
+  }
+  __syncthreads();
+  for (int u = tid; u < a.U; u += blockDim.x) {
+    const float uf = (float)u;
+    float phi = 0.0f;
+    for (int i = 0; i < A; ++i) {
+      const float d = __fsub_rn(sh_abk[2 * A + i], uf);
+      const float d2 = __fmul_rn(d, d);
+      float term;
+      if (a.type == 1) {
+        const float t1 = __fmul_rn(sh_abk[i], sqrtf(sh_abk[A + i]));
+        term = __fmul_rn(t1, expf(__fmul_rn(__fmul_rn(-0.5f, sh_abk[A + i]), d2)));
+      } else {
+        term = __fmul_rn(sh_abk[i], expf(__fmul_rn(-sh_abk[A + i], d2)));
+      }
+      phi = __fadd_rn(phi, term);
+    }
+    if (a.type == 1) phi = __fmul_rn(SQRT_1_2PI_F, phi);
+    sh_phi[u] = phi;
+    if (part == 0) a.phi_out[(long long)b * a.U + u] = phi;
+  }
+  __syncthreads();
+  // w[c] for c in [c_base, c_base + Cs): warp w reduces its slice of text positions (same partition and order as
+  // attention_fwd_body: the result is bit-identical to the one-CTA-per-row kernel)
+  const int Cs = a.C / nparts, c_base = part * Cs;
+  float* sh_part = sh_phi + ((a.U + 3) & ~3);   // [nwarp][Cs]
+  const float* cb = a.ctx + (long long)b * a.U * a.C + c_base;
+  const int nwarp = blockDim.x >> 5;
+  const int per = (a.U + nwarp - 1) / nwarp;
+  const int u0 = warp * per, u1 = min(a.U, u0 + per);
+  if (WIDE && (Cs & 3) == 0 && (a.C & 3) == 0) {
+    for (int c = lane * 4; c < Cs; c += 128) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int ub = u0; ub < u1; ub += 16) {
+        float4 x[16];
+#pragma unroll
+        for (int r = 0; r < 16; ++r)
+          x[r] = (ub + r < u1) ? __ldg(reinterpret_cast<const float4*>(cb + (long long)(ub + r) * a.C + c))
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+          if (ub + r < u1) {
+            const float p = sh_phi[ub + r];
+            acc.x = fmaf(p, x[r].x, acc.x); acc.y = fmaf(p, x[r].y, acc.y);
+            acc.z = fmaf(p, x[r].z, acc.z); acc.w = fmaf(p, x[r].w, acc.w);
+          }
+        }
+      }
+      *reinterpret_cast<float4*>(sh_part + (long long)warp * Cs + c) = acc;
+    }
+  } else {
+    for (int c = lane; c < Cs; c += 32) {
+      float acc = 0.0f;
+      for (int u = u0; u < u1; ++u) acc = fmaf(sh_phi[u], cb[(long long)u * a.C + c], acc);
+      sh_part[(long long)warp * Cs + c] = acc;
+    }
+  }
+  __syncthreads();
+  for (int c = tid; c < Cs; c += blockDim.x) {
+    float w = 0.0f;
+    for (int q = 0; q < nwarp; ++q) w += sh_part[(long long)q * Cs + c];
+    a.w_out[(long long)b * a.C + c_base + c] = w;
+    if (a.w_hi) {
+      bf16 hh, ll;
+      split_bf16(w, hh, ll);
+      a.w_hi[(long long)b * a.Cp + c_base + c] = hh;
+      a.w_lo[(long long)b * a.Cp + c_base + c] = ll;
+    }
+  }
+  __syncthreads();
+}
+// CTAs per batch row of the window stage for a grid of `ctas`: C must split into float4-aligned slices
+__host__ __device__ __forceinline__ int attention_nparts(int B, int C, int ctas) {
+  int n = 1;
+  while (n < 4 && 2 * n * B <= ctas && C % (8 * n) == 0 && C / (2 * n) >= 64) n *= 2;
+  return n;
+}
+__global__ void __launch_bounds__(256) attention_proj_slice_kernel(const AttnFwdArgs a) {
+  extern __shared__ float sh[];
+  attention_proj_slice(a, blockIdx.x, sh);
+}
+__global__ void __launch_bounds__(256) attention_window_kernel(const AttnFwdArgs a, const int nparts, const int nslices) {
+  extern __shared__ float sh[];
+  attention_window_part<true>(a, blockIdx.x / nparts, blockIdx.x % nparts, nparts, nslices, sh);
 }
 
 __global__ void __launch_bounds__(256) attention_fwd_kernel(const AttnFwdArgs a, const int precomputed_hat) {
@@ -511,24 +687,33 @@ __global__ void gru_bwd_pre_kernel(const ScanCtx* cp, const PreArgs pa) {
 // kernel boundaries; the GEMM pipeline state (smem ring, TMEM accumulators) lives across phases.
 // =========================================================================
 constexpr int ATT_SMEM_BYTES = 24 * 1024;
+// Chunk-lagged layer wavefront.  Layer l runs `l * Tc` decoder steps behind layer 1 (forward; reversed in the
+// backward sweep), so every product whose operand comes from a LOWER layer (h1 -> rnn2/rnn3, h2 -> rnn3, w_t -> rnn2/3)
+// or from the teacher-forced frames is hoisted out of the per-step recurrence into a batched "chunk" product over
+// Tc steps at a time, executed by the same persistent kernel every Tc ticks.  Per tick the recurrent phases stream
+// only state_to_gates / state_to_state (+ the attention context product of layer 1): 41 MB of operand planes at the
+// base configuration instead of 86 MB, a set that stays L2-resident.
 struct ScanFwdParams {
-  EngineParams A, B;   // tables fwdA (gates) / fwdB (candidates)
+  EngineParams A, B;   // gates / candidates of all three layers (lags 0, Tc, 2 Tc)
+  EngineParams G;      // chunk products: pre2 of chunk e, pre3 of chunk e - 1 (njobs may be 0)
   AttnFwdArgs att;     // pointers of step 0
   long long s_h1, s_k, s_w, s_wp, s_phi, s_ab, s_e;   // per-step strides (elements)
-  int T;
+  int T, Tc, nticks;
+  int att_parts, att_slices;    // window CTAs per batch row, projection slices
   unsigned int* gridbar;
   unsigned long long* stamps;   // debug: [cta][bar][2] globaltimer at (barrier wait done, arrival) or null
   int stamp_bars;
-  unsigned long long* tl_buf;   // debug: [2 phases][cta][16] intra-phase milestones of tick tl_tick
+  unsigned long long* tl_buf;   // debug (unused by the kernel since the quad finish; kept for the tools)
   int tl_tick;
   int prefetch;                 // 1: weight tiles of the next phase are issued before its grid barrier
 };
 struct ScanBwdParams {
-  EngineParams B1, B2;  // tables bwd1 / bwd2
+  EngineParams B1, B2;  // d(r*h) products / recurrent state dgrads of all three layers
+  EngineParams G;       // chunk dgrads: from da3 of range e into dh2 / dh1 / dw, from da2 of range e - 1 into dh1 / dw
   AttnBwdArgs att;      // pointers of step 0
   long long s_dw, s_ab, s_e, s_k, s_dh1, s_datt, s_dattp;
   const ScanCtx* ctx;
-  int T;
+  int T, Tc, nticks;
   unsigned int* gridbar;
   unsigned long long* stamps;
   int stamp_bars;
@@ -552,6 +737,9 @@ __device__ __forceinline__ void persistent_gemm_phase(Pipe& p, const EngineParam
   (void)which;
   unsigned int* gridbar = S.gridbar;
   const unsigned int target = bar * gridDim.x;
+  // the accumulator width of this phase (the smem ring keeps the stage stride chosen at kernel start)
+  p.n_cols = P.n_cols;
+  p.b_bytes = (uint32_t)P.n_cols * KB * 2;
   if (warp == 0) {
     if (lane == 0) {
       if (S.prefetch) producer_run(p, P, tick, gridbar, target);   // weight tiles ahead of the barrier
@@ -566,11 +754,11 @@ __device__ __forceinline__ void persistent_gemm_phase(Pipe& p, const EngineParam
   } else {
     if (warp == 2 && lane == 0 && bar) grid_wait(gridbar, target);   // one poller for the epilogue warps
     epi_group_sync();
-    if (threadIdx.x == 64) STAMP(S, bar, 0);
+    if (threadIdx.x == 64) { STAMP(S, bar, 0); TL(1); }
     epilogue_run(p, P, tick);
     asm volatile("fence.proxy.async.global;" ::: "memory");
     epi_group_sync();
-    if (threadIdx.x == 64) { STAMP(S, bar, 1); grid_arrive(gridbar); }
+    if (threadIdx.x == 64) { STAMP(S, bar, 1); TL(8); grid_arrive(gridbar); }
   }
   ++bar;
 }
@@ -578,33 +766,37 @@ __device__ __forceinline__ void persistent_gemm_phase(Pipe& p, const EngineParam
 __global__ void __launch_bounds__(ENGINE_THREADS, 1) scan_fwd_persistent(const ScanFwdParams S) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   Pipe p;
-  float* att_sh = reinterpret_cast<float*>(pipe_setup(p, align_smem(smem_raw), S.A.n_cols));
+  const int max_cols = S.G.njobs > 0 && S.G.n_cols > S.A.n_cols ? S.G.n_cols : S.A.n_cols;
+  float* att_sh = reinterpret_cast<float*>(pipe_setup(p, align_smem(smem_raw), max_cols));
   unsigned int bar = 0;
-  for (int tick = 0; tick < S.T + 2; ++tick) {
+  for (int tick = 0; tick < S.nticks; ++tick) {
     persistent_gemm_phase(p, S.A, tick, S, bar, 0);
     persistent_gemm_phase(p, S.B, tick, S, bar, 1);
     if (tick < S.T) {
-      if (threadIdx.x == 0) { grid_wait(S.gridbar, bar * gridDim.x); STAMP(S, bar, 0); }
-      __syncthreads();
       AttnFwdArgs a = S.att;
       a.h1 += tick * S.s_h1; a.k_prev += tick * S.s_k; a.k_out += tick * S.s_k; a.w_out += tick * S.s_w;
       a.w_hi += tick * S.s_wp; a.w_lo += tick * S.s_wp; a.phi_out += tick * S.s_phi; a.ab_out += tick * S.s_ab;
       a.e_out += tick * S.s_e;
-      // stage 1 (all CTAs): h1 . Watt^T, one dot product per warp ; stage 2 (B CTAs): window + context
-      attention_proj_body(a);
+      // stage 1 (att_slices CTAs): K-sliced partial projections of h1_t ; stage 2 (att_parts CTAs per batch row):
+      // window + context slice.  CTAs without work only pass the barriers.
+      // (every CTA observes barrier k before it arrives at barrier k + 1: the arrival counter is monotonic)
+      if (threadIdx.x == 0) { grid_wait(S.gridbar, bar * gridDim.x); STAMP(S, bar, 0); }
+      __syncthreads();
+      for (int sl = blockIdx.x; sl < S.att_slices; sl += gridDim.x) attention_proj_slice(a, sl, att_sh);
       __syncthreads();
       if (threadIdx.x == 0) { STAMP(S, bar, 1); grid_arrive(S.gridbar); }
       ++bar;
-      if ((int)blockIdx.x < a.B) {
-        if (threadIdx.x == 0) { grid_wait(S.gridbar, bar * gridDim.x); STAMP(S, bar, 0); }
-        __syncthreads();
-        for (int b = blockIdx.x; b < a.B; b += gridDim.x) attention_fwd_body<PB_ATT_WIDE != 0>(a, b, att_sh, true);
-        asm volatile("fence.proxy.async.global;" ::: "memory");
-        __syncthreads();
-      }
+      const int nwork = a.B * S.att_parts;
+      if (threadIdx.x == 0) { grid_wait(S.gridbar, bar * gridDim.x); STAMP(S, bar, 0); }
+      __syncthreads();
+      for (int i = blockIdx.x; i < nwork; i += gridDim.x)
+        attention_window_part<true>(a, i / S.att_parts, i % S.att_parts, S.att_parts, S.att_slices, att_sh);
+      asm volatile("fence.proxy.async.global;" ::: "memory");
+      __syncthreads();
       if (threadIdx.x == 0) { STAMP(S, bar, 1); grid_arrive(S.gridbar); }
       ++bar;
     }
+    if (S.G.njobs > 0 && (tick + 1) % S.Tc == 0) persistent_gemm_phase(p, S.G, (tick + 1) / S.Tc - 1, S, bar, 2);
   }
   pipe_teardown(p);
 }
@@ -612,15 +804,17 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) scan_fwd_persistent(const S
 __global__ void __launch_bounds__(ENGINE_THREADS, 1) scan_bwd_persistent(const ScanBwdParams S) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   Pipe p;
-  float* att_sh = reinterpret_cast<float*>(pipe_setup(p, align_smem(smem_raw), S.B1.n_cols));
+  const int max_cols = S.G.njobs > 0 && S.G.n_cols > S.B1.n_cols ? S.G.n_cols : S.B1.n_cols;
+  float* att_sh = reinterpret_cast<float*>(pipe_setup(p, align_smem(smem_raw), max_cols));
   unsigned int bar = 0;
   const ScanCtx& c = *S.ctx;
-  for (int tick = 0; tick < S.T + 2; ++tick) {
-    const int s = S.T - 1 - tick;   // layer 3 at step s, layer 2 at s + 1, attention + layer 1 at s + 2
-    const int ta = s + 2;
-    // Phase 0: attention backward of step s+2 on the first B CTAs, each followed by the (row-local) GRU pre-pass of
-    // layer 1 for its batch row; meanwhile the other CTAs run the pre-pass of layers 3 (step s) and 2 (step s+1),
-    // which do not depend on the attention.
+  for (int tick = 0; tick < S.nticks; ++tick) {
+    // layer 3 at step s3, layer 2 at s3 + Tc, attention + layer 1 at s3 + 2 Tc
+    const int s3 = S.T - 1 - tick;
+    const int ta = s3 + 2 * S.Tc;
+    // Phase 0: attention backward of step ta on the first B CTAs, each followed by the (row-local) GRU pre-pass of
+    // layer 1 for its batch row; meanwhile the other CTAs run the pre-pass of layers 3 and 2, which do not depend
+    // on the attention.
     {
       if (threadIdx.x == 0 && bar) grid_wait(S.gridbar, bar * gridDim.x);
       if (threadIdx.x == 0) STAMP(S, bar, 0);
@@ -639,7 +833,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) scan_bwd_persistent(const S
         const int nworkers = (int)gridDim.x - nB;
         const int wid = (int)blockIdx.x - nB;
         for (int l = 2; l >= 1; --l) {
-          const int t = s + (2 - l);
+          const int t = s3 + (2 - l) * S.Tc;
           if (t >= 0 && t < S.T) gru_bwd_pre_rows(c, l, t, 0, c.B, wid * (int)blockDim.x + threadIdx.x, nworkers * (int)blockDim.x);
         }
       }
@@ -650,6 +844,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) scan_bwd_persistent(const S
     }
     persistent_gemm_phase(p, S.B1, tick, S, bar, 0);
     persistent_gemm_phase(p, S.B2, tick, S, bar, 1);
+    if (S.G.njobs > 0 && (tick + 1) % S.Tc == 0) persistent_gemm_phase(p, S.G, (tick + 1) / S.Tc - 1, S, bar, 2);
   }
   pipe_teardown(p);
 }

@@ -9,25 +9,7 @@ TINY = dict(input_dim=24, output_dim=63, rnn_h_dim=64, readouts_dim=64, num_char
             encoder_type='bidirectional')
 
 
-def make_batch(cfg, B, T, U, seed=0, ragged=True, dtype=np.float32):
-    """features (T+1,B,D) ~ N(0,1); masks with lengths ~ U{0.6..1}; labels ~ U{0..num_characters}."""
-    rng = np.random.default_rng(seed)
-    D = cfg.get('output_dim', 63)
-    feats = rng.standard_normal((T + 1, B, D)).astype(dtype)
-    fm = np.ones((T + 1, B), dtype)
-    lm = np.ones((B, U), dtype)
-    if ragged:
-        for b in range(B):
-            fl = int(rng.integers(int(0.6 * (T + 1)), T + 2))
-            fm[fl:, b] = 0
-            ul = int(rng.integers(max(2, int(0.6 * U)), U + 1))
-            lm[b, ul:] = 0
-    labels = rng.integers(0, cfg.get('num_characters', 43), (B, U)).astype(np.int32)
-    spk = rng.integers(0, cfg.get('num_speakers', 21), (B, 1)).astype(np.int32)
-    return dict(features=feats, features_mask=fm, labels=labels, labels_mask=lm, speaker=spk,
-                feedback_noise=rng.standard_normal((T, B, D)).astype(dtype),
-                gmm_unis=rng.random((T, B)).astype(dtype),
-                gmm_normals=rng.standard_normal((T, B, D)).astype(dtype))
+from parrot_b200.synthetic import make_batch  # noqa: E402,F401  (shared with bench.py; product code)
 
 
 def make_oracle(cfg, seed=0, gain=None, dtype=np.float32, encoder_time_axis=0, bias_std=0.1):
