@@ -423,7 +423,7 @@ static const int SGEMM_SPLIT = 64;   // K chunks of the split SIMT GEMM (encoder
 static Seg mkseg(int a_map, int a_row, int a_k, int b_map, int b_row, int b_k, int b_slot, int nkb) {
   Seg s;
   s.a_map = a_map; s.a_row = a_row; s.a_k = a_k; s.b_map = b_map; s.b_row = b_row; s.b_k = b_k;
-  s.b_slot = b_slot; s.nkb = nkb; s.a_nkb = 0; s.pad_ = 0;
+  s.b_slot = b_slot; s.nkb = nkb; s.a_nkb = 0; s.b_slots = 1;
   return s;
 }
 static Job blank_job() {
@@ -561,7 +561,10 @@ static void push_table(parrot_model& M, const std::string& name, const std::vect
                        int split_target = 0, int chunk_samples = 0) {
   std::vector<Job> js = js_in;
   for (auto& j : js)
-    for (int s = 0; s < j.nseg; ++s) j.seg[s].a_nkb = M.raws[j.seg[s].a_map].tiled_nkb;   // tile-contiguous packs
+    for (int s = 0; s < j.nseg; ++s) {
+      j.seg[s].a_nkb = M.raws[j.seg[s].a_map].tiled_nkb;   // tile-contiguous packs
+      j.seg[s].b_slots = M.raws[j.seg[s].b_map].slots;
+    }
   Table t;
   t.off = (int)M.jobs.size();
   t.n_cols = n_cols;
@@ -865,6 +868,10 @@ static void build(parrot_model& M) {
         pa.scale = 1.0f;
         pa.out = M.dry ? nullptr : M.fbuf("pre" + l);
         pa.ldo = 3 * H; pa.n_pad = Np; pa.n_valid = B; pa.n_total = T * Np;
+        // the time-constant term base_l[b][3H] (summed Fork biases + speaker) is folded into pre_l here, so that
+        // the scan epilogues read ONE pre-activation array
+        pa.bias = M.dry ? nullptr : M.fbuf("base" + l);
+        pa.rowbias_ld = 3 * H;
         std::vector<PlainSeg> segs;
         for (auto& sc : src)
           segs.push_back({M.packs[sc.pack + "/fork_rnn" + l + (part == 0 ? "_inputs" : "_gates")].fwd_map, 0,
@@ -1655,7 +1662,7 @@ static AttnFwdArgs attn_fwd_args(parrot_model& M, int t, bool sampling) {
   a.hat_part = M.fbuf("att_hat_part");
   return a;
 }
-static size_t att_proj_smem(const Dims& d) { return (size_t)(d.B + 3 * d.A) * (ATT_KS + 1) * 4; }
+static size_t att_proj_smem(const Dims& d) { return (size_t)(d.B + 3 * d.A) * (ATT_KS + 4) * 4; }
 static size_t att_window_smem(const Dims& d, int nparts) {
   return (size_t)(2 * rup(3 * d.A, 4) + rup(d.U, 4) + 8 * (d.C / nparts)) * 4;
 }
@@ -1721,9 +1728,9 @@ static AttnBwdArgs attn_bwd_args(parrot_model& M, int t);
 static bool scan_fwd_persistent_launch(parrot_model& M, cudaStream_t st) {
   const Dims& d = M.d;
   ScanFwdParams S;
-  S.A = table_params(M, "fwdA", 0, 0);
-  S.B = table_params(M, "fwdB", 0, 1);
-  S.G = table_params(M, "chunkF", 0);
+  S.ph[0] = table_params(M, "fwdA", 0, 0);
+  S.ph[1] = table_params(M, "fwdB", 0, 1);
+  S.ph[2] = table_params(M, "chunkF", 0);
   S.Tc = M.Tc; S.nticks = d.T + 2 * M.Tc;
   S.att_parts = attention_nparts(d.B, d.C, 148); S.att_slices = M.att_slices;
   S.att = attn_fwd_args(M, 0, false);
@@ -1754,9 +1761,9 @@ static bool scan_fwd_persistent_launch(parrot_model& M, cudaStream_t st) {
 static bool scan_bwd_persistent_launch(parrot_model& M, cudaStream_t st) {
   const Dims& d = M.d;
   ScanBwdParams S;
-  S.B1 = table_params(M, "bwd1", 1, 0);
-  S.B2 = table_params(M, "bwd2", 1, 1);
-  S.G = table_params(M, "chunkB", 1);
+  S.ph[0] = table_params(M, "bwd1", 1, 0);
+  S.ph[1] = table_params(M, "bwd2", 1, 1);
+  S.ph[2] = table_params(M, "chunkB", 1);
   S.Tc = M.Tc; S.nticks = d.T + 2 * M.Tc;
   S.att = attn_bwd_args(M, 0);
   S.s_dw = (long long)d.B * d.C; S.s_ab = (long long)d.B * 2 * d.A; S.s_e = (long long)d.B * 3 * d.A;

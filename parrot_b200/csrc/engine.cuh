@@ -186,17 +186,18 @@ __device__ __forceinline__ bool chunk_window(const EngineParams& P, const Job& j
   shift = 0; limit = jb.pa.n_total;
   if (P.chunk_samples <= 0) return true;
   if (ce < 0) return false;
-  const long long cs = P.chunk_samples, nt = jb.pa.n_total;
+  const int cs = P.chunk_samples, nt = jb.pa.n_total;   // (sample counts are far below 2^31 / chunks)
+  if (ce > nt / cs) return false;
   if (!P.reverse) {
     if (ce * cs >= nt) return false;
-    shift = (int)(ce * cs);
-    limit = (int)((ce + 1) * cs < nt ? (ce + 1) * cs : nt);
+    shift = ce * cs;
+    limit = (ce + 1) * cs < nt ? (ce + 1) * cs : nt;
   } else {
-    const long long hi = nt - ce * cs;
+    const int hi = nt - ce * cs;
     if (hi <= 0) return false;
-    const long long lo = hi - cs;
-    shift = (int)(lo > 0 ? lo : 0);
-    limit = (int)hi;
+    const int lo = hi - cs;
+    shift = lo > 0 ? lo : 0;
+    limit = hi;
   }
   return true;
 }
@@ -225,8 +226,8 @@ __device__ __forceinline__ int job_total_kb(const EngineParams& P, const Job& jb
 // k-block range [lo, hi) of the flattened (valid segment, block) sequence owned by this split part
 __device__ __forceinline__ void job_kb_range(const Job& jb, int total_kb, int& lo, int& hi) {
   if (jb.ksplit <= 1) { lo = 0; hi = total_kb; return; }
-  lo = (int)(((long long)total_kb * jb.kpart) / jb.ksplit);
-  hi = (int)(((long long)total_kb * (jb.kpart + 1)) / jb.ksplit);
+  lo = (total_kb * jb.kpart) / jb.ksplit;          // (total_kb < 2^20, kpart < 8: 32-bit arithmetic is enough)
+  hi = (total_kb * (jb.kpart + 1)) / jb.ksplit;
 }
 
 // ------------------------------------------------------------------ epilogues
@@ -375,8 +376,7 @@ __device__ __forceinline__ void epi_gates_load(const EpiLocal& E, int t, int row
   for (int j = 0; j < W; ++j) {
     const int b = n_base + j;
     const bool ok = row < E.m_valid && j < ncols && b < B;
-    o.a[j] = ok ? __ldg(basep + (long long)b * 3 * H) : 0.0f;
-    if (prep && ok) o.a[j] += __ldcg(prep + (long long)b * 3 * H);
+    o.a[j] = !ok ? 0.0f : (prep ? __ldcg(prep + (long long)b * 3 * H) : __ldg(basep + (long long)b * 3 * H));
     o.b[j] = (ok && !is_z) ? hprev[(long long)b * H] : 0.0f;
   }
 }
@@ -419,8 +419,7 @@ __device__ __forceinline__ void epi_cand_load(const EpiLocal& E, int t, int row,
   for (int j = 0; j < W; ++j) {
     const int b = n_base + j;
     const bool ok = row < E.m_valid && j < ncols && b < B;
-    o.a[j] = ok ? __ldg(basep + (long long)b * 3 * H) : 0.0f;
-    if (prep && ok) o.a[j] += __ldcg(prep + (long long)b * 3 * H);
+    o.a[j] = !ok ? 0.0f : (prep ? __ldcg(prep + (long long)b * 3 * H) : __ldg(basep + (long long)b * 3 * H));
     o.b[j] = ok ? zp[(long long)b * H] : 0.0f;
     o.c[j] = ok ? hp_[(long long)b * H] : 0.0f;
   }
@@ -571,7 +570,7 @@ __device__ __forceinline__ void split4(float4 x, uint2& hi, uint2& lo) {
   hi.x = *reinterpret_cast<const uint32_t*>(&h01); hi.y = *reinterpret_cast<const uint32_t*>(&h23);
   lo.x = *reinterpret_cast<const uint32_t*>(&l01); lo.y = *reinterpret_cast<const uint32_t*>(&l23);
 }
-struct QOps { float4 a, b, c, d; };
+struct QOps { float4 a, b, c; };
 
 // can this job's split-K finish use the quad path?  (feature counts divisible by 4, aligned stashes)
 __device__ __forceinline__ bool quad_ok(const EpiLocal& E) {
@@ -580,46 +579,61 @@ __device__ __forceinline__ bool quad_ok(const EpiLocal& E) {
   if (E.epi == EPI_BWD_STATE) return (E.dstF & 3) == 0;
   return (E.H & 3) == 0 && (E.Hp & 3) == 0;
 }
-
-__device__ __forceinline__ void q_load(const EpiLocal& E, int t, int rq, int b, QOps& o) {
+// memory operands of the quad epilogues: array 0 / 1 / 2 of (t, row quad rq, sample b); null = not needed
+//   GATES      0: hoisted-or-base pre-activation term   1: h_prev (reset rows only)
+//   CAND       0: hoisted-or-base term   1: z   2: h_prev
+//   BWD_RH     0: r   1: h_prev   2: dh
+//   BWD_STATE  0: destination
+template <int DIR = 0>
+__device__ __forceinline__ int q_narr(int epi) {
+  if (DIR == 1) return epi == EPI_GATES ? 2 : 3;
+  if (DIR == 2) return epi == EPI_BWD_STATE ? 1 : 3;
+  return epi == EPI_GATES ? 2 : (epi == EPI_BWD_STATE ? 1 : 3);
+}
+template <int DIR = 0>
+__device__ __forceinline__ const float* q_src(const EpiLocal& E, int t, int rq, int b, int arr) {
   const int H = E.H, B = E.B, f = E.row0 + 4 * rq;
-  o.a = o.b = o.c = o.d = f4zero();
-  if (4 * rq >= E.m_valid || b >= B) return;
-  switch (E.epi) {
-    case EPI_GATES: {
-      const bool is_z = f < H;
-      const int fr = is_z ? f : f - H;
-      o.a = ldg4((const float*)E.p0 + (long long)t * E.l0 + (long long)b * 3 * H + H + f);
-      if (E.pre) o.d = ldcg4(E.pre + ((long long)t * B + b) * 3 * H + H + f);
-      if (!is_z) o.b = ldcg4((const float*)E.p1 + ((long long)t * B + b) * H + fr);
-    } break;
-    case EPI_CAND: {
-      const long long tb = ((long long)t * B + b) * H + f;
-      o.a = ldg4((const float*)E.p0 + (long long)t * E.l0 + (long long)b * 3 * H + f);
-      if (E.pre) o.d = ldcg4(E.pre + ((long long)t * B + b) * 3 * H + f);
-      o.b = ldcg4((const float*)E.p2 + tb);
-      o.c = ldcg4((const float*)E.p1 + tb);
-    } break;
-    case EPI_BWD_RH: {
-      const long long tb = ((long long)t * B + b) * H + f;
-      o.a = ldcg4((const float*)E.p0 + tb);
-      o.b = ldcg4((const float*)E.p1 + tb);
-      o.c = ldcg4((const float*)E.p2 + tb);
-    } break;
+  if (4 * rq >= E.m_valid || b >= B) return nullptr;
+  const long long tb = ((long long)t * B + b) * H;
+  int epi = E.epi;
+  if (DIR == 1 && epi != EPI_GATES) epi = EPI_CAND;        // (compile-time pruning of the cases a kernel cannot see)
+  if (DIR == 2 && epi != EPI_BWD_STATE) epi = EPI_BWD_RH;
+  switch (epi) {
+    case EPI_GATES:
+      if (arr == 0)
+        return (E.pre ? E.pre + ((long long)t * B + b) * 3 * H
+                      : (const float*)E.p0 + (long long)t * E.l0 + (long long)b * 3 * H) + H + f;
+      return (arr == 1 && f >= H) ? (const float*)E.p1 + tb + (f - H) : nullptr;
+    case EPI_CAND:
+      if (arr == 0)
+        return (E.pre ? E.pre + ((long long)t * B + b) * 3 * H
+                      : (const float*)E.p0 + (long long)t * E.l0 + (long long)b * 3 * H) + f;
+      return (const float*)(arr == 1 ? E.p2 : E.p1) + tb + f;
+    case EPI_BWD_RH:
+      return (const float*)(arr == 0 ? E.p0 : (arr == 1 ? E.p1 : E.p2)) + tb + f;
     case EPI_BWD_STATE:
-      o.a = ldcg4((const float*)E.p0 + ((long long)(t + E.slot_off) * B + b) * E.dstF + f);
-      break;
-    default: break;
+      return arr == 0 ? (const float*)E.p0 + ((long long)(t + E.slot_off) * B + b) * E.dstF + f : nullptr;
+    default: return nullptr;
   }
 }
+template <int DIR = 0>
+__device__ __forceinline__ void q_load(const EpiLocal& E, int t, int rq, int b, QOps& o) {
+  const float* p0 = q_src<DIR>(E, t, rq, b, 0);
+  const float* p1 = q_src<DIR>(E, t, rq, b, 1);
+  const float* p2 = q_src<DIR>(E, t, rq, b, 2);
+  o.a = p0 ? ldcg4(p0) : f4zero();
+  o.b = p1 ? ldcg4(p1) : f4zero();
+  o.c = p2 ? ldcg4(p2) : f4zero();
+}
 
-// after ALL loads of a batch have been issued: fold the hoisted term into the base term (frees o.d)
-__device__ __forceinline__ void q_merge(QOps& o) { o.a = f4add(o.a, o.d); }
-
+template <int DIR = 0>
 __device__ __forceinline__ void q_apply(const EpiLocal& E, int t, int rq, int b, float4 v, const QOps& o) {
   const int H = E.H, B = E.B, f = E.row0 + 4 * rq;
   if (4 * rq >= E.m_valid || b >= B) return;
-  switch (E.epi) {
+  int epi = E.epi;
+  if (DIR == 1 && epi != EPI_GATES) epi = EPI_CAND;
+  if (DIR == 2 && epi != EPI_BWD_STATE) epi = EPI_BWD_RH;
+  switch (epi) {
     case EPI_GATES: {
       const bool is_z = f < H;
       const int fr = is_z ? f : f - H;
@@ -671,63 +685,97 @@ __device__ __forceinline__ void q_apply(const EpiLocal& E, int t, int rq, int b,
   }
 }
 
-// Finish of one split-K part, flat layout: per batch a thread handles CB = min(QC, QS / ksplit) columns and keeps
-// ksplit * CB <= QS partial-tile quads in flight (slot i <-> column i / ksplit, part i % ksplit), so the register
-// footprint does not depend on how a table happens to be split.  Column sums run in part order (deterministic).
-constexpr int QC = 4;    // columns per batch (operand registers)
-constexpr int QS = 12;   // partial-tile slots per batch
-struct QBatch { float4 a[QC], b[QC], c[QC]; };
+// ---- operand staging: the finish operands of a part's columns are copied global -> shared with cp.async (no
+// registers, no waiting) as soon as the phase starts; the finish reads them back from shared memory after the
+// partial-tile exchange.  Slot (column cs of the part, array arr): 128 rows x 4 bytes; thread `lane` owns bytes
+// [16 lane, 16 lane + 16) of every slot it fills and is the only reader of them (no CTA barrier needed).
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-__device__ __forceinline__ int q_cols_per_batch(int ksplit) { return ksplit <= 3 ? QC : (QS / ksplit < QC ? QS / ksplit : QC); }
-
-// request the operands of batch k0 (columns c_lo + ew + nwarps * (k0 + k), k < cb); all loads first, merges after
-__device__ __forceinline__ void q_batch_load(const EpiLocal& E, int t, int lane, int ew, int nwarps, int c_lo, int c_hi,
-                                             int cb, int k0, QBatch& q) {
-  float4 d[QC];
+template <int DIR = 0>
+__device__ __forceinline__ void q_stage(const EpiLocal& E, int t, int lane, int ew, int nwarps, int c_lo, int c_hi,
+                                        uint8_t* stg, int stg_cols) {
+  const int narr = q_narr<DIR>(E.epi);
+  for (int c = c_lo + ew; c < c_hi; c += nwarps) {
+    const int cs = c - c_lo;
+    if (cs >= stg_cols) break;
 #pragma unroll
-  for (int k = 0; k < QC; ++k) {
-    const int c = c_lo + ew + nwarps * (k0 + k);
-    QOps o;
-    q_load(E, t, lane, (k < cb && c < c_hi) ? c : (1 << 30), o);
-    q.a[k] = o.a; q.b[k] = o.b; q.c[k] = o.c; d[k] = o.d;
+    for (int arr = 0; arr < 3; ++arr) {
+      if (arr < narr) {
+        const float* src = q_src<DIR>(E, t, lane, c, arr);
+        if (src) cp_async16(stg + ((size_t)(cs * narr + arr) * TILE_M + 4 * lane) * 4, src);
+      }
+    }
   }
-#pragma unroll
-  for (int k = 0; k < QC; ++k) q.a[k] = f4add(q.a[k], d[k]);
+}
+template <int DIR = 0>
+__device__ __forceinline__ void q_fetch(const EpiLocal& E, int t, int lane, int c, int c_lo, const uint8_t* stg,
+                                        int stg_cols, QOps& o) {
+  const int cs = c - c_lo;
+  if (cs >= stg_cols) { q_load<DIR>(E, t, lane, c, o); return; }
+  const int narr = q_narr<DIR>(E.epi);
+  const float4* s0 = reinterpret_cast<const float4*>(stg + ((size_t)(cs * narr) * TILE_M + 4 * lane) * 4);
+  o.a = s0[0];
+  o.b = narr > 1 ? s0[TILE_M / 4] : f4zero();
+  o.c = narr > 2 ? s0[2 * (TILE_M / 4)] : f4zero();
 }
 
+// Finish of one split-K part: per batch a thread handles cb = min(QC, QS / ksplit) columns and keeps ksplit * cb <= QS
+// partial-tile quads in flight (slot i <-> column i / ksplit, part i % ksplit), so the register footprint does not
+// depend on how a table happens to be split.  Column sums run in part order (deterministic).
+constexpr int QC = 4;    // columns per batch
+constexpr int QS = 12;   // partial-tile slots per batch
+__device__ __forceinline__ int q_cols_per_batch(int ksplit) { return ksplit <= 3 ? QC : (QS / ksplit < QC ? QS / ksplit : QC); }
+
+template <int DIR = 0>
 __device__ __forceinline__ void q_finish(const EpiLocal& E, int t, int lane, int ew, int nwarps, int c_lo, int c_hi,
-                                         int ksplit, int n_cols, const float* base, QBatch& q) {
+                                         int ksplit, int n_cols, const float* base, const uint8_t* stg, int stg_cols) {
   const int cb = q_cols_per_batch(ksplit);
+  const size_t part_stride = (size_t)n_cols * TILE_M;
   for (int k0 = 0; c_lo + ew + nwarps * k0 < c_hi; k0 += cb) {
     float4 x[QS];
     {
       int kk = 0, pp = 0;
+      const float* colp = base + (size_t)(c_lo + ew + nwarps * k0) * TILE_M + 4 * lane;   // column kk, part 0
+      const float* ptr = colp;
 #pragma unroll
       for (int i = 0; i < QS; ++i) {
-        const int c = c_lo + ew + nwarps * (k0 + kk);
-        x[i] = (kk < cb && c < c_hi) ? ldcg4(base + ((size_t)pp * n_cols + c) * TILE_M + 4 * lane) : f4zero();
-        if (++pp == ksplit) { pp = 0; ++kk; }
+        const bool live = kk < cb && c_lo + ew + nwarps * (k0 + kk) < c_hi;
+        x[i] = live ? ldcg4(ptr) : f4zero();
+        ptr += part_stride;
+        if (++pp == ksplit) { pp = 0; ++kk; colp += (size_t)nwarps * TILE_M; ptr = colp; }
       }
     }
-    if (k0 > 0) q_batch_load(E, t, lane, ew, nwarps, c_lo, c_hi, cb, k0, q);   // first batch: requested at phase start
-#pragma unroll
-    for (int k = 0; k < QC; ++k) {
+    if (k0 == 0) cp_async_wait_all();   // this thread's staged operands (requested at the start of the phase)
+#pragma unroll 1
+    for (int k = 0; k < cb; ++k) {      // (not unrolled: one copy of the epilogue code; x[] keeps static indices)
+      const int c = c_lo + ew + nwarps * (k0 + k);
+      if (c >= c_hi) break;
       float4 v = f4zero();
       int kk = 0, pp = 0;
 #pragma unroll
       for (int i = 0; i < QS; ++i) {
-        if (kk == k) v = f4add(v, x[i]);
+        if (kk == k) v = f4add(v, x[i]);   // part order: deterministic
         if (++pp == ksplit) { pp = 0; ++kk; }
       }
-      const int c = c_lo + ew + nwarps * (k0 + k);
-      if (k < cb && c < c_hi) {
-        QOps o;
-        o.a = q.a[k]; o.b = q.b[k]; o.c = q.c[k]; o.d = f4zero();
-        q_apply(E, t, lane, c, v, o);
-      }
+      QOps o;
+      q_fetch<DIR>(E, t, lane, c, c_lo, stg, stg_cols, o);
+      q_apply<DIR>(E, t, lane, c, v, o);
     }
   }
 }
+
+// Per-CTA copy of the ONE job a CTA runs in a scan table of a persistent kernel (job index = CTA index, every tick)
+// and of its epilogue context, kept in shared memory: the roles read them with LDS instead of chains of dependent
+// global loads behind every grid barrier.
+struct PhaseCache {
+  Job job;
+  EpiLocal epi;
+  int valid;
+  int pad_[3];
+};
 
 // grid barrier wait (defined with the persistent-kernel helpers below)
 __device__ __forceinline__ void grid_wait_ext(const unsigned int* ctr, unsigned int target);
@@ -746,6 +794,9 @@ struct Pipe {
   int stage;       // producer / MMA: ring position
   uint32_t phase;  // producer / MMA: ring parity
   int it;          // MMA / epilogue: accumulator uses so far
+  uint8_t* stg;    // epilogue: operand staging region of the quad finish (persistent kernels) or null
+  int stg_bytes;
+  uint8_t* cache_area;   // >= 1536 bytes behind the barriers (PhaseCache copies of the persistent kernels)
 };
 
 // returns the first byte after the pipeline's shared memory (1024-aligned ring + barriers)
@@ -765,6 +816,8 @@ __device__ __forceinline__ uint8_t* pipe_setup(Pipe& p, uint8_t* smem, int n_col
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p.tempty_bar + 2);
   p.split_flag = tmem_slot + 1;
   p.stage = 0; p.phase = 0; p.it = 0;
+  p.stg = nullptr; p.stg_bytes = 0;
+  p.cache_area = reinterpret_cast<uint8_t*>(p.full_bar) + 256;   // the ring leaves >= 2048 bytes here
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.nstages; ++s) {
       mbar_init(&p.full_bar[s], 1);
@@ -828,7 +881,8 @@ __device__ __forceinline__ void producer_load_b(Pipe& p, const Seg& sg, int kb, 
 // on it.  The producer therefore fills the free ring slots with weight tiles first (expect_tx without arrive),
 // waits for the barrier, and completes those slots with the activation tiles (arrive + expect_tx).
 __device__ __forceinline__ void producer_run(Pipe& p, const EngineParams& P, int tick,
-                                             const unsigned int* gridbar = nullptr, unsigned int target = 0) {
+                                             const unsigned int* gridbar = nullptr, unsigned int target = 0,
+                                             const PhaseCache* pc = nullptr) {
   // debug_flags bit 0: no per-instruction L2 hint on the weight tiles; bits 1-2: evict_last on a fraction of lines
   uint64_t pol_keep = 0;
   if (!(P.debug_flags & 1)) {
@@ -838,7 +892,7 @@ __device__ __forceinline__ void producer_run(Pipe& p, const EngineParams& P, int
   bool waited = (gridbar == nullptr) || target == 0;
   const uint32_t tx_bytes = 2 * p.a_bytes + 2 * p.b_bytes;   // <= stage_bytes (the ring is sized for the widest phase)
   for (int j = blockIdx.x; j < P.njobs; j += gridDim.x) {
-    const Job& jb = P.jobs[j];
+    const Job& jb = pc ? pc->job : P.jobs[j];
     const int t = job_time(P, jb, tick);
     const int total_kb = job_total_kb(P, jb, t);
     if (total_kb == 0) continue;
@@ -898,11 +952,11 @@ __device__ __forceinline__ void producer_run(Pipe& p, const EngineParams& P, int
 }
 
 // ------------------------------------------------ MMA issuer (warp 1; lane 0 issues)
-__device__ __forceinline__ void mma_run(Pipe& p, const EngineParams& P, int tick) {
+__device__ __forceinline__ void mma_run(Pipe& p, const EngineParams& P, int tick, const PhaseCache* pc = nullptr) {
   const int lane = threadIdx.x & 31;
   const uint32_t idesc = umma_idesc_bf16(TILE_M, p.n_cols);
   for (int j = blockIdx.x; j < P.njobs; j += gridDim.x) {
-    const Job& jb = P.jobs[j];
+    const Job& jb = pc ? pc->job : P.jobs[j];
     const int t = job_time(P, jb, tick);
     const int all_kb = job_total_kb(P, jb, t);
     if (all_kb == 0) continue;
@@ -962,7 +1016,8 @@ __device__ __forceinline__ void mma_run(Pipe& p, const EngineParams& P, int tick
 // apply the epilogue; the helpers skip.  Split jobs: warps 2..5 park the partial tile in scratch, then ALL ten
 // warps share the post-reduction epilogue of this part's column slice as 4-column work items (the reduction
 // reads global memory, so any warp can do it; the helpers hide load / MUFU latencies).
-__device__ __forceinline__ void epilogue_run(Pipe& p, const EngineParams& P, int tick) {
+template <bool CACHED>
+__device__ __forceinline__ void epilogue_run(Pipe& p, const EngineParams& P, int tick, const PhaseCache* pc = nullptr) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_cols = p.n_cols;
   const bool tmem_warp = warp < 6;
@@ -970,7 +1025,7 @@ __device__ __forceinline__ void epilogue_run(Pipe& p, const EngineParams& P, int
   const int row = q * 32 + lane;
   const int gtid = threadIdx.x - 64;   // 0..319 inside the epilogue group
   for (int j = blockIdx.x; j < P.njobs; j += gridDim.x) {
-    const Job& jb = P.jobs[j];
+    const Job& jb = CACHED ? pc->job : P.jobs[j];
     const int t = job_time(P, jb, tick);
     const int all_kb = job_total_kb(P, jb, t);
     if (all_kb == 0) continue;
@@ -980,19 +1035,22 @@ __device__ __forceinline__ void epilogue_run(Pipe& p, const EngineParams& P, int
     const int buf = p.it & 1;
     const uint32_t use = (uint32_t)(p.it >> 1);
     int cw_shift = 0, cw_limit = 0;
-    if (jb.epi == EPI_PLAIN && P.chunk_samples > 0) chunk_window(P, jb, t, cw_shift, cw_limit);
-    const EpiLocal E = make_epi_local(jb, P.ctx, cw_shift, cw_limit);
+    if (!CACHED && jb.epi == EPI_PLAIN && P.chunk_samples > 0) chunk_window(P, jb, t, cw_shift, cw_limit);
+    // CACHED: the epilogue context sits in shared memory (fields are read with LDS when needed: no registers held,
+    // no dependent global loads); otherwise it is rebuilt from the job table / scan context in registers
+    const EpiLocal Ereg = CACHED ? EpiLocal() : make_epi_local(jb, P.ctx, cw_shift, cw_limit);
+    const EpiLocal& E = CACHED ? pc->epi : Ereg;
     const int ksplit = jb.ksplit, kpart = jb.kpart, group = jb.group;
     // Quad finish (cooperative split-K only): this part finishes columns [qc_lo, qc_hi) of the tile; warp ew takes
-    // columns qc_lo + ew, + NEW, ...; lane = row quad.  The epilogue operands of the first QMAX columns are requested
-    // NOW, before the accumulator is complete: they only depend on the previous phase (already behind the grid
-    // barrier), so their latency hides under the MMAs and the partial-tile exchange.
+    // columns qc_lo + ew, + NEW, ...; lane = row quad.  The epilogue operands are requested NOW (cp.async into the
+    // staging region), before the accumulator is complete: they only depend on the previous phase (already behind
+    // the grid barrier), so their latency hides under the MMAs and the partial-tile exchange.
     const bool quad = ksplit > 1 && P.coop_epilogue && quad_ok(E);
     constexpr int NEW = EPI_GROUP_THREADS / 32;
     const int ew = warp - 2;
     const int qc_lo = (n_cols * kpart) / ksplit, qc_hi = (n_cols * (kpart + 1)) / ksplit;
-    QBatch qb;
-    if (quad) q_batch_load(E, t, lane, ew, NEW, qc_lo, qc_hi, q_cols_per_batch(ksplit), 0, qb);
+    const int stg_cols = p.stg ? p.stg_bytes / (q_narr(E.epi) * TILE_M * 4) : 0;
+    if (quad) q_stage(E, t, lane, ew, NEW, qc_lo, qc_hi, p.stg, stg_cols);
     if (threadIdx.x == 64) TL(9);
     if (tmem_warp) {
       const uint32_t taddr = p.tmem_base + (uint32_t)buf * 256u + ((uint32_t)(q * 32) << 16);
@@ -1073,7 +1131,7 @@ __device__ __forceinline__ void epilogue_run(Pipe& p, const EngineParams& P, int
           unsigned int seen, spins = 0;
           do {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(P.split_count + group) : "memory");
-            if (++spins > (1u << 24)) { printf("parrot_b200: split-K arrival wait timed out\n"); __trap(); }
+            if (++spins > (1u << 24)) pb_timeout(2);
           } while ((seen & 0xffffu) < (unsigned int)ksplit);
         }
         epi_group_sync();
@@ -1092,7 +1150,7 @@ __device__ __forceinline__ void epilogue_run(Pipe& p, const EngineParams& P, int
         if (*p.split_flag) { c_lo = 0; c_hi = n_cols; }
       }
       if (quad) {
-        q_finish(E, t, lane, ew, NEW, qc_lo, qc_hi, ksplit, n_cols, base, qb);
+        q_finish(E, t, lane, ew, NEW, qc_lo, qc_hi, ksplit, n_cols, base, p.stg, stg_cols);
       } else {
       __threadfence();
       // work item = (row, group of 4 columns); consecutive threads take consecutive rows (coalesced).  All loads of
@@ -1159,6 +1217,127 @@ __device__ __forceinline__ void epilogue_run(Pipe& p, const EngineParams& P, int
   }
 }
 
+// ------------------------------------------------ compact epilogues of the persistent kernels
+// The generic epilogue_run above carries every job kind (five epilogues x split / unsplit x thread-per-row paths) and
+// compiles to ~14 K instructions per inlined copy; three copies made the persistent scan kernels ~750 KB of SASS, far
+// beyond the instruction caches, and every phase of every tick started on cold code.  The persistent kernels
+// therefore use two specialised epilogues: scan phases (one cached job per CTA, always the quad split-K finish --
+// an unsplit job is simply a 1-part split) and chunk phases (plain unsplit jobs only).
+// DIR: 1 forward scan (GATES / CAND), 2 backward scan (BWD_RH / BWD_STATE).
+template <int DIR>
+__device__ __forceinline__ void epilogue_scan(Pipe& p, const EngineParams& P, int tick, const PhaseCache* pc) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_cols = p.n_cols;
+  if ((int)blockIdx.x >= P.njobs) return;
+  const Job& jb = pc->job;
+  const int t = job_time(P, jb, tick);
+  const int all_kb = job_total_kb(P, jb, t);
+  if (all_kb == 0) return;
+  int klo, khi;
+  job_kb_range(jb, all_kb, klo, khi);
+  const bool have_acc = khi > klo;
+  const int buf = p.it & 1;
+  const uint32_t use = (uint32_t)(p.it >> 1);
+  const EpiLocal& E = pc->epi;
+  const int ksplit = jb.ksplit, kpart = jb.kpart, group = jb.group;
+  constexpr int NEW = EPI_GROUP_THREADS / 32;
+  const int ew = warp - 2;
+  const int c_lo = (n_cols * kpart) / ksplit, c_hi = (n_cols * (kpart + 1)) / ksplit;
+  const int stg_cols = p.stg_bytes / (q_narr<DIR>(E.epi) * TILE_M * 4);
+  // operands of this part's columns: global -> shared, asynchronously, as soon as the grid barrier is behind us
+  q_stage<DIR>(E, t, lane, ew, NEW, c_lo, c_hi, p.stg, stg_cols);
+  if (threadIdx.x == 64) TL(9);
+  const float* base = P.split_scratch + (size_t)group * MAX_KSPLIT * (size_t)n_cols * TILE_M;
+  if (warp < 6) {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t taddr = p.tmem_base + (uint32_t)buf * 256u + ((uint32_t)(q * 32) << 16);
+    if (have_acc) {
+      mbar_wait(&p.tfull_bar[buf], use & 1);
+      tc_fence_after();
+    }
+    if (threadIdx.x == 64) TL(4);
+    // park the partial tile: scratch[group][part][col][row]  (row fastest -> coalesced)
+    float* part = const_cast<float*>(base) + (size_t)kpart * (size_t)n_cols * TILE_M;
+#pragma unroll 1
+    for (int n0 = 0; n0 < n_cols; n0 += 16) {
+      float v[16];
+      if (have_acc) {
+        tmem_ld_32x16(taddr + n0, v);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = 0.0f;
+      }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) __stcg(part + (size_t)(n0 + i) * TILE_M + row, v[i]);
+    }
+    if (have_acc) {
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p.tempty_bar[buf]);
+    }
+    if (threadIdx.x == 64) TL(5);
+    __threadfence();
+  }
+  epi_group_sync();   // partial tile written by warps 2..5
+  if (warp == 2 && lane == 0) {
+    atomicAdd(P.split_count + group, 1u);
+    unsigned int seen, spins = 0;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(P.split_count + group) : "memory");
+      if (++spins > (1u << 24)) pb_timeout(2);
+    } while ((seen & 0xffffu) < (unsigned int)ksplit);
+  }
+  epi_group_sync();
+  if (threadIdx.x == 64) TL(6);
+  q_finish<DIR>(E, t, lane, ew, NEW, c_lo, c_hi, ksplit, n_cols, base, p.stg, stg_cols);
+  if (threadIdx.x == 64) TL(7);
+  epi_group_sync();
+  if (warp == 2 && lane == 0) {
+    // the last part to finish resets the arrival counter for the next use
+    const unsigned int old = atomicAdd(P.split_count + group, 0x10000u);
+    if ((old >> 16) == (unsigned int)(ksplit - 1)) P.split_count[group] = 0u;
+  }
+  if (have_acc) ++p.it;
+}
+
+__device__ __forceinline__ void epilogue_chunk(Pipe& p, const EngineParams& P, int tick) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_cols = p.n_cols;
+  if (warp >= 6) return;   // plain unsplit jobs: the four TMEM warps do all the work
+  const int q = warp & 3;
+  const int row = q * 32 + lane;
+#pragma unroll 1
+  for (int j = blockIdx.x; j < P.njobs; j += gridDim.x) {
+    const Job& jb = P.jobs[j];
+    const int t = job_time(P, jb, tick);
+    const int all_kb = job_total_kb(P, jb, t);
+    if (all_kb == 0) continue;
+    const int buf = p.it & 1;
+    const uint32_t use = (uint32_t)(p.it >> 1);
+    int cw_shift = 0, cw_limit = 0;
+    if (P.chunk_samples > 0) chunk_window(P, jb, t, cw_shift, cw_limit);
+    const EpiLocal E = make_epi_local(jb, P.ctx, cw_shift, cw_limit);
+    const uint32_t taddr = p.tmem_base + (uint32_t)buf * 256u + ((uint32_t)(q * 32) << 16);
+    mbar_wait(&p.tfull_bar[buf], use & 1);
+    tc_fence_after();
+#pragma unroll 1
+    for (int n0 = 0; n0 < n_cols; n0 += 8) {
+      float v[8];
+      EpiOps<8> ops;
+      tmem_ld_32x8(taddr + n0, v);
+      epi_plain_load<8>(E, t, row, n0, 8, ops);
+      tmem_ld_wait();
+      epi_plain<8>(E, t, row, n0, 8, v, ops);
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&p.tempty_bar[buf]);
+    ++p.it;
+  }
+}
+
 __device__ __forceinline__ uint8_t* align_smem(uint8_t* raw) {
   // 1024-byte alignment is required by the 128B swizzle atoms
   return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
@@ -1178,7 +1357,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) job_kernel_tc(const EngineP
   } else if (warp == 1) {
     mma_run(p, P, P.tick);
   } else {
-    epilogue_run(p, P, P.tick);
+    epilogue_run<false>(p, P, P.tick);
   }
   pipe_teardown(p);
   if (threadIdx.x == 0) TL(8);
@@ -1198,7 +1377,7 @@ __device__ __forceinline__ void grid_wait(const unsigned int* ctr, unsigned int 
   unsigned int seen, spins = 0;
   do {
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(ctr) : "memory");
-    if (++spins > (1u << 26)) { printf("parrot_b200: grid barrier timed out (block %d)\n", blockIdx.x); __trap(); }
+    if (++spins > (1u << 26)) pb_timeout(1);
   } while (seen < target);
   asm volatile("fence.proxy.async.global;" ::: "memory");
 }

@@ -234,30 +234,51 @@ __device__ __forceinline__ void attention_fwd_body(const AttnFwdArgs& a, const i
 
 // ---- projection stage, K-sliced (persistent scan and stand-alone step): CTA `slice` owns ATT_KS consecutive
 // features of h1 and produces hat_part[slice][b][j] = sum_{k in slice} h1[b][k] * wT[j][k] for all rows / outputs.
-// The window stage adds the slices in slice order (deterministic).  sh: (B + 3A) * (ATT_KS + 1) floats.
+// The window stage adds the slices in slice order (deterministic).  sh: (B + 3A) * (ATT_KS + 4) floats.
 __device__ __forceinline__ void attention_proj_slice(const AttnFwdArgs& a, const int slice, float* sh) {
+  constexpr int LD = ATT_KS + 4;   // row stride in floats: 16-byte aligned rows, conflict-free 128-bit reads
   const int A3 = 3 * a.A, k0 = slice * ATT_KS;
-  float* sh_h = sh;                              // [B][ATT_KS + 1]
-  float* sh_w = sh + a.B * (ATT_KS + 1);         // [3A][ATT_KS + 1]
+  float* sh_h = sh;                 // [B][LD]
+  float* sh_w = sh + a.B * LD;      // [3A][LD]
   const int tid = threadIdx.x, nt = blockDim.x;
-  for (int i = tid; i < a.B * ATT_KS; i += nt) {
-    const int b = i / ATT_KS, k = i % ATT_KS;
-    sh_h[b * (ATT_KS + 1) + k] = __ldcg(a.h1 + (long long)b * a.H + k0 + k);
+  // global -> shared with cp.async: all requests of a thread are in flight together (a load -> store loop costs one
+  // L2 round trip per iteration)
+  for (int i = tid; i < a.B * (ATT_KS / 4); i += nt) {
+    const int b = i / (ATT_KS / 4), ch = i % (ATT_KS / 4);
+    cp_async16(sh_h + b * LD + 4 * ch, a.h1 + (long long)b * a.H + k0 + 4 * ch);
   }
-  for (int i = tid; i < A3 * ATT_KS; i += nt) {
-    const int j = i / ATT_KS, k = i % ATT_KS;
-    sh_w[j * (ATT_KS + 1) + k] = __ldg(a.wT + (long long)j * a.H + k0 + k);
+  for (int i = tid; i < A3 * (ATT_KS / 4); i += nt) {
+    const int j = i / (ATT_KS / 4), ch = i % (ATT_KS / 4);
+    cp_async16(sh_w + j * LD + 4 * ch, a.wT + (long long)j * a.H + k0 + 4 * ch);
   }
+  cp_async_wait_all();
   __syncthreads();
   float* out = a.hat_part + (long long)slice * a.B * A3;
-  for (int i = tid; i < a.B * A3; i += nt) {
-    const int b = i / A3, j = i % A3;
-    const float* hr = sh_h + b * (ATT_KS + 1);
-    const float* wr = sh_w + j * (ATT_KS + 1);
-    float s = 0.0f;
+  // thread <-> (row b, output group jg): outputs j = jg + 4 i
+  for (int idx = tid; idx < a.B * 4; idx += nt) {
+    const int b = idx >> 2, jg = idx & 3;
+    const float4* hr = reinterpret_cast<const float4*>(sh_h + b * LD);
+    float acc[16];
 #pragma unroll
-    for (int k = 0; k < ATT_KS; ++k) s = fmaf(hr[k], wr[k], s);
-    out[i] = s;
+    for (int i = 0; i < 16; ++i) acc[i] = 0.0f;
+#pragma unroll
+    for (int k4 = 0; k4 < ATT_KS / 4; ++k4) {
+      const float4 hv = hr[k4];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int j = jg + 4 * i;
+        if (j < A3) {
+          const float4 wv = reinterpret_cast<const float4*>(sh_w + j * LD)[k4];
+          acc[i] = fmaf(hv.x, wv.x, acc[i]); acc[i] = fmaf(hv.y, wv.y, acc[i]);
+          acc[i] = fmaf(hv.z, wv.z, acc[i]); acc[i] = fmaf(hv.w, wv.w, acc[i]);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int j = jg + 4 * i;
+      if (j < A3) out[b * A3 + j] = acc[i];
+    }
   }
   __syncthreads();
 }
@@ -279,11 +300,16 @@ __device__ __forceinline__ void attention_window_part(const AttnFwdArgs& a, cons
   if (tid < 3 * A) {
     float s;
     if (nslices > 0) {
-      s = 0.0f;
       const float* src = a.hat_part + (long long)b * 3 * A + tid;
       const long long sstride = (long long)a.B * 3 * A;
-#pragma unroll 8
-      for (int q = 0; q < nslices; ++q) s += __ldcg(src + q * sstride);   // slice order
+      s = 0.0f;
+      for (int q0 = 0; q0 < nslices; q0 += 32) {   // 32 partials requested together, added in slice order
+        float x[32];
+#pragma unroll
+        for (int q = 0; q < 32; ++q) x[q] = (q0 + q < nslices) ? __ldcg(src + (q0 + q) * sstride) : 0.0f;
+#pragma unroll
+        for (int q = 0; q < 32; ++q) s += x[q];
+      }
       s += __ldg(a.batt + tid);
     } else {
       s = __ldcg(a.hat + (long long)b * 3 * A + tid);
@@ -585,12 +611,34 @@ __device__ __forceinline__ void attention_bwd_body(const AttnBwdArgs& a, const i
     a.datt_hi[(long long)b * a.Ap + tid] = hh;
     a.datt_lo[(long long)b * a.Ap + tid] = ll;
   }
-  for (int f = tid; f < a.H; f += blockDim.x) {
-    float s = 0.0f;
-    const float prev = a.dh1[(long long)b * a.H + f];
-#pragma unroll 10   // independent L2 loads in flight (3A = 30 rows of the transposed projection)
-    for (int j = 0; j < 3 * A; ++j) s = fmaf(sh_datt[j], __ldg(a.watt + (long long)j * a.H + f), s);
-    a.dh1[(long long)b * a.H + f] = prev + s;
+  if ((a.H & 3) == 0) {
+    for (int f = tid * 4; f < a.H; f += blockDim.x * 4) {
+      const float4 prev = ldcg4(a.dh1 + (long long)b * a.H + f);
+      float4 sacc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int j0 = 0; j0 < 3 * A; j0 += 16) {   // 16 rows of the transposed projection requested together
+        float4 w4[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          w4[j] = (j0 + j < 3 * A) ? ldg4(a.watt + (long long)(j0 + j) * a.H + f) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          if (j0 + j < 3 * A) {
+            const float dv = sh_datt[j0 + j];
+            sacc.x = fmaf(dv, w4[j].x, sacc.x); sacc.y = fmaf(dv, w4[j].y, sacc.y);
+            sacc.z = fmaf(dv, w4[j].z, sacc.z); sacc.w = fmaf(dv, w4[j].w, sacc.w);
+          }
+        }
+      }
+      *reinterpret_cast<float4*>(a.dh1 + (long long)b * a.H + f) =
+          make_float4(prev.x + sacc.x, prev.y + sacc.y, prev.z + sacc.z, prev.w + sacc.w);
+    }
+  } else {
+    for (int f = tid; f < a.H; f += blockDim.x) {
+      float s = 0.0f;
+      const float prev = a.dh1[(long long)b * a.H + f];
+      for (int j = 0; j < 3 * A; ++j) s = fmaf(sh_datt[j], __ldg(a.watt + (long long)j * a.H + f), s);
+      a.dh1[(long long)b * a.H + f] = prev + s;
+    }
   }
   __syncthreads();
 }
@@ -640,11 +688,13 @@ __device__ __forceinline__ void gru_bwd_pre_body(const ScanCtx& c, const int lay
     plo[po + Hp + f] = ll;
   }
 }
-// same as gru_bwd_pre_body restricted to batch rows [b0, b1), strided over an arbitrary worker set
+// same as gru_bwd_pre_body restricted to batch rows [b0, b1), strided over an arbitrary worker set.  One item = four
+// consecutive features of one row (128-bit accesses); two items of a thread are loaded before either is used.
+struct PreItem { float4 dh1, z, c, h, dh0; };
 __device__ __forceinline__ void gru_bwd_pre_rows(const ScanCtx& c, const int layer, const int t, const int b0,
                                                  const int b1, const int worker, const int nworkers) {
   const LayerBuf L = c.L[layer];
-  const int H = c.H, B = c.B, Np = c.Np, Hp = c.Hp;
+  const int H = c.H, B = c.B, Np = c.Np, Hp = c.Hp, H4 = H >> 2;
   const long long n = (long long)B * H;
   const float* __restrict__ zp = L.z + (long long)t * n;
   const float* __restrict__ cp = L.c + (long long)t * n;
@@ -653,26 +703,44 @@ __device__ __forceinline__ void gru_bwd_pre_rows(const ScanCtx& c, const int lay
   float* __restrict__ dap = L.da + (long long)t * B * 3 * H;
   bf16* __restrict__ phi = L.da_hi + (long long)t * Np * (3 * Hp);
   bf16* __restrict__ plo = L.da_lo + (long long)t * Np * (3 * Hp);
-  for (long long i = (long long)b0 * H + worker; i < (long long)b1 * H; i += nworkers) {
+  const long long n4 = (long long)(b1 - b0) * H4;
+  auto load = [&](long long i4, PreItem& it) {
+    const long long i = (long long)b0 * H + i4 * 4;
+    it.dh1 = ldcg4(dhp + i + n); it.z = ldcg4(zp + i); it.c = ldcg4(cp + i); it.h = ldcg4(hp + i); it.dh0 = ldcg4(dhp + i);
+  };
+  auto finish = [&](long long i4, const PreItem& it) {
+    const long long i = (long long)b0 * H + i4 * 4;
     const int b = (int)(i / H), f = (int)(i % H);
-    const float dh = dhp[i + n];
-    const float z = zp[i], cc = cp[i], hpv = hp[i];
-    const float dc = dh * z;
-    const float dz = dh * (cc - hpv);
-    dhp[i] += dh * (1.0f - z);
-    const float dac = dc * (1.0f - cc * cc);
-    const float dagz = dz * z * (1.0f - z);
+    float4 dh0, dac, dagz;
+#define PB_PRE1(m)                                             \
+    {                                                          \
+      const float dh = it.dh1.m, z = it.z.m, cc = it.c.m;      \
+      dh0.m = it.dh0.m + dh * (1.0f - z);                      \
+      dac.m = (dh * z) * (1.0f - cc * cc);                     \
+      dagz.m = (dh * (cc - it.h.m)) * z * (1.0f - z);          \
+    }
+    PB_PRE1(x) PB_PRE1(y) PB_PRE1(z) PB_PRE1(w)
+#undef PB_PRE1
+    *reinterpret_cast<float4*>(dhp + i) = dh0;
     const long long ao = (long long)b * 3 * H;
-    dap[ao + f] = dac;
-    dap[ao + H + f] = dagz;
+    *reinterpret_cast<float4*>(dap + ao + f) = dac;
+    *reinterpret_cast<float4*>(dap + ao + H + f) = dagz;
     const long long po = (long long)b * (3 * Hp);
-    bf16 hh, ll;
-    split_bf16(dac, hh, ll);
-    phi[po + f] = hh;
-    plo[po + f] = ll;
-    split_bf16(dagz, hh, ll);
-    phi[po + Hp + f] = hh;
-    plo[po + Hp + f] = ll;
+    uint2 hh, ll;
+    split4(dac, hh, ll);
+    *reinterpret_cast<uint2*>(phi + po + f) = hh;
+    *reinterpret_cast<uint2*>(plo + po + f) = ll;
+    split4(dagz, hh, ll);
+    *reinterpret_cast<uint2*>(phi + po + Hp + f) = hh;
+    *reinterpret_cast<uint2*>(plo + po + Hp + f) = ll;
+  };
+  for (long long i0 = worker; i0 < n4; i0 += 2LL * nworkers) {
+    const long long i1 = i0 + nworkers;
+    PreItem a0, a1;
+    load(i0, a0);
+    if (i1 < n4) load(i1, a1);
+    finish(i0, a0);
+    if (i1 < n4) finish(i1, a1);
   }
 }
 __global__ void gru_bwd_pre_kernel(const ScanCtx* cp, const PreArgs pa) {
@@ -694,8 +762,8 @@ constexpr int ATT_SMEM_BYTES = 24 * 1024;
 // only state_to_gates / state_to_state (+ the attention context product of layer 1): 41 MB of operand planes at the
 // base configuration instead of 86 MB, a set that stays L2-resident.
 struct ScanFwdParams {
-  EngineParams A, B;   // gates / candidates of all three layers (lags 0, Tc, 2 Tc)
-  EngineParams G;      // chunk products: pre2 of chunk e, pre3 of chunk e - 1 (njobs may be 0)
+  EngineParams ph[3];  // [0] gates / [1] candidates of all three layers (lags 0, Tc, 2 Tc) ;
+                       // [2] chunk products: pre2 of chunk e, pre3 of chunk e - 1 (njobs may be 0)
   AttnFwdArgs att;     // pointers of step 0
   long long s_h1, s_k, s_w, s_wp, s_phi, s_ab, s_e;   // per-step strides (elements)
   int T, Tc, nticks;
@@ -708,8 +776,8 @@ struct ScanFwdParams {
   int prefetch;                 // 1: weight tiles of the next phase are issued before its grid barrier
 };
 struct ScanBwdParams {
-  EngineParams B1, B2;  // d(r*h) products / recurrent state dgrads of all three layers
-  EngineParams G;       // chunk dgrads: from da3 of range e into dh2 / dh1 / dw, from da2 of range e - 1 into dh1 / dw
+  EngineParams ph[3];   // [0] d(r*h) products / [1] recurrent state dgrads of all three layers ;
+                        // [2] chunk dgrads: from da3 of range e into dh2 / dh1 / dw, from da2 of range e - 1 into dh1 / dw
   AttnBwdArgs att;      // pointers of step 0
   long long s_dw, s_ab, s_e, s_k, s_dh1, s_datt, s_dattp;
   const ScanCtx* ctx;
@@ -729,12 +797,14 @@ struct ScanBwdParams {
 
 // one GEMM phase of a persistent kernel: wait for the previous grid barrier where data produced by other
 // CTAs is consumed (producer: TMA of activation planes; epilogue: stashes), run the roles, arrive.
-template <class SP>
+// One GEMM phase of a persistent kernel.  DIR 1 / 2: forward / backward sweep.  `chunk`: plain chunk table (jobs read
+// from global memory) instead of a scan table (this CTA's job and epilogue context cached in shared memory).  There
+// is ONE call site per kernel (the phases share the code; EngineParams live in shared memory): the persistent loop
+// must stay small enough for the instruction caches.
+template <int DIR, class SP>
 __device__ __forceinline__ void persistent_gemm_phase(Pipe& p, const EngineParams& P, int tick, const SP& S,
-                                                      unsigned int& bar, int which) {
-  // P stays in kernel-parameter (constant) space: copying it would cost ~25 registers
+                                                      unsigned int& bar, const PhaseCache* pc, const bool chunk) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  (void)which;
   unsigned int* gridbar = S.gridbar;
   const unsigned int target = bar * gridDim.x;
   // the accumulator width of this phase (the smem ring keeps the stage stride chosen at kernel start)
@@ -742,20 +812,21 @@ __device__ __forceinline__ void persistent_gemm_phase(Pipe& p, const EngineParam
   p.b_bytes = (uint32_t)P.n_cols * KB * 2;
   if (warp == 0) {
     if (lane == 0) {
-      if (S.prefetch) producer_run(p, P, tick, gridbar, target);   // weight tiles ahead of the barrier
+      if (S.prefetch) producer_run(p, P, tick, gridbar, target, pc);   // weight tiles ahead of the barrier
       else {
         if (bar) grid_wait(gridbar, target);
-        producer_run(p, P, tick);
+        producer_run(p, P, tick, nullptr, 0, pc);
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    mma_run(p, P, tick);
+    mma_run(p, P, tick, pc);
   } else {
     if (warp == 2 && lane == 0 && bar) grid_wait(gridbar, target);   // one poller for the epilogue warps
     epi_group_sync();
     if (threadIdx.x == 64) { STAMP(S, bar, 0); TL(1); }
-    epilogue_run(p, P, tick);
+    if (chunk) epilogue_chunk(p, P, tick);
+    else epilogue_scan<DIR>(p, P, tick, pc);
     asm volatile("fence.proxy.async.global;" ::: "memory");
     epi_group_sync();
     if (threadIdx.x == 64) { STAMP(S, bar, 1); TL(8); grid_arrive(gridbar); }
@@ -763,40 +834,79 @@ __device__ __forceinline__ void persistent_gemm_phase(Pipe& p, const EngineParam
   ++bar;
 }
 
+// Shared-memory copies used by the persistent loops: the three EngineParams and, for the two scan tables, this CTA's
+// job and epilogue context (job index = CTA index, every tick).  All threads call this; ends with a CTA barrier.
+struct PersistShared {
+  EngineParams P[3];
+  PhaseCache pc[2];
+};
+__device__ __forceinline__ PersistShared* persist_shared_fill(uint8_t* area, const EngineParams* ph) {
+  PersistShared* ps = reinterpret_cast<PersistShared*>(area);
+  {
+    const int* src = reinterpret_cast<const int*>(ph);
+    int* dst = reinterpret_cast<int*>(ps->P);
+    for (int i = threadIdx.x; i < (int)(3 * sizeof(EngineParams) / 4); i += blockDim.x) dst[i] = src[i];
+  }
+  for (int k = 0; k < 2; ++k)
+    if ((int)blockIdx.x < ph[k].njobs) {
+      const int* src = reinterpret_cast<const int*>(ph[k].jobs + blockIdx.x);
+      int* dst = reinterpret_cast<int*>(&ps->pc[k].job);
+      for (int i = threadIdx.x; i < (int)(sizeof(Job) / 4); i += blockDim.x) dst[i] = src[i];
+    }
+  __syncthreads();
+  if (threadIdx.x == 0)
+    for (int k = 0; k < 2; ++k)
+      if ((int)blockIdx.x < ph[k].njobs) {
+        ps->pc[k].epi = make_epi_local(ps->pc[k].job, ph[k].ctx);
+        ps->pc[k].valid = 1;
+      }
+  __syncthreads();
+  return ps;
+}
+static_assert(sizeof(PersistShared) <= 1792, "PersistShared must fit behind the pipeline barriers");
+
 __global__ void __launch_bounds__(ENGINE_THREADS, 1) scan_fwd_persistent(const ScanFwdParams S) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   Pipe p;
-  const int max_cols = S.G.njobs > 0 && S.G.n_cols > S.A.n_cols ? S.G.n_cols : S.A.n_cols;
+  const int max_cols = S.ph[2].njobs > 0 && S.ph[2].n_cols > S.ph[0].n_cols ? S.ph[2].n_cols : S.ph[0].n_cols;
   float* att_sh = reinterpret_cast<float*>(pipe_setup(p, align_smem(smem_raw), max_cols));
+  p.stg = reinterpret_cast<uint8_t*>(att_sh); p.stg_bytes = ATT_SMEM_BYTES;   // finish operands (GEMM phases only)
+  const PersistShared* ps = persist_shared_fill(p.cache_area, S.ph);
   unsigned int bar = 0;
   for (int tick = 0; tick < S.nticks; ++tick) {
-    persistent_gemm_phase(p, S.A, tick, S, bar, 0);
-    persistent_gemm_phase(p, S.B, tick, S, bar, 1);
-    if (tick < S.T) {
-      AttnFwdArgs a = S.att;
-      a.h1 += tick * S.s_h1; a.k_prev += tick * S.s_k; a.k_out += tick * S.s_k; a.w_out += tick * S.s_w;
-      a.w_hi += tick * S.s_wp; a.w_lo += tick * S.s_wp; a.phi_out += tick * S.s_phi; a.ab_out += tick * S.s_ab;
-      a.e_out += tick * S.s_e;
-      // stage 1 (att_slices CTAs): K-sliced partial projections of h1_t ; stage 2 (att_parts CTAs per batch row):
-      // window + context slice.  CTAs without work only pass the barriers.
-      // (every CTA observes barrier k before it arrives at barrier k + 1: the arrival counter is monotonic)
-      if (threadIdx.x == 0) { grid_wait(S.gridbar, bar * gridDim.x); STAMP(S, bar, 0); }
-      __syncthreads();
-      for (int sl = blockIdx.x; sl < S.att_slices; sl += gridDim.x) attention_proj_slice(a, sl, att_sh);
-      __syncthreads();
-      if (threadIdx.x == 0) { STAMP(S, bar, 1); grid_arrive(S.gridbar); }
-      ++bar;
-      const int nwork = a.B * S.att_parts;
-      if (threadIdx.x == 0) { grid_wait(S.gridbar, bar * gridDim.x); STAMP(S, bar, 0); }
-      __syncthreads();
-      for (int i = blockIdx.x; i < nwork; i += gridDim.x)
-        attention_window_part<true>(a, i / S.att_parts, i % S.att_parts, S.att_parts, S.att_slices, att_sh);
-      asm volatile("fence.proxy.async.global;" ::: "memory");
-      __syncthreads();
-      if (threadIdx.x == 0) { STAMP(S, bar, 1); grid_arrive(S.gridbar); }
-      ++bar;
+    const bool event = ps->P[2].njobs > 0 && (tick + 1) % S.Tc == 0;
+#pragma unroll 1
+    for (int ph = 0; ph < 3; ++ph) {
+      if (ph == 2) {
+        if (tick < S.T) {
+          AttnFwdArgs a = S.att;
+          a.h1 += tick * S.s_h1; a.k_prev += tick * S.s_k; a.k_out += tick * S.s_k; a.w_out += tick * S.s_w;
+          a.w_hi += tick * S.s_wp; a.w_lo += tick * S.s_wp; a.phi_out += tick * S.s_phi; a.ab_out += tick * S.s_ab;
+          a.e_out += tick * S.s_e;
+          // stage 1 (att_slices CTAs): K-sliced partial projections of h1_t ; stage 2 (att_parts CTAs per batch
+          // row): window + context slice.  CTAs without work only pass the barriers.
+          // (every CTA observes barrier k before it arrives at barrier k + 1: the arrival counter is monotonic)
+          if (threadIdx.x == 0) { grid_wait(S.gridbar, bar * gridDim.x); STAMP(S, bar, 0); }
+          __syncthreads();
+          for (int sl = blockIdx.x; sl < S.att_slices; sl += gridDim.x) attention_proj_slice(a, sl, att_sh);
+          __syncthreads();
+          if (threadIdx.x == 0) { STAMP(S, bar, 1); grid_arrive(S.gridbar); }
+          ++bar;
+          const int nwork = a.B * S.att_parts;
+          if (threadIdx.x == 0) { grid_wait(S.gridbar, bar * gridDim.x); STAMP(S, bar, 0); }
+          __syncthreads();
+          for (int i = blockIdx.x; i < nwork; i += gridDim.x)
+            attention_window_part<true>(a, i / S.att_parts, i % S.att_parts, S.att_parts, S.att_slices, att_sh);
+          asm volatile("fence.proxy.async.global;" ::: "memory");
+          __syncthreads();
+          if (threadIdx.x == 0) { STAMP(S, bar, 1); grid_arrive(S.gridbar); }
+          ++bar;
+        }
+        if (!event) break;
+      }
+      persistent_gemm_phase<1>(p, ps->P[ph], ph == 2 ? (tick + 1) / S.Tc - 1 : tick, S, bar,
+                               ph < 2 ? &ps->pc[ph] : nullptr, ph == 2);
     }
-    if (S.G.njobs > 0 && (tick + 1) % S.Tc == 0) persistent_gemm_phase(p, S.G, (tick + 1) / S.Tc - 1, S, bar, 2);
   }
   pipe_teardown(p);
 }
@@ -804,8 +914,10 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) scan_fwd_persistent(const S
 __global__ void __launch_bounds__(ENGINE_THREADS, 1) scan_bwd_persistent(const ScanBwdParams S) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   Pipe p;
-  const int max_cols = S.G.njobs > 0 && S.G.n_cols > S.B1.n_cols ? S.G.n_cols : S.B1.n_cols;
+  const int max_cols = S.ph[2].njobs > 0 && S.ph[2].n_cols > S.ph[0].n_cols ? S.ph[2].n_cols : S.ph[0].n_cols;
   float* att_sh = reinterpret_cast<float*>(pipe_setup(p, align_smem(smem_raw), max_cols));
+  p.stg = reinterpret_cast<uint8_t*>(att_sh); p.stg_bytes = ATT_SMEM_BYTES;   // finish operands (GEMM phases only)
+  const PersistShared* ps = persist_shared_fill(p.cache_area, S.ph);
   unsigned int bar = 0;
   const ScanCtx& c = *S.ctx;
   for (int tick = 0; tick < S.nticks; ++tick) {
@@ -842,9 +954,11 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) scan_bwd_persistent(const S
       if (threadIdx.x == 0) { STAMP(S, bar, 1); grid_arrive(S.gridbar); }
       ++bar;
     }
-    persistent_gemm_phase(p, S.B1, tick, S, bar, 0);
-    persistent_gemm_phase(p, S.B2, tick, S, bar, 1);
-    if (S.G.njobs > 0 && (tick + 1) % S.Tc == 0) persistent_gemm_phase(p, S.G, (tick + 1) / S.Tc - 1, S, bar, 2);
+    const bool event = ps->P[2].njobs > 0 && (tick + 1) % S.Tc == 0;
+#pragma unroll 1
+    for (int ph = 0; ph < (event ? 3 : 2); ++ph)
+      persistent_gemm_phase<2>(p, ps->P[ph], ph == 2 ? (tick + 1) / S.Tc - 1 : tick, S, bar,
+                               ph < 2 ? &ps->pc[ph] : nullptr, ph == 2);
   }
   pipe_teardown(p);
 }

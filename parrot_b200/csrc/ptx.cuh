@@ -47,14 +47,17 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded spin: a mis-programmed pipeline traps instead of hanging the GPU box.
+// Bounded spins: a mis-programmed pipeline traps instead of hanging the GPU box.  The report is one out-of-line
+// function: an inlined printf costs ~30 instructions at every wait site of the persistent kernels.
+__device__ __noinline__ void pb_timeout(int what) {
+  printf("parrot_b200: %s timed out (block %d thread %d)\n",
+         what == 0 ? "mbarrier wait" : (what == 1 ? "grid barrier" : "split-K arrival wait"), blockIdx.x, threadIdx.x);
+  __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) {
-      printf("parrot_b200: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
-      __trap();
-    }
+    if (++spins > (1u << 26)) pb_timeout(0);
   }
 }
 
