@@ -141,6 +141,24 @@ int parrot_adam_clip_step(float* d_params, const float* d_grads, float* d_m, flo
                           float beta1, float beta2, float epsilon, int64_t time_step, float* d_stats,
                           double* d_scratch, void* stream);
 
+/* ---- data-parallel collective: ONE ncclAllReduce(SUM, fp32) per optimizer step over the
+ * flat [un-normalised gradients || sum(mask)] buffer, enqueued on the caller's stream right behind the last weight
+ * gradient kernel.  The reference is single-process (no collective anywhere): this replaces nothing in it,
+ * it is what train.py:100-108's GradientDescent step becomes when the minibatch is sharded over GPUs.
+ * NCCL is resolved at run time (dlopen of libnccl.so.2, the copy the process already loaded if any); a 1-rank
+ * communicator needs neither NCCL nor a GPU and its allreduce is the identity.
+ *   rank 0:      parrot_comm_unique_id(id)            -> 128 bytes, broadcast by the launcher (any side channel)
+ *   every rank:  parrot_comm_init(nranks, rank, id, &comm)   (cudaSetDevice must already be done)
+ *   per step:    parrot_comm_allreduce(comm, d_flat, count, stream)      in place, fp32 SUM
+ */
+typedef struct parrot_comm parrot_comm;
+#define PARROT_COMM_ID_BYTES 128
+int parrot_comm_unique_id(void* id128);
+int parrot_comm_init(int32_t nranks, int32_t rank, const void* id128, parrot_comm** out);
+int parrot_comm_allreduce(parrot_comm* comm, float* d_buf, int64_t count, void* stream);
+int parrot_comm_info(parrot_comm* comm, int32_t* nranks, int32_t* rank, int32_t* nccl_version);
+int parrot_comm_destroy(parrot_comm* comm);
+
 /* generic bf16x3 tensor-core GEMM used by the tests:  C[M][N] = A[M][K] * B[N][K]^T  (fp32 in/out) */
 int parrot_gemm_nt(const float* d_A, const float* d_B, float* d_C, int32_t M, int32_t N, int32_t K,
                    int32_t impl, void* d_workspace, size_t workspace_bytes, void* stream);

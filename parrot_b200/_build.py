@@ -29,7 +29,7 @@ def build(force=False, verbose=False):
     if not os.path.exists(nvcc):
         raise RuntimeError('parrot_b200: nvcc not found and %s is missing or stale' % LIB)
     cmd = [nvcc, '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
-           '-Xcompiler', '-fPIC', '-shared', '-o', LIB] + [os.path.join(CSRC, s) for s in SOURCES] + ['-lcuda']
+           '-Xcompiler', '-fPIC', '-shared', '-o', LIB] + [os.path.join(CSRC, s) for s in SOURCES] + ['-lcuda', '-ldl']
     if verbose:
         print(' '.join(cmd))
     subprocess.check_call(cmd)

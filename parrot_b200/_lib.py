@@ -36,6 +36,7 @@ SYMBOLS = [
     'parrot_readout_emit_bwd', 'parrot_attention_step', 'parrot_compute_cost', 'parrot_backward',
     'parrot_sample_scan', 'parrot_adam_clip_step', 'parrot_gemm_nt',
     'parrot_gemm_nt_workspace_bytes', 'parrot_launch_count',
+    'parrot_comm_unique_id', 'parrot_comm_init', 'parrot_comm_allreduce', 'parrot_comm_info', 'parrot_comm_destroy',
 ]
 
 
@@ -92,6 +93,11 @@ def load():
     lib.parrot_set_profiling.argtypes = [vp, C.c_int]
     lib.parrot_get_profile.argtypes = [vp, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     lib.parrot_gemm_nt.argtypes = [vp, vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, C.c_size_t, vp]
+    lib.parrot_comm_unique_id.argtypes = [vp]
+    lib.parrot_comm_init.argtypes = [C.c_int32, C.c_int32, vp, C.POINTER(vp)]
+    lib.parrot_comm_allreduce.argtypes = [vp, vp, C.c_int64, vp]
+    lib.parrot_comm_info.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    lib.parrot_comm_destroy.argtypes = [vp]
     _LIB = lib
     return lib
 

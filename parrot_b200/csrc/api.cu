@@ -353,25 +353,30 @@ struct parrot_model {
       } else {
         r.slot_pitch = (long long)p.rows * p.pitch; r.rows = p.rows; r.slots = p.slots;
       }
-      if (!dry) {
-        cuuint64_t dims[3] = {(cuuint64_t)p.pitch, (cuuint64_t)(rank == 2 ? p.rows_alloc : p.rows),
-                              (cuuint64_t)p.slots};
-        cuuint64_t strides[2] = {(cuuint64_t)p.pitch * 2, (cuuint64_t)p.rows * p.pitch * 2};
+      if (!dry && w == 0) {
+        // dims: k, rows[, slots], plane (hi, lo): one instruction loads both planes of a tile (lo tile behind the hi tile)
+        cuuint64_t dims[4] = {(cuuint64_t)p.pitch, (cuuint64_t)(rank == 2 ? p.rows_alloc : p.rows),
+                              (cuuint64_t)p.slots, 2};
+        const cuuint64_t plane_stride = (cuuint64_t)((const uint8_t*)p.lo - (const uint8_t*)p.hi);
+        cuuint64_t strides[3] = {(cuuint64_t)p.pitch * 2, (cuuint64_t)p.rows * p.pitch * 2, plane_stride};
         if (p.tiled_nkb > 0) {
           // tile-contiguous pack seen as a [tiles*128][64] matrix: every 128 x 64 box is one contiguous 16 KB block
           dims[0] = 64;
           dims[1] = (cuuint64_t)(p.rows_alloc / 128) * p.tiled_nkb * 128;
           strides[0] = 128;
         }
-        cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
-        cuuint32_t es[3] = {1, 1, 1};
-        CUresult res = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, (void*)r.base, dims,
+        cuuint32_t box[4] = {64, (cuuint32_t)box_rows, 1, 2};
+        cuuint32_t es[4] = {1, 1, 1, 1};
+        int trank = rank + 1;
+        if (rank == 2) { dims[2] = 2; strides[1] = plane_stride; box[2] = 2; }
+        REQUIRE(plane_stride % 16 == 0 && plane_stride > 0, "operand planes must be 16-byte aligned and hi < lo");
+        CUresult res = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)trank, (void*)r.base, dims,
                                     strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (res != CUDA_SUCCESS) {
           char b[256];
           snprintf(b, sizeof b, "cuTensorMapEncodeTiled failed (%d) rank %d rows %d pitch %d box %d", (int)res,
-                   rank, p.rows, p.pitch, box_rows);
+                   trank, p.rows, p.pitch, box_rows);
           throw std::runtime_error(b);
         }
       }
@@ -603,7 +608,7 @@ static void run_table(parrot_model& M, const std::string& name, int tick, int T,
   P.tick = tick; P.T = T; P.n_cols = t.n_cols; P.reverse = reverse;
   P.chunk_samples = t.chunk_samples;
   P.split_scratch = M.d_split_scratch; P.split_count = M.d_split_count;
-  P.timeline = M.timeline; P.tl_tick = -1;
+  P.timeline = M.tl_tick >= 0 ? nullptr : M.timeline; P.tl_tick = -1;   // (tl_tick >= 0: persistent-tick debugging)
   P.coop_epilogue = (t.count <= 148 && M.sm_count >= 148) ? 1 : 0;
   P.debug_flags = 0;
   cudaEvent_t pe = M.prof_begin(name, st);
@@ -1770,7 +1775,7 @@ static bool scan_bwd_persistent_launch(parrot_model& M, cudaStream_t st) {
   S.s_k = (long long)d.B * d.A; S.s_dh1 = (long long)d.B * d.H; S.s_datt = (long long)d.B * 3 * d.A;
   S.s_dattp = (long long)d.Np * M.planes.at("datt").pitch;
   S.ctx = M.d_ctx; S.T = d.T; S.gridbar = M.d_gridbar;
-  S.stamps = M.stamps_bwd; S.stamp_bars = M.stamps_bwd ? M.stamp_bars : 0; S.tl_buf = nullptr; S.tl_tick = -1;
+  S.stamps = M.stamps_bwd; S.stamp_bars = M.stamps_bwd ? M.stamp_bars : 0; S.tl_buf = M.timeline; S.tl_tick = M.tl_tick;
   S.prefetch = prefetch_enabled();
   CK(cudaMemsetAsync(M.d_gridbar, 0, 4, st));
   void* args[] = {&S};
@@ -1950,6 +1955,7 @@ static AttnBwdArgs attn_bwd_args(parrot_model& M, int t) {
   const Plane& p = M.planes.at("datt");
   a.datt_hi = p.hi + (long long)t * d.Np * p.pitch;
   a.datt_lo = p.lo + (long long)t * d.Np * p.pitch;
+  a.dbg = nullptr;
   return a;
 }
 static void attention_bwd_step(parrot_model& M, int t, cudaStream_t st) {
@@ -2534,6 +2540,110 @@ int parrot_adam_clip_step(float* d_params, const float* d_grads, float* d_m, flo
                                (1.0 - std::pow((double)beta1, t1)));
     LAUNCH(adam_kernel, 148 * 8, 256, 0, st, d_params, d_grads, d_m, d_v, (long long)n, d_stats, lr_t, beta1, beta2,
            epsilon);
+  });
+}
+
+// ------------------------------------------------------------------ data-parallel collective (NCCL, run-time bound)
+}  // extern "C"
+#include <dlfcn.h>
+namespace {
+struct NcclId { char internal[PARROT_COMM_ID_BYTES]; };
+typedef void* NcclComm;
+struct NcclApi {
+  void* handle = nullptr;
+  int (*GetVersion)(int*) = nullptr;
+  int (*GetUniqueId)(NcclId*) = nullptr;
+  int (*CommInitRank)(NcclComm*, int, NcclId, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+  int (*CommDestroy)(NcclComm) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+NcclApi& nccl_api() {
+  static NcclApi api;
+  if (api.handle) return api;
+  // the copy the process already uses (torch bundles one) before anything else: two NCCL instances in one process
+  // would each build their own transports
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+  if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  REQUIRE(h != nullptr, std::string("libnccl.so.2 not found: ") + (dlerror() ? dlerror() : ""));
+  auto sym = [&](const char* n) {
+    void* p = dlsym(h, n);
+    REQUIRE(p != nullptr, std::string("NCCL symbol missing: ") + n);
+    return p;
+  };
+  api.GetVersion = (int (*)(int*))sym("ncclGetVersion");
+  api.GetUniqueId = (int (*)(NcclId*))sym("ncclGetUniqueId");
+  api.CommInitRank = (int (*)(NcclComm*, int, NcclId, int))sym("ncclCommInitRank");
+  api.AllReduce = (int (*)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t))sym("ncclAllReduce");
+  api.CommDestroy = (int (*)(NcclComm))sym("ncclCommDestroy");
+  api.GetErrorString = (const char* (*)(int))sym("ncclGetErrorString");
+  api.handle = h;
+  return api;
+}
+void nccl_check(int rc, const char* what) {
+  if (rc != 0) {
+    const char* es = nccl_api().GetErrorString ? nccl_api().GetErrorString(rc) : "?";
+    throw std::runtime_error(std::string("parrot_b200: ") + what + " failed: " + es);
+  }
+}
+}  // namespace
+struct parrot_comm {
+  int nranks = 1, rank = 0, version = 0;
+  NcclComm comm = nullptr;
+};
+extern "C" {
+
+int parrot_comm_unique_id(void* id128) {
+  return guard([&] {
+    REQUIRE(id128 != nullptr, "id buffer is null");
+    NcclId id;
+    nccl_check(nccl_api().GetUniqueId(&id), "ncclGetUniqueId");
+    memcpy(id128, &id, sizeof id);
+  });
+}
+int parrot_comm_init(int32_t nranks, int32_t rank, const void* id128, parrot_comm** out) {
+  return guard([&] {
+    REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, "bad rank / nranks");
+    parrot_comm* c = new parrot_comm;
+    c->nranks = nranks; c->rank = rank;
+    if (nranks > 1) {
+      try {
+        REQUIRE(id128 != nullptr, "a communicator of more than one rank needs the unique id of rank 0");
+        NcclId id;
+        memcpy(&id, id128, sizeof id);
+        nccl_check(nccl_api().GetVersion(&c->version), "ncclGetVersion");
+        nccl_check(nccl_api().CommInitRank(&c->comm, nranks, id, rank), "ncclCommInitRank");
+      } catch (...) {
+        delete c;
+        throw;
+      }
+    }
+    *out = c;
+  });
+}
+int parrot_comm_allreduce(parrot_comm* comm, float* d_buf, int64_t count, void* stream) {
+  return guard([&] {
+    REQUIRE(comm != nullptr, "communicator is null");
+    if (comm->nranks == 1) return;   // identity
+    const int kFloat = 7, kSum = 0;  // ncclFloat32, ncclSum
+    nccl_check(nccl_api().AllReduce(d_buf, d_buf, (size_t)count, kFloat, kSum, comm->comm, (cudaStream_t)stream),
+               "ncclAllReduce");
+  });
+}
+int parrot_comm_info(parrot_comm* comm, int32_t* nranks, int32_t* rank, int32_t* nccl_version) {
+  return guard([&] {
+    REQUIRE(comm != nullptr, "communicator is null");
+    if (nranks) *nranks = comm->nranks;
+    if (rank) *rank = comm->rank;
+    if (nccl_version) *nccl_version = comm->version;
+  });
+}
+int parrot_comm_destroy(parrot_comm* comm) {
+  return guard([&] {
+    if (!comm) return;
+    if (comm->comm) nccl_check(nccl_api().CommDestroy(comm->comm), "ncclCommDestroy");
+    delete comm;
   });
 }
 

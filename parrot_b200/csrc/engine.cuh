@@ -848,32 +848,24 @@ __device__ __forceinline__ void pipe_teardown(Pipe& p) {
 }
 
 // ------------------------------------------------ TMA producer (one thread: warp 0, lane 0)
+// Every operand is a (hi, lo) pair of bf16 planes at a constant distance; the tensor map of a pair has one extra
+// "plane" dimension of extent 2, so ONE cp.async.bulk.tensor brings the hi tile and, right behind it in shared memory,
+// the lo tile (the single producer thread issues half as many instructions; each costs ~0.5 us of issue latency).
 __device__ __forceinline__ void producer_load_a(Pipe& p, const Seg& sg, int kb, const CUtensorMap* ma, uint8_t* st,
                                                 uint64_t* fb, uint64_t pol_keep) {
   if (sg.a_nkb > 0) {
     // tile-contiguous weight pack: one 16 KB contiguous block per plane, kept in L2 (re-read every step)
     const int trow = ((sg.a_row >> 7) * sg.a_nkb + (sg.a_k >> 6) + kb) << 7;
-    if (pol_keep) {
-      tma_load_2d_hint(st, ma, fb, 0, trow, pol_keep);
-      tma_load_2d_hint(st + p.a_bytes, ma + 1, fb, 0, trow, pol_keep);
-    } else {   // no per-instruction hint: the stream's access-policy window decides
-      tma_load_2d(st, ma, fb, 0, trow);
-      tma_load_2d(st + p.a_bytes, ma + 1, fb, 0, trow);
-    }
+    if (pol_keep) tma_load_3d_hint(st, ma, fb, 0, trow, 0, pol_keep);
+    else tma_load_3d(st, ma, fb, 0, trow, 0);   // no per-instruction hint: the stream's access-policy window decides
   } else {
-    tma_load_2d(st, ma, fb, sg.a_k + kb * KB, sg.a_row);
-    tma_load_2d(st + p.a_bytes, ma + 1, fb, sg.a_k + kb * KB, sg.a_row);
+    tma_load_3d(st, ma, fb, sg.a_k + kb * KB, sg.a_row, 0);
   }
 }
 __device__ __forceinline__ void producer_load_b(Pipe& p, const Seg& sg, int kb, int t, const CUtensorMap* mb,
                                                 uint8_t* st, uint64_t* fb, int n_shift) {
-  if (sg.b_slot == NO_SLOT) {
-    tma_load_2d(st + 2 * p.a_bytes, mb, fb, sg.b_k + kb * KB, sg.b_row + n_shift);
-    tma_load_2d(st + 2 * p.a_bytes + p.b_bytes, mb + 1, fb, sg.b_k + kb * KB, sg.b_row + n_shift);
-  } else {
-    tma_load_3d(st + 2 * p.a_bytes, mb, fb, sg.b_k + kb * KB, sg.b_row, t + sg.b_slot);
-    tma_load_3d(st + 2 * p.a_bytes + p.b_bytes, mb + 1, fb, sg.b_k + kb * KB, sg.b_row, t + sg.b_slot);
-  }
+  if (sg.b_slot == NO_SLOT) tma_load_3d(st + 2 * p.a_bytes, mb, fb, sg.b_k + kb * KB, sg.b_row + n_shift, 0);
+  else tma_load_4d(st + 2 * p.a_bytes, mb, fb, sg.b_k + kb * KB, sg.b_row, t + sg.b_slot, 0);
 }
 
 // gridbar != nullptr (persistent kernels): the activation (B) operands of this phase are produced by other CTAs
@@ -900,6 +892,15 @@ __device__ __forceinline__ void producer_run(Pipe& p, const EngineParams& P, int
     job_kb_range(jb, total_kb, klo, khi);
     int n_shift = 0;
     if (jb.epi == EPI_PLAIN && P.chunk_samples > 0) { int lim; chunk_window(P, jb, t, n_shift, lim); }
+    if (!waited) {
+      // descriptors of ALL operands (they are static; only the activation DATA waits for the barrier): fetched
+      // together now instead of one L2 round trip in front of every first use after the barrier
+      for (int s = 0; s < jb.nseg; ++s) {
+        const Seg& sg = jb.seg[s];
+        tma_prefetch_desc(P.maps + sg.a_map);
+        tma_prefetch_desc(P.maps + sg.b_map);
+      }
+    }
     int early = 0;   // k blocks of this job whose weight tiles were issued before the barrier
     if (!waited) {
       // ---- pass 1: weight tiles of the first min(nstages, khi - klo) k blocks
@@ -972,6 +973,7 @@ __device__ __forceinline__ void mma_run(Pipe& p, const EngineParams& P, int tick
     for (int kbi = 0; kbi < total_kb; ++kbi) {
       mbar_wait(&p.full_bar[p.stage], p.phase);
       tc_fence_after();
+      if (lane == 0 && kbi == 0) TL(11);
       if (lane == 0) {
         const uint8_t* st = p.tiles + (size_t)p.stage * p.stage_bytes;
         const uint64_t da_hi = umma_desc_sw128(st);

@@ -296,6 +296,22 @@ __device__ __forceinline__ void attention_window_part(const AttnFwdArgs& a, cons
   float* sh_phi = sh_abk + A3p;     // U
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int A = a.A;
+  // the first block of context rows of this warp is requested before anything else: it does not depend on phi, and a
+  // dependent global round trip costs 1-2 us inside the scan
+  const int Cs = a.C / nparts, c_base = part * Cs;
+  const float* cb = a.ctx + (long long)b * a.U * a.C + c_base;
+  const int nwarp = blockDim.x >> 5;
+  const int per = (a.U + nwarp - 1) / nwarp;
+  const int u0 = warp * per, u1 = min(a.U, u0 + per);
+  const bool wide = WIDE && (Cs & 3) == 0 && (a.C & 3) == 0;
+  float4 x0[16];
+  if (wide) {
+#pragma unroll
+    for (int r = 0; r < 16; ++r)
+      x0[r] = (u0 + r < u1 && lane * 4 < Cs)
+                  ? __ldg(reinterpret_cast<const float4*>(cb + (long long)(u0 + r) * a.C + lane * 4))
+                  : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   const float k_prev_reg = (tid < A) ? __ldcg(a.k_prev + (long long)b * A + tid) : 0.0f;
   if (tid < 3 * A) {
     float s;
@@ -369,21 +385,18 @@ __device__ __forceinline__ void attention_window_part(const AttnFwdArgs& a, cons
   __syncthreads();
   // w[c] for c in [c_base, c_base + Cs): warp w reduces its slice of text positions (same partition and order as
   // attention_fwd_body: the result is bit-identical to the one-CTA-per-row kernel)
-  const int Cs = a.C / nparts, c_base = part * Cs;
   float* sh_part = sh_phi + ((a.U + 3) & ~3);   // [nwarp][Cs]
-  const float* cb = a.ctx + (long long)b * a.U * a.C + c_base;
-  const int nwarp = blockDim.x >> 5;
-  const int per = (a.U + nwarp - 1) / nwarp;
-  const int u0 = warp * per, u1 = min(a.U, u0 + per);
-  if (WIDE && (Cs & 3) == 0 && (a.C & 3) == 0) {
+  if (wide) {
     for (int c = lane * 4; c < Cs; c += 128) {
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int ub = u0; ub < u1; ub += 16) {
         float4 x[16];
+        const bool first = (c == lane * 4) && (ub == u0);
 #pragma unroll
         for (int r = 0; r < 16; ++r)
-          x[r] = (ub + r < u1) ? __ldg(reinterpret_cast<const float4*>(cb + (long long)(ub + r) * a.C + c))
-                               : make_float4(0.f, 0.f, 0.f, 0.f);
+          x[r] = first ? x0[r]
+                       : ((ub + r < u1) ? __ldg(reinterpret_cast<const float4*>(cb + (long long)(ub + r) * a.C + c))
+                                        : make_float4(0.f, 0.f, 0.f, 0.f));
 #pragma unroll
         for (int r = 0; r < 16; ++r) {
           if (ub + r < u1) {
@@ -459,16 +472,42 @@ struct AttnBwdArgs {
   float* datt;          // [B][3A] fp32
   bf16* datt_hi;        // [Np][Ap]
   bf16* datt_lo;
+  unsigned long long* dbg;   // debug: [8] globaltimer milestones of batch row 0 (or null)
 };
+#define ADBG(i) do { if (a.dbg && b == 0 && threadIdx.x == 0) a.dbg[i] = gtime(); } while (0)
 
-__device__ __forceinline__ void attention_bwd_body(const AttnBwdArgs& a, const int b, float* sh) {
+__device__ __forceinline__ void gru_bwd_pre_rows(const ScanCtx& c, const int layer, const int t, const int b0,
+                                                 const int b1, const int worker, const int nworkers);
+// pre != nullptr (persistent backward scan): the GRU backward pre-pass of layer 1, step pre_t, row b is fused into the
+// last stage (dh1 of that row is complete exactly there), see gru_bwd_pre_rows for the arithmetic.
+// Load scheduling matters more than arithmetic here (every dependent global round trip costs 1-2 us inside the
+// scan): the first block of context rows is requested before anything else, the first 16 rows of the transposed
+// projection before the reductions (they do not depend on their results), the rest together with the pre-pass operands.
+__device__ __forceinline__ void attention_bwd_body(const AttnBwdArgs& a, const int b, float* sh,
+                                                   const ScanCtx* pre = nullptr, const int pre_t = 0) {
   float* sh_dw = sh;                    // C
   float* sh_dphi = sh_dw + a.C;         // U
   float* sh_red = sh_dphi + a.U;        // 3A * 16 warps
   float* sh_datt = sh_red + 3 * a.A * 16;// 3A, then 7A of prefetched per-row vectors
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int A = a.A, nwarp = blockDim.x >> 5;
-  for (int i = tid; i < a.C; i += blockDim.x) sh_dw[i] = a.dw[(long long)b * a.C + i];
+  const float* cb = a.ctx + (long long)b * a.U * a.C;
+  const bool fast = (a.C & 3) == 0 && a.C <= 256;
+  float4 x[8][2];
+  ADBG(0);
+  if (fast) {
+    const int u = warp * 8;
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c = lane * 4 + h * 128;
+        x[r][h] = (u + r < a.U && c < a.C)
+                      ? __ldg(reinterpret_cast<const float4*>(cb + (long long)(u + r) * a.C + c))
+                      : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+  }
+  for (int i = tid; i < a.C; i += blockDim.x) sh_dw[i] = __ldcg(a.dw + (long long)b * a.C + i);
   // small per-row vectors needed after the reductions: fetch them now, off the dependent chain
   float* sh_small = sh_datt + 3 * A;   // [ab 2A | kappa A | e 3A | dk_carry A]
   for (int i = tid; i < 7 * A; i += blockDim.x) {
@@ -476,24 +515,25 @@ __device__ __forceinline__ void attention_bwd_body(const AttnBwdArgs& a, const i
     if (i < 2 * A) v = a.ab[(long long)b * 2 * A + i];
     else if (i < 3 * A) v = a.kappa[(long long)b * A + (i - 2 * A)];
     else if (i < 6 * A) v = a.e[(long long)b * 3 * A + (i - 3 * A)];
-    else v = a.dk_carry[(long long)b * A + (i - 6 * A)];
+    else v = __ldcg(a.dk_carry + (long long)b * A + (i - 6 * A));
     sh_small[i] = v;
   }
   __syncthreads();
-  const float* cb = a.ctx + (long long)b * a.U * a.C;
-  if ((a.C & 3) == 0 && a.C <= 256) {
+  ADBG(1);
+  if (fast) {
     // 8 text positions per warp pass, all loads of a pass (<= 16 x 128 bit per lane) issued before the first use
     for (int u = warp * 8; u < a.U; u += nwarp * 8) {
-      float4 x[8][2];
+      if (u != warp * 8) {
 #pragma unroll
-      for (int r = 0; r < 8; ++r)
+        for (int r = 0; r < 8; ++r)
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int c = lane * 4 + h * 128;
-          x[r][h] = (u + r < a.U && c < a.C)
-                        ? __ldg(reinterpret_cast<const float4*>(cb + (long long)(u + r) * a.C + c))
-                        : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+          for (int h = 0; h < 2; ++h) {
+            const int c = lane * 4 + h * 128;
+            x[r][h] = (u + r < a.U && c < a.C)
+                          ? __ldg(reinterpret_cast<const float4*>(cb + (long long)(u + r) * a.C + c))
+                          : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+      }
       float4 d[2];
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
@@ -520,8 +560,8 @@ __device__ __forceinline__ void attention_bwd_body(const AttnBwdArgs& a, const i
 #pragma unroll
         for (int r = 0; r < 4; ++r)
           if (u + r < a.U) {
-            const float4 x = __ldg(reinterpret_cast<const float4*>(cb + (long long)(u + r) * a.C + c));
-            s4[r] += d.x * x.x + d.y * x.y + d.z * x.z + d.w * x.w;
+            const float4 xx = __ldg(reinterpret_cast<const float4*>(cb + (long long)(u + r) * a.C + c));
+            s4[r] += d.x * xx.x + d.y * xx.y + d.z * xx.z + d.w * xx.w;
           }
       }
     } else {
@@ -538,7 +578,19 @@ __device__ __forceinline__ void attention_bwd_body(const AttnBwdArgs& a, const i
       if (lane == 0 && u + r < a.U) sh_dphi[u + r] = sv;
     }
   }
+  // first half of the dh1 update's operands (this thread's first feature quad): requested now, consumed after the
+  // reductions
+  const bool vec = (a.H & 3) == 0;
+  const int f0 = tid * 4;
+  float4 prev0 = make_float4(0.f, 0.f, 0.f, 0.f), w4[16];
+  if (vec && f0 < a.H) {
+    prev0 = ldcg4(a.dh1 + (long long)b * a.H + f0);
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      w4[j] = (j < 3 * A) ? ldg4(a.watt + (long long)j * a.H + f0) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   __syncthreads();
+  ADBG(2);
   // per-component reductions over u
   for (int i = 0; i < A; ++i) {
     const float al = sh_small[i];
@@ -611,26 +663,73 @@ __device__ __forceinline__ void attention_bwd_body(const AttnBwdArgs& a, const i
     a.datt_hi[(long long)b * a.Ap + tid] = hh;
     a.datt_lo[(long long)b * a.Ap + tid] = ll;
   }
-  if ((a.H & 3) == 0) {
-    for (int f = tid * 4; f < a.H; f += blockDim.x * 4) {
-      const float4 prev = ldcg4(a.dh1 + (long long)b * a.H + f);
-      float4 sacc = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int j0 = 0; j0 < 3 * A; j0 += 16) {   // 16 rows of the transposed projection requested together
-        float4 w4[16];
+  ADBG(3);
+  if (vec) {
+    // dh1[b][f..f+3] += sum_j datt[j] * watt[j][f..f+3]; with `pre`, the row's GRU backward pre-pass follows at once
+    const LayerBuf* L = pre ? &pre->L[0] : nullptr;
+    for (int f = f0; f < a.H; f += blockDim.x * 4) {
+      float4 prev = prev0;
+      if (f != f0) {
+        prev = ldcg4(a.dh1 + (long long)b * a.H + f);
 #pragma unroll
         for (int j = 0; j < 16; ++j)
-          w4[j] = (j0 + j < 3 * A) ? ldg4(a.watt + (long long)(j0 + j) * a.H + f) : make_float4(0.f, 0.f, 0.f, 0.f);
+          w4[j] = (j < 3 * A) ? ldg4(a.watt + (long long)j * a.H + f) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      // second request block: the remaining projection rows and the pre-pass operands
+      float4 w5[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          if (j0 + j < 3 * A) {
-            const float dv = sh_datt[j0 + j];
-            sacc.x = fmaf(dv, w4[j].x, sacc.x); sacc.y = fmaf(dv, w4[j].y, sacc.y);
-            sacc.z = fmaf(dv, w4[j].z, sacc.z); sacc.w = fmaf(dv, w4[j].w, sacc.w);
-          }
+      for (int j = 0; j < 16; ++j)
+        w5[j] = (16 + j < 3 * A) ? ldg4(a.watt + (long long)(16 + j) * a.H + f) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 pz = prev, pc = prev, phv = prev, pd0 = prev;
+      long long pi = 0;
+      if (L) {
+        pi = ((long long)pre_t * pre->B + b) * a.H + f;
+        pz = ldcg4(L->z + pi); pc = ldcg4(L->c + pi); phv = ldcg4(L->h + pi); pd0 = ldcg4(L->dh + pi);
+      }
+      float4 sacc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        if (j < 3 * A) {
+          const float dv = sh_datt[j];
+          sacc.x = fmaf(dv, w4[j].x, sacc.x); sacc.y = fmaf(dv, w4[j].y, sacc.y);
+          sacc.z = fmaf(dv, w4[j].z, sacc.z); sacc.w = fmaf(dv, w4[j].w, sacc.w);
         }
       }
-      *reinterpret_cast<float4*>(a.dh1 + (long long)b * a.H + f) =
-          make_float4(prev.x + sacc.x, prev.y + sacc.y, prev.z + sacc.z, prev.w + sacc.w);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        if (16 + j < 3 * A) {
+          const float dv = sh_datt[16 + j];
+          sacc.x = fmaf(dv, w5[j].x, sacc.x); sacc.y = fmaf(dv, w5[j].y, sacc.y);
+          sacc.z = fmaf(dv, w5[j].z, sacc.z); sacc.w = fmaf(dv, w5[j].w, sacc.w);
+        }
+      }
+      const float4 dh1 = make_float4(prev.x + sacc.x, prev.y + sacc.y, prev.z + sacc.z, prev.w + sacc.w);
+      *reinterpret_cast<float4*>(a.dh1 + (long long)b * a.H + f) = dh1;
+      if (L) {
+        const int H = a.H, Hp = pre->Hp;
+        float4 dh0, dac, dagz;
+#define PB_PRE1(m)                                           \
+        {                                                    \
+          const float dh = dh1.m, z = pz.m, cc = pc.m;       \
+          dh0.m = pd0.m + dh * (1.0f - z);                   \
+          dac.m = (dh * z) * (1.0f - cc * cc);               \
+          dagz.m = (dh * (cc - phv.m)) * z * (1.0f - z);     \
+        }
+        PB_PRE1(x) PB_PRE1(y) PB_PRE1(z) PB_PRE1(w)
+#undef PB_PRE1
+        *reinterpret_cast<float4*>(L->dh + pi) = dh0;
+        float* dap = L->da + ((long long)pre_t * pre->B + b) * 3 * H;
+        *reinterpret_cast<float4*>(dap + f) = dac;
+        *reinterpret_cast<float4*>(dap + H + f) = dagz;
+        const long long po = ((long long)pre_t * pre->Np + b) * (3 * Hp);
+        uint2 hh, ll;
+        split4(dac, hh, ll);
+        *reinterpret_cast<uint2*>(L->da_hi + po + f) = hh;
+        *reinterpret_cast<uint2*>(L->da_lo + po + f) = ll;
+        split4(dagz, hh, ll);
+        *reinterpret_cast<uint2*>(L->da_hi + po + Hp + f) = hh;
+        *reinterpret_cast<uint2*>(L->da_lo + po + Hp + f) = ll;
+      }
     }
   } else {
     for (int f = tid; f < a.H; f += blockDim.x) {
@@ -639,8 +738,14 @@ __device__ __forceinline__ void attention_bwd_body(const AttnBwdArgs& a, const i
       for (int j = 0; j < 3 * A; ++j) s = fmaf(sh_datt[j], __ldg(a.watt + (long long)j * a.H + f), s);
       a.dh1[(long long)b * a.H + f] = prev + s;
     }
+    if (pre) {
+      __syncthreads();
+      gru_bwd_pre_rows(*pre, 0, pre_t, b, b + 1, tid, blockDim.x);
+    }
   }
+  ADBG(4);
   __syncthreads();
+  ADBG(5);
 }
 
 __global__ void __launch_bounds__(256) attention_bwd_kernel(const AttnBwdArgs a) {
@@ -935,11 +1040,11 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) scan_bwd_persistent(const S
       const int nB = att_valid ? min(S.att.B, (int)gridDim.x / 2) : 0;   // CTAs doing attention rows
       if ((int)blockIdx.x < nB) {
         AttnBwdArgs a = S.att;
+        a.dbg = (S.tl_buf && tick == S.tl_tick) ? S.tl_buf + 2 * 148 * 16 : nullptr;
         a.dw += ta * S.s_dw; a.ab += ta * S.s_ab; a.e += ta * S.s_e; a.kappa += ta * S.s_k; a.dh1 += ta * S.s_dh1;
         a.datt += ta * S.s_datt; a.datt_hi += ta * S.s_dattp; a.datt_lo += ta * S.s_dattp;
         for (int b = blockIdx.x; b < a.B; b += nB) {
-          attention_bwd_body(a, b, att_sh);
-          gru_bwd_pre_rows(c, 0, ta, b, b + 1, threadIdx.x, blockDim.x);
+          attention_bwd_body(a, b, att_sh, &c, ta);   // + the row's GRU backward pre-pass of layer 1
         }
       } else {
         const int nworkers = (int)gridDim.x - nB;

@@ -82,6 +82,16 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* map, uin
       : "memory");
 }
 
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const void* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      :
+      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1),
+        "r"(c2), "r"(c3)
+      : "memory");
+}
+
 // L2 eviction-priority policies for TMA loads: recurrent weights are re-read every decoder step (keep),
 // activation planes are consumed once or twice (stream).
 __device__ __forceinline__ uint64_t l2_policy_evict_last() {

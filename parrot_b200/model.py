@@ -76,6 +76,7 @@ class _Handle(object):
         try:
             if self.ptr:
                 self.lib.parrot_destroy(self.ptr)
+                self.ptr = None
         except Exception:
             pass
 
@@ -112,8 +113,10 @@ class Parrot(object):
                 raise RuntimeError('parrot_b200 needs a CUDA device (sm_100a); there is no CPU fallback')
             device = torch.device('cuda', torch.cuda.current_device())
         self.device = torch.device(device)
-        self._handles = {}
+        self._handles = OrderedDict()          # (B, T, U, sampling) -> _Handle, least recently used first
+        self.max_handles = 4                   # each handle owns a full workspace (GBs at base size): LRU eviction
         self._last = None
+        self._gen = None                       # torch.Generator of the default noise draws, see seed_noise()
         self.flat_params = None
         layout, total = _lib.param_layout(self._make_cfg(1, 1, 1, 0))
         self._layout, self.num_floats = layout, total
@@ -167,6 +170,7 @@ class Parrot(object):
             host[off:off + k] = (rng.standard_normal(shape) * sd).astype(np.float32).ravel()
         self.flat_params.copy_(torch.from_numpy(host))
         self.mark_dirty()
+        self.seed_noise(seed)
         return self
 
     def set_parameter_values(self, values):
@@ -180,6 +184,22 @@ class Parrot(object):
     def get_parameter_values(self):
         return OrderedDict((n, p.detach().cpu().numpy().copy()) for n, p in self.parameters.items())
 
+    def seed_noise(self, seed, rank=None):
+        """Seed the generator of the default feedback-noise / GMM draws from (seed, rank): runs are reproducible from
+        ``--seed`` and data-parallel ranks draw DIFFERENT noise for their shards (a global default generator would give
+        every rank the same stream)."""
+        import os
+        if rank is None:
+            rank = int(os.environ.get('RANK', '0'))
+        self._gen = torch.Generator(device=self.device)
+        self._gen.manual_seed((int(seed) * 1000003 + 7919 * int(rank) + 17) % (2 ** 63 - 1))
+        return self
+
+    def _generator(self):
+        if self._gen is None:
+            self.seed_noise(0)
+        return self._gen
+
     def mark_dirty(self):
         """Tell the device handles that the fp32 parameters changed (operand planes are re-derived)."""
         for h in self._handles.values():
@@ -191,13 +211,27 @@ class Parrot(object):
         key = (B, T, U, bool(sampling))
         h = self._handles.get(key)
         if h is None:
+            # least-recently-used eviction: U (padded text length) changes from batch to batch on real data and every
+            # handle owns packed weight planes + all activation stashes, so an unbounded cache runs out of memory
+            while len(self._handles) >= max(1, self.max_handles):
+                old_key = next(k for k in self._handles if self._handles[k] is not self._last or len(self._handles) == 1)
+                old = self._handles.pop(old_key)
+                if old is self._last:
+                    self._last = None
+                old.lib.parrot_destroy(old.ptr)
+                old.ptr = None
+                del old
             h = _Handle(self, B, T, U, sampling)
             self._handles[key] = h
-            # carried state follows the model, not the handle (model.py:534-546 shared variables)
-            prev = self._last
-            if prev is not None and prev is not h and prev.B == B and not sampling and not prev.sampling:
-                for nm, shp in self._state_shapes(B):
-                    h.buffer(nm, shp).copy_(prev.buffer(nm, shp))
+        else:
+            self._handles.move_to_end(key)
+        # carried state follows the MODEL, not the handle (model.py:534-546: one set of last_* shared variables):
+        # whenever the handle changes, the state of the previous training call moves with it
+        prev = self._last
+        if (not sampling and prev is not None and prev is not h and not prev.sampling and prev.B == B
+                and prev.ptr):
+            for nm, shp in self._state_shapes(B):
+                h.buffer(nm, shp).copy_(prev.buffer(nm, shp))
         return h
 
     def _state_shapes(self, B):
@@ -288,13 +322,13 @@ class Parrot(object):
         if self.feedback_noise_level:                                    # truthiness gate (hazard H6)
             level = float(self.feedback_noise_level if noise_level is None else noise_level)
             if feedback_noise is None:
-                feedback_noise = torch.randn(T, B, self.output_dim, device=self.device)
+                feedback_noise = torch.randn(T, B, self.output_dim, device=self.device, generator=self._generator())
             noise = self._dev(feedback_noise, torch.float32)
         unis = normals = None
         if self.which_cost == 'GMM':
             if gmm_noise is None:
-                gmm_noise = (torch.rand(T, B, device=self.device),
-                             torch.randn(T, B, self.output_dim, device=self.device))
+                gmm_noise = (torch.rand(T, B, device=self.device, generator=self._generator()),
+                             torch.randn(T, B, self.output_dim, device=self.device, generator=self._generator()))
             unis = self._dev(gmm_noise[0], torch.float32)
             normals = self._dev(gmm_noise[1], torch.float32)
         stream = torch.cuda.current_stream(self.device).cuda_stream

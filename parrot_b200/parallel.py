@@ -55,10 +55,82 @@ def shard_batch(batch, rank, world):
     return out
 
 
+class Comm(object):
+    """The C-ABI collective of the data-parallel step (include/parrot_b200.h ``parrot_comm_*``): NCCL bound at run
+    time, ONE in-place fp32 SUM allreduce per optimizer step on the caller's CUDA stream.  ``torch.distributed`` is used
+    for the rendezvous only (broadcast of the 128-byte NCCL unique id)."""
+
+    def __init__(self, nranks, rank, unique_id=None):
+        import ctypes as C
+        from . import _lib
+        self._C, self._lib = C, _lib.load()
+        self.nranks, self.rank = int(nranks), int(rank)
+        self.ptr = C.c_void_p()
+        buf = C.create_string_buffer(bytes(unique_id), 128) if unique_id is not None else None
+        _lib.check(self._lib.parrot_comm_init(self.nranks, self.rank, buf, C.byref(self.ptr)))
+
+    @staticmethod
+    def unique_id():
+        import ctypes as C
+        from . import _lib
+        buf = C.create_string_buffer(128)
+        _lib.check(_lib.load().parrot_comm_unique_id(buf))
+        return buf.raw
+
+    def allreduce(self, flat):
+        """In-place SUM of a contiguous float32 tensor on the current CUDA stream (identity for one rank)."""
+        from . import _lib
+        C = self._C
+        assert flat.dtype == torch.float32 and flat.is_contiguous()
+        stream = torch.cuda.current_stream(flat.device).cuda_stream if flat.is_cuda else 0
+        _lib.check(self._lib.parrot_comm_allreduce(self.ptr, C.c_void_p(flat.data_ptr()), flat.numel(),
+                                                   C.c_void_p(stream)))
+        return flat
+
+    def info(self):
+        C = self._C
+        n, r, v = C.c_int32(), C.c_int32(), C.c_int32()
+        self._lib.parrot_comm_info(self.ptr, C.byref(n), C.byref(r), C.byref(v))
+        return n.value, r.value, v.value
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                self._lib.parrot_comm_destroy(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
+
+
+_COMM = None
+
+
+def get_comm():
+    """The process-wide NCCL communicator of the C ABI, created on first use from the torch.distributed rendezvous
+    (rank 0 draws the unique id, everyone receives it).  None for a single process or a CPU-only (gloo) run."""
+    global _COMM
+    if _COMM is not None:
+        return _COMM
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return None
+    if not torch.cuda.is_available():
+        return None
+    box = [Comm.unique_id() if dist.get_rank() == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    _COMM = Comm(dist.get_world_size(), dist.get_rank(), box[0])
+    return _COMM
+
+
 def allreduce_flat(flat, group=None):
-    """SUM-allreduce of the flat [grads || sum(mask)] buffer, in place.  Identity for one rank."""
+    """SUM-allreduce of the flat [grads || sum(mask)] buffer, in place.  Identity for one rank.  CUDA tensors go
+    through the C-ABI NCCL communicator on the current stream; CPU tensors (the gloo tests of the host logic) through
+    torch.distributed."""
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        comm = get_comm() if (flat.is_cuda and group is None) else None
+        if comm is not None:
+            comm.allreduce(flat)
+        else:
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
     return flat
 
 

@@ -106,3 +106,20 @@ def test_parrot_without_cuda_fails_loudly():
     from parrot_b200.model import Parrot
     with pytest.raises(RuntimeError, match='no CPU fallback'):
         Parrot(**util.TINY)
+
+
+def test_comm_single_rank_is_the_identity_without_nccl_or_gpu():
+    """parrot_comm_* (SURVEY 8b C1): a 1-rank communicator needs neither NCCL nor a device; allreduce leaves the buffer
+    untouched, info reports (1, 0).  The N-rank path is covered on hardware by tests/test_gpu_multirank.py."""
+    import torch
+    from parrot_b200 import parallel
+    c = parallel.Comm(1, 0)
+    x = torch.arange(16, dtype=torch.float32)
+    y = c.allreduce(x.clone())
+    assert torch.equal(x, y)
+    assert c.info()[:2] == (1, 0)
+    lib = _lib().load()
+    # bad arguments come back as error codes, never as exceptions across the C boundary
+    ptr = C.c_void_p()
+    assert lib.parrot_comm_init(2, 5, None, C.byref(ptr)) != 0
+    assert b'rank' in lib.parrot_last_error()

@@ -1,7 +1,8 @@
 """GPU parity tests: parrot_b200.Parrot (CUDA, through the C ABI) vs the numpy oracle on seeded inputs.
 
 Gates (BASELINE.json north_star): emitted frames within 1e-3 relative of the oracle, argmax of the
-alignment phi bit-exact wherever the oracle's own argmax is unambiguous (tests/util.stable_argmax_mask).
+alignment phi EQUAL to the oracle's on every frame whose top-2 gap exceeds 1e-4 relative, coverage >= 0.9 printed
+(tests/util.argmax_parity); element-wise relative error of the frames above 1e-2 * max also gated (5e-3).
 Gradients are held to 2e-3 of each tensor's max-abs (bf16x3 operands, different summation order).
 """
 import numpy as np
@@ -53,10 +54,8 @@ def _run_pair(cfg, B, T, U, gain, impl, start_flags=(1.0,), axis=0, align=None, 
                 continue
             err = util.rel_err(a.cpu().numpy(), b)
             assert err < FWD_TOL, (nm, err)
-        ok = util.stable_argmax_mask(av_o[4], av64[4])
-        am_d = av_d[4].cpu().numpy().argmax(-1)
-        assert ok.mean() > 0.5
-        assert (am_d[ok] == av_o[4].argmax(-1)[ok]).all()
+        util.argmax_parity(av_d[4].cpu().numpy(), av_o[4], 'vs float32 oracle')
+        assert util.rel_err_elementwise(av_d[0].cpu().numpy(), av_o[0]) < 5e-3
         for (n1, v1), (n2, v2) in zip(up_d, up_o):
             assert n1 == n2 and util.rel_err(v1.cpu().numpy(), v2) < FWD_TOL, n1
         if check_grads:
@@ -165,10 +164,7 @@ def test_device_matches_golden_fixtures(name):
             if key in z.files and v is not None:
                 assert util.rel_err(v.cpu().numpy(), z[key]) < FWD_TOL, nm
         phi = z[p + 'out:phi']
-        top2 = np.sort(phi, -1)[..., -2:]
-        ok = (top2[..., 1] - top2[..., 0]) > 1e-4 * np.abs(top2[..., 1])
-        assert ok.mean() > 0.5
-        assert (av[4].cpu().numpy().argmax(-1)[ok] == z[p + 'argmax_phi'][ok]).all()
+        util.argmax_parity(av[4].cpu().numpy(), phi, 'vs frozen oracle vectors')
         for nm, v in updates:
             assert util.rel_err(v.cpu().numpy(), z[p + 'update:' + nm]) < FWD_TOL, nm
         g = dev.backward()
@@ -209,10 +205,7 @@ def test_device_matches_reference_source_fixtures(name):
         for nm, v in zip(['next_x', 'k', 'w', 'coeff', 'phi', 'pi_att'], av):
             assert util.rel_err(v.cpu().numpy(), z[p + 'out:' + nm]) < FWD_TOL, (nm, seg)
         phi = z[p + 'out:phi']
-        top2 = np.sort(phi, -1)[..., -2:]
-        ok = (top2[..., 1] - top2[..., 0]) > 1e-4 * np.abs(top2[..., 1])
-        assert ok.mean() > 0.5
-        assert (av[4].cpu().numpy().argmax(-1)[ok] == phi.argmax(-1)[ok]).all()
+        util.argmax_parity(av[4].cpu().numpy(), phi, 'vs reference-source fixtures')
         for nm, v in updates:
             assert util.rel_err(v.cpu().numpy(), z[p + 'update:' + nm]) < FWD_TOL, nm
     smp = Parrot(**dict(cfg, **SAMP))

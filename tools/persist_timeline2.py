@@ -71,13 +71,16 @@ print('sum per tick (chunk amortised): %.2f us' % tot)
 
 # ---- intra-phase milestones of one steady-state tick (both GEMM phases)
 tick = 2 * Tc + 8
-tl = torch.zeros(2 * 148 * 16, dtype=torch.int64, device='cuda')
+tl = torch.zeros(3 * 148 * 16, dtype=torch.int64, device='cuda')
 lib.parrot_debug_set_stamps(h.ptr, C.c_void_p(tl.data_ptr()), -tick)
 step()
 torch.cuda.synchronize()
 lib.parrot_debug_set_stamps(h.ptr, None, 0)
-tl = tl.cpu().numpy().reshape(2, 148, 16).astype(np.float64)
-names = {1: 'barrier_passed(epi)', 10: 'barrier_passed(tma)', 9: 'operands_requested', 2: 'tma_all_issued', 3: 'mma_all_issued', 4: 'acc_ready',
+dbg = tl.cpu().numpy()[2 * 148 * 16:2 * 148 * 16 + 8].astype(np.float64)
+if (dbg > 0).any():
+    print('attention-bwd row 0 milestones (us):', [round((x - dbg[0]) / 1e3, 2) for x in dbg[:6]])
+tl = tl.cpu().numpy()[:2 * 148 * 16].reshape(2, 148, 16).astype(np.float64)
+names = {1: 'barrier_passed(epi)', 10: 'barrier_passed(tma)', 9: 'operands_requested', 11: 'first_stage_landed', 2: 'tma_all_issued', 3: 'mma_all_issued', 4: 'acc_ready',
          5: 'part_written', 6: 'all_arrived', 7: 'finish_done', 8: 'phase_done'}
 for ph in range(2):
     a = tl[ph]
@@ -85,7 +88,7 @@ for ph in range(2):
         continue
     t0 = a[a > 0].min()
     print('phase', ph)
-    for i in (1, 10, 9, 2, 3, 4, 5, 6, 7, 8):
+    for i in (1, 10, 9, 11, 2, 3, 4, 5, 6, 7, 8):
         col = a[:, i]; ok = col > 0
         if ok.any():
             d = (col[ok] - t0) / 1e3
