@@ -238,6 +238,11 @@ struct WPack {
 struct Table {
   int off = 0, count = 0, n_cols = 0;
   int chunk_samples = 0;   // > 0: chunk table (engine.cuh chunk_window)
+  // split-K scratch of the table: tables that only ever run one after the other share region 0; tables of the
+  // grouped persistent scans (several tables in flight at once) own a region behind it (uniq >= 0: float / counter
+  // offsets relative to the end of the shared region)
+  long long uniq_floats = -1;
+  int uniq_groups = -1;
 };
 struct Buf {
   size_t off;
@@ -273,7 +278,11 @@ struct parrot_model {
   std::vector<WGrad> wgrads;
   int max_groups = 0;
   size_t max_split_floats = 0;
+  long long uniq_split_floats = 0;   // total of the per-table scratch regions (grouped scans)
+  int uniq_split_groups = 0;
   int Tc = 0;              // chunk length of the chunk-lagged layer wavefront (0: not used)
+  int grp_f[3] = {0, 0, 0};   // CTAs per layer group of the grouped persistent scans (forward / backward sweep)
+  int grp_b[3] = {0, 0, 0};
   int att_slices = 0;      // K slices of the attention projection (persistent scan)
   unsigned long long* timeline = nullptr;
   unsigned long long* stamps = nullptr;   // debug: persistent forward scan per-barrier stamps
@@ -563,7 +572,7 @@ static std::vector<Job> split_jobs(const std::vector<Job>& js, int target_ctas, 
 }
 
 static void push_table(parrot_model& M, const std::string& name, const std::vector<Job>& js_in, int n_cols,
-                       int split_target = 0, int chunk_samples = 0) {
+                       int split_target = 0, int chunk_samples = 0, bool own_scratch = false) {
   std::vector<Job> js = js_in;
   for (auto& j : js)
     for (int s = 0; s < j.nseg; ++s) {
@@ -588,8 +597,14 @@ static void push_table(parrot_model& M, const std::string& name, const std::vect
       fprintf(stderr, "\n");
     }
     M.jobs.insert(M.jobs.end(), sp.begin(), sp.end());
-    M.max_groups = std::max(M.max_groups, groups);
-    M.max_split_floats = std::max(M.max_split_floats, (size_t)groups * MAX_KSPLIT * n_cols * TILE_M);
+    if (own_scratch) {
+      t.uniq_floats = M.uniq_split_floats; t.uniq_groups = M.uniq_split_groups;
+      M.uniq_split_floats += (long long)groups * MAX_KSPLIT * n_cols * TILE_M;
+      M.uniq_split_groups += groups;
+    } else {
+      M.max_groups = std::max(M.max_groups, groups);
+      M.max_split_floats = std::max(M.max_split_floats, (size_t)groups * MAX_KSPLIT * n_cols * TILE_M);
+    }
   } else {
     t.count = (int)js.size();
     M.jobs.insert(M.jobs.end(), js.begin(), js.end());
@@ -610,16 +625,49 @@ static void run_table(parrot_model& M, const std::string& name, int tick, int T,
   P.split_scratch = M.d_split_scratch; P.split_count = M.d_split_count;
   P.timeline = M.tl_tick >= 0 ? nullptr : M.timeline; P.tl_tick = -1;   // (tl_tick >= 0: persistent-tick debugging)
   P.coop_epilogue = (t.count <= 148 && M.sm_count >= 148) ? 1 : 0;
-  P.debug_flags = 0;
+  { const char* e = getenv("PARROT_DEBUG_FLAGS"); P.debug_flags = e ? atoi(e) : 0; }
   cudaEvent_t pe = M.prof_begin(name, st);
+  P.cta0 = 0;
   if (M.cfg.gemm_impl == 1) {
     const int grid = std::min(t.count, 148 * 8);
+    P.ncta = grid;
     LAUNCH(job_kernel_simt, grid, 128, 0, st, P);
   } else {
     const int grid = std::min(t.count, 148);
+    P.ncta = grid;
     LAUNCH(job_kernel_tc, grid, ENGINE_THREADS, SMEM_BYTES + 1024, st, P);
   }
   parrot_model::prof_end(pe, st);
+}
+
+// Grouped persistent scans: CTA r of a layer group runs job r of the group's two scan tables every step.  The weight
+// tiles of up to GROUP_RES_KB of its k blocks stay resident in the CTA's tensor memory for the whole sweep (engine.cuh
+// resident_preload / mma_scan): first table first, the second table gets what is left.
+static void assign_resident(parrot_model& M, const std::string& ta, const std::string& tb) {
+  if (!M.tables.count(ta) || !M.tables.count(tb)) return;
+  if (const char* e = getenv("PARROT_NO_RESIDENT")) { if (e[0] && e[0] != '0') return; }
+  const Table& A = M.tables.at(ta);
+  const Table& B = M.tables.at(tb);
+  auto part_kb = [](const Job& j) {
+    const int total = job_kb(j);
+    if (j.ksplit <= 1) return total;
+    return (total * (j.kpart + 1)) / j.ksplit - (total * j.kpart) / j.ksplit;
+  };
+  auto tiled = [&](const Job& j) {
+    for (int s = 0; s < j.nseg; ++s)
+      if (j.seg[s].a_nkb <= 0) return false;
+    return true;
+  };
+  for (int r = 0; r < std::max(A.count, B.count); ++r) {
+    int left = GROUP_RES_KB, col = GROUP_RES_COL0;
+    for (const Table* t : {&A, &B}) {
+      if (r >= t->count) continue;
+      Job& j = M.jobs[t->off + r];
+      const int take = tiled(j) ? std::min(part_kb(j), left) : 0;
+      j.res_kb = take; j.res_col = col;
+      left -= take; col += 64 * take;
+    }
+  }
 }
 
 // ------------------------------------------------------------------ build
@@ -628,6 +676,7 @@ static void build(parrot_model& M) {
   M.ws_used = 0;
   M.bufs.clear(); M.maps.clear(); M.raws.clear(); M.jobs.clear(); M.packs.clear(); M.planes.clear();
   M.tables.clear(); M.wgrads.clear(); M.max_groups = 0; M.max_split_floats = 0; M.pack_order.clear();
+  M.uniq_split_floats = 0; M.uniq_split_groups = 0;
   const int T = d.T, B = d.B, H = d.H, Np = d.Np;
   const bool train = !d.sampling;
 
@@ -744,6 +793,21 @@ static void build(parrot_model& M) {
     }
   }
   M.Tc = (train && !d.ln) ? (T >= 64 ? 16 : 8) : 0;
+  if (const char* e = getenv("PARROT_TC")) { if (M.Tc > 0 && atoi(e) > 0) M.Tc = atoi(e); }
+  {
+    // CTAs per layer group of the grouped persistent scans.  Layer 1 (+ attention) is the longest dependent chain and
+    // needs >= B CTAs for the window stage; layers 2 / 3 also run the hoisted chunk products.
+    auto parse = [](const char* name, int* out, int a, int b, int c) {
+      out[0] = a; out[1] = b; out[2] = c;
+      const char* e = getenv(name);
+      int x, y, z;
+      if (e && sscanf(e, "%d,%d,%d", &x, &y, &z) == 3 && x > 0 && y > 0 && z > 0 && x + y + z <= 148) {
+        out[0] = x; out[1] = y; out[2] = z;
+      }
+    };
+    parse("PARROT_GROUPS_F", M.grp_f, 64, 40, 44);
+    parse("PARROT_GROUPS_B", M.grp_b, 64, 40, 44);
+  }
   M.att_slices = H / ATT_KS;
   M.falloc("att_hat_part", (long long)M.att_slices * B * 3 * d.A);
   M.falloc("w", (long long)(T + 1) * B * d.C);
@@ -905,6 +969,23 @@ static void build(parrot_model& M) {
       hoist(js, 2, (long long)Tc * Np, s3, 1);   // the longer jobs first
       hoist(js, 1, (long long)Tc * Np, s2, 0);
       push_table(M, "chunkF", js, NT, 0, Tc * Np);
+      // grouped persistent scan (kernels.cuh): one table set per layer group, every job at lag 0 (a group's tick IS
+      // its layer's step), split over the CTAs of the group, own split-K scratch (the groups run concurrently)
+      for (int l = 0; l < 3; ++l) {
+        std::vector<Job> ga, gb;
+        build_fwd_layer_jobs(M, ga, l, true, 0, false, true);
+        build_fwd_layer_jobs(M, gb, l, false, 0, false, true);
+        push_table(M, "gA" + LN(l), ga, Np, M.grp_f[l], 0, true);
+        push_table(M, "gB" + LN(l), gb, Np, M.grp_f[l], 0, true);
+        assign_resident(M, "gA" + LN(l), "gB" + LN(l));
+      }
+      std::vector<Job> c2, c3;
+      hoist(c2, 1, (long long)Tc * Np, s2, 0);
+      hoist(c3, 2, (long long)Tc * Np, s3, 0);
+      sort_by_sample_tile(c2);
+      sort_by_sample_tile(c3);
+      push_table(M, "gC2", c2, NT, 0, Tc * Np);
+      push_table(M, "gC3", c3, NT, 0, Tc * Np);
     }
   } else if (train) {
     // layer_norm: one layer at a time (lag 0); the normalised Fork outputs reach the epilogues through preT
@@ -1204,6 +1285,12 @@ static void build(parrot_model& M) {
           js.push_back(j);
         }
       push_table(M, "bwd1", js, Np, PB_SPLIT_TARGET);
+      for (int l = 0; l < 3; ++l) {   // grouped backward scan: layer tables at lag 0
+        std::vector<Job> gj;
+        for (auto& j : js)
+          if (j.layer == l) { gj.push_back(j); gj.back().lag = 0; }
+        push_table(M, "hA" + LN(l), gj, Np, M.grp_b[l], 0, true);
+      }
     }
     // backward scan, product 2: the dgrads that stay in the recurrence -- da_g . Wg^T into dh_l[slot t] (the state
     // entering step t) and, for layer 1, da_1 . Wi1^T into dw[slot t] (layer 1 consumes w_{t-1}).
@@ -1232,6 +1319,13 @@ static void build(parrot_model& M) {
       add(H, 0, 0, {"/rnn1.state_to_gates"});
       add(d.C, 3, 0, {"/inp_to_h1/fork_rnn1_inputs", "/inp_to_h1/fork_rnn1_gates"});
       push_table(M, "bwd2", js, Np, PB_SPLIT_TARGET);
+      for (int l = 0; l < 3; ++l) {
+        std::vector<Job> gj;
+        for (auto& j : js)
+          if (j.layer == l) { gj.push_back(j); gj.back().lag = 0; }
+        push_table(M, "hB" + LN(l), gj, Np, M.grp_b[l], 0, true);
+        assign_resident(M, "hA" + LN(l), "hB" + LN(l));
+      }
       // hoisted dgrads, one range of Tc steps at a time (accumulated into slot t + 1 of the consumer's gradient):
       // event e: from da3 of range e into dh2 / dh1 / dw ; from da2 of range e - 1 into dh1 / dw
       std::vector<Job> cj;
@@ -1258,6 +1352,13 @@ static void build(parrot_model& M) {
       chunk(H, dh1s, H, 1, "/h1_to_h2", 1);
       chunk(d.C, dws, d.C, 1, "/inp_to_h2", 1);
       push_table(M, "chunkB", cj, NT, 0, Tc * Np);
+      for (int l = 1; l < 3; ++l) {   // grouped backward scan: chunk dgrads of layer l + 1, event = the group's own range
+        std::vector<Job> gj;
+        for (auto& j : cj)
+          if (j.lag == 2 - l) { gj.push_back(j); gj.back().lag = 0; }
+        sort_by_sample_tile(gj);
+        push_table(M, "hC" + LN(l), gj, NT, 0, Tc * Np);
+      }
     }
     // weight gradients: dW[in][out] = sum_samples X[s][in] * dY[s][out]
     {
@@ -1313,9 +1414,9 @@ static void build_device_tables(parrot_model& M) {
   M.d_raws = (MapRaw*)M.alloc("dev_raws", M.raws.size() * sizeof(MapRaw));
   M.d_jobs = (Job*)M.alloc("dev_jobs", M.jobs.size() * sizeof(Job));
   M.d_ctx = (ScanCtx*)M.alloc("dev_ctx", sizeof(ScanCtx));
-  M.d_split_scratch = (float*)M.alloc("split_scratch", std::max<size_t>(M.max_split_floats, 1) * 4);
-  M.d_split_count = (unsigned int*)M.alloc("split_count", (size_t)std::max(M.max_groups, 1) * 4);
-  M.d_gridbar = (unsigned int*)M.alloc("gridbar", 64);
+  M.d_split_scratch = (float*)M.alloc("split_scratch", (std::max<size_t>(M.max_split_floats, 1) + M.uniq_split_floats) * 4);
+  M.d_split_count = (unsigned int*)M.alloc("split_count", (size_t)(std::max(M.max_groups, 1) + M.uniq_split_groups) * 4);
+  M.d_gridbar = (unsigned int*)M.alloc("gridbar", 1024);   // [8] counters, 128 bytes apart (grouped scans: one per group)
 }
 
 static void upload_tables(parrot_model& M, cudaStream_t st) {
@@ -1331,6 +1432,8 @@ static void ensure_kernel_attrs() {
   CK(cudaFuncSetAttribute(job_kernel_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES + 1024));
   CK(cudaFuncSetAttribute(scan_fwd_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES + 1024 + ATT_SMEM_BYTES));
   CK(cudaFuncSetAttribute(scan_bwd_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES + 1024 + ATT_SMEM_BYTES));
+  CK(cudaFuncSetAttribute(scan_fwd_grouped, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES + 1024 + ATT_SMEM_BYTES));
+  CK(cudaFuncSetAttribute(scan_bwd_grouped, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES + 1024 + ATT_SMEM_BYTES));
   CK(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
   CK(cudaFuncSetAttribute(attention_proj_slice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   CK(cudaFuncSetAttribute(attention_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
@@ -1686,6 +1789,15 @@ static int prefetch_enabled() {
   const char* e = getenv("PARROT_NO_PREFETCH");
   return (e && e[0] && e[0] != '0') ? 0 : 1;
 }
+static int scan_mode() {
+  // 0: chunk-lagged wavefront kernels (all CTAs in lock step) ; 1: grouped kernels (default)
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("PARROT_SCAN_MODE");
+    mode = (e && !strcmp(e, "wave")) ? 0 : 1;
+  }
+  return mode;
+}
 static bool use_persistent(parrot_model& M) {
   if (M.d.ln) return false;   // the normalisations sit between the layers: one launch per phase
   static int env = -1;
@@ -1702,6 +1814,12 @@ static bool use_persistent(parrot_model& M) {
     auto it = M.tables.find(nm);
     if (it != M.tables.end() && it->second.count > 148) return false;
   }
+  if (scan_mode() == 1)
+    for (int l = 0; l < 3; ++l)
+      for (const char* nm : {"gA", "gB", "hA", "hB"}) {
+        auto it = M.tables.find(std::string(nm) + LN(l));
+        if (it != M.tables.end() && it->second.count > (nm[0] == 'g' ? M.grp_f[l] : M.grp_b[l])) return false;
+      }
   return true;
 }
 
@@ -1712,10 +1830,15 @@ static EngineParams table_params(parrot_model& M, const std::string& name, int r
   P.tick = 0; P.T = M.d.T; P.n_cols = t.n_cols; P.reverse = reverse;
   P.chunk_samples = t.chunk_samples;
   P.split_scratch = M.d_split_scratch; P.split_count = M.d_split_count;
+  if (t.uniq_floats >= 0) {
+    P.split_scratch += std::max<size_t>(M.max_split_floats, 1) + t.uniq_floats;
+    P.split_count += std::max(M.max_groups, 1) + t.uniq_groups;
+  }
   // debug: intra-phase milestones of persistent tick M.tl_tick, one [148][16] block per phase
   P.timeline = (M.timeline && tl_slot >= 0) ? M.timeline + (size_t)tl_slot * 148 * 16 : nullptr;
   P.tl_tick = M.tl_tick;
   P.coop_epilogue = 1;
+  P.cta0 = 0; P.ncta = 148;
   {
     const char* e = getenv("PARROT_DEBUG_FLAGS");
     P.debug_flags = e ? atoi(e) : 0;
@@ -1792,6 +1915,82 @@ static bool scan_bwd_persistent_launch(parrot_model& M, cudaStream_t st) {
   return true;
 }
 
+// ---- grouped persistent scans (kernels.cuh): three layer groups with their own barrier domains
+static GroupSched group_sched(parrot_model& M, const char* a, const char* b, const char* c, int l, int reverse,
+                              const int* grp) {
+  GroupSched G;
+  int cta0 = 0;
+  for (int i = 0; i < l; ++i) cta0 += grp[i];
+  G.cta0 = cta0; G.ncta = grp[l];
+  const std::string names[3] = {std::string(a) + LN(l), std::string(b) + LN(l), std::string(c) + LN(l)};
+  for (int k = 0; k < 3; ++k) {
+    if (M.tables.count(names[k])) {
+      G.ph[k] = table_params(M, names[k], reverse, k < 2 ? k : -1);
+    } else {
+      G.ph[k] = table_params(M, names[0], reverse);
+      G.ph[k].njobs = 0;
+    }
+    G.ph[k].cta0 = G.cta0; G.ph[k].ncta = G.ncta;
+    REQUIRE(k == 2 || G.ph[k].njobs <= G.ncta, "grouped scan: more split jobs than CTAs in the group");
+  }
+  return G;
+}
+static bool scan_fwd_grouped_launch(parrot_model& M, cudaStream_t st) {
+  const Dims& d = M.d;
+  ScanFwdGParams S;
+  for (int l = 0; l < 3; ++l) S.g[l] = group_sched(M, "gA", "gB", "gC", l, 0, M.grp_f);
+  S.Tc = M.Tc; S.T = d.T;
+  S.att_parts = attention_nparts(d.B, d.C, M.grp_f[0]); S.att_slices = M.att_slices;
+  S.att = attn_fwd_args(M, 0, false);
+  S.s_h1 = (long long)d.B * d.H; S.s_k = (long long)d.B * d.A; S.s_w = (long long)d.B * d.C;
+  S.s_wp = (long long)d.Np * M.planes.at("w").pitch; S.s_phi = (long long)d.B * d.U;
+  S.s_ab = (long long)d.B * 2 * d.A; S.s_e = (long long)d.B * 3 * d.A;
+  S.bars = M.d_gridbar;
+  S.stamps = M.stamps; S.stamp_bars = M.stamp_bars;
+  S.prefetch = prefetch_enabled();
+  CK(cudaMemsetAsync(M.d_gridbar, 0, 1024, st));
+  void* args[] = {&S};
+  g_ctx = "scan_fwd_grouped";
+  const int grid = M.grp_f[0] + M.grp_f[1] + M.grp_f[2];
+  cudaError_t le = cudaLaunchCooperativeKernel((void*)scan_fwd_grouped, dim3(grid), dim3(ENGINE_THREADS), args,
+                                               SMEM_BYTES + 1024 + ATT_SMEM_BYTES, st);
+  if (le != cudaSuccess) {
+    cudaGetLastError();
+    M.persistent_ok = false;
+    return false;
+  }
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (debug_sync()) CK(cudaStreamSynchronize(st));
+  return true;
+}
+static bool scan_bwd_grouped_launch(parrot_model& M, cudaStream_t st) {
+  const Dims& d = M.d;
+  ScanBwdGParams S;
+  for (int l = 0; l < 3; ++l) S.g[l] = group_sched(M, "hA", "hB", "hC", l, 1, M.grp_b);
+  S.Tc = M.Tc; S.T = d.T;
+  S.att = attn_bwd_args(M, 0);
+  S.s_dw = (long long)d.B * d.C; S.s_ab = (long long)d.B * 2 * d.A; S.s_e = (long long)d.B * 3 * d.A;
+  S.s_k = (long long)d.B * d.A; S.s_dh1 = (long long)d.B * d.H; S.s_datt = (long long)d.B * 3 * d.A;
+  S.s_dattp = (long long)d.Np * M.planes.at("datt").pitch;
+  S.ctx = M.d_ctx; S.bars = M.d_gridbar;
+  S.stamps = M.stamps_bwd; S.stamp_bars = M.stamps_bwd ? M.stamp_bars : 0;
+  S.prefetch = prefetch_enabled();
+  CK(cudaMemsetAsync(M.d_gridbar, 0, 1024, st));
+  void* args[] = {&S};
+  g_ctx = "scan_bwd_grouped";
+  const int grid = M.grp_b[0] + M.grp_b[1] + M.grp_b[2];
+  cudaError_t le = cudaLaunchCooperativeKernel((void*)scan_bwd_grouped, dim3(grid), dim3(ENGINE_THREADS), args,
+                                               SMEM_BYTES + 1024 + ATT_SMEM_BYTES, st);
+  if (le != cudaSuccess) {
+    cudaGetLastError();
+    M.persistent_ok = false;
+    return false;
+  }
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (debug_sync()) CK(cudaStreamSynchronize(st));
+  return true;
+}
+
 // layer_norm=True forward scan (model.py:571-603, 692-722 with _apply_norm active): every Fork output except
 // inp_to_h* is normalised before it is summed, so the layers cannot share one accumulator.  preT_l[t] collects
 // bias + norm(speaker) + norm(feedback) (+ norm(q12/q13/q23) as the lower layers finish step t).
@@ -1841,7 +2040,7 @@ static void scan_fwd(parrot_model& M, const float* d_features, const float* d_no
   M.last_start_flag = start_flag;
   if (d.ln) { scan_fwd_ln(M, st); return; }
   if (d.weak) run_table(M, "hoist1", 0, 1, 0, st);   // pre1 = x_{t-1} . out_to_h1 for all frames
-  if (use_persistent(M) && scan_fwd_persistent_launch(M, st)) return;
+  if (use_persistent(M) && (scan_mode() == 1 ? scan_fwd_grouped_launch(M, st) : scan_fwd_persistent_launch(M, st))) return;
   // chunk-lagged layer wavefront, one launch per phase: tick tau runs layer 1 at step tau, layer 2 at tau - Tc,
   // layer 3 at tau - 2 Tc; every Tc ticks the hoisted products of the chunk just finished
   const int Tc = M.Tc;
@@ -2000,7 +2199,7 @@ static void scan_bwd(parrot_model& M, cudaStream_t st) {
   const Dims& d = M.d;
   CK(cudaMemsetAsync(M.fbuf("dk_carry"), 0, (size_t)d.B * d.A * 4, st));
   if (d.ln) { scan_bwd_ln(M, st); return; }
-  if (use_persistent(M) && scan_bwd_persistent_launch(M, st)) return;
+  if (use_persistent(M) && (scan_mode() == 1 ? scan_bwd_grouped_launch(M, st) : scan_bwd_persistent_launch(M, st))) return;
   const int blocks = std::min(gs_blocks((long long)d.B * d.H), 148);
   // reverse chunk-lagged wavefront: tick tau -> layer 3 at s = T-1-tau, layer 2 at s + Tc, attention + layer 1 at
   // s + 2 Tc; every Tc ticks the hoisted dgrads of the ranges just finished

@@ -101,7 +101,12 @@ struct Job {
   // split-K: `ksplit` jobs share one output tile (`group`); part `kpart` contracts its share of the
   // k blocks, parks the partial tile in scratch, and the last part to arrive sums all parts in part
   // order (deterministic) and runs the epilogue.
-  int ksplit, kpart, group, pad_;
+  int ksplit, kpart, group;
+  // grouped persistent scans: the LAST `res_kb` k blocks of this part's range keep their weight tiles resident in
+  // tensor memory (A operand of tcgen05.mma read from TMEM: no TMA traffic, no shared-memory operand reads);
+  // hi plane of resident block i at TMEM column res_col + 64 i, lo plane 32 columns behind it
+  int res_kb;
+  int res_col, pad0_, pad1_, pad2_;
   Seg seg[MAX_SEG];
   PlainArgs pa;
 };
@@ -159,7 +164,9 @@ struct EngineParams {
   int coop_epilogue;           // 1: all parts of a split tile share the final epilogue (needs <= 1 job per CTA)
   unsigned long long* timeline;  // debug: [cta][16] globaltimer stamps at pipeline milestones (or null)
   int tl_tick;                   // debug: only the launch / persistent tick with this value writes the timeline (-1: any)
+  int cta0, ncta;                // the CTAs [cta0, cta0 + ncta) of the grid run this table (CTA rank r takes jobs r, r + ncta, ..)
 };
+__device__ __forceinline__ int cta_rank(const EngineParams& P) { return (int)blockIdx.x - P.cta0; }
 
 __device__ __forceinline__ unsigned long long gtime() {
   unsigned long long t;
@@ -797,6 +804,7 @@ struct Pipe {
   uint8_t* stg;    // epilogue: operand staging region of the quad finish (persistent kernels) or null
   int stg_bytes;
   uint8_t* cache_area;   // >= 1536 bytes behind the barriers (PhaseCache copies of the persistent kernels)
+  uint32_t acc_stride;   // TMEM columns between the two accumulator buffers (256; grouped scans: the widest n_cols)
 };
 
 // returns the first byte after the pipeline's shared memory (1024-aligned ring + barriers)
@@ -816,6 +824,7 @@ __device__ __forceinline__ uint8_t* pipe_setup(Pipe& p, uint8_t* smem, int n_col
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p.tempty_bar + 2);
   p.split_flag = tmem_slot + 1;
   p.stage = 0; p.phase = 0; p.it = 0;
+  p.acc_stride = 256u;
   p.stg = nullptr; p.stg_bytes = 0;
   p.cache_area = reinterpret_cast<uint8_t*>(p.full_bar) + 256;   // the ring leaves >= 2048 bytes here
   if (threadIdx.x == 0) {
@@ -883,7 +892,7 @@ __device__ __forceinline__ void producer_run(Pipe& p, const EngineParams& P, int
   }
   bool waited = (gridbar == nullptr) || target == 0;
   const uint32_t tx_bytes = 2 * p.a_bytes + 2 * p.b_bytes;   // <= stage_bytes (the ring is sized for the widest phase)
-  for (int j = blockIdx.x; j < P.njobs; j += gridDim.x) {
+  for (int j = cta_rank(P); j < P.njobs; j += P.ncta) {
     const Job& jb = pc ? pc->job : P.jobs[j];
     const int t = job_time(P, jb, tick);
     const int total_kb = job_total_kb(P, jb, t);
@@ -956,7 +965,7 @@ __device__ __forceinline__ void producer_run(Pipe& p, const EngineParams& P, int
 __device__ __forceinline__ void mma_run(Pipe& p, const EngineParams& P, int tick, const PhaseCache* pc = nullptr) {
   const int lane = threadIdx.x & 31;
   const uint32_t idesc = umma_idesc_bf16(TILE_M, p.n_cols);
-  for (int j = blockIdx.x; j < P.njobs; j += gridDim.x) {
+  for (int j = cta_rank(P); j < P.njobs; j += P.ncta) {
     const Job& jb = pc ? pc->job : P.jobs[j];
     const int t = job_time(P, jb, tick);
     const int all_kb = job_total_kb(P, jb, t);
@@ -969,7 +978,7 @@ __device__ __forceinline__ void mma_run(Pipe& p, const EngineParams& P, int tick
     const uint32_t use = (uint32_t)(p.it >> 1);
     mbar_wait(&p.tempty_bar[buf], (use & 1) ^ 1);
     tc_fence_after();
-    const uint32_t tmem_d = p.tmem_base + (uint32_t)buf * 256u;
+    const uint32_t tmem_d = p.tmem_base + (uint32_t)buf * p.acc_stride;
     for (int kbi = 0; kbi < total_kb; ++kbi) {
       mbar_wait(&p.full_bar[p.stage], p.phase);
       tc_fence_after();
@@ -998,6 +1007,191 @@ __device__ __forceinline__ void mma_run(Pipe& p, const EngineParams& P, int tick
   if (lane == 0) TL(3);
 }
 
+// ------------------------------------------------ scan phases of the persistent kernels: ONE cached job per CTA
+// k-block order of a part's range [klo, khi): first the STREAMED blocks (weight tile through the TMA ring), then the
+// RESIDENT blocks (weight tile in tensor memory since kernel start, only the activation tile is loaded).
+__device__ __forceinline__ int job_full_kb(const Job& jb) {
+  int n = 0;
+  for (int s = 0; s < jb.nseg; ++s) n += jb.seg[s].nkb;
+  return n;
+}
+__device__ __forceinline__ void kb_locate(const Job& jb, int kidx, int& seg, int& kb) {
+  seg = 0; kb = kidx;
+  for (int s = 0; s < jb.nseg; ++s) {
+    if (kb < jb.seg[s].nkb) { seg = s; return; }
+    kb -= jb.seg[s].nkb;
+  }
+}
+// resident blocks of this part at time t (0 when a segment is out of range: the range no longer matches the tiles
+// that were loaded at kernel start -- cannot happen in the grouped tables, every segment is valid for t in [0, T))
+__device__ __forceinline__ int job_resident(const Job& jb, int total_kb, int n) {
+  if (jb.res_kb <= 0 || total_kb != job_full_kb(jb)) return 0;
+  return jb.res_kb < n ? jb.res_kb : n;
+}
+
+// weight tiles of the resident blocks: global (tile-contiguous pack, 128 B per row and plane) -> tensor memory.
+// Called by all threads once per kernel and job; warps 2..5 do the work (one TMEM lane quarter each).
+__device__ __forceinline__ void resident_preload(Pipe& p, const EngineParams& P, const PhaseCache* pc) {
+  if (cta_rank(P) < 0 || cta_rank(P) >= P.njobs) return;
+  const Job& jb = pc->job;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (jb.res_kb <= 0 || warp < 2 || warp >= 6) return;
+  int klo, khi;
+  job_kb_range(jb, job_full_kb(jb), klo, khi);
+  const int n = khi - klo, nres = jb.res_kb < n ? jb.res_kb : n;
+  const int q = warp & 3, row = q * 32 + lane;
+  for (int i = 0; i < nres; ++i) {
+    int seg, kb;
+    kb_locate(jb, klo + (n - nres) + i, seg, kb);
+    const Seg& sg = jb.seg[seg];
+    const long long trow = ((long long)(sg.a_row >> 7) * sg.a_nkb + (sg.a_k >> 6) + kb) << 7;
+#pragma unroll 1
+    for (int w = 0; w < 2; ++w) {
+      const uint4* src = reinterpret_cast<const uint4*>(P.raws[sg.a_map + w].base + (trow + row) * KB);
+      uint32_t r[32];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const uint4 v = __ldg(src + c);
+        r[4 * c] = v.x; r[4 * c + 1] = v.y; r[4 * c + 2] = v.z; r[4 * c + 3] = v.w;
+      }
+      tmem_st_32x32(p.tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(jb.res_col + i * 64 + w * 32), r);
+    }
+  }
+  tmem_st_wait();
+}
+
+__device__ __forceinline__ void producer_scan(Pipe& p, const EngineParams& P, int tick, const PhaseCache* pc,
+                                              const unsigned int* gridbar, unsigned int target, bool prefetch) {
+  const uint64_t pol_keep = (P.debug_flags & 1) ? 0 : l2_policy_evict_last();
+  bool waited = (gridbar == nullptr) || target == 0;
+  const uint32_t tx_bytes = 2 * p.a_bytes + 2 * p.b_bytes;
+  if (cta_rank(P) < P.njobs) {
+    const Job& jb = pc->job;
+    const int t = job_time(P, jb, tick);
+    const int total_kb = job_total_kb(P, jb, t);
+    if (total_kb > 0) {
+      int klo, khi;
+      job_kb_range(jb, total_kb, klo, khi);
+      const int n = khi - klo, nres = job_resident(jb, total_kb, n), nstream = n - nres;
+      // flattened (valid segment, block) sequence of this part: seg / kb of block klo + i
+      auto locate = [&](int i, int& sgi, int& kb) {
+        int kidx = klo + i;
+        sgi = 0; kb = 0;
+        for (int s = 0; s < jb.nseg; ++s) {
+          if (!seg_valid(P, jb.seg[s], t)) continue;
+          if (kidx < jb.seg[s].nkb) { sgi = s; kb = kidx; return; }
+          kidx -= jb.seg[s].nkb;
+        }
+      };
+      int early = 0;
+      if (!waited) {
+        for (int s = 0; s < jb.nseg; ++s) {
+          tma_prefetch_desc(P.maps + jb.seg[s].a_map);
+          tma_prefetch_desc(P.maps + jb.seg[s].b_map);
+        }
+        if (prefetch) {
+          // weight tiles of the first streamed blocks do not depend on the barrier: issue them now (expect_tx without
+          // arrive), complete the slots with the activation tiles afterwards
+          int st_i = p.stage;
+          uint32_t ph = p.phase;
+          for (; early < nstream && early < p.nstages; ++early) {
+            int sgi, kb;
+            locate(early, sgi, kb);
+            const Seg& sg = jb.seg[sgi];
+            mbar_wait(&p.empty_bar[st_i], ph ^ 1);
+            uint8_t* st = p.tiles + (size_t)st_i * p.stage_bytes;
+            mbar_expect_tx_only(&p.full_bar[st_i], 2 * p.a_bytes);
+            producer_load_a(p, sg, kb, P.maps + sg.a_map, st, &p.full_bar[st_i], pol_keep);
+            if (++st_i == p.nstages) { st_i = 0; ph ^= 1; }
+          }
+        }
+        grid_wait_ext(gridbar, target);
+        TL(10);
+        waited = true;
+      }
+      for (int i = 0; i < n; ++i) {
+        int sgi, kb;
+        locate(i, sgi, kb);
+        const Seg& sg = jb.seg[sgi];
+        uint8_t* st = p.tiles + (size_t)p.stage * p.stage_bytes;
+        uint64_t* fb = &p.full_bar[p.stage];
+        if (i < early) {
+          mbar_expect_tx(fb, 2 * p.b_bytes);
+          producer_load_b(p, sg, kb, t, P.maps + sg.b_map, st, fb, 0);
+        } else {
+          mbar_wait(&p.empty_bar[p.stage], p.phase ^ 1);
+          if (i < nstream) {
+            mbar_expect_tx(fb, tx_bytes);
+            producer_load_a(p, sg, kb, P.maps + sg.a_map, st, fb, pol_keep);
+          } else {
+            mbar_expect_tx(fb, 2 * p.b_bytes);
+          }
+          producer_load_b(p, sg, kb, t, P.maps + sg.b_map, st, fb, 0);
+        }
+        if (++p.stage == p.nstages) { p.stage = 0; p.phase ^= 1; }
+      }
+    }
+  }
+  if (!waited) grid_wait_ext(gridbar, target);
+  TL(2);
+}
+
+__device__ __forceinline__ void mma_scan(Pipe& p, const EngineParams& P, int tick, const PhaseCache* pc) {
+  const int lane = threadIdx.x & 31;
+  if (cta_rank(P) >= P.njobs) return;
+  const uint32_t idesc = umma_idesc_bf16(TILE_M, p.n_cols);
+  const Job& jb = pc->job;
+  const int t = job_time(P, jb, tick);
+  const int all_kb = job_total_kb(P, jb, t);
+  if (all_kb == 0) return;
+  int klo, khi;
+  job_kb_range(jb, all_kb, klo, khi);
+  const int n = khi - klo;
+  if (n == 0) return;
+  const int nres = job_resident(jb, all_kb, n), nstream = n - nres;
+  const int buf = p.it & 1;
+  const uint32_t use = (uint32_t)(p.it >> 1);
+  mbar_wait(&p.tempty_bar[buf], (use & 1) ^ 1);
+  tc_fence_after();
+  const uint32_t tmem_d = p.tmem_base + (uint32_t)buf * p.acc_stride;
+  for (int kbi = 0; kbi < n; ++kbi) {
+    mbar_wait(&p.full_bar[p.stage], p.phase);
+    tc_fence_after();
+    if (lane == 0 && kbi == 0) TL(11);
+    if (lane == 0) {
+      const uint8_t* st = p.tiles + (size_t)p.stage * p.stage_bytes;
+      const uint64_t db_hi = umma_desc_sw128(st + 2 * p.a_bytes);
+      const uint64_t db_lo = umma_desc_sw128(st + 2 * p.a_bytes + p.b_bytes);
+      if (kbi < nstream) {
+        const uint64_t da_hi = umma_desc_sw128(st);
+        const uint64_t da_lo = umma_desc_sw128(st + p.a_bytes);
+#pragma unroll
+        for (int k = 0; k < KB / 16; ++k) {
+          const uint64_t adv = (uint64_t)((k * 16 * 2) >> 4);
+          umma_bf16(tmem_d, da_hi + adv, db_hi + adv, idesc, (kbi | k) != 0);
+          umma_bf16(tmem_d, da_lo + adv, db_hi + adv, idesc, 1);
+          umma_bf16(tmem_d, da_hi + adv, db_lo + adv, idesc, 1);
+        }
+      } else {
+        const uint32_t ta_hi = p.tmem_base + (uint32_t)(jb.res_col + (kbi - nstream) * 64), ta_lo = ta_hi + 32;
+#pragma unroll
+        for (int k = 0; k < KB / 16; ++k) {
+          const uint64_t adv = (uint64_t)((k * 16 * 2) >> 4);
+          umma_bf16_ts(tmem_d, ta_hi + k * 8, db_hi + adv, idesc, (kbi | k) != 0);
+          umma_bf16_ts(tmem_d, ta_lo + k * 8, db_hi + adv, idesc, 1);
+          umma_bf16_ts(tmem_d, ta_hi + k * 8, db_lo + adv, idesc, 1);
+        }
+      }
+      umma_commit(&p.empty_bar[p.stage]);
+      if (kbi == n - 1) umma_commit(&p.tfull_bar[buf]);
+    }
+    __syncwarp();
+    if (++p.stage == p.nstages) { p.stage = 0; p.phase ^= 1; }
+  }
+  ++p.it;
+  if (lane == 0) TL(3);
+}
+
 #ifndef PB_SPLIT_BATCH
 #define PB_SPLIT_BATCH 3   // partial tiles summed in batches of 3 parts: 111.5 vs 115.0 ms/step unbatched (8 warps)
 #endif
@@ -1013,6 +1207,127 @@ __device__ __forceinline__ void mma_run(Pipe& p, const EngineParams& P, int tick
 #ifndef PB_TMEM_W
 #define PB_TMEM_W 8   // columns per tcgen05.ld chunk of the unsplit (TMEM) epilogue path
 #endif
+// Unsplit tile straight out of tensor memory, 8 columns per step.  The memory operands of step i + 1 (old value for
+// PF_ACC, row bias) are requested BEFORE step i is applied, so a tile costs one exposed L2 round trip instead of one
+// per step (measured: 31 us per 128 x 128 tile with 8-column steps whose loads were issued and consumed in place).
+template <class LOAD, class APPLY>
+__device__ __forceinline__ void tmem_tile_pipelined(uint32_t taddr, int n_cols, LOAD load, APPLY apply) {
+  EpiOps<8> ops[2];
+  load(0, ops[0]);
+#pragma unroll 1
+  for (int n0 = 0; n0 < n_cols; n0 += 16) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int c0 = n0 + 8 * h;
+      if (c0 < n_cols) {
+        float v[8];
+        tmem_ld_32x8(taddr + c0, v);
+        if (c0 + 8 < n_cols) load(c0 + 8, ops[h ^ 1]);
+        tmem_ld_wait();
+        apply(c0, v, ops[h]);
+      }
+    }
+  }
+}
+
+// ---- lean plain epilogue (EPI_PLAIN, not transposed): chunk products of the persistent scans, readout / dgrad /
+// hoisted products outside them.  The generic epi_plain keeps its context in a 150-byte struct that the 255-register
+// kernels hold in local memory: every field use was a dependent local load, 2.8 k cycles per 8-column step, 38 us per
+// 128 x 128 tile (measured; the MMAs of the same tile take 9 us).  Here the loop state is a cursor of pointers that
+// advance by constant strides, and the memory operands of step i + 1 (old value for PF_ACC, row bias) are requested
+// before step i is applied.
+struct PlainK {
+  long long ldo, ldp, rb_ld;
+  const float* pb0;
+  bf16 *hi, *lo;
+  int n_pad, n_valid, n_total, flags;
+  float scale, bias;
+  bool rb, acc, has_out;
+};
+struct PlainCur { float* po; const float* pb; long long pl; int r, n; };
+__device__ __forceinline__ void plain_setup(const EpiLocal& E, int t, int row, PlainK& k, PlainCur& c) {
+  const int f = E.row0 + row;
+  k.ldo = E.l0; k.ldp = E.l1; k.rb_ld = E.rowbias_ld;
+  k.hi = (bf16*)E.p2; k.lo = (bf16*)E.p3;
+  k.n_pad = E.n_pad > 0 ? E.n_pad : (1 << 30);
+  k.n_valid = E.n_pad > 0 ? E.n_valid : (1 << 30);
+  k.n_total = E.n_total; k.flags = E.flags; k.scale = E.scale;
+  k.rb = E.rowbias_ld > 0; k.acc = (E.flags & PF_ACC) != 0; k.has_out = E.p0 != nullptr;
+  const float* biasp = (const float*)E.p1;
+  k.bias = (biasp && !k.rb && row < E.m_valid) ? __ldg(biasp + f) : 0.0f;
+  k.pb0 = k.rb ? biasp + f : nullptr;
+  const int n = E.n0;
+  int q = 0, r = n;
+  if (E.n_pad > 0) { q = n / E.n_pad; r = n - q * E.n_pad; }
+  const long long srow = (long long)q * (E.n_pad > 0 ? E.n_valid : 0) + (r < k.n_valid ? r : k.n_valid) +
+                         (E.n_pad > 0 ? 0 : 0);
+  c.n = n; c.r = r;
+  c.po = (float*)E.p0 + (long long)t * E.l2 + (E.n_pad > 0 ? srow : (long long)n) * k.ldo + f;
+  c.pb = k.rb ? k.pb0 + (long long)r * k.rb_ld : nullptr;
+  c.pl = ((E.flags & PF_PLANE_PADDED) ? (long long)n : (E.n_pad > 0 ? srow : (long long)n)) * k.ldp + f;
+}
+__device__ __forceinline__ void plain_next(const PlainK& k, PlainCur& c) {
+  const bool valid = c.r < k.n_valid;
+  if (valid) c.po += k.ldo;
+  if (valid || (k.flags & PF_PLANE_PADDED)) c.pl += k.ldp;
+  ++c.n;
+  if (++c.r == k.n_pad) { c.r = 0; c.pb = k.pb0; }
+  else if (k.rb) c.pb += k.rb_ld;
+}
+template <int W>
+__device__ __forceinline__ void plain_load(const PlainK& k, PlainCur& c, bool row_ok, float* a, float* b) {
+#pragma unroll
+  for (int j = 0; j < W; ++j) {
+    const bool live = row_ok && c.n < k.n_total && c.r < k.n_valid;
+    a[j] = (live && k.acc && k.has_out) ? __ldcg(c.po) : 0.0f;
+    b[j] = (live && k.rb) ? __ldg(c.pb) : 0.0f;
+    plain_next(k, c);
+  }
+}
+template <int W>
+__device__ __forceinline__ void plain_apply(const PlainK& k, PlainCur& c, bool row_ok, const float* v, const float* a,
+                                            const float* b) {
+#pragma unroll
+  for (int j = 0; j < W; ++j) {
+    const bool live = row_ok && c.n < k.n_total && c.r < k.n_valid;
+    if (live) {
+      const float y = v[j] * k.scale + k.bias + b[j] + a[j];
+      if (k.has_out) *c.po = y;
+      if (k.hi) {
+        bf16 h, l;
+        split_bf16(y, h, l);
+        k.hi[c.pl] = h;
+        k.lo[c.pl] = l;
+      }
+    }
+    plain_next(k, c);
+  }
+}
+// one unsplit plain tile out of tensor memory (thread <-> output row)
+__device__ __forceinline__ void plain_tile(const EpiLocal& E, int t, int row, uint32_t taddr, int n_cols) {
+  PlainK k;
+  PlainCur cl, ca;
+  plain_setup(E, t, row, k, cl);
+  ca = cl;
+  const bool row_ok = row < E.m_valid;
+  float a[2][8], b[2][8];
+  plain_load<8>(k, cl, row_ok, a[0], b[0]);
+#pragma unroll 1
+  for (int n0 = 0; n0 < n_cols; n0 += 16) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int c0 = n0 + 8 * h;
+      if (c0 < n_cols) {
+        float v[8];
+        tmem_ld_32x8(taddr + c0, v);
+        if (c0 + 8 < n_cols) plain_load<8>(k, cl, row_ok, a[h ^ 1], b[h ^ 1]);
+        tmem_ld_wait();
+        plain_apply<8>(k, ca, row_ok, v, a[h], b[h]);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------ epilogue (warps 2..5 read TMEM; warps 6.. help after split-K)
 // All epilogue warps run this loop.  Unsplit jobs: warps 2..5 read the accumulator (one TMEM lane quarter each) and
 // apply the epilogue; the helpers skip.  Split jobs: warps 2..5 park the partial tile in scratch, then ALL ten
@@ -1026,7 +1341,7 @@ __device__ __forceinline__ void epilogue_run(Pipe& p, const EngineParams& P, int
   const int q = warp & 3;  // TMEM lane quarter this warp may access
   const int row = q * 32 + lane;
   const int gtid = threadIdx.x - 64;   // 0..319 inside the epilogue group
-  for (int j = blockIdx.x; j < P.njobs; j += gridDim.x) {
+  for (int j = cta_rank(P); j < P.njobs; j += P.ncta) {
     const Job& jb = CACHED ? pc->job : P.jobs[j];
     const int t = job_time(P, jb, tick);
     const int all_kb = job_total_kb(P, jb, t);
@@ -1055,32 +1370,18 @@ __device__ __forceinline__ void epilogue_run(Pipe& p, const EngineParams& P, int
     if (quad) q_stage(E, t, lane, ew, NEW, qc_lo, qc_hi, p.stg, stg_cols);
     if (threadIdx.x == 64) TL(9);
     if (tmem_warp) {
-      const uint32_t taddr = p.tmem_base + (uint32_t)buf * 256u + ((uint32_t)(q * 32) << 16);
+      const uint32_t taddr = p.tmem_base + (uint32_t)buf * p.acc_stride + ((uint32_t)(q * 32) << 16);
       if (have_acc) {
         mbar_wait(&p.tfull_bar[buf], use & 1);
         tc_fence_after();
       }
       if (threadIdx.x == 64) TL(4);
-      if (ksplit <= 1) {
-#if PB_TMEM_W == 16
-        for (int n0 = 0; n0 < n_cols; n0 += 16) {
-          float v[16];
-          EpiOps<16> ops;
-          tmem_ld_32x16(taddr + n0, v);
-          epilogue_load<16>(E, t, row, n0, 16, ops);
-          tmem_ld_wait();
-          epilogue_apply<16>(E, t, row, n0, 16, v, ops);
-        }
-#else
-        for (int n0 = 0; n0 < n_cols; n0 += 8) {
-          float v[8];
-          EpiOps<8> ops;
-          tmem_ld_32x8(taddr + n0, v);
-          epilogue_load<8>(E, t, row, n0, 8, ops);
-          tmem_ld_wait();
-          epilogue_apply<8>(E, t, row, n0, 8, v, ops);
-        }
-#endif
+      if (ksplit <= 1 && E.epi == EPI_PLAIN && !(E.flags & PF_TRANS)) {
+        plain_tile(E, t, row, taddr, n_cols);
+      } else if (ksplit <= 1) {
+        tmem_tile_pipelined(
+            taddr, n_cols, [&](int c0, EpiOps<8>& o) { epilogue_load<8>(E, t, row, c0, 8, o); },
+            [&](int c0, const float* v, const EpiOps<8>& o) { epilogue_apply<8>(E, t, row, c0, 8, v, o); });
       } else {
         // park the partial tile: scratch[group][part][col][row]  (row fastest -> coalesced)
         float* part = P.split_scratch + ((size_t)group * MAX_KSPLIT + kpart) * (size_t)n_cols * TILE_M;
@@ -1230,7 +1531,7 @@ template <int DIR>
 __device__ __forceinline__ void epilogue_scan(Pipe& p, const EngineParams& P, int tick, const PhaseCache* pc) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_cols = p.n_cols;
-  if ((int)blockIdx.x >= P.njobs) return;
+  if (cta_rank(P) >= P.njobs) return;
   const Job& jb = pc->job;
   const int t = job_time(P, jb, tick);
   const int all_kb = job_total_kb(P, jb, t);
@@ -1253,7 +1554,7 @@ __device__ __forceinline__ void epilogue_scan(Pipe& p, const EngineParams& P, in
   if (warp < 6) {
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    const uint32_t taddr = p.tmem_base + (uint32_t)buf * 256u + ((uint32_t)(q * 32) << 16);
+    const uint32_t taddr = p.tmem_base + (uint32_t)buf * p.acc_stride + ((uint32_t)(q * 32) << 16);
     if (have_acc) {
       mbar_wait(&p.tfull_bar[buf], use & 1);
       tc_fence_after();
@@ -1311,7 +1612,7 @@ __device__ __forceinline__ void epilogue_chunk(Pipe& p, const EngineParams& P, i
   const int q = warp & 3;
   const int row = q * 32 + lane;
 #pragma unroll 1
-  for (int j = blockIdx.x; j < P.njobs; j += gridDim.x) {
+  for (int j = cta_rank(P); j < P.njobs; j += P.ncta) {
     const Job& jb = P.jobs[j];
     const int t = job_time(P, jb, tick);
     const int all_kb = job_total_kb(P, jb, t);
@@ -1321,18 +1622,10 @@ __device__ __forceinline__ void epilogue_chunk(Pipe& p, const EngineParams& P, i
     int cw_shift = 0, cw_limit = 0;
     if (P.chunk_samples > 0) chunk_window(P, jb, t, cw_shift, cw_limit);
     const EpiLocal E = make_epi_local(jb, P.ctx, cw_shift, cw_limit);
-    const uint32_t taddr = p.tmem_base + (uint32_t)buf * 256u + ((uint32_t)(q * 32) << 16);
+    const uint32_t taddr = p.tmem_base + (uint32_t)buf * p.acc_stride + ((uint32_t)(q * 32) << 16);
     mbar_wait(&p.tfull_bar[buf], use & 1);
     tc_fence_after();
-#pragma unroll 1
-    for (int n0 = 0; n0 < n_cols; n0 += 8) {
-      float v[8];
-      EpiOps<8> ops;
-      tmem_ld_32x8(taddr + n0, v);
-      epi_plain_load<8>(E, t, row, n0, 8, ops);
-      tmem_ld_wait();
-      epi_plain<8>(E, t, row, n0, 8, v, ops);
-    }
+    plain_tile(E, t, row, taddr, n_cols);
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(&p.tempty_bar[buf]);
@@ -1392,7 +1685,7 @@ __global__ void __launch_bounds__(128) job_kernel_simt(const EngineParams P) {
   __shared__ float As[TILE_M][KB + 1];
   __shared__ float Bs[32][KB + 1];
   const int tid = threadIdx.x;
-  for (int j = blockIdx.x; j < P.njobs; j += gridDim.x) {
+  for (int j = cta_rank(P); j < P.njobs; j += P.ncta) {
     const Job& jb = P.jobs[j];
     const int t = job_time(P, jb, P.tick);
     if (job_total_kb(P, jb, t) == 0) continue;

@@ -906,37 +906,53 @@ struct ScanBwdParams {
 // from global memory) instead of a scan table (this CTA's job and epilogue context cached in shared memory).  There
 // is ONE call site per kernel (the phases share the code; EngineParams live in shared memory): the persistent loop
 // must stay small enough for the instruction caches.
+// `ctr` / `ncta`: the barrier domain of the phase -- the whole grid in the wavefront kernels, one layer group in the
+// grouped kernels.  `xctr` / `xtarget` (optional): a second, foreign counter that must reach `xtarget` before data of
+// another group is touched (chunk products of the grouped kernels read the lower / upper layer's planes).
 template <int DIR, class SP>
-__device__ __forceinline__ void persistent_gemm_phase(Pipe& p, const EngineParams& P, int tick, const SP& S,
-                                                      unsigned int& bar, const PhaseCache* pc, const bool chunk) {
+__device__ __forceinline__ void group_gemm_phase(Pipe& p, const EngineParams& P, int tick, const SP& S,
+                                                 unsigned int* ctr, const int ncta, unsigned int& bar,
+                                                 const PhaseCache* pc, const bool chunk,
+                                                 const unsigned int* xctr = nullptr, const unsigned int xtarget = 0) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  unsigned int* gridbar = S.gridbar;
-  const unsigned int target = bar * gridDim.x;
+  const unsigned int target = bar * (unsigned int)ncta;
   // the accumulator width of this phase (the smem ring keeps the stage stride chosen at kernel start)
   p.n_cols = P.n_cols;
   p.b_bytes = (uint32_t)P.n_cols * KB * 2;
   if (warp == 0) {
     if (lane == 0) {
-      if (S.prefetch) producer_run(p, P, tick, gridbar, target, pc);   // weight tiles ahead of the barrier
-      else {
-        if (bar) grid_wait(gridbar, target);
+      if (!chunk) {
+        // scan phase: this CTA's cached job, weight tiles resident in tensor memory or prefetched ahead of the barrier
+        producer_scan(p, P, tick, pc, ctr, target, S.prefetch != 0);
+      } else {
+        if (bar) grid_wait(ctr, target);
+        if (xctr) grid_wait(xctr, xtarget);
         producer_run(p, P, tick, nullptr, 0, pc);
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    mma_run(p, P, tick, pc);
+    if (!chunk) mma_scan(p, P, tick, pc);
+    else mma_run(p, P, tick, pc);
   } else {
-    if (warp == 2 && lane == 0 && bar) grid_wait(gridbar, target);   // one poller for the epilogue warps
+    if (warp == 2 && lane == 0) {   // one poller for the epilogue warps
+      if (bar) grid_wait(ctr, target);
+      if (xctr) grid_wait(xctr, xtarget);
+    }
     epi_group_sync();
     if (threadIdx.x == 64) { STAMP(S, bar, 0); TL(1); }
     if (chunk) epilogue_chunk(p, P, tick);
     else epilogue_scan<DIR>(p, P, tick, pc);
     asm volatile("fence.proxy.async.global;" ::: "memory");
     epi_group_sync();
-    if (threadIdx.x == 64) { STAMP(S, bar, 1); TL(8); grid_arrive(gridbar); }
+    if (threadIdx.x == 64) { STAMP(S, bar, 1); TL(8); grid_arrive(ctr); }
   }
   ++bar;
+}
+template <int DIR, class SP>
+__device__ __forceinline__ void persistent_gemm_phase(Pipe& p, const EngineParams& P, int tick, const SP& S,
+                                                      unsigned int& bar, const PhaseCache* pc, const bool chunk) {
+  group_gemm_phase<DIR>(p, P, tick, S, S.gridbar, (int)gridDim.x, bar, pc, chunk);
 }
 
 // Shared-memory copies used by the persistent loops: the three EngineParams and, for the two scan tables, this CTA's
@@ -952,16 +968,17 @@ __device__ __forceinline__ PersistShared* persist_shared_fill(uint8_t* area, con
     int* dst = reinterpret_cast<int*>(ps->P);
     for (int i = threadIdx.x; i < (int)(3 * sizeof(EngineParams) / 4); i += blockDim.x) dst[i] = src[i];
   }
+  const int rank = (int)blockIdx.x - ph[0].cta0;
   for (int k = 0; k < 2; ++k)
-    if ((int)blockIdx.x < ph[k].njobs) {
-      const int* src = reinterpret_cast<const int*>(ph[k].jobs + blockIdx.x);
+    if (rank >= 0 && rank < ph[k].njobs) {
+      const int* src = reinterpret_cast<const int*>(ph[k].jobs + rank);
       int* dst = reinterpret_cast<int*>(&ps->pc[k].job);
       for (int i = threadIdx.x; i < (int)(sizeof(Job) / 4); i += blockDim.x) dst[i] = src[i];
     }
   __syncthreads();
   if (threadIdx.x == 0)
     for (int k = 0; k < 2; ++k)
-      if ((int)blockIdx.x < ph[k].njobs) {
+      if (rank >= 0 && rank < ph[k].njobs) {
         ps->pc[k].epi = make_epi_local(ps->pc[k].job, ph[k].ctx);
         ps->pc[k].valid = 1;
       }
@@ -1064,6 +1081,180 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) scan_bwd_persistent(const S
     for (int ph = 0; ph < (event ? 3 : 2); ++ph)
       persistent_gemm_phase<2>(p, ps->P[ph], ph == 2 ? (tick + 1) / S.Tc - 1 : tick, S, bar,
                                ph < 2 ? &ps->pc[ph] : nullptr, ph == 2);
+  }
+  pipe_teardown(p);
+}
+
+// =========================================================================
+// Grouped persistent scans.  The 148 CTAs are partitioned into three LAYER GROUPS, each with its own barrier counter
+// and its own tick loop: group l runs the recurrence of layer l + 1 (gates phase, candidate phase; group 0 also the
+// two attention stages) and, once per chunk of Tc steps, the hoisted "chunk" products that feed it.  The groups are
+// coupled only through chunk-level dependencies (forward: group l waits until group l - 1 has finished the steps of
+// the chunk; backward: group l waits for group l + 1), checked against the other group's monotonic barrier counter.
+// A tick therefore costs max over groups instead of the sum of all phases of all layers: layers 2 / 3 (two phases per
+// step) and the throughput-bound chunk products hide under the four dependent phases of layer 1 + attention.
+// =========================================================================
+// accumulators of the grouped kernels: two buffers GROUP_ACC_STRIDE columns apart at the bottom of the CTA's tensor
+// memory; the columns above hold the resident weight tiles of the CTA's two scan jobs (Job::res_col / res_kb, set by
+// the host: api.cu assign_resident)
+constexpr int GROUP_ACC_STRIDE = 128;
+constexpr int GROUP_RES_COL0 = 2 * GROUP_ACC_STRIDE;
+constexpr int GROUP_RES_KB = (512 - GROUP_RES_COL0) / 64;   // resident k blocks (hi + lo plane, 64 columns) per CTA
+__device__ __forceinline__ void group_resident_setup(Pipe& p, const PersistShared* ps) {
+  p.acc_stride = GROUP_ACC_STRIDE;
+  for (int k = 0; k < 2; ++k) resident_preload(p, ps->P[k], &ps->pc[k]);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+}
+struct GroupSched {
+  EngineParams ph[3];   // [0] / [1] the two recurrent phases of the layer, [2] its chunk table (njobs may be 0)
+  int cta0, ncta;
+};
+constexpr int BAR_STRIDE = 32;   // uints between the barrier counters of the groups (128 bytes)
+struct ScanFwdGParams {
+  GroupSched g[3];
+  AttnFwdArgs att;     // pointers of step 0
+  long long s_h1, s_k, s_w, s_wp, s_phi, s_ab, s_e;   // per-step strides (elements)
+  int T, Tc;
+  int att_parts, att_slices;
+  unsigned int* bars;           // [3][BAR_STRIDE]
+  unsigned long long* stamps;   // debug: [cta][bar][2]
+  int stamp_bars;
+  int prefetch;
+};
+struct ScanBwdGParams {
+  GroupSched g[3];
+  AttnBwdArgs att;     // pointers of step 0
+  long long s_dw, s_ab, s_e, s_k, s_dh1, s_datt, s_dattp;
+  const ScanCtx* ctx;
+  int T, Tc;
+  unsigned int* bars;
+  unsigned long long* stamps;
+  int stamp_bars;
+  int prefetch;
+};
+// barriers group `g` of the forward kernel has completed once it has finished `nt` steps
+__device__ __forceinline__ unsigned int fwd_bars_after(int g, int nt, int Tc, bool has_chunk) {
+  const unsigned int chunks = has_chunk ? (unsigned int)((nt + Tc - 1) / Tc) : 0u;
+  return (g == 0 ? 4u : 2u) * (unsigned int)nt + chunks;
+}
+__device__ __forceinline__ unsigned int bwd_bars_after(int nt, int Tc, bool has_chunk) {
+  const unsigned int chunks = has_chunk ? (unsigned int)((nt + Tc - 1) / Tc) : 0u;   // (the last range may be short)
+  return 3u * (unsigned int)nt + chunks;
+}
+
+__global__ void __launch_bounds__(ENGINE_THREADS, 1) scan_fwd_grouped(const ScanFwdGParams S) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  Pipe p;
+  int max_cols = S.g[0].ph[0].n_cols;
+  for (int g = 1; g < 3; ++g)
+    if (S.g[g].ph[2].njobs > 0 && S.g[g].ph[2].n_cols > max_cols) max_cols = S.g[g].ph[2].n_cols;
+  float* att_sh = reinterpret_cast<float*>(pipe_setup(p, align_smem(smem_raw), max_cols));
+  p.stg = reinterpret_cast<uint8_t*>(att_sh); p.stg_bytes = ATT_SMEM_BYTES;   // finish operands (GEMM phases only)
+  const int gi = (int)blockIdx.x >= S.g[2].cta0 ? 2 : ((int)blockIdx.x >= S.g[1].cta0 ? 1 : 0);
+  const GroupSched& G = S.g[gi];
+  const PersistShared* ps = persist_shared_fill(p.cache_area, G.ph);
+  group_resident_setup(p, ps);
+  const int rank = (int)blockIdx.x - G.cta0, ncta = G.ncta;
+  unsigned int* ctr = S.bars + gi * BAR_STRIDE;
+  const unsigned int* lower = gi > 0 ? S.bars + (gi - 1) * BAR_STRIDE : nullptr;
+  const int lower_ncta = gi > 0 ? S.g[gi - 1].ncta : 0;
+  const bool lower_chunk = gi > 0 && S.g[gi - 1].ph[2].njobs > 0;
+  const bool has_chunk = ps->P[2].njobs > 0;
+  unsigned int bar = 0;
+  for (int t = 0; t < S.T; ++t) {
+    if (has_chunk && t % S.Tc == 0) {
+      // hoisted products of chunk e = t / Tc: their operands are the lower layers' states of steps [t, t + Tc)
+      const int need = min(t + S.Tc, S.T);
+      const unsigned int xt = fwd_bars_after(gi - 1, need, S.Tc, lower_chunk) * (unsigned int)lower_ncta;
+      group_gemm_phase<1>(p, ps->P[2], t / S.Tc, S, ctr, ncta, bar, nullptr, true, lower, xt);
+    }
+#pragma unroll 1
+    for (int ph = 0; ph < 2; ++ph) group_gemm_phase<1>(p, ps->P[ph], t, S, ctr, ncta, bar, &ps->pc[ph], false);
+    if (gi == 0) {
+      AttnFwdArgs a = S.att;
+      a.h1 += t * S.s_h1; a.k_prev += t * S.s_k; a.k_out += t * S.s_k; a.w_out += t * S.s_w;
+      a.w_hi += t * S.s_wp; a.w_lo += t * S.s_wp; a.phi_out += t * S.s_phi; a.ab_out += t * S.s_ab;
+      a.e_out += t * S.s_e;
+      // stage 1 (att_slices CTAs): K-sliced partial projections of h1_t ; stage 2 (att_parts CTAs per batch row):
+      // window + context slice
+      if (threadIdx.x == 0) { grid_wait(ctr, bar * ncta); STAMP(S, bar, 0); }
+      __syncthreads();
+      for (int sl = rank; sl < S.att_slices; sl += ncta) attention_proj_slice(a, sl, att_sh);
+      __syncthreads();
+      if (threadIdx.x == 32) { STAMP(S, bar, 1); grid_arrive(ctr); }   // (not thread 0: it is the next phase's TMA producer)
+      ++bar;
+      const int nwork = a.B * S.att_parts;
+      if (threadIdx.x == 0) { grid_wait(ctr, bar * ncta); STAMP(S, bar, 0); }
+      __syncthreads();
+      for (int i = rank; i < nwork; i += ncta)
+        attention_window_part<true>(a, i / S.att_parts, i % S.att_parts, S.att_parts, S.att_slices, att_sh);
+      asm volatile("fence.proxy.async.global;" ::: "memory");
+      __syncthreads();
+      if (threadIdx.x == 32) { STAMP(S, bar, 1); grid_arrive(ctr); }   // (not thread 0: it is the next phase's TMA producer)
+      ++bar;
+    }
+  }
+  pipe_teardown(p);
+}
+
+__global__ void __launch_bounds__(ENGINE_THREADS, 1) scan_bwd_grouped(const ScanBwdGParams S) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  Pipe p;
+  int max_cols = S.g[0].ph[0].n_cols;
+  for (int g = 0; g < 3; ++g)
+    if (S.g[g].ph[2].njobs > 0 && S.g[g].ph[2].n_cols > max_cols) max_cols = S.g[g].ph[2].n_cols;
+  float* att_sh = reinterpret_cast<float*>(pipe_setup(p, align_smem(smem_raw), max_cols));
+  p.stg = reinterpret_cast<uint8_t*>(att_sh); p.stg_bytes = ATT_SMEM_BYTES;
+  const int gi = (int)blockIdx.x >= S.g[2].cta0 ? 2 : ((int)blockIdx.x >= S.g[1].cta0 ? 1 : 0);
+  const GroupSched& G = S.g[gi];
+  const PersistShared* ps = persist_shared_fill(p.cache_area, G.ph);
+  group_resident_setup(p, ps);
+  const int rank = (int)blockIdx.x - G.cta0, ncta = G.ncta;
+  unsigned int* ctr = S.bars + gi * BAR_STRIDE;
+  const unsigned int* upper = gi < 2 ? S.bars + (gi + 1) * BAR_STRIDE : nullptr;
+  const int upper_ncta = gi < 2 ? S.g[gi + 1].ncta : 0;
+  const bool upper_chunk = gi < 2 && S.g[gi + 1].ph[2].njobs > 0;
+  const bool has_chunk = ps->P[2].njobs > 0;
+  const ScanCtx& c = *S.ctx;
+  unsigned int bar = 0;
+  for (int k = 0; k < S.T; ++k) {
+    const int s = S.T - 1 - k;
+    // phase 0: everything of the step that is elementwise in dh_s -- group 0: attention backward of step s, each row
+    // followed by its GRU pre-pass of layer 1 ; groups 1 / 2: the GRU pre-pass of their layer.  At the start of a
+    // range of Tc steps the upper group must have delivered its chunk dgrads (dh / dw contributions of the range).
+    {
+      if (threadIdx.x == 0) {
+        if (bar) grid_wait(ctr, bar * ncta);
+        // (a) first step of a range: the upper group's chunk dgrads of this range (slots s + 1 .. of dh / dw) ;
+        // (b) last step of a range: its chunk dgrads of the NEXT range, whose highest slot is the slot s this step
+        //     read-modify-writes (the only slot the two ranges share)
+        if (upper && k % S.Tc == 0)
+          grid_wait(upper, bwd_bars_after(min(k + S.Tc, S.T), S.Tc, upper_chunk) * (unsigned int)upper_ncta);
+        else if (upper && (k + 1) % S.Tc == 0 && k + 1 < S.T)
+          grid_wait(upper, bwd_bars_after(min(k + 1 + S.Tc, S.T), S.Tc, upper_chunk) * (unsigned int)upper_ncta);
+        STAMP(S, bar, 0);
+      }
+      __syncthreads();
+      if (gi == 0) {
+        AttnBwdArgs a = S.att;
+        a.dbg = nullptr;
+        a.dw += s * S.s_dw; a.ab += s * S.s_ab; a.e += s * S.s_e; a.kappa += s * S.s_k; a.dh1 += s * S.s_dh1;
+        a.datt += s * S.s_datt; a.datt_hi += s * S.s_dattp; a.datt_lo += s * S.s_dattp;
+        for (int b = rank; b < a.B; b += ncta) attention_bwd_body(a, b, att_sh, &c, s);
+      } else {
+        gru_bwd_pre_rows(c, gi, s, 0, c.B, rank * (int)blockDim.x + (int)threadIdx.x, ncta * (int)blockDim.x);
+      }
+      asm volatile("fence.proxy.async.global;" ::: "memory");
+      __syncthreads();
+      if (threadIdx.x == 32) { STAMP(S, bar, 1); grid_arrive(ctr); }   // (not thread 0: it is the next phase's TMA producer)
+      ++bar;
+    }
+#pragma unroll 1
+    for (int ph = 0; ph < 2; ++ph) group_gemm_phase<2>(p, ps->P[ph], k, S, ctr, ncta, bar, &ps->pc[ph], false);
+    if (has_chunk && ((k + 1) % S.Tc == 0 || k == S.T - 1))
+      group_gemm_phase<2>(p, ps->P[2], k / S.Tc, S, ctr, ncta, bar, nullptr, true);
   }
   pipe_teardown(p);
 }

@@ -38,6 +38,6 @@ for name, rev in (('fwdA', 0), ('fwdB', 0), ('bwd1', 1), ('bwd2', 1)):
         if ok.any():
             d = (col[ok] - t0) / 1e3
             print('    %-13s n=%3d  min %7.2f  median %7.2f  max %7.2f us' % (n, ok.sum(), d.min(), np.median(d), d.max()))
-for name in ('readout', 'wgrad', 'dread'):
+for name in ('readout', 'wgrad', 'dread', 'gC2', 'gC3', 'chunkF'):
     us, _ = tt(name, 0, 0, reps=5)
     print('%-8s %.1f us' % (name, us))
