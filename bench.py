@@ -151,6 +151,20 @@ class ClockSampler(threading.Thread):
 
 
 # --------------------------------------------------------------------------- CPU arms
+def set_blas_threads(n):
+    """The CPU arms run the numpy oracle on BLAS threads.  torchrun exports OMP_NUM_THREADS=1, which made the same
+    arm 6x slower under the launcher than stand-alone: the thread count is set explicitly (all host cores unless
+    --blas_threads says otherwise) and the count actually in effect is reported."""
+    want = n if n and n > 0 else (os.cpu_count() or 1)
+    try:
+        import threadpoolctl
+        threadpoolctl.threadpool_limits(limits=want, user_api='blas')
+        info = [d for d in threadpoolctl.threadpool_info() if d.get('user_api') == 'blas']
+        return int(info[0]['num_threads']) if info else want
+    except Exception:
+        return int(os.environ.get('OMP_NUM_THREADS', want))
+
+
 def oracle_step_time(cfg, B, T, U, steps, warmup, with_adam=True):
     """Oracle (numpy, BLAS-threaded) fwd + bwd (+ Adam) on a (B, T) sample; returns seconds per step."""
     from oracle.parrot_oracle import OracleAdamClip
@@ -179,9 +193,9 @@ def run_reference(args):
         return
     cfg, B, T, U = workload_config(args, 1)
     Ts = min(T, args.ref_frames)
+    cores = set_blas_threads(args.blas_threads)
     sec = oracle_step_time(cfg, B, Ts, U, max(1, args.steps), max(0, min(args.warmup, 1)))
     fps = B * Ts / sec
-    cores = os.cpu_count()
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': fps, 'unit': UNIT, 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True,
@@ -190,7 +204,8 @@ def run_reference(args):
                                'frames (per-step cost is T-independent)' % (B, cfg['rnn_h_dim'], cfg['encoder_dim'], U, Ts, T),
                    'which_cost': cfg['which_cost']},
         'cpu_baseline': {'value': fps, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-                         'sample': 'numpy restatement of the Theano CPU path, fwd+bwd+Adam, B=%d T=%d' % (B, Ts)},
+                         'sample': 'numpy restatement of the Theano CPU path, fwd+bwd+Adam, B=%d T=%d, %d BLAS threads '
+                                   'of %d host cores' % (B, Ts, cores, os.cpu_count() or 0)},
         'e2e': {'value': fps, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
     print(json.dumps(line))
@@ -211,6 +226,12 @@ def main():
     ap.add_argument('--ref_frames', type=int, default=40, help='bounded T of the CPU arms')
     ap.add_argument('--profile_steps', type=int, default=1)
     ap.add_argument('--no_cpu_baseline', action='store_true')
+    ap.add_argument('--gain', type=float, default=None,
+                    help="'trained-like' parameter set of SURVEY 8d: W ~ N(0, (gain/sqrt(fan_in))^2) instead of the "
+                         'init scale 0.01 (same kernels, same work; larger activations)')
+    ap.add_argument('--scaling', type=str, default='weak', choices=['weak', 'strong'],
+                    help='weak: 64 rows per GPU (default) ; strong: the 64-row batch of configs[1] split over the GPUs')
+    ap.add_argument('--blas_threads', type=int, default=0, help='BLAS threads of the CPU arms (0: all host cores)')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
@@ -229,11 +250,14 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     cfg, B, T, U = workload_config(args, world)
+    if args.scaling == 'strong':
+        assert B % world == 0, 'strong scaling splits the %d-row batch over the GPUs' % B
+        B //= world
     W = max(3, args.warmup)
     K = max(1, args.steps)
 
     model = Parrot(device=dev, **cfg)
-    model.initialize(seed=0)                       # identical replicas (train.py:30-31 init)
+    model.initialize(seed=0, gain=args.gain)       # identical replicas (train.py:30-31 init; --gain: trained-like)
     algo = GradientDescent(model=model, parameters=None,
                            step_rule=CompositeRule([StepClipping(9.0), Adam(1e-4)]))
     bt = make_batch(cfg, B, T, U, seed=100 + rank)
@@ -315,23 +339,37 @@ def main():
 
         pk = peaks()
         per_step_flops, _ = algorithmic_flops(cfg, B, T)
-        # the forward scan is ONE persistent launch (scan_fwd_persistent): all T decoder steps, gate GEMMs +
-        # attention + grid barriers.  Its CUDA-event duration is the denominator (conservative: the attention
-        # phases and barriers are inside it).
+        # the forward scan is ONE persistent launch (scan_fwd_grouped): all T decoder steps, gate GEMMs, hoisted
+        # chunk products, attention and the group barriers.  Its CUDA-event duration is the denominator
+        # (conservative: attention phases and barriers are inside it).
         scan_ms = sec['sec_scan_fwd'][0] / P
+        bwd_ms = sec['sec_scan_bwd'][0] / P
         achieved_tf = per_step_flops * T / (scan_ms * 1e-3) / 1e12
+        # dram bytes of the same kernels from the committed ncu --set full capture of the shipped binary
+        # (tools/summarize_ncu.py writes profiles/r02_scan_traffic.json); base workload only
+        traffic, traffic_bwd, traffic_src = None, None, None
+        tj = os.path.join(ROOT, 'profiles', 'r02_scan_traffic.json')
+        if (B, T, U, cfg['rnn_h_dim'], cfg['which_cost']) == (64, 800, 128, 1024, 'MSE') and os.path.exists(tj):
+            td = json.load(open(tj))
+            traffic, traffic_bwd, traffic_src = td.get('scan_fwd_grouped'), td.get('scan_bwd_grouped'), td.get('source')
         roof = {'bound': 'tensor',
-                'kernel': 'scan_fwd_persistent (T decoder steps in one launch: tcgen05 gate GEMMs + attention)',
+                'kernel': 'scan_fwd_grouped (T decoder steps in one launch: three layer groups, tcgen05 gate GEMMs '
+                          'with TMEM-resident weights, hoisted chunk products, attention)',
                 'achieved': achieved_tf, 'peak': pk['tf_sustained'], 'unit': 'TFLOP/s',
                 'frac': achieved_tf / pk['tf_sustained'],
-                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full
-                # capture of the same command (profiles/r01_scan_persistent_ncu_T800_final.txt); base workload only
-                'traffic': (56.268694e9 + 7.882148e9) if (B, T, U, cfg['rnn_h_dim']) == (64, 800, 128, 1024) else None,
-                'traffic_source': 'profiles/r01_scan_persistent_ncu_T800_final.txt',
+                'traffic': traffic, 'traffic_source': traffic_src,
                 'peak_source': pk['source'] + ' bf16 sustained (kernel timed inside a long step)',
                 'algorithmic_flops_per_launch': per_step_flops * T,
                 'avg_launch_us': scan_ms * 1e3, 'launches_per_step': 1,
                 'us_per_decoder_step': scan_ms * 1e3 / T}
+        bwd_tf = per_step_flops * T / (bwd_ms * 1e-3) / 1e12     # the dgrads contract the same weights once
+        extra['roofline_bwd'] = {
+            'bound': 'tensor', 'kernel': 'scan_bwd_grouped (reverse sweep: attention backward, GRU dgrads, hoisted '
+                                         'chunk dgrads)',
+            'achieved': bwd_tf, 'peak': pk['tf_sustained'], 'unit': 'TFLOP/s', 'frac': bwd_tf / pk['tf_sustained'],
+            'traffic': traffic_bwd, 'traffic_source': traffic_src,
+            'algorithmic_flops_per_launch': per_step_flops * T, 'avg_launch_us': bwd_ms * 1e3,
+            'us_per_decoder_step': bwd_ms * 1e3 / T}
         # why the tensor fraction is small: at batch 64 every decoder step re-streams the bf16x3 weight planes
         # (hi+lo, 4 bytes per parameter on the recurrent path) -- report that stream against the HBM peak too
         Hh, Cc2 = cfg['rnn_h_dim'], 2 * cfg['encoder_dim']
@@ -340,7 +378,8 @@ def main():
             'bound': 'hbm', 'kernel': roof['kernel'], 'achieved': wbytes * T / (scan_ms * 1e-3) / 1e9,
             'peak': pk['hbm'], 'unit': 'GB/s', 'frac': wbytes * T / (scan_ms * 1e-3) / 1e9 / pk['hbm'],
             'algorithmic_bytes_per_decoder_step': wbytes,
-            'note': 'operand planes of the in-scan weights read once per decoder step (no reuse across steps yet)'}
+            'note': 'hi+lo operand planes of every in-scan weight counted once per decoder step; since round 2 the '
+                    'recurrent part (41 MB) is partly resident in tensor memory and the rest stays in L2'}
         # attention-step latency (second half of the BASELINE metric): one stand-alone parrot_attention_step call
         # (projection kernel + window kernel) at B x U x C of the workload, CUDA events over 200 back-to-back calls
         H, Cc, A = cfg['rnn_h_dim'], 2 * cfg['encoder_dim'], cfg['attention_size']
@@ -389,21 +428,25 @@ def main():
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
         Ts = min(T, args.ref_frames)
+        cores = set_blas_threads(args.blas_threads)
         sec = oracle_step_time(cfg, B, Ts, U, 2, 1, with_adam=False)
-        cpu = {'value': B * Ts / sec, 'unit': UNIT, 'cores': os.cpu_count(), 'kind': 'port',
+        cpu = {'value': B * Ts / sec, 'unit': UNIT, 'cores': cores, 'kind': 'port',
                'sample': 'numpy float32 restatement of the Theano CPU path (oracle), fwd+bwd, B=%d T=%d U=%d '
-                         '(per-step cost is T-independent), BLAS threads = host cores' % (B, Ts, U)}
+                         '(per-step cost is T-independent), %d BLAS threads of %d host cores'
+                         % (B, Ts, U, cores, os.cpu_count() or 0)}
 
     if rank == 0:
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W,
-            'ms_per_step': ms_dev / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'ms_per_step': ms_dev / K, 'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None,
             'dtype': 'bf16x3 (fp32 operands split hi+lo in bf16, 3 tcgen05 MMAs, fp32 accumulate)',
             'data': 'synthetic',
             'config': {'workload': 'Parrot base (BASELINE configs[1]): 1xBiGRU enc E=%d + 3xGRU dec H=%d, '
                                    'batch=%d/GPU, T_text=%d, T_frames=%d, %s cost, weak feedback, fwd+bwd+Adam'
                                    % (cfg['encoder_dim'], cfg['rnn_h_dim'], B, U, T, cfg['which_cost']),
                        'global_batch': B * world, 'parallelism': 'dp%d' % world,
+                       'parameters': 'init scale N(0, 0.01^2) (train.py:30-31)' if args.gain is None
+                       else 'trained-like N(0, (%g/sqrt(fan_in))^2)' % args.gain,
                        'l2': 'working set (13 GB workspace) far exceeds the 126 MB L2; no explicit flush',
                        'encoder_time_axis': 0},
             'e2e': {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4,

@@ -1430,8 +1430,6 @@ static void ensure_kernel_attrs() {
   static bool done = false;
   if (done) return;
   CK(cudaFuncSetAttribute(job_kernel_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES + 1024));
-  CK(cudaFuncSetAttribute(scan_fwd_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES + 1024 + ATT_SMEM_BYTES));
-  CK(cudaFuncSetAttribute(scan_bwd_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES + 1024 + ATT_SMEM_BYTES));
   CK(cudaFuncSetAttribute(scan_fwd_grouped, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES + 1024 + ATT_SMEM_BYTES));
   CK(cudaFuncSetAttribute(scan_bwd_grouped, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES + 1024 + ATT_SMEM_BYTES));
   CK(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
@@ -1789,15 +1787,6 @@ static int prefetch_enabled() {
   const char* e = getenv("PARROT_NO_PREFETCH");
   return (e && e[0] && e[0] != '0') ? 0 : 1;
 }
-static int scan_mode() {
-  // 0: chunk-lagged wavefront kernels (all CTAs in lock step) ; 1: grouped kernels (default)
-  static int mode = -1;
-  if (mode < 0) {
-    const char* e = getenv("PARROT_SCAN_MODE");
-    mode = (e && !strcmp(e, "wave")) ? 0 : 1;
-  }
-  return mode;
-}
 static bool use_persistent(parrot_model& M) {
   if (M.d.ln) return false;   // the normalisations sit between the layers: one launch per phase
   static int env = -1;
@@ -1807,15 +1796,14 @@ static bool use_persistent(parrot_model& M) {
   }
   const Dims& d = M.d;
   if (!env || !M.persistent_ok || M.cfg.gemm_impl == 1 || M.profiling >= 2 || M.sm_count < 148) return false;
-  const size_t att_f = std::max(att_proj_smem(d), att_window_smem(d, attention_nparts(d.B, d.C, 148)));
+  const size_t att_f = std::max(att_proj_smem(d), att_window_smem(d, attention_nparts(d.B, d.C, M.grp_f[0])));
   const size_t att_b = ((size_t)d.C + d.U + 3 * d.A * 16 + 10 * d.A) * 4;
   if (std::max(att_f, att_b) > (size_t)ATT_SMEM_BYTES) return false;
   for (const char* nm : {"fwdA", "fwdB", "bwd1", "bwd2"}) {
     auto it = M.tables.find(nm);
     if (it != M.tables.end() && it->second.count > 148) return false;
   }
-  if (scan_mode() == 1)
-    for (int l = 0; l < 3; ++l)
+  for (int l = 0; l < 3; ++l)
       for (const char* nm : {"gA", "gB", "hA", "hB"}) {
         auto it = M.tables.find(std::string(nm) + LN(l));
         if (it != M.tables.end() && it->second.count > (nm[0] == 'g' ? M.grp_f[l] : M.grp_b[l])) return false;
@@ -1848,72 +1836,6 @@ static EngineParams table_params(parrot_model& M, const std::string& name, int r
 
 static AttnFwdArgs attn_fwd_args(parrot_model& M, int t, bool sampling);
 static AttnBwdArgs attn_bwd_args(parrot_model& M, int t);
-
-// (Measured and removed: a cudaAccessPolicyWindow with hitProp = persisting over the contiguous weight-plane
-// region, sized to the 79 MB persisting carve-out, left the DRAM traffic of the scan unchanged -- 75 MB per decoder
-// step with or without it, ncu -- and cost 3 % because the carve-out shrinks the L2 left for everything else;
-// per-instruction evict_last hints, full or fractional, are equally neutral.  DESIGN.md section 6.)
-static bool scan_fwd_persistent_launch(parrot_model& M, cudaStream_t st) {
-  const Dims& d = M.d;
-  ScanFwdParams S;
-  S.ph[0] = table_params(M, "fwdA", 0, 0);
-  S.ph[1] = table_params(M, "fwdB", 0, 1);
-  S.ph[2] = table_params(M, "chunkF", 0);
-  S.Tc = M.Tc; S.nticks = d.T + 2 * M.Tc;
-  S.att_parts = attention_nparts(d.B, d.C, 148); S.att_slices = M.att_slices;
-  S.att = attn_fwd_args(M, 0, false);
-  S.s_h1 = (long long)d.B * d.H; S.s_k = (long long)d.B * d.A; S.s_w = (long long)d.B * d.C;
-  S.s_wp = (long long)d.Np * M.planes.at("w").pitch; S.s_phi = (long long)d.B * d.U;
-  S.s_ab = (long long)d.B * 2 * d.A; S.s_e = (long long)d.B * 3 * d.A;
-  S.T = d.T;
-  S.gridbar = M.d_gridbar;
-  S.stamps = M.stamps; S.stamp_bars = M.stamp_bars;
-  S.tl_buf = M.timeline; S.tl_tick = M.tl_tick;
-  S.prefetch = prefetch_enabled();
-  CK(cudaMemsetAsync(M.d_gridbar, 0, 4, st));
-  void* args[] = {&S};
-  g_ctx = "scan_fwd_persistent";
-  cudaError_t le = cudaLaunchCooperativeKernel((void*)scan_fwd_persistent, dim3(148), dim3(ENGINE_THREADS), args,
-                                               SMEM_BYTES + 1024 + ATT_SMEM_BYTES, st);
-  if (le != cudaSuccess) {
-    // co-residency of 148 CTAs refused (shared GPU, MPS limits ...): use one launch per phase from now on
-    cudaGetLastError();
-    M.persistent_ok = false;
-    return false;
-  }
-  g_launches.fetch_add(1, std::memory_order_relaxed);
-  if (debug_sync()) CK(cudaStreamSynchronize(st));
-  return true;
-}
-
-static bool scan_bwd_persistent_launch(parrot_model& M, cudaStream_t st) {
-  const Dims& d = M.d;
-  ScanBwdParams S;
-  S.ph[0] = table_params(M, "bwd1", 1, 0);
-  S.ph[1] = table_params(M, "bwd2", 1, 1);
-  S.ph[2] = table_params(M, "chunkB", 1);
-  S.Tc = M.Tc; S.nticks = d.T + 2 * M.Tc;
-  S.att = attn_bwd_args(M, 0);
-  S.s_dw = (long long)d.B * d.C; S.s_ab = (long long)d.B * 2 * d.A; S.s_e = (long long)d.B * 3 * d.A;
-  S.s_k = (long long)d.B * d.A; S.s_dh1 = (long long)d.B * d.H; S.s_datt = (long long)d.B * 3 * d.A;
-  S.s_dattp = (long long)d.Np * M.planes.at("datt").pitch;
-  S.ctx = M.d_ctx; S.T = d.T; S.gridbar = M.d_gridbar;
-  S.stamps = M.stamps_bwd; S.stamp_bars = M.stamps_bwd ? M.stamp_bars : 0; S.tl_buf = M.timeline; S.tl_tick = M.tl_tick;
-  S.prefetch = prefetch_enabled();
-  CK(cudaMemsetAsync(M.d_gridbar, 0, 4, st));
-  void* args[] = {&S};
-  g_ctx = "scan_bwd_persistent";
-  cudaError_t le = cudaLaunchCooperativeKernel((void*)scan_bwd_persistent, dim3(148), dim3(ENGINE_THREADS), args,
-                                               SMEM_BYTES + 1024 + ATT_SMEM_BYTES, st);
-  if (le != cudaSuccess) {
-    cudaGetLastError();
-    M.persistent_ok = false;
-    return false;
-  }
-  g_launches.fetch_add(1, std::memory_order_relaxed);
-  if (debug_sync()) CK(cudaStreamSynchronize(st));
-  return true;
-}
 
 // ---- grouped persistent scans (kernels.cuh): three layer groups with their own barrier domains
 static GroupSched group_sched(parrot_model& M, const char* a, const char* b, const char* c, int l, int reverse,
@@ -2040,7 +1962,7 @@ static void scan_fwd(parrot_model& M, const float* d_features, const float* d_no
   M.last_start_flag = start_flag;
   if (d.ln) { scan_fwd_ln(M, st); return; }
   if (d.weak) run_table(M, "hoist1", 0, 1, 0, st);   // pre1 = x_{t-1} . out_to_h1 for all frames
-  if (use_persistent(M) && (scan_mode() == 1 ? scan_fwd_grouped_launch(M, st) : scan_fwd_persistent_launch(M, st))) return;
+  if (use_persistent(M) && scan_fwd_grouped_launch(M, st)) return;
   // chunk-lagged layer wavefront, one launch per phase: tick tau runs layer 1 at step tau, layer 2 at tau - Tc,
   // layer 3 at tau - 2 Tc; every Tc ticks the hoisted products of the chunk just finished
   const int Tc = M.Tc;
@@ -2199,7 +2121,7 @@ static void scan_bwd(parrot_model& M, cudaStream_t st) {
   const Dims& d = M.d;
   CK(cudaMemsetAsync(M.fbuf("dk_carry"), 0, (size_t)d.B * d.A * 4, st));
   if (d.ln) { scan_bwd_ln(M, st); return; }
-  if (use_persistent(M) && (scan_mode() == 1 ? scan_bwd_grouped_launch(M, st) : scan_bwd_persistent_launch(M, st))) return;
+  if (use_persistent(M) && scan_bwd_grouped_launch(M, st)) return;
   const int blocks = std::min(gs_blocks((long long)d.B * d.H), 148);
   // reverse chunk-lagged wavefront: tick tau -> layer 3 at s = T-1-tau, layer 2 at s + Tc, attention + layer 1 at
   // s + 2 Tc; every Tc ticks the hoisted dgrads of the ranges just finished
@@ -2527,6 +2449,11 @@ int parrot_create(const parrot_config* cfg, float* d_params, float* d_grads, voi
       build(*M);
       build_device_tables(*M);
       upload_tables(*M, st);
+      // split-K scratch of the grouped scans: every slot starts as SPLIT_SENTINEL (engine.cuh q_finish); the readers
+      // restore the sentinel after consuming a slot, so this is needed once
+      if (M->uniq_split_floats > 0)
+        CK(cudaMemsetAsync(M->d_split_scratch + std::max<size_t>(M->max_split_floats, 1), 0xFF,
+                           (size_t)M->uniq_split_floats * 4, st));
       // constant 1.0 for unnormalised backward: cost[4]
       const float one = 1.0f;
       CK(cudaMemcpyAsync(M->fbuf("cost") + 4, &one, 4, cudaMemcpyHostToDevice, st));

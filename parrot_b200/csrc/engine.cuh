@@ -736,14 +736,26 @@ constexpr int QC = 4;    // columns per batch
 constexpr int QS = 12;   // partial-tile slots per batch
 __device__ __forceinline__ int q_cols_per_batch(int ksplit) { return ksplit <= 3 ? QC : (QS / ksplit < QC ? QS / ksplit : QC); }
 
-template <int DIR = 0>
+// SENT: the partial tiles are exchanged without a counter.  The scratch starts filled with SPLIT_SENTINEL (a NaN bit
+// pattern no partial sum takes); a reader polls its quads until every float differs from it and writes the sentinel
+// back once the quad is consumed -- the next writer of the slot is a full tick (>= 2 group barriers) away.  Saves the
+// writer's fence + atomic + the reader's poll of the counter + the dependent re-read: ~1.5 us per phase.
+constexpr uint32_t SPLIT_SENTINEL = 0xFFFFFFFFu;
+__device__ __forceinline__ bool quad_ready(const float4& x) {
+  return __float_as_uint(x.x) != SPLIT_SENTINEL && __float_as_uint(x.y) != SPLIT_SENTINEL &&
+         __float_as_uint(x.z) != SPLIT_SENTINEL && __float_as_uint(x.w) != SPLIT_SENTINEL;
+}
+template <int DIR = 0, bool SENT = false>
 __device__ __forceinline__ void q_finish(const EpiLocal& E, int t, int lane, int ew, int nwarps, int c_lo, int c_hi,
                                          int ksplit, int n_cols, const float* base, const uint8_t* stg, int stg_cols) {
   const int cb = q_cols_per_batch(ksplit);
   const size_t part_stride = (size_t)n_cols * TILE_M;
   for (int k0 = 0; c_lo + ew + nwarps * k0 < c_hi; k0 += cb) {
     float4 x[QS];
-    {
+    unsigned int spins = 0;
+    bool again;
+    do {
+      again = false;
       int kk = 0, pp = 0;
       const float* colp = base + (size_t)(c_lo + ew + nwarps * k0) * TILE_M + 4 * lane;   // column kk, part 0
       const float* ptr = colp;
@@ -751,6 +763,25 @@ __device__ __forceinline__ void q_finish(const EpiLocal& E, int t, int lane, int
       for (int i = 0; i < QS; ++i) {
         const bool live = kk < cb && c_lo + ew + nwarps * (k0 + kk) < c_hi;
         x[i] = live ? ldcg4(ptr) : f4zero();
+        ptr += part_stride;
+        if (++pp == ksplit) { pp = 0; ++kk; colp += (size_t)nwarps * TILE_M; ptr = colp; }
+      }
+      if (SENT) {
+#pragma unroll
+        for (int i = 0; i < QS; ++i) again |= !quad_ready(x[i]);
+        if (again && ++spins > (1u << 22)) pb_timeout(2);
+      }
+    } while (SENT && again);
+    if (SENT) {
+      // consumed: hand the slots back (sentinel) for the same phase of the next tick
+      int kk = 0, pp = 0;
+      float* colp = const_cast<float*>(base) + (size_t)(c_lo + ew + nwarps * k0) * TILE_M + 4 * lane;
+      float* ptr = colp;
+      const float s = __uint_as_float(SPLIT_SENTINEL);
+#pragma unroll
+      for (int i = 0; i < QS; ++i) {
+        const bool live = kk < cb && c_lo + ew + nwarps * (k0 + kk) < c_hi;
+        if (live) __stcg(reinterpret_cast<float4*>(ptr), make_float4(s, s, s, s));
         ptr += part_stride;
         if (++pp == ksplit) { pp = 0; ++kk; colp += (size_t)nwarps * TILE_M; ptr = colp; }
       }
@@ -1560,7 +1591,8 @@ __device__ __forceinline__ void epilogue_scan(Pipe& p, const EngineParams& P, in
       tc_fence_after();
     }
     if (threadIdx.x == 64) TL(4);
-    // park the partial tile: scratch[group][part][col][row]  (row fastest -> coalesced)
+    // park the partial tile: scratch[group][part][col][row]  (row fastest -> coalesced); the stores themselves
+    // publish it (sentinel exchange, see q_finish)
     float* part = const_cast<float*>(base) + (size_t)kpart * (size_t)n_cols * TILE_M;
 #pragma unroll 1
     for (int n0 = 0; n0 < n_cols; n0 += 16) {
@@ -1573,7 +1605,11 @@ __device__ __forceinline__ void epilogue_scan(Pipe& p, const EngineParams& P, in
         for (int i = 0; i < 16; ++i) v[i] = 0.0f;
       }
 #pragma unroll
-      for (int i = 0; i < 16; ++i) __stcg(part + (size_t)(n0 + i) * TILE_M + row, v[i]);
+      for (int i = 0; i < 16; ++i) {
+        // (a partial sum that happens to carry the sentinel's bits -- only a NaN can -- becomes the canonical NaN)
+        const float y = __float_as_uint(v[i]) == SPLIT_SENTINEL ? __uint_as_float(0x7FFFFFFFu) : v[i];
+        __stcg(part + (size_t)(n0 + i) * TILE_M + row, y);
+      }
     }
     if (have_acc) {
       tc_fence_before();
@@ -1581,27 +1617,9 @@ __device__ __forceinline__ void epilogue_scan(Pipe& p, const EngineParams& P, in
       if (lane == 0) mbar_arrive(&p.tempty_bar[buf]);
     }
     if (threadIdx.x == 64) TL(5);
-    __threadfence();
   }
-  epi_group_sync();   // partial tile written by warps 2..5
-  if (warp == 2 && lane == 0) {
-    atomicAdd(P.split_count + group, 1u);
-    unsigned int seen, spins = 0;
-    do {
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(P.split_count + group) : "memory");
-      if (++spins > (1u << 24)) pb_timeout(2);
-    } while ((seen & 0xffffu) < (unsigned int)ksplit);
-  }
-  epi_group_sync();
-  if (threadIdx.x == 64) TL(6);
-  q_finish<DIR>(E, t, lane, ew, NEW, c_lo, c_hi, ksplit, n_cols, base, p.stg, stg_cols);
+  q_finish<DIR, true>(E, t, lane, ew, NEW, c_lo, c_hi, ksplit, n_cols, base, p.stg, stg_cols);
   if (threadIdx.x == 64) TL(7);
-  epi_group_sync();
-  if (warp == 2 && lane == 0) {
-    // the last part to finish resets the arrival counter for the next use
-    const unsigned int old = atomicAdd(P.split_count + group, 0x10000u);
-    if ((old >> 16) == (unsigned int)(ksplit - 1)) P.split_count[group] = 0u;
-  }
   if (have_acc) ++p.it;
 }
 

@@ -860,40 +860,6 @@ __global__ void gru_bwd_pre_kernel(const ScanCtx* cp, const PreArgs pa) {
 // kernel boundaries; the GEMM pipeline state (smem ring, TMEM accumulators) lives across phases.
 // =========================================================================
 constexpr int ATT_SMEM_BYTES = 24 * 1024;
-// Chunk-lagged layer wavefront.  Layer l runs `l * Tc` decoder steps behind layer 1 (forward; reversed in the
-// backward sweep), so every product whose operand comes from a LOWER layer (h1 -> rnn2/rnn3, h2 -> rnn3, w_t -> rnn2/3)
-// or from the teacher-forced frames is hoisted out of the per-step recurrence into a batched "chunk" product over
-// Tc steps at a time, executed by the same persistent kernel every Tc ticks.  Per tick the recurrent phases stream
-// only state_to_gates / state_to_state (+ the attention context product of layer 1): 41 MB of operand planes at the
-// base configuration instead of 86 MB, a set that stays L2-resident.
-struct ScanFwdParams {
-  EngineParams ph[3];  // [0] gates / [1] candidates of all three layers (lags 0, Tc, 2 Tc) ;
-                       // [2] chunk products: pre2 of chunk e, pre3 of chunk e - 1 (njobs may be 0)
-  AttnFwdArgs att;     // pointers of step 0
-  long long s_h1, s_k, s_w, s_wp, s_phi, s_ab, s_e;   // per-step strides (elements)
-  int T, Tc, nticks;
-  int att_parts, att_slices;    // window CTAs per batch row, projection slices
-  unsigned int* gridbar;
-  unsigned long long* stamps;   // debug: [cta][bar][2] globaltimer at (barrier wait done, arrival) or null
-  int stamp_bars;
-  unsigned long long* tl_buf;   // debug (unused by the kernel since the quad finish; kept for the tools)
-  int tl_tick;
-  int prefetch;                 // 1: weight tiles of the next phase are issued before its grid barrier
-};
-struct ScanBwdParams {
-  EngineParams ph[3];   // [0] d(r*h) products / [1] recurrent state dgrads of all three layers ;
-                        // [2] chunk dgrads: from da3 of range e into dh2 / dh1 / dw, from da2 of range e - 1 into dh1 / dw
-  AttnBwdArgs att;      // pointers of step 0
-  long long s_dw, s_ab, s_e, s_k, s_dh1, s_datt, s_dattp;
-  const ScanCtx* ctx;
-  int T, Tc, nticks;
-  unsigned int* gridbar;
-  unsigned long long* stamps;
-  int stamp_bars;
-  unsigned long long* tl_buf;
-  int tl_tick;
-  int prefetch;
-};
 #define STAMP(S, bar, k)                                                                                \
   do {                                                                                                  \
     if ((S).stamps && (int)(bar) < (S).stamp_bars)                                                      \
@@ -949,12 +915,6 @@ __device__ __forceinline__ void group_gemm_phase(Pipe& p, const EngineParams& P,
   }
   ++bar;
 }
-template <int DIR, class SP>
-__device__ __forceinline__ void persistent_gemm_phase(Pipe& p, const EngineParams& P, int tick, const SP& S,
-                                                      unsigned int& bar, const PhaseCache* pc, const bool chunk) {
-  group_gemm_phase<DIR>(p, P, tick, S, S.gridbar, (int)gridDim.x, bar, pc, chunk);
-}
-
 // Shared-memory copies used by the persistent loops: the three EngineParams and, for the two scan tables, this CTA's
 // job and epilogue context (job index = CTA index, every tick).  All threads call this; ends with a CTA barrier.
 struct PersistShared {
@@ -986,104 +946,6 @@ __device__ __forceinline__ PersistShared* persist_shared_fill(uint8_t* area, con
   return ps;
 }
 static_assert(sizeof(PersistShared) <= 1792, "PersistShared must fit behind the pipeline barriers");
-
-__global__ void __launch_bounds__(ENGINE_THREADS, 1) scan_fwd_persistent(const ScanFwdParams S) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  Pipe p;
-  const int max_cols = S.ph[2].njobs > 0 && S.ph[2].n_cols > S.ph[0].n_cols ? S.ph[2].n_cols : S.ph[0].n_cols;
-  float* att_sh = reinterpret_cast<float*>(pipe_setup(p, align_smem(smem_raw), max_cols));
-  p.stg = reinterpret_cast<uint8_t*>(att_sh); p.stg_bytes = ATT_SMEM_BYTES;   // finish operands (GEMM phases only)
-  const PersistShared* ps = persist_shared_fill(p.cache_area, S.ph);
-  unsigned int bar = 0;
-  for (int tick = 0; tick < S.nticks; ++tick) {
-    const bool event = ps->P[2].njobs > 0 && (tick + 1) % S.Tc == 0;
-#pragma unroll 1
-    for (int ph = 0; ph < 3; ++ph) {
-      if (ph == 2) {
-        if (tick < S.T) {
-          AttnFwdArgs a = S.att;
-          a.h1 += tick * S.s_h1; a.k_prev += tick * S.s_k; a.k_out += tick * S.s_k; a.w_out += tick * S.s_w;
-          a.w_hi += tick * S.s_wp; a.w_lo += tick * S.s_wp; a.phi_out += tick * S.s_phi; a.ab_out += tick * S.s_ab;
-          a.e_out += tick * S.s_e;
-          // stage 1 (att_slices CTAs): K-sliced partial projections of h1_t ; stage 2 (att_parts CTAs per batch
-          // row): window + context slice.  CTAs without work only pass the barriers.
-          // (every CTA observes barrier k before it arrives at barrier k + 1: the arrival counter is monotonic)
-          if (threadIdx.x == 0) { grid_wait(S.gridbar, bar * gridDim.x); STAMP(S, bar, 0); }
-          __syncthreads();
-          for (int sl = blockIdx.x; sl < S.att_slices; sl += gridDim.x) attention_proj_slice(a, sl, att_sh);
-          __syncthreads();
-          if (threadIdx.x == 0) { STAMP(S, bar, 1); grid_arrive(S.gridbar); }
-          ++bar;
-          const int nwork = a.B * S.att_parts;
-          if (threadIdx.x == 0) { grid_wait(S.gridbar, bar * gridDim.x); STAMP(S, bar, 0); }
-          __syncthreads();
-          for (int i = blockIdx.x; i < nwork; i += gridDim.x)
-            attention_window_part<true>(a, i / S.att_parts, i % S.att_parts, S.att_parts, S.att_slices, att_sh);
-          asm volatile("fence.proxy.async.global;" ::: "memory");
-          __syncthreads();
-          if (threadIdx.x == 0) { STAMP(S, bar, 1); grid_arrive(S.gridbar); }
-          ++bar;
-        }
-        if (!event) break;
-      }
-      persistent_gemm_phase<1>(p, ps->P[ph], ph == 2 ? (tick + 1) / S.Tc - 1 : tick, S, bar,
-                               ph < 2 ? &ps->pc[ph] : nullptr, ph == 2);
-    }
-  }
-  pipe_teardown(p);
-}
-
-__global__ void __launch_bounds__(ENGINE_THREADS, 1) scan_bwd_persistent(const ScanBwdParams S) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  Pipe p;
-  const int max_cols = S.ph[2].njobs > 0 && S.ph[2].n_cols > S.ph[0].n_cols ? S.ph[2].n_cols : S.ph[0].n_cols;
-  float* att_sh = reinterpret_cast<float*>(pipe_setup(p, align_smem(smem_raw), max_cols));
-  p.stg = reinterpret_cast<uint8_t*>(att_sh); p.stg_bytes = ATT_SMEM_BYTES;   // finish operands (GEMM phases only)
-  const PersistShared* ps = persist_shared_fill(p.cache_area, S.ph);
-  unsigned int bar = 0;
-  const ScanCtx& c = *S.ctx;
-  for (int tick = 0; tick < S.nticks; ++tick) {
-    // layer 3 at step s3, layer 2 at s3 + Tc, attention + layer 1 at s3 + 2 Tc
-    const int s3 = S.T - 1 - tick;
-    const int ta = s3 + 2 * S.Tc;
-    // Phase 0: attention backward of step ta on the first B CTAs, each followed by the (row-local) GRU pre-pass of
-    // layer 1 for its batch row; meanwhile the other CTAs run the pre-pass of layers 3 and 2, which do not depend
-    // on the attention.
-    {
-      if (threadIdx.x == 0 && bar) grid_wait(S.gridbar, bar * gridDim.x);
-      if (threadIdx.x == 0) STAMP(S, bar, 0);
-      __syncthreads();
-      const bool att_valid = ta >= 0 && ta < S.T;
-      const int nB = att_valid ? min(S.att.B, (int)gridDim.x / 2) : 0;   // CTAs doing attention rows
-      if ((int)blockIdx.x < nB) {
-        AttnBwdArgs a = S.att;
-        a.dbg = (S.tl_buf && tick == S.tl_tick) ? S.tl_buf + 2 * 148 * 16 : nullptr;
-        a.dw += ta * S.s_dw; a.ab += ta * S.s_ab; a.e += ta * S.s_e; a.kappa += ta * S.s_k; a.dh1 += ta * S.s_dh1;
-        a.datt += ta * S.s_datt; a.datt_hi += ta * S.s_dattp; a.datt_lo += ta * S.s_dattp;
-        for (int b = blockIdx.x; b < a.B; b += nB) {
-          attention_bwd_body(a, b, att_sh, &c, ta);   // + the row's GRU backward pre-pass of layer 1
-        }
-      } else {
-        const int nworkers = (int)gridDim.x - nB;
-        const int wid = (int)blockIdx.x - nB;
-        for (int l = 2; l >= 1; --l) {
-          const int t = s3 + (2 - l) * S.Tc;
-          if (t >= 0 && t < S.T) gru_bwd_pre_rows(c, l, t, 0, c.B, wid * (int)blockDim.x + threadIdx.x, nworkers * (int)blockDim.x);
-        }
-      }
-      asm volatile("fence.proxy.async.global;" ::: "memory");
-      __syncthreads();
-      if (threadIdx.x == 0) { STAMP(S, bar, 1); grid_arrive(S.gridbar); }
-      ++bar;
-    }
-    const bool event = ps->P[2].njobs > 0 && (tick + 1) % S.Tc == 0;
-#pragma unroll 1
-    for (int ph = 0; ph < (event ? 3 : 2); ++ph)
-      persistent_gemm_phase<2>(p, ps->P[ph], ph == 2 ? (tick + 1) / S.Tc - 1 : tick, S, bar,
-                               ph < 2 ? &ps->pc[ph] : nullptr, ph == 2);
-  }
-  pipe_teardown(p);
-}
 
 // =========================================================================
 // Grouped persistent scans.  The 148 CTAs are partitioned into three LAYER GROUPS, each with its own barrier counter
