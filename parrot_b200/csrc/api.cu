@@ -283,6 +283,7 @@ struct parrot_model {
   int Tc = 0;              // chunk length of the chunk-lagged layer wavefront (0: not used)
   int grp_f[3] = {0, 0, 0};   // CTAs per layer group of the grouped persistent scans (forward / backward sweep)
   int grp_b[3] = {0, 0, 0};
+  bool pfold = false;         // attention projection folded into the layer-1 candidate finish (grouped forward scan)
   int att_slices = 0;      // K slices of the attention projection (persistent scan)
   unsigned long long* timeline = nullptr;
   unsigned long long* stamps = nullptr;   // debug: persistent forward scan per-barrier stamps
@@ -805,6 +806,7 @@ static void build(parrot_model& M) {
         out[0] = x; out[1] = y; out[2] = z;
       }
     };
+    M.pfold = train && !d.ln && 3 * d.A <= 32 && H % 128 == 0 && !getenv("PARROT_NO_PFOLD");
     parse("PARROT_GROUPS_F", M.grp_f, 64, 40, 44);
     parse("PARROT_GROUPS_B", M.grp_b, 64, 40, 44);
   }
@@ -826,6 +828,8 @@ static void build(parrot_model& M) {
   }
   if (train) {
     X.dw = M.falloc("dw", (long long)(T + 1) * B * d.C);
+    X.att_wT = M.dry ? nullptr : M.fbuf("att_wT");
+    X.att_hat_part = M.dry ? nullptr : M.fbuf("att_hat_part");
     M.falloc("dk_carry", (long long)B * d.A);
     M.falloc("datt", (long long)T * B * 3 * d.A);
     M.make_plane("datt", Np, d.Ap, T);
@@ -975,6 +979,8 @@ static void build(parrot_model& M) {
         std::vector<Job> ga, gb;
         build_fwd_layer_jobs(M, ga, l, true, 0, false, true);
         build_fwd_layer_jobs(M, gb, l, false, 0, false, true);
+        if (l == 0 && M.pfold)
+          for (auto& j : gb) j.pa.flags |= QF_ATT_PROJ;   // layer-1 candidate finish also emits the attention projection
         push_table(M, "gA" + LN(l), ga, Np, M.grp_f[l], 0, true);
         push_table(M, "gB" + LN(l), gb, Np, M.grp_f[l], 0, true);
         assign_resident(M, "gA" + LN(l), "gB" + LN(l));
@@ -1322,7 +1328,11 @@ static void build(parrot_model& M) {
       for (int l = 0; l < 3; ++l) {
         std::vector<Job> gj;
         for (auto& j : js)
-          if (j.layer == l) { gj.push_back(j); gj.back().lag = 0; }
+          if (j.layer == l) {
+            gj.push_back(j); gj.back().lag = 0;
+            // groups 1 / 2: the finish of the own-layer state dgrad also runs the GRU pre-pass of step t - 1
+            if (l > 0 && j.aux == l && H % 4 == 0 && d.Hp % 4 == 0 && !getenv("PARROT_NO_FUSED_PRE")) gj.back().pa.flags |= QF_FUSED_PRE;
+          }
         push_table(M, "hB" + LN(l), gj, Np, M.grp_b[l], 0, true);
         assign_resident(M, "hA" + LN(l), "hB" + LN(l));
       }
@@ -1862,7 +1872,9 @@ static bool scan_fwd_grouped_launch(parrot_model& M, cudaStream_t st) {
   ScanFwdGParams S;
   for (int l = 0; l < 3; ++l) S.g[l] = group_sched(M, "gA", "gB", "gC", l, 0, M.grp_f);
   S.Tc = M.Tc; S.T = d.T;
-  S.att_parts = attention_nparts(d.B, d.C, M.grp_f[0]); S.att_slices = M.att_slices;
+  S.att_parts = attention_nparts(d.B, d.C, M.grp_f[0]);
+  S.pfold = M.pfold ? 1 : 0;
+  S.att_slices = M.pfold ? d.H / 128 : M.att_slices;
   S.att = attn_fwd_args(M, 0, false);
   S.s_h1 = (long long)d.B * d.H; S.s_k = (long long)d.B * d.A; S.s_w = (long long)d.B * d.C;
   S.s_wp = (long long)d.Np * M.planes.at("w").pitch; S.s_phi = (long long)d.B * d.U;
@@ -1895,6 +1907,8 @@ static bool scan_bwd_grouped_launch(parrot_model& M, cudaStream_t st) {
   S.s_k = (long long)d.B * d.A; S.s_dh1 = (long long)d.B * d.H; S.s_datt = (long long)d.B * 3 * d.A;
   S.s_dattp = (long long)d.Np * M.planes.at("datt").pitch;
   S.ctx = M.d_ctx; S.bars = M.d_gridbar;
+  S.fused_pre = (d.H % 4 == 0 && d.Hp % 4 == 0) ? 1 : 0;   // (same condition as QF_FUSED_PRE in the hB tables)
+  if (const char* e = getenv("PARROT_NO_FUSED_PRE")) { if (e[0] && e[0] != '0') S.fused_pre = 0; }
   S.stamps = M.stamps_bwd; S.stamp_bars = M.stamps_bwd ? M.stamp_bars : 0;
   S.prefetch = prefetch_enabled();
   CK(cudaMemsetAsync(M.d_gridbar, 0, 1024, st));

@@ -91,6 +91,8 @@ struct PlainArgs {
   int rowbias_ld;      // > 0: `bias` is a [n_pad rows][rowbias_ld] matrix indexed by (sample % n_pad, feature)
 };
 enum { PF_ACC = 1, PF_TRANS = 2, PF_PLANE_PADDED = 4 };
+enum { QF_FUSED_PRE = 256, QF_ATT_PROJ = 512 };   // QF_ATT_PROJ: EPI_CAND job of layer 1: the finish also emits the
+                                                   // tile's partial attention projection (h1_t . W_att), see q_apply   // EPI_BWD_STATE job flag (Job::pa.flags): run the GRU pre-pass of step t - 1 in the finish
 
 struct Job {
   int nseg, epi, lag, layer;
@@ -144,6 +146,8 @@ struct ScanCtx {
   long long base_tstride;   // 0: L.base is [B][3H] ; layer_norm mode: [T][B][3H] (per-step pre-activation terms)
   LayerBuf L[3];
   float* dw;           // [T+1][B][C] gradient wrt w slot s
+  const float* att_wT;      // [3A][H] transposed h1_to_att weights (attention projection folded into the layer-1 finish)
+  float* att_hat_part;      // [H/128][B][3A] per-feature-tile partial projections of the current step
 };
 
 struct EngineParams {
@@ -256,6 +260,9 @@ struct EpiLocal {
   void *p0, *p1, *p2, *p3, *p4, *p5;
   const float* pre;   // GATES / CAND: hoisted pre-activation terms [T][B][3H] (or null), added to base
   long long l0, l1, l2;
+  const float* att_w;   // CAND + QF_ATT_PROJ: wT[3A][H] ; att_part: [tile][B][3A] ; att_n = 3A
+  float* att_part;
+  int att_n, pad_e_;
 };
 __device__ __forceinline__ EpiLocal make_epi_local(const Job& jb, const ScanCtx* ctx, int n_shift = 0,
                                                    int n_limit = 0) {
@@ -267,6 +274,7 @@ __device__ __forceinline__ EpiLocal make_epi_local(const Job& jb, const ScanCtx*
   E.p0 = E.p1 = E.p2 = E.p3 = E.p4 = E.p5 = nullptr;
   E.pre = nullptr;
   E.l0 = E.l1 = E.l2 = 0;
+  E.att_w = nullptr; E.att_part = nullptr; E.att_n = 0; E.pad_e_ = 0;
   if (jb.epi == EPI_PLAIN) {
     E.p0 = jb.pa.out; E.p1 = (void*)jb.pa.bias; E.p2 = jb.pa.hi; E.p3 = jb.pa.lo;
     E.l0 = jb.pa.ldo; E.l1 = jb.pa.ldp; E.l2 = jb.pa.out_tstride;
@@ -284,12 +292,23 @@ __device__ __forceinline__ EpiLocal make_epi_local(const Job& jb, const ScanCtx*
     case EPI_GATES:
       E.p0 = (void*)L.base; E.p1 = L.h; E.p2 = L.z; E.p3 = L.r; E.p4 = L.rh_hi; E.p5 = L.rh_lo; E.pre = L.pre; break;
     case EPI_CAND:
-      E.p0 = (void*)L.base; E.p1 = L.h; E.p2 = L.z; E.p3 = L.c; E.p4 = L.h_hi; E.p5 = L.h_lo; E.pre = L.pre; break;
+      E.p0 = (void*)L.base; E.p1 = L.h; E.p2 = L.z; E.p3 = L.c; E.p4 = L.h_hi; E.p5 = L.h_lo; E.pre = L.pre;
+      if ((jb.pa.flags & QF_ATT_PROJ) && ctx->att_wT) {
+        E.flags = QF_ATT_PROJ; E.att_w = ctx->att_wT; E.att_part = ctx->att_hat_part; E.att_n = 3 * ctx->A;
+      }
+      break;
     case EPI_BWD_RH:
       E.p0 = L.r; E.p1 = L.h; E.p2 = L.dh; E.p3 = L.da; E.p4 = L.da_hi; E.p5 = L.da_lo; break;
     case EPI_BWD_STATE:
       if (jb.aux == 3) { E.p0 = ctx->dw; E.dstF = ctx->C; }
-      else { E.p0 = ctx->L[jb.aux].dh; E.dstF = ctx->H; }
+      else {
+        const LayerBuf& D = ctx->L[jb.aux];
+        E.p0 = D.dh; E.dstF = ctx->H;
+        if (jb.pa.flags & QF_FUSED_PRE) {
+          E.flags = QF_FUSED_PRE;
+          E.p1 = D.z; E.p2 = D.c; E.p3 = D.h; E.p4 = D.da_hi; E.p5 = D.da_lo; E.pre = D.da;
+        }
+      }
       break;
   }
   return E;
@@ -577,7 +596,7 @@ __device__ __forceinline__ void split4(float4 x, uint2& hi, uint2& lo) {
   hi.x = *reinterpret_cast<const uint32_t*>(&h01); hi.y = *reinterpret_cast<const uint32_t*>(&h23);
   lo.x = *reinterpret_cast<const uint32_t*>(&l01); lo.y = *reinterpret_cast<const uint32_t*>(&l23);
 }
-struct QOps { float4 a, b, c; };
+struct QOps { float4 a, b, c, d, e; };
 
 // can this job's split-K finish use the quad path?  (feature counts divisible by 4, aligned stashes)
 __device__ __forceinline__ bool quad_ok(const EpiLocal& E) {
@@ -591,11 +610,16 @@ __device__ __forceinline__ bool quad_ok(const EpiLocal& E) {
 //   CAND       0: hoisted-or-base term   1: z   2: h_prev
 //   BWD_RH     0: r   1: h_prev   2: dh
 //   BWD_STATE  0: destination
+//   BWD_STATE + QF_FUSED_PRE (grouped backward scan, own-layer state dgrad): the finish owns the FINAL dh[slot t] of
+//   its elements, so it also runs the elementwise GRU backward pre-pass of step t - 1 on them (gru_bwd_pre_rows):
+//              1: z   2: c   3: h (slot t - 1)   4: dh (slot t - 1)      -- all of step t - 1
 template <int DIR = 0>
-__device__ __forceinline__ int q_narr(int epi) {
+__device__ __forceinline__ int q_narr(const EpiLocal& E) {
+  const int epi = E.epi;
   if (DIR == 1) return epi == EPI_GATES ? 2 : 3;
-  if (DIR == 2) return epi == EPI_BWD_STATE ? 1 : 3;
-  return epi == EPI_GATES ? 2 : (epi == EPI_BWD_STATE ? 1 : 3);
+  if (epi == EPI_BWD_STATE) return (E.flags & QF_FUSED_PRE) ? 5 : 1;
+  if (DIR == 2) return 3;
+  return epi == EPI_GATES ? 2 : 3;
 }
 template <int DIR = 0>
 __device__ __forceinline__ const float* q_src(const EpiLocal& E, int t, int rq, int b, int arr) {
@@ -619,7 +643,9 @@ __device__ __forceinline__ const float* q_src(const EpiLocal& E, int t, int rq, 
     case EPI_BWD_RH:
       return (const float*)(arr == 0 ? E.p0 : (arr == 1 ? E.p1 : E.p2)) + tb + f;
     case EPI_BWD_STATE:
-      return arr == 0 ? (const float*)E.p0 + ((long long)(t + E.slot_off) * B + b) * E.dstF + f : nullptr;
+      if (arr == 0) return (const float*)E.p0 + ((long long)(t + E.slot_off) * B + b) * E.dstF + f;
+      if (!(E.flags & QF_FUSED_PRE) || t < 1) return nullptr;
+      return (const float*)(arr == 1 ? E.p1 : (arr == 2 ? E.p2 : (arr == 3 ? E.p3 : E.p0))) + tb - (long long)B * H + f;
     default: return nullptr;
   }
 }
@@ -631,12 +657,21 @@ __device__ __forceinline__ void q_load(const EpiLocal& E, int t, int rq, int b, 
   o.a = p0 ? ldcg4(p0) : f4zero();
   o.b = p1 ? ldcg4(p1) : f4zero();
   o.c = p2 ? ldcg4(p2) : f4zero();
+  o.d = f4zero(); o.e = f4zero();
+  if (DIR != 1 && E.epi == EPI_BWD_STATE && (E.flags & QF_FUSED_PRE)) {
+    const float* p3 = q_src<DIR>(E, t, rq, b, 3);
+    const float* p4 = q_src<DIR>(E, t, rq, b, 4);
+    o.d = p3 ? ldcg4(p3) : f4zero();
+    o.e = p4 ? ldcg4(p4) : f4zero();
+  }
 }
 
 template <int DIR = 0>
 __device__ __forceinline__ void q_apply(const EpiLocal& E, int t, int rq, int b, float4 v, const QOps& o) {
   const int H = E.H, B = E.B, f = E.row0 + 4 * rq;
-  if (4 * rq >= E.m_valid || b >= B) return;
+  const bool proj = DIR == 1 && E.epi == EPI_CAND && (E.flags & QF_ATT_PROJ);   // warp-uniform
+  const bool live = !(4 * rq >= E.m_valid || b >= B);
+  if (!live && !proj) return;
   int epi = E.epi;
   if (DIR == 1 && epi != EPI_GATES) epi = EPI_CAND;
   if (DIR == 2 && epi != EPI_BWD_STATE) epi = EPI_BWD_RH;
@@ -663,13 +698,42 @@ __device__ __forceinline__ void q_apply(const EpiLocal& E, int t, int rq, int b,
       cc.z = tanhf_fast(v.z + o.a.z); cc.w = tanhf_fast(v.w + o.a.w);
       hn.x = cc.x * o.b.x + o.c.x * (1.0f - o.b.x); hn.y = cc.y * o.b.y + o.c.y * (1.0f - o.b.y);
       hn.z = cc.z * o.b.z + o.c.z * (1.0f - o.b.z); hn.w = cc.w * o.b.w + o.c.w * (1.0f - o.b.w);
-      *reinterpret_cast<float4*>((float*)E.p3 + tb) = cc;
-      *reinterpret_cast<float4*>((float*)E.p1 + tb + (long long)B * H) = hn;   // slot t + 1
-      uint2 hh, ll;
-      split4(hn, hh, ll);
-      const long long po = ((long long)(t + 1) * E.Np + b) * E.Hp + f;
-      *reinterpret_cast<uint2*>((bf16*)E.p4 + po) = hh;
-      *reinterpret_cast<uint2*>((bf16*)E.p5 + po) = ll;
+      if (live) {
+        *reinterpret_cast<float4*>((float*)E.p3 + tb) = cc;
+        *reinterpret_cast<float4*>((float*)E.p1 + tb + (long long)B * H) = hn;   // slot t + 1
+        uint2 hh, ll;
+        split4(hn, hh, ll);
+        const long long po = ((long long)(t + 1) * E.Np + b) * E.Hp + f;
+        *reinterpret_cast<uint2*>((bf16*)E.p4 + po) = hh;
+        *reinterpret_cast<uint2*>((bf16*)E.p5 + po) = ll;
+      }
+      if (proj) {
+        // attention projection folded into the layer-1 finish (model.py:664-669): this warp holds h1_t[b] for the 128
+        // features of the tile (4 per lane); every lane forms its share of the 3A dot products, a transpose-reduce
+        // (31 shuffles) leaves output j on lane j, and the tile's partial goes to hat_part[tile][b][j] -- the window
+        // stage adds the H/128 partials in tile order (deterministic) and the bias.  Replaces a grid phase + barrier.
+        float pv[32];
+        const float* wrow = E.att_w + f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          pv[j] = 0.0f;
+          if (j < E.att_n && live) {
+            const float4 w4 = ldg4(wrow + (long long)j * H);
+            pv[j] = hn.x * w4.x + hn.y * w4.y + hn.z * w4.z + hn.w * w4.w;
+          }
+        }
+#pragma unroll
+        for (int k = 16; k >= 1; k >>= 1) {
+          const bool up = (rq & k) != 0;
+#pragma unroll
+          for (int i = 0; i < k; ++i) {
+            const float send = up ? pv[i] : pv[i + k];
+            const float keep = up ? pv[i + k] : pv[i];
+            pv[i] = keep + __shfl_xor_sync(0xffffffffu, send, k);
+          }
+        }
+        if (rq < E.att_n && b < B) E.att_part[((long long)(E.row0 >> 7) * B + b) * E.att_n + rq] = pv[0];
+      }
     } break;
     case EPI_BWD_RH: {
       const long long tb = ((long long)t * B + b) * H + f;
@@ -685,9 +749,36 @@ __device__ __forceinline__ void q_apply(const EpiLocal& E, int t, int rq, int b,
       *reinterpret_cast<uint2*>((bf16*)E.p4 + po) = hh;
       *reinterpret_cast<uint2*>((bf16*)E.p5 + po) = ll;
     } break;
-    case EPI_BWD_STATE:
-      *reinterpret_cast<float4*>((float*)E.p0 + ((long long)(t + E.slot_off) * B + b) * E.dstF + f) = f4add(o.a, v);
-      break;
+    case EPI_BWD_STATE: {
+      const float4 dh1 = f4add(o.a, v);
+      *reinterpret_cast<float4*>((float*)E.p0 + ((long long)(t + E.slot_off) * B + b) * E.dstF + f) = dh1;
+      if ((E.flags & QF_FUSED_PRE) && t >= 1) {
+        // GRU backward pre-pass of step t - 1 on these elements (same arithmetic as gru_bwd_pre_rows)
+        const int tp = t - 1;
+        float4 dh0, dac, dagz;
+#define PB_PRE1(m)                                              \
+        {                                                       \
+          const float dh = dh1.m, z = o.b.m, cc = o.c.m;        \
+          dh0.m = o.e.m + dh * (1.0f - z);                      \
+          dac.m = (dh * z) * (1.0f - cc * cc);                  \
+          dagz.m = (dh * (cc - o.d.m)) * z * (1.0f - z);        \
+        }
+        PB_PRE1(x) PB_PRE1(y) PB_PRE1(z) PB_PRE1(w)
+#undef PB_PRE1
+        *reinterpret_cast<float4*>((float*)E.p0 + ((long long)tp * B + b) * H + f) = dh0;
+        float* dap = const_cast<float*>(E.pre) + ((long long)tp * B + b) * 3 * H;
+        *reinterpret_cast<float4*>(dap + f) = dac;
+        *reinterpret_cast<float4*>(dap + H + f) = dagz;
+        const long long po = ((long long)tp * E.Np + b) * (3 * E.Hp);
+        uint2 hh, ll;
+        split4(dac, hh, ll);
+        *reinterpret_cast<uint2*>((bf16*)E.p4 + po + f) = hh;
+        *reinterpret_cast<uint2*>((bf16*)E.p5 + po + f) = ll;
+        split4(dagz, hh, ll);
+        *reinterpret_cast<uint2*>((bf16*)E.p4 + po + E.Hp + f) = hh;
+        *reinterpret_cast<uint2*>((bf16*)E.p5 + po + E.Hp + f) = ll;
+      }
+    } break;
     default: break;
   }
 }
@@ -704,13 +795,13 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 template <int DIR = 0>
 __device__ __forceinline__ void q_stage(const EpiLocal& E, int t, int lane, int ew, int nwarps, int c_lo, int c_hi,
                                         uint8_t* stg, int stg_cols) {
-  const int narr = q_narr<DIR>(E.epi);
+  const int narr = q_narr<DIR>(E);
   for (int c = c_lo + ew; c < c_hi; c += nwarps) {
     const int cs = c - c_lo;
     if (cs >= stg_cols) break;
 #pragma unroll
-    for (int arr = 0; arr < 3; ++arr) {
-      if (arr < narr) {
+    for (int arr = 0; arr < 5; ++arr) {
+      if (arr < narr && (arr < 3 || DIR != 1)) {
         const float* src = q_src<DIR>(E, t, lane, c, arr);
         if (src) cp_async16(stg + ((size_t)(cs * narr + arr) * TILE_M + 4 * lane) * 4, src);
       }
@@ -722,11 +813,13 @@ __device__ __forceinline__ void q_fetch(const EpiLocal& E, int t, int lane, int 
                                         int stg_cols, QOps& o) {
   const int cs = c - c_lo;
   if (cs >= stg_cols) { q_load<DIR>(E, t, lane, c, o); return; }
-  const int narr = q_narr<DIR>(E.epi);
+  const int narr = q_narr<DIR>(E);
   const float4* s0 = reinterpret_cast<const float4*>(stg + ((size_t)(cs * narr) * TILE_M + 4 * lane) * 4);
   o.a = s0[0];
   o.b = narr > 1 ? s0[TILE_M / 4] : f4zero();
   o.c = narr > 2 ? s0[2 * (TILE_M / 4)] : f4zero();
+  o.d = (DIR != 1 && narr > 3) ? s0[3 * (TILE_M / 4)] : f4zero();
+  o.e = (DIR != 1 && narr > 4) ? s0[4 * (TILE_M / 4)] : f4zero();
 }
 
 // Finish of one split-K part: per batch a thread handles cb = min(QC, QS / ksplit) columns and keeps ksplit * cb <= QS
@@ -1397,7 +1490,7 @@ __device__ __forceinline__ void epilogue_run(Pipe& p, const EngineParams& P, int
     constexpr int NEW = EPI_GROUP_THREADS / 32;
     const int ew = warp - 2;
     const int qc_lo = (n_cols * kpart) / ksplit, qc_hi = (n_cols * (kpart + 1)) / ksplit;
-    const int stg_cols = p.stg ? p.stg_bytes / (q_narr(E.epi) * TILE_M * 4) : 0;
+    const int stg_cols = p.stg ? p.stg_bytes / (q_narr(E) * TILE_M * 4) : 0;
     if (quad) q_stage(E, t, lane, ew, NEW, qc_lo, qc_hi, p.stg, stg_cols);
     if (threadIdx.x == 64) TL(9);
     if (tmem_warp) {
@@ -1577,7 +1670,7 @@ __device__ __forceinline__ void epilogue_scan(Pipe& p, const EngineParams& P, in
   constexpr int NEW = EPI_GROUP_THREADS / 32;
   const int ew = warp - 2;
   const int c_lo = (n_cols * kpart) / ksplit, c_hi = (n_cols * (kpart + 1)) / ksplit;
-  const int stg_cols = p.stg_bytes / (q_narr<DIR>(E.epi) * TILE_M * 4);
+  const int stg_cols = p.stg_bytes / (q_narr<DIR>(E) * TILE_M * 4);
   // operands of this part's columns: global -> shared, asynchronously, as soon as the grid barrier is behind us
   q_stage<DIR>(E, t, lane, ew, NEW, c_lo, c_hi, p.stg, stg_cols);
   if (threadIdx.x == 64) TL(9);

@@ -591,13 +591,14 @@ __device__ __forceinline__ void attention_bwd_body(const AttnBwdArgs& a, const i
   }
   __syncthreads();
   ADBG(2);
-  // per-component reductions over u
-  for (int i = 0; i < A; ++i) {
+  // per-component reductions over u: warp w owns components w, w + nwarp, ...; lane l sums u = l, l + 32, ...; one
+  // shuffle tree per component (the earlier form ran the A components one after the other on U of the threads)
+  for (int i = warp; i < A; i += nwarp) {
     const float al = sh_small[i];
     const float be = sh_small[A + i];
     const float ka = sh_small[2 * A + i];
     float da = 0.0f, db = 0.0f, dk = 0.0f;
-    for (int u = tid; u < a.U; u += blockDim.x) {
+    for (int u = lane; u < a.U; u += 32) {
       const float d = ka - (float)u;
       const float d2 = d * d;
       float g = sh_dphi[u];
@@ -622,16 +623,10 @@ __device__ __forceinline__ void attention_bwd_body(const AttnBwdArgs& a, const i
       dk += __shfl_xor_sync(0xffffffffu, dk, o);
     }
     if (lane == 0) {
-      sh_red[(0 * A + i) * 16 + warp] = da;
-      sh_red[(1 * A + i) * 16 + warp] = db;
-      sh_red[(2 * A + i) * 16 + warp] = dk;
+      sh_red[(0 * A + i) * 16] = da;
+      sh_red[(1 * A + i) * 16] = db;
+      sh_red[(2 * A + i) * 16] = dk;
     }
-  }
-  __syncthreads();
-  if (tid < 3 * A) {
-    float s = 0.0f;
-    for (int w = 0; w < nwarp; ++w) s += sh_red[tid * 16 + w];
-    sh_red[tid * 16] = s;
   }
   __syncthreads();
   if (tid < A) {
@@ -980,6 +975,8 @@ struct ScanFwdGParams {
   long long s_h1, s_k, s_w, s_wp, s_phi, s_ab, s_e;   // per-step strides (elements)
   int T, Tc;
   int att_parts, att_slices;
+  int pfold;                    // 1: the attention projection is produced by the layer-1 candidate finish (QF_ATT_PROJ):
+                                // no projection stage, att_slices = H / 128 feature-tile partials
   unsigned int* bars;           // [3][BAR_STRIDE]
   unsigned long long* stamps;   // debug: [cta][bar][2]
   int stamp_bars;
@@ -995,15 +992,19 @@ struct ScanBwdGParams {
   unsigned long long* stamps;
   int stamp_bars;
   int prefetch;
+  int fused_pre;   // groups 1 / 2 run the GRU pre-pass inside the state-dgrad finish (QF_FUSED_PRE set in their tables)
 };
 // barriers group `g` of the forward kernel has completed once it has finished `nt` steps
-__device__ __forceinline__ unsigned int fwd_bars_after(int g, int nt, int Tc, bool has_chunk) {
+__device__ __forceinline__ unsigned int fwd_bars_after(int g, int nt, int Tc, bool has_chunk, bool pfold) {
   const unsigned int chunks = has_chunk ? (unsigned int)((nt + Tc - 1) / Tc) : 0u;
-  return (g == 0 ? 4u : 2u) * (unsigned int)nt + chunks;
+  return (g == 0 ? (pfold ? 3u : 4u) : 2u) * (unsigned int)nt + chunks;
 }
-__device__ __forceinline__ unsigned int bwd_bars_after(int nt, int Tc, bool has_chunk) {
+// backward kernel: group 0 runs three barriers per step (attention backward + pre-pass, two dgrad phases); groups
+// 1 / 2 run the stand-alone pre-pass only at their first step (afterwards it is fused into the state-dgrad finish,
+// engine.cuh QF_FUSED_PRE) and one chunk event per finished range
+__device__ __forceinline__ unsigned int bwd_bars_after(int g, int nt, int Tc, bool has_chunk, bool fused) {
   const unsigned int chunks = has_chunk ? (unsigned int)((nt + Tc - 1) / Tc) : 0u;   // (the last range may be short)
-  return 3u * (unsigned int)nt + chunks;
+  return ((g == 0 || !fused) ? 3u * (unsigned int)nt : 2u * (unsigned int)nt + (nt > 0 ? 1u : 0u)) + chunks;
 }
 
 __global__ void __launch_bounds__(ENGINE_THREADS, 1) scan_fwd_grouped(const ScanFwdGParams S) {
@@ -1029,7 +1030,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) scan_fwd_grouped(const Scan
     if (has_chunk && t % S.Tc == 0) {
       // hoisted products of chunk e = t / Tc: their operands are the lower layers' states of steps [t, t + Tc)
       const int need = min(t + S.Tc, S.T);
-      const unsigned int xt = fwd_bars_after(gi - 1, need, S.Tc, lower_chunk) * (unsigned int)lower_ncta;
+      const unsigned int xt = fwd_bars_after(gi - 1, need, S.Tc, lower_chunk, S.pfold != 0) * (unsigned int)lower_ncta;
       group_gemm_phase<1>(p, ps->P[2], t / S.Tc, S, ctr, ncta, bar, nullptr, true, lower, xt);
     }
 #pragma unroll 1
@@ -1041,12 +1042,14 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) scan_fwd_grouped(const Scan
       a.e_out += t * S.s_e;
       // stage 1 (att_slices CTAs): K-sliced partial projections of h1_t ; stage 2 (att_parts CTAs per batch row):
       // window + context slice
-      if (threadIdx.x == 0) { grid_wait(ctr, bar * ncta); STAMP(S, bar, 0); }
-      __syncthreads();
-      for (int sl = rank; sl < S.att_slices; sl += ncta) attention_proj_slice(a, sl, att_sh);
-      __syncthreads();
-      if (threadIdx.x == 32) { STAMP(S, bar, 1); grid_arrive(ctr); }   // (not thread 0: it is the next phase's TMA producer)
-      ++bar;
+      if (!S.pfold) {
+        if (threadIdx.x == 0) { grid_wait(ctr, bar * ncta); STAMP(S, bar, 0); }
+        __syncthreads();
+        for (int sl = rank; sl < S.att_slices; sl += ncta) attention_proj_slice(a, sl, att_sh);
+        __syncthreads();
+        if (threadIdx.x == 32) { STAMP(S, bar, 1); grid_arrive(ctr); }   // (not thread 0: it is the next phase's TMA producer)
+        ++bar;
+      }
       const int nwork = a.B * S.att_parts;
       if (threadIdx.x == 0) { grid_wait(ctr, bar * ncta); STAMP(S, bar, 0); }
       __syncthreads();
@@ -1083,19 +1086,24 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) scan_bwd_grouped(const Scan
   unsigned int bar = 0;
   for (int k = 0; k < S.T; ++k) {
     const int s = S.T - 1 - k;
+    // What the step needs from the upper group (chunk dgrads accumulated into this layer's dh / dw slots):
+    // (a) first step of a range: the upper group's chunk dgrads of this range (slots s + 1 ..) ;
+    // (b) last step of a range: its chunk dgrads of the NEXT range, whose highest slot is the slot s this step
+    //     read-modify-writes (the only slot two ranges share) -- and which the fused pre-pass of step s - 1 reads.
+    const unsigned int* xw = nullptr;
+    unsigned int xt = 0;
+    if (upper && k % S.Tc == 0) {
+      xw = upper; xt = bwd_bars_after(gi + 1, min(k + S.Tc, S.T), S.Tc, upper_chunk, S.fused_pre != 0) * (unsigned int)upper_ncta;
+    } else if (upper && (k + 1) % S.Tc == 0 && k + 1 < S.T) {
+      xw = upper; xt = bwd_bars_after(gi + 1, min(k + 1 + S.Tc, S.T), S.Tc, upper_chunk, S.fused_pre != 0) * (unsigned int)upper_ncta;
+    }
     // phase 0: everything of the step that is elementwise in dh_s -- group 0: attention backward of step s, each row
-    // followed by its GRU pre-pass of layer 1 ; groups 1 / 2: the GRU pre-pass of their layer.  At the start of a
-    // range of Tc steps the upper group must have delivered its chunk dgrads (dh / dw contributions of the range).
-    {
+    // followed by its GRU pre-pass of layer 1 ; groups 1 / 2: the GRU pre-pass of their layer, needed as a phase of
+    // its own only at the first step (later steps: fused into the previous step's state-dgrad finish)
+    if (gi == 0 || k == 0 || !S.fused_pre) {
       if (threadIdx.x == 0) {
         if (bar) grid_wait(ctr, bar * ncta);
-        // (a) first step of a range: the upper group's chunk dgrads of this range (slots s + 1 .. of dh / dw) ;
-        // (b) last step of a range: its chunk dgrads of the NEXT range, whose highest slot is the slot s this step
-        //     read-modify-writes (the only slot the two ranges share)
-        if (upper && k % S.Tc == 0)
-          grid_wait(upper, bwd_bars_after(min(k + S.Tc, S.T), S.Tc, upper_chunk) * (unsigned int)upper_ncta);
-        else if (upper && (k + 1) % S.Tc == 0 && k + 1 < S.T)
-          grid_wait(upper, bwd_bars_after(min(k + 1 + S.Tc, S.T), S.Tc, upper_chunk) * (unsigned int)upper_ncta);
+        if (xw) grid_wait(xw, xt);
         STAMP(S, bar, 0);
       }
       __syncthreads();
@@ -1112,9 +1120,10 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) scan_bwd_grouped(const Scan
       __syncthreads();
       if (threadIdx.x == 32) { STAMP(S, bar, 1); grid_arrive(ctr); }   // (not thread 0: it is the next phase's TMA producer)
       ++bar;
+      xw = nullptr;
     }
-#pragma unroll 1
-    for (int ph = 0; ph < 2; ++ph) group_gemm_phase<2>(p, ps->P[ph], k, S, ctr, ncta, bar, &ps->pc[ph], false);
+    group_gemm_phase<2>(p, ps->P[0], k, S, ctr, ncta, bar, &ps->pc[0], false, xw, xt);
+    group_gemm_phase<2>(p, ps->P[1], k, S, ctr, ncta, bar, &ps->pc[1], false);
     if (has_chunk && ((k + 1) % S.Tc == 0 || k == S.T - 1))
       group_gemm_phase<2>(p, ps->P[2], k / S.Tc, S, ctr, ncta, bar, nullptr, true);
   }

@@ -41,9 +41,11 @@ def sequence(g):
                 seq.append(('chunk', k))
             seq += [('G', k), ('C', k)]
             if g == 0:
-                seq += [('proj', k), ('window', k)]
+                seq += [('window', k)] if not os.environ.get('PARROT_NO_PFOLD') else [('proj', k), ('window', k)]
         else:
-            seq += [('pre', k), ('bwd1', k), ('bwd2', k)]
+            if g == 0 or k == 0 or os.environ.get('PARROT_NO_FUSED_PRE'):
+                seq.append(('pre', k))
+            seq += [('bwd1', k), ('bwd2', k)]
             if g > 0 and ((k + 1) % Tc == 0 or k == T - 1):
                 seq.append(('chunk', k))
     return seq
