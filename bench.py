@@ -232,6 +232,7 @@ def main():
     ap.add_argument('--scaling', type=str, default='weak', choices=['weak', 'strong'],
                     help='weak: 64 rows per GPU (default) ; strong: the 64-row batch of configs[1] split over the GPUs')
     ap.add_argument('--blas_threads', type=int, default=0, help='BLAS threads of the CPU arms (0: all host cores)')
+    ap.add_argument('--no_sample', action='store_true', help='skip the sampling section (B=10, 2048 steps)')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
@@ -414,6 +415,33 @@ def main():
             'frac': att_bytes / (att_us * 1e-6) / 1e9 / pk['hbm'], 'traffic': None,
             'algorithmic_bytes_per_launch': att_bytes, 'avg_launch_us': att_us,
             'note': 'ctx (8.4 MB) is L2-resident when the step is called back to back'}
+        # free-running generation (model.py:827-1083) at the reference's own sampling shape (utils.py:270-273:
+        # num_samples 10, num_steps 2048): per-step latency bound -- every step consumes the frame the previous one
+        # emitted.  One call = input copies + ONE CUDA-graph launch of the whole loop.
+        if not args.no_sample:
+            SB, ST = 10, 2048
+            lab, lm = bt['labels'][:SB], bt['labels_mask'][:SB]
+            model.sample_model(lab, lm, None, None, SB, ST, as_numpy=False)       # builds the handle + the graph
+            torch.cuda.synchronize()
+            ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            for _ in range(3):
+                model.sample_model(lab, lm, None, None, SB, ST, as_numpy=False)
+            ev1.record()
+            torch.cuda.synchronize()
+            s_ms = ev0.elapsed_time(ev1) / 3
+            extra['sample'] = {'batch': SB, 'steps': ST, 'frames_per_s': SB * ST / (s_ms * 1e-3),
+                               'us_per_step': s_ms * 1e3 / ST, 'ms_per_call': s_ms,
+                               'launch': 'CUDA graph of the per-phase launches, one graph launch per call',
+                               'workload': 'sample_model, %d rows x %d steps, U=%d, %s emitter'
+                                           % (SB, ST, U, cfg['which_cost'])}
+            if not args.no_cpu_baseline:
+                from tests import util as _u
+                orc = _u.make_oracle(cfg, gain=None, bias_std=0)
+                set_blas_threads(args.blas_threads)
+                t0 = time.perf_counter()
+                orc.sample_model(lab, lm, None, None, SB, 16)
+                extra['sample']['cpu_port_us_per_step'] = (time.perf_counter() - t0) * 1e6 / 16
         sections = {k: {'ms': round(v[0] / P, 3), 'launches': v[1] // P} for k, v in sec.items()}
         extra['sections_ms_persistent'] = sections
         diag = {}

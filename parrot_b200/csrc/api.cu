@@ -283,7 +283,7 @@ struct parrot_model {
   int Tc = 0;              // chunk length of the chunk-lagged layer wavefront (0: not used)
   int grp_f[3] = {0, 0, 0};   // CTAs per layer group of the grouped persistent scans (forward / backward sweep)
   int grp_b[3] = {0, 0, 0};
-  bool pfold = false;         // attention projection folded into the layer-1 candidate finish (grouped forward scan)
+  std::map<int, cudaGraphExec_t> samp_graphs;   // sampling loop as a CUDA graph, keyed by (speaker, injected noise)
   int att_slices = 0;      // K slices of the attention projection (persistent scan)
   unsigned long long* timeline = nullptr;
   unsigned long long* stamps = nullptr;   // debug: persistent forward scan per-barrier stamps
@@ -794,7 +794,7 @@ static void build(parrot_model& M) {
     }
   }
   M.Tc = (train && !d.ln) ? (T >= 64 ? 16 : 8) : 0;
-  if (const char* e = getenv("PARROT_TC")) { if (M.Tc > 0 && atoi(e) > 0) M.Tc = atoi(e); }
+  if (const char* e = getenv("PARROT_TC")) { if (M.Tc > 0 && atoi(e) >= 4) M.Tc = atoi(e); }   // (>= 4: see scan_bwd_grouped)
   {
     // CTAs per layer group of the grouped persistent scans.  Layer 1 (+ attention) is the longest dependent chain and
     // needs >= B CTAs for the window stage; layers 2 / 3 also run the hoisted chunk products.
@@ -806,9 +806,8 @@ static void build(parrot_model& M) {
         out[0] = x; out[1] = y; out[2] = z;
       }
     };
-    M.pfold = train && !d.ln && 3 * d.A <= 32 && H % 128 == 0 && !getenv("PARROT_NO_PFOLD");
     parse("PARROT_GROUPS_F", M.grp_f, 64, 40, 44);
-    parse("PARROT_GROUPS_B", M.grp_b, 64, 40, 44);
+    parse("PARROT_GROUPS_B", M.grp_b, 64, 36, 48);   // (layer 3 carries the largest chunk dgrads)
   }
   M.att_slices = H / ATT_KS;
   M.falloc("att_hat_part", (long long)M.att_slices * B * 3 * d.A);
@@ -828,8 +827,6 @@ static void build(parrot_model& M) {
   }
   if (train) {
     X.dw = M.falloc("dw", (long long)(T + 1) * B * d.C);
-    X.att_wT = M.dry ? nullptr : M.fbuf("att_wT");
-    X.att_hat_part = M.dry ? nullptr : M.fbuf("att_hat_part");
     M.falloc("dk_carry", (long long)B * d.A);
     M.falloc("datt", (long long)T * B * 3 * d.A);
     M.make_plane("datt", Np, d.Ap, T);
@@ -843,6 +840,13 @@ static void build(parrot_model& M) {
   M.falloc("pred", (long long)TR * B * d.Dtot);
   M.falloc("cost_tb", (long long)TR * B);
   if (d.sampling) {
+    // staged copies of the per-call inputs: the sampling loop is replayed as a CUDA graph whose nodes read these
+    M.alloc("samp_in_labels", (size_t)B * d.U * 4);
+    M.falloc("samp_in_lmask", (long long)B * d.U);
+    M.alloc("samp_in_speaker", (size_t)B * 4);
+    M.falloc("samp_in_unis", (long long)T * B);
+    M.falloc("samp_in_normals", (long long)T * B * d.D);
+    M.alloc("samp_in_seed", 16);
     M.falloc("samp_x", (long long)T * B * d.D);
     M.falloc("samp_pi", (long long)T * B * (d.gmm ? d.K : d.D));
   }
@@ -979,8 +983,6 @@ static void build(parrot_model& M) {
         std::vector<Job> ga, gb;
         build_fwd_layer_jobs(M, ga, l, true, 0, false, true);
         build_fwd_layer_jobs(M, gb, l, false, 0, false, true);
-        if (l == 0 && M.pfold)
-          for (auto& j : gb) j.pa.flags |= QF_ATT_PROJ;   // layer-1 candidate finish also emits the attention projection
         push_table(M, "gA" + LN(l), ga, Np, M.grp_f[l], 0, true);
         push_table(M, "gB" + LN(l), gb, Np, M.grp_f[l], 0, true);
         assign_resident(M, "gA" + LN(l), "gB" + LN(l));
@@ -1007,8 +1009,10 @@ static void build(parrot_model& M) {
       std::vector<Job> A, Bj;
       build_fwd_layer_jobs(M, A, l, true, 0, d.ln);
       build_fwd_layer_jobs(M, Bj, l, false, 0, d.ln);
-      push_table(M, "sampA" + LN(l), A, Np);
-      push_table(M, "sampB" + LN(l), Bj, Np);
+      // split over K like the training scan phases: a sampling step is a chain of ~11 dependent launches, and an
+      // unsplit tile contracts its whole K (up to 36 k-blocks) alone -- 24 us per launch on 16-24 of the 148 SMs
+      push_table(M, "sampA" + LN(l), A, Np, 148);
+      push_table(M, "sampB" + LN(l), Bj, Np, 148);
     }
   }
   auto planes_of = [&](const std::string& nm) -> Plane& { return M.planes.at(nm); };
@@ -1098,7 +1102,7 @@ static void build(parrot_model& M) {
         j.pa = pa;
         js.push_back(j);
       }
-      push_table(M, "readout", js, Np);
+      push_table(M, "readout", js, Np, 148);
     }
   }
   if (d.ln) {
@@ -1186,7 +1190,7 @@ static void build(parrot_model& M) {
       }
     }
     if (train) sort_by_sample_tile(js);
-    push_table(M, "output", js, train ? NT : Np);
+    push_table(M, "output", js, train ? NT : Np, train ? 0 : 148);
   }
   if (train) {
     // dread = dpred . Wout^T
@@ -1872,9 +1876,7 @@ static bool scan_fwd_grouped_launch(parrot_model& M, cudaStream_t st) {
   ScanFwdGParams S;
   for (int l = 0; l < 3; ++l) S.g[l] = group_sched(M, "gA", "gB", "gC", l, 0, M.grp_f);
   S.Tc = M.Tc; S.T = d.T;
-  S.att_parts = attention_nparts(d.B, d.C, M.grp_f[0]);
-  S.pfold = M.pfold ? 1 : 0;
-  S.att_slices = M.pfold ? d.H / 128 : M.att_slices;
+  S.att_parts = attention_nparts(d.B, d.C, M.grp_f[0]); S.att_slices = M.att_slices;
   S.att = attn_fwd_args(M, 0, false);
   S.s_h1 = (long long)d.B * d.H; S.s_k = (long long)d.B * d.A; S.s_w = (long long)d.B * d.C;
   S.s_wp = (long long)d.Np * M.planes.at("w").pitch; S.s_phi = (long long)d.B * d.U;
@@ -2337,11 +2339,10 @@ static void backward(parrot_model& M, int unnormalised, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------ sampling
-static void sample_scan(parrot_model& M, const int32_t* d_labels, const float* d_lmask, const int32_t* d_speaker,
-                        const float* d_unis, const float* d_normals, uint64_t seed, cudaStream_t st) {
+static void sample_scan_body(parrot_model& M, const int32_t* d_labels, const float* d_lmask, const int32_t* d_speaker,
+                             const float* d_unis, const float* d_normals, uint64_t seed,
+                             const unsigned long long* d_seed, cudaStream_t st) {
   const Dims& d = M.d;
-  REQUIRE(d.sampling, "parrot_sample_scan needs a handle created with cfg.sampling = 1");
-  if (M.dirty) pack_weights(M, st);
   prep_base(M, d_speaker, st);
   encoder_fwd(M, d_labels, d_lmask, st);
   init_slots(M, true, st);   // model.py:830-832: always the initial states
@@ -2401,7 +2402,7 @@ static void sample_scan(parrot_model& M, const int32_t* d_labels, const float* d
     a.pred = M.fbuf("pred");
     a.unis = d_unis ? d_unis + (long long)t * d.B : nullptr;
     a.normals = d_normals ? d_normals + (long long)t * d.B * d.D : nullptr;
-    a.seed = seed; a.step = t;
+    a.seed = seed; a.step = t; a.seed_ptr = d_seed;
     a.x_out = M.fbuf("samp_x") + (long long)t * d.B * d.D;
     a.pi_out = M.fbuf("samp_pi") + (long long)t * d.B * (d.gmm ? d.K : d.D);
     if (px) {
@@ -2411,6 +2412,71 @@ static void sample_scan(parrot_model& M, const int32_t* d_labels, const float* d
     }
     LAUNCH(sample_emit_kernel, cdiv((long long)d.B * 32, 128), 128, 0, st, a);
   }
+}
+
+// parrot_sample_scan: the T-step loop above is ~11 dependent launches per step (each step consumes the frame the
+// previous one emitted), i.e. launch-latency bound.  The whole loop is captured ONCE per handle into a CUDA graph whose
+// nodes read staged copies of the call's inputs (labels, masks, speaker ids, injected noise, Philox seed) from fixed
+// workspace buffers; a call then costs the input copies + one graph launch.  PARROT_NO_GRAPH=1 (or per-launch
+// profiling / debug sync) runs the plain loop.
+static bool sample_graph_enabled(parrot_model& M) {
+  static int env = -1;
+  if (env < 0) {
+    const char* e = getenv("PARROT_NO_GRAPH");
+    env = (e && e[0] && e[0] != '0') ? 0 : 1;
+  }
+  return env && !M.profiling && !debug_sync();
+}
+static void sample_scan(parrot_model& M, const int32_t* d_labels, const float* d_lmask, const int32_t* d_speaker,
+                        const float* d_unis, const float* d_normals, uint64_t seed, cudaStream_t st) {
+  const Dims& d = M.d;
+  REQUIRE(d.sampling, "parrot_sample_scan needs a handle created with cfg.sampling = 1");
+  if (M.dirty) pack_weights(M, st);
+  if (!sample_graph_enabled(M)) {
+    sample_scan_body(M, d_labels, d_lmask, d_speaker, d_unis, d_normals, seed, nullptr, st);
+    return;
+  }
+  int32_t* s_lab = (int32_t*)(M.ws + M.bufs.at("samp_in_labels").off);
+  int32_t* s_spk = (int32_t*)(M.ws + M.bufs.at("samp_in_speaker").off);
+  unsigned long long* s_seed = (unsigned long long*)(M.ws + M.bufs.at("samp_in_seed").off);
+  float* s_lm = M.fbuf("samp_in_lmask");
+  float* s_un = M.fbuf("samp_in_unis");
+  float* s_no = M.fbuf("samp_in_normals");
+  CK(cudaMemcpyAsync(s_lab, d_labels, (size_t)d.B * d.U * 4, cudaMemcpyDeviceToDevice, st));
+  CK(cudaMemcpyAsync(s_lm, d_lmask, (size_t)d.B * d.U * 4, cudaMemcpyDeviceToDevice, st));
+  if (d_speaker) CK(cudaMemcpyAsync(s_spk, d_speaker, (size_t)d.B * 4, cudaMemcpyDeviceToDevice, st));
+  if (d_unis) CK(cudaMemcpyAsync(s_un, d_unis, (size_t)d.T * d.B * 4, cudaMemcpyDeviceToDevice, st));
+  if (d_normals) CK(cudaMemcpyAsync(s_no, d_normals, (size_t)d.T * d.B * d.D * 4, cudaMemcpyDeviceToDevice, st));
+  const unsigned long long seed64 = seed;
+  CK(cudaMemcpyAsync(s_seed, &seed64, 8, cudaMemcpyHostToDevice, st));   // (pageable source: copied before return)
+  const int key = (d_speaker ? 1 : 0) | (d_unis ? 2 : 0) | (d_normals ? 4 : 0);
+  auto it = M.samp_graphs.find(key);
+  if (it == M.samp_graphs.end()) {
+    // captured on a private stream (the caller's may be the legacy default stream, which cannot be captured)
+    cudaGraph_t graph = nullptr;
+    cudaStream_t cap = nullptr;
+    CK(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
+    cudaError_t be = cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal);
+    if (be != cudaSuccess) { cudaStreamDestroy(cap); CK(be); }
+    try {
+      sample_scan_body(M, s_lab, s_lm, d_speaker ? s_spk : nullptr, d_unis ? s_un : nullptr,
+                       d_normals ? s_no : nullptr, 0, s_seed, cap);
+    } catch (...) {
+      cudaStreamEndCapture(cap, &graph);
+      if (graph) cudaGraphDestroy(graph);
+      cudaStreamDestroy(cap);
+      throw;
+    }
+    cudaError_t ee = cudaStreamEndCapture(cap, &graph);
+    cudaStreamDestroy(cap);
+    CK(ee);
+    cudaGraphExec_t exec = nullptr;
+    CK(cudaGraphInstantiate(&exec, graph, 0));
+    CK(cudaGraphDestroy(graph));
+    it = M.samp_graphs.emplace(key, exec).first;
+  }
+  CK(cudaGraphLaunch(it->second, st));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
 }
 
 // =========================================================================== C ABI
@@ -2488,6 +2554,7 @@ int parrot_create(const parrot_config* cfg, float* d_params, float* d_grads, voi
 }
 int parrot_destroy(parrot_model* m) {
   return guard([&] {
+    for (auto& kv : m->samp_graphs) cudaGraphExecDestroy(kv.second);
     g_inputs.erase(m);
     delete m;
   });

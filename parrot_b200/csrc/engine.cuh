@@ -91,8 +91,7 @@ struct PlainArgs {
   int rowbias_ld;      // > 0: `bias` is a [n_pad rows][rowbias_ld] matrix indexed by (sample % n_pad, feature)
 };
 enum { PF_ACC = 1, PF_TRANS = 2, PF_PLANE_PADDED = 4 };
-enum { QF_FUSED_PRE = 256, QF_ATT_PROJ = 512 };   // QF_ATT_PROJ: EPI_CAND job of layer 1: the finish also emits the
-                                                   // tile's partial attention projection (h1_t . W_att), see q_apply   // EPI_BWD_STATE job flag (Job::pa.flags): run the GRU pre-pass of step t - 1 in the finish
+enum { QF_FUSED_PRE = 256 };   // EPI_BWD_STATE job flag (Job::pa.flags): run the GRU pre-pass of step t - 1 in the finish   // EPI_BWD_STATE job flag (Job::pa.flags): run the GRU pre-pass of step t - 1 in the finish
 
 struct Job {
   int nseg, epi, lag, layer;
@@ -146,8 +145,6 @@ struct ScanCtx {
   long long base_tstride;   // 0: L.base is [B][3H] ; layer_norm mode: [T][B][3H] (per-step pre-activation terms)
   LayerBuf L[3];
   float* dw;           // [T+1][B][C] gradient wrt w slot s
-  const float* att_wT;      // [3A][H] transposed h1_to_att weights (attention projection folded into the layer-1 finish)
-  float* att_hat_part;      // [H/128][B][3A] per-feature-tile partial projections of the current step
 };
 
 struct EngineParams {
@@ -260,9 +257,6 @@ struct EpiLocal {
   void *p0, *p1, *p2, *p3, *p4, *p5;
   const float* pre;   // GATES / CAND: hoisted pre-activation terms [T][B][3H] (or null), added to base
   long long l0, l1, l2;
-  const float* att_w;   // CAND + QF_ATT_PROJ: wT[3A][H] ; att_part: [tile][B][3A] ; att_n = 3A
-  float* att_part;
-  int att_n, pad_e_;
 };
 __device__ __forceinline__ EpiLocal make_epi_local(const Job& jb, const ScanCtx* ctx, int n_shift = 0,
                                                    int n_limit = 0) {
@@ -274,7 +268,6 @@ __device__ __forceinline__ EpiLocal make_epi_local(const Job& jb, const ScanCtx*
   E.p0 = E.p1 = E.p2 = E.p3 = E.p4 = E.p5 = nullptr;
   E.pre = nullptr;
   E.l0 = E.l1 = E.l2 = 0;
-  E.att_w = nullptr; E.att_part = nullptr; E.att_n = 0; E.pad_e_ = 0;
   if (jb.epi == EPI_PLAIN) {
     E.p0 = jb.pa.out; E.p1 = (void*)jb.pa.bias; E.p2 = jb.pa.hi; E.p3 = jb.pa.lo;
     E.l0 = jb.pa.ldo; E.l1 = jb.pa.ldp; E.l2 = jb.pa.out_tstride;
@@ -292,11 +285,7 @@ __device__ __forceinline__ EpiLocal make_epi_local(const Job& jb, const ScanCtx*
     case EPI_GATES:
       E.p0 = (void*)L.base; E.p1 = L.h; E.p2 = L.z; E.p3 = L.r; E.p4 = L.rh_hi; E.p5 = L.rh_lo; E.pre = L.pre; break;
     case EPI_CAND:
-      E.p0 = (void*)L.base; E.p1 = L.h; E.p2 = L.z; E.p3 = L.c; E.p4 = L.h_hi; E.p5 = L.h_lo; E.pre = L.pre;
-      if ((jb.pa.flags & QF_ATT_PROJ) && ctx->att_wT) {
-        E.flags = QF_ATT_PROJ; E.att_w = ctx->att_wT; E.att_part = ctx->att_hat_part; E.att_n = 3 * ctx->A;
-      }
-      break;
+      E.p0 = (void*)L.base; E.p1 = L.h; E.p2 = L.z; E.p3 = L.c; E.p4 = L.h_hi; E.p5 = L.h_lo; E.pre = L.pre; break;
     case EPI_BWD_RH:
       E.p0 = L.r; E.p1 = L.h; E.p2 = L.dh; E.p3 = L.da; E.p4 = L.da_hi; E.p5 = L.da_lo; break;
     case EPI_BWD_STATE:
@@ -669,9 +658,7 @@ __device__ __forceinline__ void q_load(const EpiLocal& E, int t, int rq, int b, 
 template <int DIR = 0>
 __device__ __forceinline__ void q_apply(const EpiLocal& E, int t, int rq, int b, float4 v, const QOps& o) {
   const int H = E.H, B = E.B, f = E.row0 + 4 * rq;
-  const bool proj = DIR == 1 && E.epi == EPI_CAND && (E.flags & QF_ATT_PROJ);   // warp-uniform
-  const bool live = !(4 * rq >= E.m_valid || b >= B);
-  if (!live && !proj) return;
+  if (4 * rq >= E.m_valid || b >= B) return;
   int epi = E.epi;
   if (DIR == 1 && epi != EPI_GATES) epi = EPI_CAND;
   if (DIR == 2 && epi != EPI_BWD_STATE) epi = EPI_BWD_RH;
@@ -698,42 +685,13 @@ __device__ __forceinline__ void q_apply(const EpiLocal& E, int t, int rq, int b,
       cc.z = tanhf_fast(v.z + o.a.z); cc.w = tanhf_fast(v.w + o.a.w);
       hn.x = cc.x * o.b.x + o.c.x * (1.0f - o.b.x); hn.y = cc.y * o.b.y + o.c.y * (1.0f - o.b.y);
       hn.z = cc.z * o.b.z + o.c.z * (1.0f - o.b.z); hn.w = cc.w * o.b.w + o.c.w * (1.0f - o.b.w);
-      if (live) {
-        *reinterpret_cast<float4*>((float*)E.p3 + tb) = cc;
-        *reinterpret_cast<float4*>((float*)E.p1 + tb + (long long)B * H) = hn;   // slot t + 1
-        uint2 hh, ll;
-        split4(hn, hh, ll);
-        const long long po = ((long long)(t + 1) * E.Np + b) * E.Hp + f;
-        *reinterpret_cast<uint2*>((bf16*)E.p4 + po) = hh;
-        *reinterpret_cast<uint2*>((bf16*)E.p5 + po) = ll;
-      }
-      if (proj) {
-        // attention projection folded into the layer-1 finish (model.py:664-669): this warp holds h1_t[b] for the 128
-        // features of the tile (4 per lane); every lane forms its share of the 3A dot products, a transpose-reduce
-        // (31 shuffles) leaves output j on lane j, and the tile's partial goes to hat_part[tile][b][j] -- the window
-        // stage adds the H/128 partials in tile order (deterministic) and the bias.  Replaces a grid phase + barrier.
-        float pv[32];
-        const float* wrow = E.att_w + f;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          pv[j] = 0.0f;
-          if (j < E.att_n && live) {
-            const float4 w4 = ldg4(wrow + (long long)j * H);
-            pv[j] = hn.x * w4.x + hn.y * w4.y + hn.z * w4.z + hn.w * w4.w;
-          }
-        }
-#pragma unroll
-        for (int k = 16; k >= 1; k >>= 1) {
-          const bool up = (rq & k) != 0;
-#pragma unroll
-          for (int i = 0; i < k; ++i) {
-            const float send = up ? pv[i] : pv[i + k];
-            const float keep = up ? pv[i + k] : pv[i];
-            pv[i] = keep + __shfl_xor_sync(0xffffffffu, send, k);
-          }
-        }
-        if (rq < E.att_n && b < B) E.att_part[((long long)(E.row0 >> 7) * B + b) * E.att_n + rq] = pv[0];
-      }
+      *reinterpret_cast<float4*>((float*)E.p3 + tb) = cc;
+      *reinterpret_cast<float4*>((float*)E.p1 + tb + (long long)B * H) = hn;   // slot t + 1
+      uint2 hh, ll;
+      split4(hn, hh, ll);
+      const long long po = ((long long)(t + 1) * E.Np + b) * E.Hp + f;
+      *reinterpret_cast<uint2*>((bf16*)E.p4 + po) = hh;
+      *reinterpret_cast<uint2*>((bf16*)E.p5 + po) = ll;
     } break;
     case EPI_BWD_RH: {
       const long long tb = ((long long)t * B + b) * H + f;

@@ -975,8 +975,6 @@ struct ScanFwdGParams {
   long long s_h1, s_k, s_w, s_wp, s_phi, s_ab, s_e;   // per-step strides (elements)
   int T, Tc;
   int att_parts, att_slices;
-  int pfold;                    // 1: the attention projection is produced by the layer-1 candidate finish (QF_ATT_PROJ):
-                                // no projection stage, att_slices = H / 128 feature-tile partials
   unsigned int* bars;           // [3][BAR_STRIDE]
   unsigned long long* stamps;   // debug: [cta][bar][2]
   int stamp_bars;
@@ -995,9 +993,9 @@ struct ScanBwdGParams {
   int fused_pre;   // groups 1 / 2 run the GRU pre-pass inside the state-dgrad finish (QF_FUSED_PRE set in their tables)
 };
 // barriers group `g` of the forward kernel has completed once it has finished `nt` steps
-__device__ __forceinline__ unsigned int fwd_bars_after(int g, int nt, int Tc, bool has_chunk, bool pfold) {
+__device__ __forceinline__ unsigned int fwd_bars_after(int g, int nt, int Tc, bool has_chunk) {
   const unsigned int chunks = has_chunk ? (unsigned int)((nt + Tc - 1) / Tc) : 0u;
-  return (g == 0 ? (pfold ? 3u : 4u) : 2u) * (unsigned int)nt + chunks;
+  return (g == 0 ? 4u : 2u) * (unsigned int)nt + chunks;
 }
 // backward kernel: group 0 runs three barriers per step (attention backward + pre-pass, two dgrad phases); groups
 // 1 / 2 run the stand-alone pre-pass only at their first step (afterwards it is fused into the state-dgrad finish,
@@ -1030,7 +1028,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) scan_fwd_grouped(const Scan
     if (has_chunk && t % S.Tc == 0) {
       // hoisted products of chunk e = t / Tc: their operands are the lower layers' states of steps [t, t + Tc)
       const int need = min(t + S.Tc, S.T);
-      const unsigned int xt = fwd_bars_after(gi - 1, need, S.Tc, lower_chunk, S.pfold != 0) * (unsigned int)lower_ncta;
+      const unsigned int xt = fwd_bars_after(gi - 1, need, S.Tc, lower_chunk) * (unsigned int)lower_ncta;
       group_gemm_phase<1>(p, ps->P[2], t / S.Tc, S, ctr, ncta, bar, nullptr, true, lower, xt);
     }
 #pragma unroll 1
@@ -1042,14 +1040,12 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) scan_fwd_grouped(const Scan
       a.e_out += t * S.s_e;
       // stage 1 (att_slices CTAs): K-sliced partial projections of h1_t ; stage 2 (att_parts CTAs per batch row):
       // window + context slice
-      if (!S.pfold) {
-        if (threadIdx.x == 0) { grid_wait(ctr, bar * ncta); STAMP(S, bar, 0); }
-        __syncthreads();
-        for (int sl = rank; sl < S.att_slices; sl += ncta) attention_proj_slice(a, sl, att_sh);
-        __syncthreads();
-        if (threadIdx.x == 32) { STAMP(S, bar, 1); grid_arrive(ctr); }   // (not thread 0: it is the next phase's TMA producer)
-        ++bar;
-      }
+      if (threadIdx.x == 0) { grid_wait(ctr, bar * ncta); STAMP(S, bar, 0); }
+      __syncthreads();
+      for (int sl = rank; sl < S.att_slices; sl += ncta) attention_proj_slice(a, sl, att_sh);
+      __syncthreads();
+      if (threadIdx.x == 32) { STAMP(S, bar, 1); grid_arrive(ctr); }   // (not thread 0: it is the next phase's TMA producer)
+      ++bar;
       const int nwork = a.B * S.att_parts;
       if (threadIdx.x == 0) { grid_wait(ctr, bar * ncta); STAMP(S, bar, 0); }
       __syncthreads();
@@ -1092,10 +1088,13 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) scan_bwd_grouped(const Scan
     //     read-modify-writes (the only slot two ranges share) -- and which the fused pre-pass of step s - 1 reads.
     const unsigned int* xw = nullptr;
     unsigned int xt = 0;
+    //     With the fused pre-pass (groups 1 / 2) that read-modify-write happens one step EARLIER -- in the state-dgrad
+    //     finish of the step before the last one of the range -- so the wait moves one step up as well.
+    const int ahead = (gi > 0 && S.fused_pre) ? 2 : 1;
     if (upper && k % S.Tc == 0) {
       xw = upper; xt = bwd_bars_after(gi + 1, min(k + S.Tc, S.T), S.Tc, upper_chunk, S.fused_pre != 0) * (unsigned int)upper_ncta;
-    } else if (upper && (k + 1) % S.Tc == 0 && k + 1 < S.T) {
-      xw = upper; xt = bwd_bars_after(gi + 1, min(k + 1 + S.Tc, S.T), S.Tc, upper_chunk, S.fused_pre != 0) * (unsigned int)upper_ncta;
+    } else if (upper && (k + ahead) % S.Tc == 0 && k + ahead < S.T) {
+      xw = upper; xt = bwd_bars_after(gi + 1, min(k + ahead + S.Tc, S.T), S.Tc, upper_chunk, S.fused_pre != 0) * (unsigned int)upper_ncta;
     }
     // phase 0: everything of the step that is elementwise in dh_s -- group 0: attention backward of step s, each row
     // followed by its GRU pre-pass of layer 1 ; groups 1 / 2: the GRU pre-pass of their layer, needed as a phase of
@@ -1756,11 +1755,14 @@ struct SampleArgs {
   const float* unis;         // [B] or null
   const float* normals;      // [B][D] or null
   unsigned long long seed; int step;
+  const unsigned long long* seed_ptr;   // when set, the Philox key is read from here (graph replays with a new seed)
   float* x_out;              // [B][D]
   float* pi_out;             // [B][k] (GMM) / [B][D] (MSE: copy of x)
   bf16* x_hi; bf16* x_lo; int Np, Dp;   // planes of x for the feedback product (nullable)
 };
-__global__ void __launch_bounds__(128) sample_emit_kernel(const SampleArgs a) {
+__global__ void __launch_bounds__(128) sample_emit_kernel(const SampleArgs a_in) {
+  SampleArgs a = a_in;
+  if (a.seed_ptr) a.seed = *a.seed_ptr;
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (row >= a.B) return;
   const float* p = a.pred + (long long)row * a.Dtot;

@@ -41,7 +41,7 @@ def sequence(g):
                 seq.append(('chunk', k))
             seq += [('G', k), ('C', k)]
             if g == 0:
-                seq += [('window', k)] if not os.environ.get('PARROT_NO_PFOLD') else [('proj', k), ('window', k)]
+                seq += [('proj', k), ('window', k)]
         else:
             if g == 0 or k == 0 or os.environ.get('PARROT_NO_FUSED_PRE'):
                 seq.append(('pre', k))
