@@ -8,15 +8,19 @@ float32 binary ``.cmp/.mgc/.lf0/.bap`` files -- and then either runs the externa
 both tool directories exist, or stops and SAYS SO (no silent success).
 
 Column order: the reference derives the per-stream offsets by iterating a Python-2 ``dict`` literal
-(generate.py:78-88), i.e. from CPython-2 hash order, which cannot be reproduced by inspection.  The
-normalisation file name (``norm_info_mgc_lf0_vuv_bap_63_MVN.dat``, sample.py:176-178) names the
-intended order; it is hard-coded here: mgc(60) | lf0(1) | vuv(1) | bap(1).  UNPINNED by the tree.
+``{'bap': 1, 'lf0': 1, 'mgc': 60, 'vuv': 1}`` (generate.py:78-88), i.e. in CPython-2.7 hash order.  That order is
+deterministic (no hash randomisation by default) and is reproduced in tests/test_generate.py from the interpreter's
+string hash and open-addressing probe sequence (checked against known CPython-2.7 facts): 'mgc' and 'vuv' collide in
+slot 0, 'mgc' is inserted first, and the iteration order is **mgc(60) | vuv(1) | lf0(1) | bap(1)** -- Merlin, whose
+code this is, composes its ``.cmp`` files by iterating the same kind of dict, so the training features have the same
+column order.  (An earlier version of this file assumed mgc | lf0 | vuv | bap from the name of the normalisation
+file, ``norm_info_mgc_lf0_vuv_bap_63_MVN.dat``; the executed reference lines say otherwise.)
 """
 import os
 
 import numpy
 
-STREAMS = (('mgc', 60), ('lf0', 1), ('vuv', 1), ('bap', 1))
+STREAMS = (('mgc', 60), ('vuv', 1), ('lf0', 1), ('bap', 1))
 FILE_EXT = {'mgc': '.mgc', 'bap': '.bap', 'lf0': '.lf0', 'cmp': '.cmp'}
 
 

@@ -1623,7 +1623,11 @@ __device__ __forceinline__ void epilogue_scan(Pipe& p, const EngineParams& P, in
   const bool have_acc = khi > klo;
   const int buf = p.it & 1;
   const uint32_t use = (uint32_t)(p.it >> 1);
-  const EpiLocal& E = pc->epi;
+  // forward sweep: context copied into registers (31.0 vs 31.4 ms per forward scan); backward sweep: read from shared
+  // memory field by field -- the copy costs 240 B of extra spills there and 3 ms (same-box A/B, tools/ab_variants.sh)
+  EpiLocal Ereg;
+  if (DIR == 1) Ereg = pc->epi;
+  const EpiLocal& E = DIR == 1 ? Ereg : pc->epi;
   const int ksplit = jb.ksplit, kpart = jb.kpart, group = jb.group;
   constexpr int NEW = EPI_GROUP_THREADS / 32;
   const int ew = warp - 2;

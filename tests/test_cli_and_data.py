@@ -93,3 +93,87 @@ def test_segmentation_matches_the_reference_transformer():
         ours = [[int(a[0, 0, 0]), int(a[-1, 0, 0]) + 1, int(flag)]
                 for a, _, flag in datasets.segment_sequence(f, m, seq + 1, share_value=1, return_last=False)]
         assert ours == wins, key
+
+
+def test_parrot_stream_matches_the_reference_pipeline():
+    """tests/golden/stream.json: the reference's own ``parrot_stream`` (datasets.py:206-298) with its helpers and
+    transformer classes, executed on a Fuel stand-in over synthetic utterances whose feature values identify
+    (utterance, frame) (make_stream_fixture.py).  parrot_b200.datasets.parrot_stream must emit the same tuples: same
+    sources, same utterance in every batch row (sort inside windows of batch_size * sorting_mult, ragged batch
+    dropped), same TBPTT windows and start flags, same padding of features and labels."""
+    import json
+    import os
+    import numpy as np
+    from parrot_b200 import datasets
+    fx = json.load(open(os.path.join(os.path.dirname(__file__), 'golden', 'stream.json')))
+    L, U = fx['lengths'], fx['chars']
+
+    class Voice(object):
+        num_examples = len(L)
+
+        def get_example(self, i):
+            f = (1000 * i + np.arange(L[i]))[:, None].repeat(2, 1).astype(np.float32)
+            return dict(features=f, text=(100 * i + np.arange(U[i])).astype(np.int32), speaker_index=i % 5)
+
+    assert len(fx['streams']) == 3
+    for key, rows in fx['streams'].items():
+        kv = dict(p.split('=') for p in key.split(','))
+        noise = None if kv['noise'] == 'None' else float(kv['noise'])
+        use_speaker = kv['speaker'] == '1'
+        st = datasets.parrot_stream('vctk', use_speaker=use_speaker, which_sets=('valid',), batch_size=int(kv['bs']),
+                                    seq_size=int(kv['seq']), sorting_mult=int(kv['mult']), noise_level=noise,
+                                    labels_type='text', dataset=Voice())
+        got = list(st.get_epoch_iterator(as_dict=True))
+        assert len(got) == len(rows), (key, len(got), len(rows))
+        for d, r in zip(got, rows):
+            assert list(st.sources) == r['sources']
+            f, m = d['features'], d['features_mask']
+            assert f.shape[0] == r['T'] and f.shape[:2] == m.shape
+            assert [int(x) // 1000 for x in f[0, :, 0]] == r['utt']
+            assert [int(x) % 1000 for x in f[0, :, 0]] == r['first']
+            assert [int(x) for x in m.sum(0)] == r['valid']
+            # every valid frame continues its utterance; padding is zero
+            for b in range(f.shape[1]):
+                n = r['valid'][b]
+                assert (f[:n, b, 0] == 1000 * r['utt'][b] + r['first'][b] + np.arange(n)).all()
+                assert (f[n:, b] == 0).all()
+            assert list(d['labels'].shape) == r['labels_shape']
+            assert [int(x) for x in d['labels'][0]] == r['labels_row0']
+            assert [int(x) for x in d['labels_mask'].sum(1)] == r['labels_valid']
+            assert int(d['start_flag']) == r['start_flag']
+            if use_speaker:
+                assert list(np.asarray(d['speaker_index']).shape) == r['speaker_shape']
+                assert [int(x) for x in np.asarray(d['speaker_index']).ravel()] == r['speaker']
+            if noise is not None:
+                assert float(d['feedback_noise_level']) == r['noise']
+
+
+def test_learning_rate_schedule_follows_the_reference_extension(tmp_path):
+    """extensions.py:83-150: patience counter, NaN handling, reload-best + zero buffers + lr cut, stop after num_cuts."""
+    import train
+
+    class Adam(object):
+        learning_rate = 1e-3
+
+    class Algo(object):
+        zeroed = 0
+
+        def zero_buffers(self):
+            self.zeroed += 1
+
+    class Model(object):
+        loaded = 0
+
+        def set_parameter_values(self, v):
+            self.loaded += 1
+
+    path = str(tmp_path / 'best.npz')
+    np.savez(path, w=np.zeros(2))
+    adam, algo, model = Adam(), Algo(), Model()
+    s = train.LearningRateSchedule(adam, algo, model, path, patience=3, num_cuts=2, cut_size=.5)
+    assert not s.do(None) and not s.do(5.0) and not s.do(4.0)           # improving
+    assert not s.do(4.5) and not s.do(4.5) and s.counter == 2
+    assert not s.do(4.5)                                                 # third check without improvement: cut 1
+    assert s.count_cuts == 1 and adam.learning_rate == 5e-4 and algo.zeroed == 1 and model.loaded == 1 and s.counter == 0
+    assert s.do(float('nan'))                                            # NaN forces a cut at once: cut 2 -> finish
+    assert s.count_cuts == 2 and adam.learning_rate == 2.5e-4 and algo.zeroed == 2

@@ -9,5 +9,5 @@ while [ $# -ge 2 ]; do
   name=$1; flags=$2; shift 2
   echo "== $name: $flags"
   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -shared $flags -Xptxas -v \
-    -o build_variants/$name.so parrot_b200/csrc/api.cu -lcuda 2>&1 | grep -A2 -E "scan_fwd_persistent|scan_bwd_persistent" | grep -E "spill|error" || true
+    -o build_variants/$name.so parrot_b200/csrc/api.cu -lcuda 2>&1 | grep -A2 -E "scan_fwd_grouped|scan_bwd_grouped" | grep -E "spill|error" || true
 done

@@ -1,6 +1,6 @@
 """Per-group, per-phase timeline of the grouped persistent scans (debug tool, run under gpurun).
     python tools/group_timeline.py [T] [fwd|bwd]
-PARROT_GROUPS_F / PARROT_GROUPS_B / PARROT_TC select the partition (defaults 64,40,44 and Tc 16)."""
+PARROT_GROUPS_F / PARROT_GROUPS_B / PARROT_TC select the partition (defaults 64,40,44 forward, 64,36,48 backward, Tc 16)."""
 import ctypes as C
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -11,7 +11,7 @@ from parrot_b200 import Parrot, _lib
 
 T = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 which = sys.argv[2] if len(sys.argv) > 2 else 'fwd'
-env = os.environ.get('PARROT_GROUPS_F' if which == 'fwd' else 'PARROT_GROUPS_B', '64,40,44')
+env = os.environ.get('PARROT_GROUPS_F', '64,40,44') if which == 'fwd' else os.environ.get('PARROT_GROUPS_B', '64,36,48')
 grp = [int(x) for x in env.split(',')]
 Tc = int(os.environ.get('PARROT_TC', 16 if T >= 64 else 8))
 cfg = dict(bench.BASE)

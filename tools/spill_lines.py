@@ -1,5 +1,5 @@
 """Lists the source lines of local-memory spill instructions (STL/LDL) per kernel of a variant build.
-    python tools/spill_lines.py "-DPB_ENGINE_THREADS=384 -DPB_SPLIT_BATCH=3" scan_fwd_persistent"""
+    python tools/spill_lines.py "-DPB_ENGINE_THREADS=384 -DPB_SPLIT_BATCH=3" scan_fwd_grouped"""
 import collections, re, subprocess, sys
 flags = sys.argv[1].split()
 pat = sys.argv[2] if len(sys.argv) > 2 else 'persistent'

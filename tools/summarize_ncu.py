@@ -2,9 +2,12 @@
 
     python tools/summarize_ncu.py gpurun_out/prof_persist.ncu-rep profiles/r01_scan_fwd_persistent_ncu.txt
     python tools/summarize_ncu.py --launches gpurun_out/launches.csv profiles/r01_launch_list.txt
+    python tools/summarize_ncu.py --traffic gpurun_out/grouped_T800.ncu-rep profiles/r02_scan_grouped_ncu_T800.txt \
+        profiles/r02_scan_traffic.json        (dram bytes per launch of the scan kernels -> bench.py roofline.traffic)
 """
 import csv
 import collections
+import json
 import subprocess
 import sys
 
@@ -31,7 +34,7 @@ def summarize_rep(rep, out):
             f.write('\n')
         sass = subprocess.run(['cuobjdump', '-sass', 'parrot_b200/libparrot_b200.so'], capture_output=True, text=True).stdout
         cnt = collections.Counter(w for w in sass.replace(';', ' ').split() if w.split('.')[0] in
-                                  ('UTCHMMA', 'UTMALDG', 'LDTM', 'UTCBAR', 'UBLKCP', 'HMMA'))
+                                  ('UTCHMMA', 'UTMALDG', 'LDTM', 'STTM', 'UTCBAR', 'UBLKCP', 'HMMA'))
         f.write('SASS mnemonics in libparrot_b200.so: %s\n' % dict(cnt))
 
 
@@ -55,8 +58,27 @@ def summarize_launches(path, out):
         f.write('total %.1f us\n' % tot)
 
 
+def traffic_json(rep, txt, out):
+    raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units = rows[0], rows[1]
+    idx = {h: i for i, h in enumerate(hdr)}
+    scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9, 'Tbyte': 1e12}
+    res = {'source': txt}
+    for r in rows[2:]:
+        name = r[idx['Kernel Name']].split('(')[0]
+        tot = 0.0
+        for k in ('dram__bytes_read.sum', 'dram__bytes_write.sum'):
+            tot += float(r[idx[k]].replace(',', '')) * scale.get(units[idx[k]], 1.0)
+        res[name] = tot
+    json.dump(res, open(out, 'w'), indent=1)
+
+
 if __name__ == '__main__':
     if sys.argv[1] == '--launches':
         summarize_launches(sys.argv[2], sys.argv[3])
+    elif sys.argv[1] == '--traffic':
+        summarize_rep(sys.argv[2], sys.argv[3])
+        traffic_json(sys.argv[2], sys.argv[3], sys.argv[4])
     else:
         summarize_rep(sys.argv[1], sys.argv[2])

@@ -21,6 +21,41 @@ from parrot_b200.datasets import SyntheticVoice, parrot_stream
 from parrot_b200.utils import train_parse
 
 
+class LearningRateSchedule(object):
+    """extensions.py:83-150 of the reference, minus the Blocks plumbing: halve the learning rate when the tracked
+    validation cost has not improved for ``patience`` checks (or is NaN), reload the best parameters, zero the Adam
+    buffers, and ask for the end of training after ``num_cuts`` cuts (train.py:175-181: patience 10, num_cuts 5)."""
+
+    def __init__(self, adam, algorithm, model, path, patience=5, num_cuts=3, cut_size=.5):
+        self.adam, self.algorithm, self.model, self.path = adam, algorithm, model, path
+        self.patience, self.num_cuts, self.cut_size = patience, num_cuts, cut_size
+        self.counter = self.count_cuts = 0
+        self.best_value = numpy.inf
+
+    def do(self, current_value, rank=0, world=1):
+        """Returns True when training should finish.  Every rank calls this with the same (global) value."""
+        if current_value is None:
+            return False
+        if current_value < self.best_value:
+            self.best_value, self.counter = current_value, 0
+        else:
+            self.counter += 1
+        if numpy.isnan(current_value):
+            self.counter = self.patience + 1
+        if self.counter < self.patience:
+            return False
+        self.counter = 0
+        self.count_cuts += 1
+        if rank == 0 and os.path.exists(self.path):
+            self.model.set_parameter_values(dict(numpy.load(self.path)))
+        if world > 1:                                  # replicas stay identical: rank 0's reloaded parameters
+            torch.distributed.broadcast(self.model.flat_params, 0)
+            self.model.mark_dirty()
+        self.algorithm.zero_buffers()
+        self.adam.learning_rate = float(self.cut_size * self.adam.learning_rate)
+        return self.count_cuts >= self.num_cuts
+
+
 def main(argv=None):
     args = train_parse(argv)
     rank, world, local = parallel.init_from_env()
@@ -36,7 +71,12 @@ def main(argv=None):
         print('Finished saving.')
 
     assert args.batch_size % world == 0, 'global batch must divide by the number of ranks'
-    labels_type = args.labels_type if args.labels_type in ('text', 'unaligned_phonemes') else 'text'
+    labels_type = args.labels_type
+    if labels_type not in ('text', 'unaligned_phonemes'):
+        # frame-aligned label types bypass the attention path this package implements (model.py:577-583)
+        if rank == 0:
+            print("labels_type %r is not on the attention path; using 'text' (sequence-level labels)" % labels_type)
+        labels_type = 'text'
     dataset = SyntheticVoice(num_examples=max(256, 4 * args.batch_size), output_dim=args.output_dim,
                              num_characters=args.num_characters, num_speakers=args.num_speakers,
                              seed=args.seed)
@@ -69,6 +109,12 @@ def main(argv=None):
         parrot.set_parameter_values(dict(numpy.load(path)))
 
     cost_name = args.which_cost
+    schedule = None
+    if args.lr_schedule:                                                       # train.py:175-181
+        adam = step_rule.components[1]
+        schedule = LearningRateSchedule(adam, algorithm, parrot,
+                                        os.path.join(save_dir, 'pkl', 'best_' + exp_name + '.npz'),
+                                        patience=10, num_cuts=5)
     best = float('inf')
     t0 = time.time()
     running, seen = 0.0, 0
@@ -85,6 +131,11 @@ def main(argv=None):
         seen += 1
         done = args.steps is not None and it + 1 >= args.steps
         timed_out = args.time_limit is not None and (time.time() - t0) > args.time_limit * 3600   # TimedFinish
+        if world > 1 and args.time_limit is not None:
+            # every rank must leave the loop (and enter the validation collectives) at the same iteration
+            flag = torch.tensor([1.0 if timed_out else 0.0], device=parrot.device)
+            torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MAX)
+            timed_out = bool(flag.item() > 0)
         if (it + 1) % args.save_every == 0 or done or timed_out:
             train_cost = running / seen
             running, seen = 0.0, 0
@@ -112,6 +163,10 @@ def main(argv=None):
                 if vcost < best:                                                                  # TrackTheBest
                     best = vcost
                     numpy.savez(os.path.join(save_dir, 'pkl', 'best_' + exp_name + '.npz'), **vals)
+            if world > 1:
+                torch.distributed.barrier()          # the best-parameter file is complete before anyone reloads it
+            if schedule is not None and schedule.do(vcost, rank, world):
+                done = True                          # training_finish_requested (extensions.py:148-150)
         if done or timed_out:
             break
     return parrot
