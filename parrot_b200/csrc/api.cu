@@ -1912,6 +1912,7 @@ static bool scan_bwd_grouped_launch(parrot_model& M, cudaStream_t st) {
   S.fused_pre = (d.H % 4 == 0 && d.Hp % 4 == 0) ? 1 : 0;   // (same condition as QF_FUSED_PRE in the hB tables)
   if (const char* e = getenv("PARROT_NO_FUSED_PRE")) { if (e[0] && e[0] != '0') S.fused_pre = 0; }
   S.stamps = M.stamps_bwd; S.stamp_bars = M.stamps_bwd ? M.stamp_bars : 0;
+  S.tl_buf = M.timeline; S.tl_tick = M.tl_tick;
   S.prefetch = prefetch_enabled();
   CK(cudaMemsetAsync(M.d_gridbar, 0, 1024, st));
   void* args[] = {&S};

@@ -991,6 +991,8 @@ struct ScanBwdGParams {
   int stamp_bars;
   int prefetch;
   int fused_pre;   // groups 1 / 2 run the GRU pre-pass inside the state-dgrad finish (QF_FUSED_PRE set in their tables)
+  unsigned long long* tl_buf;   // debug: attention-backward milestones of batch row 0 at step tl_tick go to
+  int tl_tick;                  // tl_buf[2 * 148 * 16 ..] (tools/group_timeline.py)
 };
 // barriers group `g` of the forward kernel has completed once it has finished `nt` steps
 __device__ __forceinline__ unsigned int fwd_bars_after(int g, int nt, int Tc, bool has_chunk) {
@@ -1108,7 +1110,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) scan_bwd_grouped(const Scan
       __syncthreads();
       if (gi == 0) {
         AttnBwdArgs a = S.att;
-        a.dbg = nullptr;
+        a.dbg = (S.tl_buf && k == S.tl_tick) ? S.tl_buf + 2 * 148 * 16 : nullptr;
         a.dw += s * S.s_dw; a.ab += s * S.s_ab; a.e += s * S.s_e; a.kappa += s * S.s_k; a.dh1 += s * S.s_dh1;
         a.datt += s * S.s_datt; a.datt_hi += s * S.s_dattp; a.datt_lo += s * S.s_dattp;
         for (int b = rank; b < a.B; b += ncta) attention_bwd_body(a, b, att_sh, &c, s);
@@ -1926,11 +1928,24 @@ __global__ void __launch_bounds__(256) encoder_fwd_kernel(const EncArgs a) {
   __syncthreads();
   for (int step = 0; step < a.L; ++step) {
     const int i = dir == 0 ? step : a.L - 1 - step;
-    // gates
+    // gates.  Register-tiled: four k per pass, the state rows read as broadcast 128-bit values -- 12 shared-memory
+    // loads per 32 FMAs instead of 36 (the loop was shared-memory-issue bound: 9 us per encoder step)
     for (int j = tid; j < 2 * E; j += blockDim.x) {
       float acc[ENC_ROWS];
 #pragma unroll
       for (int n = 0; n < ENC_ROWS; ++n) acc[n] = 0.0f;
+      if ((E & 3) == 0) {
+        for (int k = 0; k < E; k += 4) {
+          const float w0 = Wg[(long long)k * 2 * E + j], w1 = Wg[(long long)(k + 1) * 2 * E + j];
+          const float w2 = Wg[(long long)(k + 2) * 2 * E + j], w3 = Wg[(long long)(k + 3) * 2 * E + j];
+#pragma unroll
+          for (int n = 0; n < ENC_ROWS; ++n) {
+            const float4 sv = *reinterpret_cast<const float4*>(s + n * E + k);
+            acc[n] = fmaf(sv.x, w0, acc[n]); acc[n] = fmaf(sv.y, w1, acc[n]);
+            acc[n] = fmaf(sv.z, w2, acc[n]); acc[n] = fmaf(sv.w, w3, acc[n]);
+          }
+        }
+      } else
       for (int k = 0; k < E; ++k) {
         const float w = Wg[(long long)k * 2 * E + j];
 #pragma unroll
@@ -1956,6 +1971,18 @@ __global__ void __launch_bounds__(256) encoder_fwd_kernel(const EncArgs a) {
       float acc[ENC_ROWS];
 #pragma unroll
       for (int n = 0; n < ENC_ROWS; ++n) acc[n] = 0.0f;
+      if ((E & 3) == 0) {
+        for (int k = 0; k < E; k += 4) {
+          const float w0 = Ws[(long long)k * E + j], w1 = Ws[(long long)(k + 1) * E + j];
+          const float w2 = Ws[(long long)(k + 2) * E + j], w3 = Ws[(long long)(k + 3) * E + j];
+#pragma unroll
+          for (int n = 0; n < ENC_ROWS; ++n) {
+            const float4 sv = *reinterpret_cast<const float4*>(rs + n * E + k);
+            acc[n] = fmaf(sv.x, w0, acc[n]); acc[n] = fmaf(sv.y, w1, acc[n]);
+            acc[n] = fmaf(sv.z, w2, acc[n]); acc[n] = fmaf(sv.w, w3, acc[n]);
+          }
+        }
+      } else
       for (int k = 0; k < E; ++k) {
         const float w = Ws[(long long)k * E + j];
 #pragma unroll
@@ -2023,17 +2050,12 @@ __global__ void __launch_bounds__(256) encoder_bwd_kernel(const EncArgs a) {
       dsn[e] = v_keep;
     }
     __syncthreads();
-    // d(rs)[n][k] = sum_j dac[n][j] * Ws[k][j]
-    for (int e = tid; e < rows * E; e += blockDim.x) {
-      const int n = e / E, k = e % E;
-      float acc = 0.0f;
-      if (a.w_in_smem) {
-#pragma unroll 8
-        for (int j = 0; j < E; ++j) acc = fmaf(dac[n * E + j], wsT[j * E + k], acc);
-      } else {
-        const float* wr = a.Ws[dir] + (long long)k * E;
-        for (int j = 0; j < E; ++j) acc = fmaf(dac[n * E + j], wr[j], acc);
-      }
+    // d(rs)[n][k] = sum_j dac[n][j] * Ws[k][j].  Register-tiled when the weights sit in shared memory and the work
+    // splits as (k, block of 4 rows) per thread: four j per pass, dac read as broadcast 128-bit values -- 8 shared-
+    // memory loads per 16 FMAs instead of 32 (the loops were shared-memory-issue bound: 12 us per encoder step)
+    const bool tiled = a.w_in_smem && (E & 3) == 0 && (int)blockDim.x * 4 == ENC_ROWS * E;
+    auto rs_epilogue = [&](const int n, const int k, const float acc) {
+      const int e = n * E + k;
       const long long o = ((long long)i * a.N + n0 + n) * E + k;
       const float r = a.r[dir][o], sp = a.sprev[dir][o];
       const float dr = acc * sp;
@@ -2041,9 +2063,54 @@ __global__ void __launch_bounds__(256) encoder_bwd_kernel(const EncArgs a) {
       const float v = dr * r * (1.0f - r);
       dag[n * 2 * E + E + k] = v;
       a.dxg[dir][((long long)i * a.N + n0 + n) * 2 * E + E + k] = v;
+    };
+    if (tiled) {
+      const int k = tid % E, nb = (tid / E) * 4;
+      float acc4[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int j = 0; j < E; j += 4) {
+        const float w0 = wsT[j * E + k], w1 = wsT[(j + 1) * E + k], w2 = wsT[(j + 2) * E + k], w3 = wsT[(j + 3) * E + k];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 dv = *reinterpret_cast<const float4*>(dac + (nb + q) * E + j);
+          acc4[q] = fmaf(dv.x, w0, acc4[q]); acc4[q] = fmaf(dv.y, w1, acc4[q]);
+          acc4[q] = fmaf(dv.z, w2, acc4[q]); acc4[q] = fmaf(dv.w, w3, acc4[q]);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (nb + q < rows) rs_epilogue(nb + q, k, acc4[q]);
+    } else {
+      for (int e = tid; e < rows * E; e += blockDim.x) {
+        const int n = e / E, k = e % E;
+        float acc = 0.0f;
+        if (a.w_in_smem) {
+#pragma unroll 8
+          for (int j = 0; j < E; ++j) acc = fmaf(dac[n * E + j], wsT[j * E + k], acc);
+        } else {
+          const float* wr = a.Ws[dir] + (long long)k * E;
+          for (int j = 0; j < E; ++j) acc = fmaf(dac[n * E + j], wr[j], acc);
+        }
+        rs_epilogue(n, k, acc);
+      }
     }
     __syncthreads();
     // ds[n][k] += sum_j dag[n][j] * Wg[k][j]
+    if (tiled) {
+      const int k = tid % E, nb = (tid / E) * 4;
+      float g4[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int j = 0; j < 2 * E; j += 4) {
+        const float w0 = wgT[j * E + k], w1 = wgT[(j + 1) * E + k], w2 = wgT[(j + 2) * E + k], w3 = wgT[(j + 3) * E + k];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 dv = *reinterpret_cast<const float4*>(dag + (nb + q) * 2 * E + j);
+          g4[q] = fmaf(dv.x, w0, g4[q]); g4[q] = fmaf(dv.y, w1, g4[q]);
+          g4[q] = fmaf(dv.z, w2, g4[q]); g4[q] = fmaf(dv.w, w3, g4[q]);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (nb + q < rows) ds[(nb + q) * E + k] = dsn[(nb + q) * E + k] + g4[q];
+    } else
     for (int e = tid; e < rows * E; e += blockDim.x) {
       const int n = e / E, k = e % E;
       float acc = 0.0f;

@@ -94,6 +94,10 @@ lib.parrot_debug_set_stamps(h.ptr, C.c_void_p(tl.data_ptr()), -tick)
 step()
 torch.cuda.synchronize()
 lib.parrot_debug_set_stamps(h.ptr, None, 0)
+dbg = tl.cpu().numpy()[2 * 148 * 16:2 * 148 * 16 + 8].astype(np.float64)
+if which == 'bwd' and (dbg > 0).any():
+    print('attention-backward, batch row 0, step %d: milestones (us) entry / operands in smem / dphi done / '
+          'reductions + datt done / dh1 + pre-pass done / exit:' % tick, [round((x - dbg[0]) / 1e3, 2) for x in dbg[:6]])
 tl = tl.cpu().numpy()[:2 * 148 * 16].reshape(2, 148, 16).astype(np.float64)
 names = {1: 'barrier_passed(epi)', 10: 'barrier_passed(tma)', 9: 'operands_requested', 11: 'first_stage_landed',
          2: 'tma_all_issued', 3: 'mma_all_issued', 4: 'acc_ready', 5: 'part_written', 6: 'all_arrived',
