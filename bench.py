@@ -382,7 +382,7 @@ def main():
             'note': 'hi+lo operand planes of every in-scan weight counted once per decoder step; since round 2 the '
                     'recurrent part (41 MB) is partly resident in tensor memory and the rest stays in L2'}
         # attention-step latency (second half of the BASELINE metric): one stand-alone parrot_attention_step call
-        # (projection kernel + window kernel) at B x U x C of the workload, CUDA events over 200 back-to-back calls
+        # (one launch: projection + window) at B x U x C of the workload, CUDA events over 200 back-to-back calls
         H, Cc, A = cfg['rnn_h_dim'], 2 * cfg['encoder_dim'], cfg['attention_size']
         att_bytes = 4.0 * (B * U * Cc + B * U + B * Cc + 3 * B * A)
         g = torch.Generator(device='cpu').manual_seed(0)
@@ -410,7 +410,7 @@ def main():
         att_us = ev0.elapsed_time(ev1) * 1e3 / 200
         extra['attn_step_latency_us'] = att_us
         extra['roofline_attention'] = {
-            'bound': 'hbm', 'kernel': 'parrot_attention_step: attention_proj_kernel + attention_fwd_kernel (K7)',
+            'bound': 'hbm', 'kernel': 'parrot_attention_step: attention_step_kernel, projection + window in one launch (K7)',
             'achieved': att_bytes / (att_us * 1e-6) / 1e9, 'peak': pk['hbm'], 'unit': 'GB/s',
             'frac': att_bytes / (att_us * 1e-6) / 1e9 / pk['hbm'], 'traffic': None,
             'algorithmic_bytes_per_launch': att_bytes, 'avg_launch_us': att_us,

@@ -1449,6 +1449,7 @@ static void ensure_kernel_attrs() {
   CK(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
   CK(cudaFuncSetAttribute(attention_proj_slice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   CK(cudaFuncSetAttribute(attention_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  CK(cudaFuncSetAttribute(attention_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
   CK(cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   CK(cudaFuncSetAttribute(encoder_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
   CK(cudaFuncSetAttribute(encoder_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
@@ -1790,10 +1791,15 @@ static void attention_step(parrot_model& M, int t, bool sampling, cudaStream_t s
   const Dims& d = M.d;
   AttnFwdArgs a = attn_fwd_args(M, t, sampling);
   cudaEvent_t pe = M.prof_begin("attn_fwd", st);
-  // stage 1: K-sliced partial projections h1 . Watt^T ; stage 2: window + context, nparts CTAs per batch row
   const int nparts = attention_nparts(d.B, d.C, 148);
-  LAUNCH(attention_proj_slice_kernel, M.att_slices, 256, att_proj_smem(d), st, a);
-  LAUNCH(attention_window_kernel, d.B * nparts, 256, att_window_smem(d, nparts), st, a, nparts, M.att_slices);
+  if (3 * d.A <= 32 && d.H % 4 == 0) {
+    // one launch: every (batch row, context-column part) CTA computes the row's projection itself
+    LAUNCH(attention_step_kernel, d.B * nparts, 256, att_window_smem(d, nparts) + 8 * 32 * 4, st, a, nparts);
+  } else {
+    // stage 1: K-sliced partial projections h1 . Watt^T ; stage 2: window + context, nparts CTAs per batch row
+    LAUNCH(attention_proj_slice_kernel, M.att_slices, 256, att_proj_smem(d), st, a);
+    LAUNCH(attention_window_kernel, d.B * nparts, 256, att_window_smem(d, nparts), st, a, nparts, M.att_slices);
+  }
   parrot_model::prof_end(pe, st);
 }
 
@@ -2683,8 +2689,13 @@ int parrot_attention_step(const parrot_config* cfg, const float* d_h1, const flo
     a.hat = d_e_out;
     (void)smem;
     const int nparts = attention_nparts(d.B, d.C, 148);
-    LAUNCH(attention_proj_kernel, 148, 256, 0, (cudaStream_t)stream, a);
-    LAUNCH(attention_window_kernel, d.B * nparts, 256, att_window_smem(d, nparts), (cudaStream_t)stream, a, nparts, 0);
+    if (3 * d.A <= 32 && d.H % 4 == 0) {
+      LAUNCH(attention_step_kernel, d.B * nparts, 256, att_window_smem(d, nparts) + 8 * 32 * 4, (cudaStream_t)stream, a,
+             nparts);
+    } else {
+      LAUNCH(attention_proj_kernel, 148, 256, 0, (cudaStream_t)stream, a);
+      LAUNCH(attention_window_kernel, d.B * nparts, 256, att_window_smem(d, nparts), (cudaStream_t)stream, a, nparts, 0);
+    }
   });
 }
 

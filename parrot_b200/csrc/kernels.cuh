@@ -287,7 +287,58 @@ __device__ __forceinline__ void attention_proj_slice(const AttnFwdArgs& a, const
 // parameters and phi for the row -- identical bits -- and reduces its own slice of the context columns; part 0
 // writes kappa / alpha / beta / phi.  hat comes from the K-sliced partials (nslices > 0) or from a.hat.
 // sh: 2*rup(3A,4) + rup(U,4) + nwarps*Cs floats (Cs = C / nparts).
-template <bool WIDE>
+// Projection of ONE batch row by the whole CTA (single-launch attention step): thread t owns features 4t .. 4t+3 (+ 4
+// blockDim per pass), forms its share of the 3A dot products with 128-bit loads of h1 and W_att^T that are all
+// independent (batches of 10 in flight), a 31-shuffle transpose-reduce leaves output j on lane j of every warp, and
+// the warps' partials are added in warp order.  hat_out[j] = h1[b] . wT[j] + batt[j], j < 3A <= 32.
+__device__ __forceinline__ void attention_proj_row(const AttnFwdArgs& a, const int b, float* sh_red, float* hat_out) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarp = blockDim.x >> 5;
+  const int A3 = 3 * a.A;
+  float pv[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) pv[j] = 0.0f;
+  const float* hr = a.h1 + (long long)b * a.H;
+  for (int k = tid * 4; k < a.H; k += blockDim.x * 4) {
+    const float4 h4 = __ldcg(reinterpret_cast<const float4*>(hr + k));
+#pragma unroll
+    for (int j0 = 0; j0 < 30; j0 += 10) {
+      float4 w4[10];
+#pragma unroll
+      for (int i = 0; i < 10; ++i)
+        w4[i] = (j0 + i < A3) ? __ldg(reinterpret_cast<const float4*>(a.wT + (long long)(j0 + i) * a.H + k))
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int i = 0; i < 10; ++i) {
+        float acc = pv[j0 + i];
+        acc = fmaf(h4.x, w4[i].x, acc); acc = fmaf(h4.y, w4[i].y, acc);
+        acc = fmaf(h4.z, w4[i].z, acc); acc = fmaf(h4.w, w4[i].w, acc);
+        pv[j0 + i] = acc;
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 16; k >= 1; k >>= 1) {
+    const bool up = (lane & k) != 0;
+#pragma unroll
+    for (int i = 0; i < k; ++i) {
+      const float send = up ? pv[i] : pv[i + k];
+      const float keep = up ? pv[i + k] : pv[i];
+      pv[i] = keep + __shfl_xor_sync(0xffffffffu, send, k);
+    }
+  }
+  sh_red[warp * 32 + lane] = pv[0];     // lane j: this warp's partial of output j
+  __syncthreads();
+  if (tid < A3) {
+    float s = 0.0f;
+    for (int w = 0; w < nwarp; ++w) s += sh_red[w * 32 + tid];
+    hat_out[tid] = s + __ldg(a.batt + tid);
+  }
+  // (the caller's next __syncthreads publishes hat_out)
+}
+
+// PROJ: the CTA computes the projection of its row itself (attention_proj_row) right after its first context rows
+// have been requested; needs 3A <= 32, H % 4 == 0 and 8 * 32 more floats of shared memory behind the window's.
+template <bool WIDE, bool PROJ = false>
 __device__ __forceinline__ void attention_window_part(const AttnFwdArgs& a, const int b, const int part,
                                                       const int nparts, const int nslices, float* sh) {
   const int A3p = (3 * a.A + 3) & ~3;
@@ -313,6 +364,10 @@ __device__ __forceinline__ void attention_window_part(const AttnFwdArgs& a, cons
                   : make_float4(0.f, 0.f, 0.f, 0.f);
   }
   const float k_prev_reg = (tid < A) ? __ldcg(a.k_prev + (long long)b * A + tid) : 0.0f;
+  if (PROJ) {
+    float* sh_red = sh_phi + ((a.U + 3) & ~3) + nwarp * Cs;   // [nwarp][32] behind the window's own arrays
+    attention_proj_row(a, b, sh_red, sh_hat);
+  } else
   if (tid < 3 * A) {
     float s;
     if (nslices > 0) {
@@ -442,6 +497,11 @@ __global__ void __launch_bounds__(256) attention_proj_slice_kernel(const AttnFwd
 __global__ void __launch_bounds__(256) attention_window_kernel(const AttnFwdArgs a, const int nparts, const int nslices) {
   extern __shared__ float sh[];
   attention_window_part<true>(a, blockIdx.x / nparts, blockIdx.x % nparts, nparts, nslices, sh);
+}
+// the whole attention step in ONE launch: projection + window per (batch row, context-column part)
+__global__ void __launch_bounds__(256) attention_step_kernel(const AttnFwdArgs a, const int nparts) {
+  extern __shared__ float sh[];
+  attention_window_part<true, true>(a, blockIdx.x / nparts, blockIdx.x % nparts, nparts, 0, sh);
 }
 
 __global__ void __launch_bounds__(256) attention_fwd_kernel(const AttnFwdArgs a, const int precomputed_hat) {
