@@ -1816,6 +1816,8 @@ static bool use_persistent(parrot_model& M) {
   }
   const Dims& d = M.d;
   if (!env || !M.persistent_ok || M.cfg.gemm_impl == 1 || M.profiling >= 2 || M.sm_count < 148) return false;
+  // the scan finishes work on quads of features (128-bit stash / plane accesses): odd sizes take the per-phase path
+  if ((d.H & 3) || (d.Hp & 3) || (d.C & 3)) return false;
   const size_t att_f = std::max(att_proj_smem(d), att_window_smem(d, attention_nparts(d.B, d.C, M.grp_f[0])));
   const size_t att_b = ((size_t)d.C + d.U + 3 * d.A * 16 + 10 * d.A) * 4;
   if (std::max(att_f, att_b) > (size_t)ATT_SMEM_BYTES) return false;
