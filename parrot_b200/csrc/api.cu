@@ -428,6 +428,12 @@ struct parrot_model {
 };
 
 static const int NT = 128;  // sample tile of the batched (outside-the-scan) products
+// output-feature tile of the weight-gradient products: N = 256 is the only width at which a tcgen05.mma of this engine
+// runs at the tensor-pipe floor behind a TMA ring (tools/tma_bw.cu: 136 cycles per MMA vs 110 at N = 128 for half the work)
+#ifndef PB_WGRAD_NT
+#define PB_WGRAD_NT 256
+#endif
+static const int WNT = PB_WGRAD_NT;
 static const int COLSUM_CHUNKS = 64;
 #ifndef PB_SPLIT_TARGET
 #define PB_SPLIT_TARGET 148   // CTAs one scan phase is split over (experiment knob)
@@ -862,7 +868,7 @@ static void build(parrot_model& M) {
     auto tplane = [&](const std::string& nm, int feat_pitch, long long samples, bool as_a) {
       Plane p = M.make_plane("T." + nm, rup(feat_pitch, 128), (int)samples, 1);
       if (as_a) M.map_tA[nm] = M.make_map(p, 2, 128);
-      else M.map_tB[nm] = M.make_map(p, 2, NT);
+      else M.map_tB[nm] = M.make_map(p, 2, WNT);
     };
     for (int l = 0; l < 3; ++l) {
       tplane("h" + LN(l), d.Hp, (long long)(T + 1) * Np, true);
@@ -1408,16 +1414,16 @@ static void build(parrot_model& M) {
       const int nkb = cdiv((long long)T * Np, 64);
       for (auto& g : M.wgrads)
         for (int mt = 0; mt < cdiv(g.in, 128); ++mt)
-          for (int nt = 0; nt < cdiv(g.out, NT); ++nt) {
+          for (int nt = 0; nt < cdiv(g.out, WNT); ++nt) {
             Job j = blank_job();
-            j.epi = EPI_PLAIN; j.row0 = mt * 128; j.m_valid = std::min(128, g.in - mt * 128); j.n0 = nt * NT;
+            j.epi = EPI_PLAIN; j.row0 = mt * 128; j.m_valid = std::min(128, g.in - mt * 128); j.n0 = nt * WNT;
             j.nseg = 1;
-            j.seg[0] = mkseg(g.xt_map, mt * 128, g.a_k, g.dyt_map, g.b_row + nt * NT, 0, NO_SLOT, nkb);
+            j.seg[0] = mkseg(g.xt_map, mt * 128, g.a_k, g.dyt_map, g.b_row + nt * WNT, 0, NO_SLOT, nkb);
             j.pa.out = M.grads ? M.grads + g.goff : nullptr;
             j.pa.ldo = g.out; j.pa.n_total = g.out; j.pa.flags = PF_TRANS; j.pa.scale = 1.0f;
             js.push_back(j);
           }
-      push_table(M, "wgrad", js, NT);
+      push_table(M, "wgrad", js, WNT);
     }
   }
 }
