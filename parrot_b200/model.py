@@ -177,6 +177,8 @@ class Parrot(object):
         """``blocks.model.Model.set_parameter_values`` equivalent: dict brick-path -> array."""
         self._allocate()
         for name, arr in values.items():
+            if name.startswith('__'):        # optimizer state riding along in a train.py checkpoint
+                continue
             p = self.parameters[name]
             p.copy_(torch.as_tensor(np.asarray(arr, np.float32)).view_as(p))
         self.mark_dirty()

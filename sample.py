@@ -16,6 +16,11 @@ from parrot_b200.utils import sample_parse, stop_heuristic
 
 def main(argv=None):
     args = sample_parse(argv)
+    # flags of the reference's parser whose code paths (sample.py:78-93, 120-134: custom phrases through the text
+    # front end, speaker mixing, random speakers, the one-step debugging sampler) are not implemented here
+    for flag in ('phrase', 'mix', 'random_speaker', 'sample_one_step'):
+        if getattr(args, flag, None):
+            raise NotImplementedError('sample.py: --%s is parsed for compatibility but not supported' % flag)
     with open(os.path.join(args.save_dir, 'config', args.experiment_name + '.pkl'), 'rb') as f:   # sample.py:24-28
         saved_args = pickle.load(f)
     assert saved_args.dataset == args.dataset

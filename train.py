@@ -83,8 +83,12 @@ def main(argv=None):
     train_stream = parrot_stream(args.dataset, args.use_speaker, ('train',), args.batch_size,
                                  noise_level=args.feedback_noise_level, labels_type=labels_type,
                                  seq_size=args.seq_size, dataset=dataset, seed=args.seed, epochs=10 ** 6)
+    # held-out utterances for the validation monitor (another seed of the synthetic source: disjoint from training)
+    valid_dataset = SyntheticVoice(num_examples=max(64, 4 * args.batch_size), output_dim=args.output_dim,
+                                   num_characters=args.num_characters, num_speakers=args.num_speakers,
+                                   seed=args.seed + 7919)
     valid_stream_args = dict(noise_level=None if args.feedback_noise_level is None else 0.,
-                             labels_type=labels_type, seq_size=args.seq_size, dataset=dataset,
+                             labels_type=labels_type, seq_size=args.seq_size, dataset=valid_dataset,
                              seed=args.seed + 1)
 
     parrot_args = {                                                            # train.py:57-77
@@ -106,7 +110,13 @@ def main(argv=None):
 
     if args.load_experiment:                                                   # train.py:136-139
         path = os.path.join(save_dir, 'pkl', 'best_' + args.load_experiment + '.npz')
-        parrot.set_parameter_values(dict(numpy.load(path)))
+        loaded = dict(numpy.load(path))
+        opt = {k: loaded.pop(k) for k in list(loaded) if k.startswith('__adam_')}
+        parrot.set_parameter_values(loaded)
+        if len(opt) == 3:                                                      # resume the optimizer as well
+            algorithm.m.copy_(torch.from_numpy(opt['__adam_m']))
+            algorithm.v.copy_(torch.from_numpy(opt['__adam_v']))
+            algorithm.time = int(opt['__adam_time'])
 
     cost_name = args.which_cost
     schedule = None
@@ -159,6 +169,9 @@ def main(argv=None):
                 print('iter %d  train_%s %.5f  valid_%s %.5f  (%.1f s)' %
                       (it + 1, cost_name, train_cost, cost_name, vcost, time.time() - t0))
                 vals = parrot.get_parameter_values()
+                # (Blocks checkpoints carry the algorithm buffers too: Adam moments and step count ride along)
+                vals.update({'__adam_m': algorithm.m.cpu().numpy(), '__adam_v': algorithm.v.cpu().numpy(),
+                             '__adam_time': numpy.int64(algorithm.time)})
                 numpy.savez(os.path.join(save_dir, 'pkl', 'last_' + exp_name + '.npz'), **vals)   # train.py:166-173
                 if vcost < best:                                                                  # TrackTheBest
                     best = vcost
