@@ -123,3 +123,49 @@ def test_comm_single_rank_is_the_identity_without_nccl_or_gpu():
     ptr = C.c_void_p()
     assert lib.parrot_comm_init(2, 5, None, C.byref(ptr)) != 0
     assert b'rank' in lib.parrot_last_error()
+
+
+def _workspace_bytes(cfg, B, T, U, sampling=0):
+    L = _lib()
+    from parrot_b200.model import Parrot, _DEFAULTS
+    m = Parrot.__new__(Parrot)
+    d = dict(_DEFAULTS); d.update(cfg)
+    if d['full_feedback']:
+        d['weak_feedback'] = True
+    m.__dict__.update(d)
+    m.encoder_time_axis = 0; m.gemm_impl = 0
+    c = m._make_cfg(B, T, U, sampling)
+    n = C.c_size_t()
+    L.check(L.load().parrot_workspace_bytes(C.byref(c), C.byref(n)))
+    return n.value
+
+
+def test_dry_table_build_for_group_partitions(monkeypatch):
+    """parrot_workspace_bytes runs the whole host-side build (planes, tensor-map slots, job tables of the grouped scans,
+    split-K scratch regions, TMEM residency assignment) without touching a GPU: every partition of the 148 CTAs into
+    layer groups must produce tables (a group never gets more split jobs than CTAs), an invalid partition falls back to
+    the default, and the per-table scratch regions make the grouped build larger than nothing else does."""
+    base = dict(input_dim=420, output_dim=63, rnn_h_dim=1024, readouts_dim=1024, weak_feedback=True,
+                which_cost='MSE', num_characters=43, attention_type='graves', attention_size=10,
+                attention_alignment=0.15, encoder_type='bidirectional', encoder_dim=128)
+    for k in ('PARROT_GROUPS_F', 'PARROT_GROUPS_B', 'PARROT_TC'):
+        monkeypatch.delenv(k, raising=False)
+    default = _workspace_bytes(base, 64, 800, 128)
+    assert default > 10 * 2 ** 30                     # 13 GB of stashes and planes at the benchmarked size
+    for part in ('100,24,24', '64,42,42', '64,36,48', '32,16,16', '50,49,49'):
+        monkeypatch.setenv('PARROT_GROUPS_F', part)
+        monkeypatch.setenv('PARROT_GROUPS_B', part)
+        assert _workspace_bytes(base, 64, 800, 128) > 0, part
+    monkeypatch.setenv('PARROT_GROUPS_F', '100,100,100')      # more than 148 CTAs: ignored
+    monkeypatch.setenv('PARROT_GROUPS_B', 'nonsense')
+    assert _workspace_bytes(base, 64, 800, 128) == default
+    for k in ('PARROT_GROUPS_F', 'PARROT_GROUPS_B'):
+        monkeypatch.delenv(k, raising=False)
+    monkeypatch.setenv('PARROT_TC', '8')
+    assert _workspace_bytes(base, 64, 800, 128) > 0
+    monkeypatch.delenv('PARROT_TC', raising=False)
+    # small and odd problems, GMM / speaker / full feedback, the sampling handle
+    tiny = dict(util.TINY, which_cost='GMM', use_speaker=True, full_feedback=True)
+    assert _workspace_bytes(tiny, 5, 7, 9) > 0
+    assert _workspace_bytes(tiny, 5, 7, 9, sampling=1) > 0
+    assert _workspace_bytes(dict(util.TINY, layer_norm=True), 4, 12, 6) > 0
